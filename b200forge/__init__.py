@@ -1,0 +1,8 @@
+"""Import alias for the `stable-diffusion-webui-forge_b200/` package directory (hyphens are not importable)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "stable-diffusion-webui-forge_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _os, _f

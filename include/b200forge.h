@@ -1,0 +1,207 @@
+/* b200forge.h — C ABI of libb200forge.so, the sm_100a kernel library that sits under
+ * stable-diffusion-webui-forge's backend/ plug points.
+ *
+ * Conventions
+ *   - The caller owns every buffer (PyTorch allocates); the library allocates nothing persistent.
+ *   - Every call enqueues on the given cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *     no hidden synchronisation, safe under CUDA-graph capture.
+ *   - Return 0 on success or a negative B200_E* code; never throws, never exits.
+ *     b200_last_error() returns a thread-local human-readable message for the last failure.
+ *   - dtype: B200_F16 or B200_BF16 for activations/weights; statistics and sampler state are fp32.
+ *   - Activations inside the UNet are channels-last: an NHWC tensor is the row-major matrix
+ *     [N*H*W, C]; a token tensor [b, L, C] is the same thing.
+ *
+ * Each entry point names the reference call site it replaces (paths relative to the reference tree).
+ */
+#ifndef B200FORGE_H
+#define B200FORGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+enum { B200_OK = 0, B200_EINVAL = -1, B200_EUNSUPPORTED = -2, B200_ECUDA = -3, B200_ENODEVICE = -4 };
+enum { B200_F16 = 0, B200_BF16 = 1 };
+enum {
+  B200_EPI_NONE = 0,
+  B200_EPI_SILU = 1,  /* y = silu(acc + bias) */
+  B200_EPI_GEGLU = 2, /* weight rows pre-interleaved per BN tile: y[:, j] = (x_j + b) * gelu_erf(gate_j + b) */
+  B200_EPI_GELU = 3   /* y = gelu_erf(acc + bias) */
+};
+
+int b200_version(void);
+const char* b200_last_error(void);
+/* 0 when a CUDA device of compute capability 10.x is visible, else B200_ENODEVICE. */
+int b200_device_ok(void);
+int b200_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM  C[M,N] = epi( A[M,K] @ B[N,K]^T + bias + rowvec + residual )       (tcgen05 + TMA + TMEM)
+ * replaces: torch.nn.functional.linear via backend/operations.py:149-156 (ForgeOperations.Linear),
+ *           1x1 Conv2d via backend/operations.py:169-176, GEGLU backend/nn/unet.py:104-111.
+ * A may be the channel concatenation [A1 | A2] (torch.cat skip, backend/nn/unet.py:741) without a copy.
+ */
+typedef struct {
+  int M, N, K;        /* K = K1 + K2 when A2 is given; K1 % 64 == 0 in that case            */
+  int lda, ldb, ldc;  /* leading dimensions in elements (multiples of 8)                    */
+  int dtype;
+  int epilogue;       /* B200_EPI_*; GEGLU: N is the interleaved width (2x the output width) */
+  int block_n;        /* 0 = choose; else multiple of 32, <= 256                              */
+  const void* bias;   /* [N] (or [M] when bias_along_m), same dtype; may be NULL             */
+  int bias_along_m;
+  const void* residual; /* [M, N_out] added after the activation; may be NULL                */
+  int ldr;
+  const void* rowvec; /* [M / rows_per_vec, N] added before the activation (time-embedding)  */
+  int ld_rowvec;
+  int rows_per_vec;
+  const void* A2;     /* second A source or NULL */
+  int lda2;
+  int K1;
+} b200_gemm_desc;
+
+int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3x3 stride-1 pad-1 convolution on NHWC as an implicit GEMM (A tiles fetched by 4-D TMA boxes per
+ * filter tap, zero fill = padding).  y[N,H,W,Cout] = epi(conv(x) + bias + temb[n, :] + residual)
+ * replaces: torch.nn.Conv2d._conv_forward via backend/operations.py:169-176 inside
+ *           ResBlock (backend/nn/unet.py:433-478), Upsample (:330-355), VAE ResnetBlock (backend/nn/vae.py:77-115).
+ * Weights are packed [Cout, 9*(C1+C2)] with k = (ky*3+kx)*(C1+C2) + c.  C1, C2 multiples of 64.
+ */
+typedef struct {
+  int N, H, W;
+  int C1, C2; /* input = concat(x1[..., C1], x2[..., C2]); C2 = 0 for a single source */
+  int Cout;
+  int dtype;
+  int epilogue;
+  int block_n;
+  const void* bias;     /* [Cout] */
+  const void* residual; /* [N*H*W, Cout] */
+  int ldr;
+  const void* temb;     /* [N, ld_temb] row n added to every pixel of image n (ResBlock emb_layers) */
+  int ld_temb;
+} b200_conv3x3_desc;
+
+int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y, const b200_conv3x3_desc* d,
+                 b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention forward  O = softmax(Q K^T * scale) V   (FlashAttention-style, S and O tiles in
+ * TMEM, K/V tiles by TMA, online softmax in registers).  No mask, no dropout, non-causal.
+ * replaces: backend/attention.py:280-321 (attention_xformers) / :324-339 (attention_pytorch).
+ * q/k/v/o point at head 0 of each operand; element (b, l, h, d) lives at
+ *   ptr + b*stride_b + l*stride_l + h*Dh + d     (strides in elements, multiples of 8).
+ * This lets q,k,v alias one fused QKV projection output without copies.  Dh must be 64 or 128.
+ */
+typedef struct {
+  int B, H, Lq, Lk, Dh;
+  long long q_stride_b, q_stride_l;
+  long long k_stride_b, k_stride_l;
+  long long v_stride_b, v_stride_l;
+  long long o_stride_b, o_stride_l;
+  float scale;
+  int dtype;
+} b200_attn_desc;
+
+int b200_attention(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm on NHWC, split in a statistics pass and a fused apply(+SiLU)(+concat) pass.
+ * replaces: torch.nn.functional.group_norm via backend/operations.py:304-310 and the following
+ *           nn.SiLU (backend/nn/unet.py:395-396,418-419,691; backend/nn/vae.py:12-13,85).
+ * sums: [N, G, 2] fp32 (sum, sum of squares), must be zeroed by the caller (b200_fill_zero).
+ */
+typedef struct {
+  int N, HW;
+  int C1, C2; /* channels of the two concatenated sources (C2 = 0: single source) */
+  int groups;
+  float eps;
+  int silu;
+  int dtype;
+} b200_gn_desc;
+
+int b200_groupnorm_stats(const void* x1, const void* x2, float* sums, const b200_gn_desc* d, b200_stream_t s);
+int b200_groupnorm_apply(const void* x1, const void* x2, const float* sums, const void* gamma, const void* beta,
+                         void* y, const b200_gn_desc* d, b200_stream_t s);
+
+/* LayerNorm over the last dimension of [rows, C]; gamma/beta may be NULL (Flux: no affine).
+ * replaces: torch.nn.functional.layer_norm via backend/operations.py:323-329. */
+int b200_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int C, float eps,
+                   int dtype, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / gather helpers (HBM-bound).
+ */
+int b200_fill_zero(void* p, size_t bytes, b200_stream_t s);
+/* nearest-neighbour x2 upsample on NHWC (F.interpolate(mode="nearest"), backend/nn/unet.py:352). */
+int b200_upsample2x(const void* x, void* y, int N, int H, int W, int C, int dtype, b200_stream_t s);
+/* im2col for 3x3 convs that the TMA path does not cover (C not a multiple of 64, stride 2):
+ * out[(n,ho,wo), (ky*3+kx)*C + c] zero padded to ldo columns.  pad_lo is the top/left zero padding
+ * (1 for the UNet convs; 0 for the VAE encoder's asymmetric (0,1,0,1) pad). */
+int b200_im2col3x3(const void* x, void* out, int N, int H, int W, int C, int stride, int pad_lo, int Ho, int Wo,
+                   int ldo, int dtype, b200_stream_t s);
+int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int in_is_f32, int dtype, b200_stream_t s);
+int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int ldx, int out_is_f32, int dtype,
+                      b200_stream_t s);
+/* y = silu(x) elementwise (SiLU in front of ResBlock.emb_layers, backend/nn/unet.py:412). */
+int b200_silu(const void* x, void* y, size_t n, int dtype, b200_stream_t s);
+/* Row softmax in place on [rows, cols] with scale (VAE single-head attention, backend/nn/vae.py:118-137). */
+int b200_softmax_rows(void* x, int rows, int cols, int ld, float scale, int dtype, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * UNet entry: sinusoidal timestep embedding (backend/nn/unet.py:55-67) -> [B, dim] in dtype,
+ * [cos | sin] order, freqs = exp(-ln(max_period) * i / half).
+ */
+int b200_timestep_embedding(const float* t, void* out, int B, int dim, float max_period, int dtype, b200_stream_t s);
+
+/* KModel input scaling + layout + im2col for conv_in in one pass
+ * (backend/modules/k_model.py:27,34; backend/modules/k_prediction.py:74-79; conv_in backend/nn/unet.py:553):
+ * x fp32 NCHW [B, C, H, W], sigma fp32 [B]  ->  cols[(b,h,w), (ky*3+kx)*C + c] = x / sqrt(sigma^2 + 1), zero padded to ldo.
+ * The batch is written `reps` times (cond/uncond batching, backend/sampling/sampling_function.py:234). */
+int b200_unet_input_im2col(const float* x, const float* sigma, void* cols, int B, int C, int H, int W, int ldo,
+                           int reps, int dtype, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused denoise epilogue + CFG + sampler update, one launch per step.
+ * replaces: KModel.apply_model tail (backend/modules/k_model.py:45-46, k_prediction.py:81-92),
+ *           the CFG combine (backend/sampling/sampling_function.py:276-289,312) and the per-step
+ *           update of k_diffusion/sampling.py:119-137 (euler), :140-159 (euler ancestral), :648-671 (dpm++ 2m).
+ * eps: UNet output, NHWC [(2 or 1)*B, H, W, ld_eps] in dtype; rows [0,B) = uncond, [B,2B) = cond
+ *      (the reference batches [uncond, cond], sampling_function.py:186-188); has_uncond = 0 -> cond only.
+ * x (fp32 NCHW [B,C,H,W]) is updated in place; denoised (fp32 NCHW) is written every step
+ * (callback 'denoised'); old_denoised is read+written for DPM++ 2M.
+ * All sigma-dependent scalars are precomputed on the host for the whole schedule (no device->host syncs):
+ *   euler / euler_a : x += (x - D)/sigma * dt  [+ noise * noise_scale]
+ *   dpmpp_2m        : x = c_x * x + c_d * D + c_old * D_old
+ */
+enum { B200_STEP_EULER = 0, B200_STEP_DPMPP_2M = 1 };
+typedef struct {
+  int kind;
+  int B, C, H, W;
+  int ld_eps;
+  int has_uncond;
+  int prediction; /* 0 = epsilon (D = x - eps*sigma), 1 = v_prediction, 2 = const/flow (D = x - v*sigma) */
+  float sigma;    /* sigma_i (sigma_hat) */
+  float cfg_scale;
+  float dt;          /* euler: sigma_down - sigma_i */
+  float noise_scale; /* euler ancestral: s_noise * sigma_up (0: no noise read) */
+  float c_x, c_d, c_old; /* dpm++ 2m coefficients */
+  int eps_dtype;
+} b200_step_desc;
+
+int b200_sampler_step(float* x, const void* eps, const float* noise, float* denoised, float* old_denoised,
+                      const b200_step_desc* d, b200_stream_t s);
+
+/* VAE post-decode: clamp((x+1)/2, 0, 1) NHWC (dtype) -> fp32 NHWC [B,H,W,3]
+ * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
+int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FORGE_H */

@@ -1,0 +1,582 @@
+// b200forge — HBM-bound kernels of the denoise path: GroupNorm (stats + apply/SiLU/concat), LayerNorm,
+// layout conversion, nearest upsample, im2col for the few convolutions the TMA path does not cover,
+// timestep embedding.  All activations are channels-last; every global access is a 16-byte vector.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+template <bool BF16>
+__device__ __forceinline__ void load8(const void* p, size_t elem_off, float (&x)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p) + elem_off * 2);
+  float2 f;
+  f = unpack2<BF16>(r.x); x[0] = f.x; x[1] = f.y;
+  f = unpack2<BF16>(r.y); x[2] = f.x; x[3] = f.y;
+  f = unpack2<BF16>(r.z); x[4] = f.x; x[5] = f.y;
+  f = unpack2<BF16>(r.w); x[6] = f.x; x[7] = f.y;
+}
+template <bool BF16>
+__device__ __forceinline__ void store8(void* p, size_t elem_off, const float (&x)[8]) {
+  uint4 o;
+  o.x = pack2<BF16>(x[0], x[1]);
+  o.y = pack2<BF16>(x[2], x[3]);
+  o.z = pack2<BF16>(x[4], x[5]);
+  o.w = pack2<BF16>(x[6], x[7]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p) + elem_off * 2) = o;
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+// grid (slabs, N), 256 threads arranged as (ry, tx): tx walks channel vectors, ry walks pixels.
+template <bool BF16>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+                                                       float* __restrict__ sums, int HW, int C1, int C2, int groups,
+                                                       int pix_per_slab) {
+  extern __shared__ float sh[];  // [C] sums, [C] sums of squares
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  float* csum = sh;
+  float* csq = sh + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int TX = CV < 256 ? CV : 256;
+  const int RY = 256 / TX;
+  const int tx = threadIdx.x % TX;
+  const int ry = threadIdx.x / TX;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_slab;
+  int p1 = p0 + pix_per_slab;
+  if (p1 > HW) p1 = HW;
+  if (ry < RY) {
+    for (int cv = tx; cv < CV; cv += TX) {
+      const int c = cv << 3;
+      const bool first = c < C1;
+      const void* src = first ? x1 : x2;
+      const int Cs = first ? C1 : C2;
+      const int cs = first ? c : c - C1;
+      float s[8], q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+      for (int px = p0 + ry; px < p1; px += RY) {
+        float v[8];
+        load8<BF16>(src, ((size_t)n * HW + px) * Cs + cs, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += v[i];
+          q[i] = fmaf(v[i], v[i], q[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&csum[c + i], s[i]);
+        atomicAdd(&csq[c + i], q[i]);
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += csum[c];
+      q += csq[c];
+    }
+    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 0], s);
+    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 1], q);
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
+                                                       const float* __restrict__ sums, const void* __restrict__ gamma,
+                                                       const void* __restrict__ beta, void* __restrict__ y, int HW,
+                                                       int C1, int C2, int groups, float eps, int silu,
+                                                       int pix_per_slab) {
+  extern __shared__ float sh[];  // [C] scale, [C] shift
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+  float* sc = sh;
+  float* sf = sh + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = sums[((size_t)n * groups + g) * 2 + 0] * inv_cnt;
+    float var = sums[((size_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = ld1<BF16>(gamma, c) * rstd;
+    sc[c] = a;
+    sf[c] = ld1<BF16>(beta, c) - mean * a;
+  }
+  __syncthreads();
+  const int TX = CV < 256 ? CV : 256;
+  const int RY = 256 / TX;
+  const int tx = threadIdx.x % TX;
+  const int ry = threadIdx.x / TX;
+  const int p0 = blockIdx.x * pix_per_slab;
+  int p1 = p0 + pix_per_slab;
+  if (p1 > HW) p1 = HW;
+  if (ry >= RY) return;
+  for (int cv = tx; cv < CV; cv += TX) {
+    const int c = cv << 3;
+    const bool first = c < C1;
+    const void* src = first ? x1 : x2;
+    const int Cs = first ? C1 : C2;
+    const int cs = first ? c : c - C1;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] = sc[c + i];
+      b[i] = sf[c + i];
+    }
+    for (int px = p0 + ry; px < p1; px += RY) {
+      float v[8];
+      load8<BF16>(src, ((size_t)n * HW + px) * Cs + cs, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = fmaf(v[i], a[i], b[i]);
+        v[i] = silu ? silu_f(t) : t;
+      }
+      store8<BF16>(y, ((size_t)n * HW + px) * C + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row, row cached in registers (C <= 8*32*MAXV)
+template <bool BF16, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
+                                                        const void* __restrict__ beta, void* __restrict__ y, int rows,
+                                                        int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int CV = C >> 3;
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = lane + k * 32;
+    if (cv < CV) {
+      load8<BF16>(x, (size_t)warp * C + (cv << 3), v[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = lane + k * 32;
+    if (cv < CV) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[k][i] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = lane + k * 32;
+    if (cv < CV) {
+      float o8[8];
+      if (gamma) {
+        float g[8], bt[8];
+        load8<BF16>(gamma, (size_t)(cv << 3), g);
+        if (beta) load8<BF16>(beta, (size_t)(cv << 3), bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] = (v[k][i] - mean) * rstd * g[i] + (beta ? bt[i] : 0.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] = (v[k][i] - mean) * rstd;
+      }
+      store8<BF16>(y, (size_t)warp * C + (cv << 3), o8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layout helpers
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV) {
+  const size_t total = (size_t)N * (2 * H) * (2 * W) * CV;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    size_t t = i / CV;
+    const int wo = (int)(t % (2 * W));
+    t /= (2 * W);
+    const int ho = (int)(t % (2 * H));
+    const int n = (int)(t / (2 * H));
+    y[i] = x[(((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * CV + cv];
+  }
+}
+
+// vector path: C % 8 == 0.  out row = (n, ho, wo); column = tap*C + c; columns [9C, ldo) zero.
+__global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int H, int W, int CV,
+                                     int stride, int pad_lo, int Ho, int Wo, int ldoV) {
+  const size_t total = (size_t)N * Ho * Wo * ldoV;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kv = (int)(i % ldoV);
+    size_t t = i / ldoV;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (kv < 9 * CV) {
+      const int tap = kv / CV, cv = kv - tap * CV;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int hi = ho * stride + ky - pad_lo, wi = wo * stride + kx - pad_lo;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)n * H + hi) * W + wi) * CV + cv];
+    }
+    out[i] = v;
+  }
+}
+
+// scalar path for odd channel counts (C = 3 or 4): 16-bit elements.
+__global__ void im2col3x3_scalar_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int N, int H, int W,
+                                        int C, int stride, int pad_lo, int Ho, int Wo, int ldo) {
+  const size_t total = (size_t)N * Ho * Wo * ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldo);
+    size_t t = i / ldo;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    uint16_t v = 0;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int hi = ho * stride + ky - pad_lo, wi = wo * stride + kx - pad_lo;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)n * H + hi) * W + wi) * C + c];
+    }
+    out[i] = v;
+  }
+}
+
+template <bool BF16>
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, int N, int C, int H, int W,
+                                    int in_is_f32) {
+  const size_t total = (size_t)N * H * W * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const size_t src = (((size_t)n * C + c) * H + h) * W + w;
+    const float v = in_is_f32 ? reinterpret_cast<const float*>(x)[src] : ld1<BF16>(x, src);
+    st1<BF16>(y, i, v);
+  }
+}
+
+template <bool BF16>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, void* __restrict__ y, int N, int C, int H, int W,
+                                    int ldx, int out_is_f32) {
+  const size_t total = (size_t)N * C * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    size_t t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const float v = ld1<BF16>(x, (((size_t)n * H + h) * W + w) * ldx + c);
+    if (out_is_f32) reinterpret_cast<float*>(y)[i] = v;
+    else st1<BF16>(y, i, v);
+  }
+}
+
+template <bool BF16>
+__global__ void silu_kernel(const void* __restrict__ x, void* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st1<BF16>(y, i, silu_f(ld1<BF16>(x, i)));
+}
+
+// out[b, i] = cos(t_b * f_i), out[b, half + i] = sin(t_b * f_i), f_i = exp(-ln(max_period) * i / half)
+template <bool BF16>
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, void* __restrict__ out, int B, int dim,
+                                          float neg_log_period) {
+  const int half = dim / 2;
+  const int total = B * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i - b * half;
+    const float f = expf(neg_log_period * (float)k / (float)half);
+    const float a = t[b] * f;
+    st1<BF16>(out, (size_t)b * dim + k, cosf(a));
+    st1<BF16>(out, (size_t)b * dim + half + k, sinf(a));
+    if ((dim & 1) && k == 0) st1<BF16>(out, (size_t)b * dim + dim - 1, 0.f);
+  }
+}
+
+// x fp32 NCHW [B,C,H,W] / sqrt(sigma_b^2 + 1) -> im2col rows for the 3x3 conv_in, written `reps` times
+template <bool BF16>
+__global__ void unet_input_im2col_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
+                                         void* __restrict__ cols, int B, int C, int H, int W, int ldo, int reps) {
+  const size_t per_rep = (size_t)B * H * W * ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_rep; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldo);
+    size_t t = i / ldo;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float v = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int hi = h + ky - 1, wi = w + kx - 1;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const float sg = sigma[b];
+        // reference: noise / (sigma ** 2 + sigma_data ** 2) ** 0.5 in fp32, then .to(fp16)
+        v = x[(((size_t)b * C + c) * H + hi) * W + wi] / sqrtf(sg * sg + 1.0f);
+      }
+    }
+    for (int r = 0; r < reps; ++r) st1<BF16>(cols, (size_t)r * per_rep + i, v);
+  }
+}
+
+template <bool BF16>
+__global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2) {
+  // one CTA per row; cols up to 64K
+  const int row = blockIdx.x;
+  __shared__ float red[32];
+  char* base = reinterpret_cast<char*>(x) + (size_t)row * ld * 2;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float v[8];
+    load8<BF16>(base, (size_t)c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float v[8];
+    load8<BF16>(base, (size_t)c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += exp2f((v[i] - mx) * scale_log2);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  const float inv = 1.0f / s;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float v[8];
+    load8<BF16>(base, (size_t)c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = exp2f((v[i] - mx) * scale_log2) * inv;
+    store8<BF16>(base, (size_t)c, v);
+  }
+}
+
+template <bool BF16>
+__global__ void vae_post_kernel(const void* __restrict__ x, float* __restrict__ out, size_t pixels, int ldx) {
+  const size_t total = pixels * 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i / 3;
+    const int c = (int)(i - px * 3);
+    float v = ld1<BF16>(x, px * ldx + c);
+    v = fminf(fmaxf((v + 1.0f) * 0.5f, 0.f), 1.f);
+    out[i] = v;
+  }
+}
+
+static inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = (size_t)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define DISPATCH_DTYPE(dtype, ...)                 \
+  do {                                             \
+    if ((dtype) == B200_BF16) {                    \
+      constexpr bool BF = true;                    \
+      __VA_ARGS__;                                 \
+    } else {                                       \
+      constexpr bool BF = false;                   \
+      __VA_ARGS__;                                 \
+    }                                              \
+  } while (0)
+
+static int gn_slabs(const b200_gn_desc* d, int* pix_per_slab) {
+  int slabs = (4 * num_sms() + d->N - 1) / d->N;
+  const int max_slabs = (d->HW + 31) / 32;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  *pix_per_slab = (d->HW + slabs - 1) / slabs;
+  slabs = (d->HW + *pix_per_slab - 1) / *pix_per_slab;
+  return slabs;
+}
+
+static int gn_check(const b200_gn_desc* d, const void* x1, const void* x2) {
+  B200_CHECK_ARG(d && x1, "groupnorm: null argument");
+  B200_CHECK_ARG(d->C1 > 0 && d->C1 % 8 == 0 && d->C2 >= 0 && d->C2 % 8 == 0, "groupnorm: channels %d/%d", d->C1,
+                 d->C2);
+  B200_CHECK_ARG((d->C2 == 0) == (x2 == nullptr), "groupnorm: x2/C2 mismatch");
+  B200_CHECK_ARG(d->groups > 0 && (d->C1 + d->C2) % d->groups == 0, "groupnorm: groups");
+  B200_CHECK_ARG((d->C1 + d->C2) * 8 <= 96 * 1024, "groupnorm: too many channels");
+  B200_CHECK_ARG(d->N > 0 && d->N <= 65535 && d->HW > 0, "groupnorm: shape");
+  return B200_OK;
+}
+
+extern "C" int b200_groupnorm_stats(const void* x1, const void* x2, float* sums, const b200_gn_desc* d,
+                                    b200_stream_t s) {
+  int rc = gn_check(d, x1, x2);
+  if (rc) return rc;
+  B200_CHECK_ARG(sums, "groupnorm_stats: null sums");
+  int pps;
+  const int slabs = gn_slabs(d, &pps);
+  const size_t smem = (size_t)(d->C1 + d->C2) * 2 * sizeof(float);
+  dim3 grid(slabs, d->N);
+  DISPATCH_DTYPE(d->dtype, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gn_stats_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    gn_stats_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, sums, d->HW, d->C1, d->C2, d->groups, pps);
+  });
+  B200_CHECK_LAUNCH("groupnorm_stats");
+  return B200_OK;
+}
+
+extern "C" int b200_groupnorm_apply(const void* x1, const void* x2, const float* sums, const void* gamma,
+                                    const void* beta, void* y, const b200_gn_desc* d, b200_stream_t s) {
+  int rc = gn_check(d, x1, x2);
+  if (rc) return rc;
+  B200_CHECK_ARG(sums && gamma && beta && y, "groupnorm_apply: null argument");
+  int pps;
+  const int slabs = gn_slabs(d, &pps);
+  const size_t smem = (size_t)(d->C1 + d->C2) * 2 * sizeof(float);
+  dim3 grid(slabs, d->N);
+  DISPATCH_DTYPE(d->dtype, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gn_apply_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    gn_apply_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, sums, gamma, beta, y, d->HW, d->C1, d->C2,
+                                                               d->groups, d->eps, d->silu, pps);
+  });
+  B200_CHECK_LAUNCH("groupnorm_apply");
+  return B200_OK;
+}
+
+extern "C" int b200_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int C, float eps,
+                              int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && y && rows > 0 && C > 0 && C % 8 == 0, "layernorm: bad arguments");
+  if (C > 8 * 32 * 16) {
+    set_error("layernorm: C=%d unsupported (max 4096)", C);
+    return B200_EUNSUPPORTED;
+  }
+  const int grid = (rows + 7) / 8;
+  DISPATCH_DTYPE(dtype, {
+    if (C <= 8 * 32 * 5) layernorm_kernel<BF, 5><<<grid, 256, 0, (cudaStream_t)s>>>(x, gamma, beta, y, rows, C, eps);
+    else layernorm_kernel<BF, 16><<<grid, 256, 0, (cudaStream_t)s>>>(x, gamma, beta, y, rows, C, eps);
+  });
+  B200_CHECK_LAUNCH("layernorm");
+  return B200_OK;
+}
+
+extern "C" int b200_upsample2x(const void* x, void* y, int N, int H, int W, int C, int dtype, b200_stream_t s) {
+  (void)dtype;
+  B200_CHECK_ARG(x && y && C % 8 == 0 && N > 0 && H > 0 && W > 0, "upsample2x: bad arguments");
+  const size_t total = (size_t)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  B200_CHECK_LAUNCH("upsample2x");
+  return B200_OK;
+}
+
+extern "C" int b200_im2col3x3(const void* x, void* out, int N, int H, int W, int C, int stride, int pad_lo, int Ho,
+                              int Wo, int ldo, int dtype, b200_stream_t s) {
+  (void)dtype;
+  B200_CHECK_ARG(x && out && N > 0 && H > 0 && W > 0 && C > 0 && stride > 0 && ldo >= 9 * C && ldo % 8 == 0,
+                 "im2col3x3: bad arguments");
+  if (C % 8 == 0) {
+    const size_t total = (size_t)N * Ho * Wo * (ldo / 8);
+    im2col3x3_vec_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)out, N, H, W,
+                                                                             C / 8, stride, pad_lo, Ho, Wo, ldo / 8);
+  } else {
+    const size_t total = (size_t)N * Ho * Wo * ldo;
+    im2col3x3_scalar_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        (const uint16_t*)x, (uint16_t*)out, N, H, W, C, stride, pad_lo, Ho, Wo, ldo);
+  }
+  B200_CHECK_LAUNCH("im2col3x3");
+  return B200_OK;
+}
+
+extern "C" int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int in_is_f32, int dtype,
+                                 b200_stream_t s) {
+  B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+  const size_t total = (size_t)N * C * H * W;
+  DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W,
+                                                                                                  in_is_f32));
+  B200_CHECK_LAUNCH("nchw_to_nhwc");
+  return B200_OK;
+}
+
+extern "C" int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int ldx, int out_is_f32,
+                                 int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && ldx >= C, "nhwc_to_nchw: bad arguments");
+  const size_t total = (size_t)N * C * H * W;
+  DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W, ldx,
+                                                                                                  out_is_f32));
+  B200_CHECK_LAUNCH("nhwc_to_nchw");
+  return B200_OK;
+}
+
+extern "C" int b200_silu(const void* x, void* y, size_t n, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && y && n > 0, "silu: bad arguments");
+  DISPATCH_DTYPE(dtype, silu_kernel<BF><<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(x, y, n));
+  B200_CHECK_LAUNCH("silu");
+  return B200_OK;
+}
+
+extern "C" int b200_softmax_rows(void* x, int rows, int cols, int ld, float scale, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "softmax_rows: bad arguments");
+  DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(x, rows, cols, ld,
+                                                                                  scale * 1.4426950408889634f));
+  B200_CHECK_LAUNCH("softmax_rows");
+  return B200_OK;
+}
+
+extern "C" int b200_timestep_embedding(const float* t, void* out, int B, int dim, float max_period, int dtype,
+                                       b200_stream_t s) {
+  B200_CHECK_ARG(t && out && B > 0 && dim > 1, "timestep_embedding: bad arguments");
+  const float neg_log = -logf(max_period);
+  DISPATCH_DTYPE(dtype, timestep_embedding_kernel<BF><<<grid_for((size_t)B * (dim / 2), 128), 128, 0, (cudaStream_t)s>>>(
+                            t, out, B, dim, neg_log));
+  B200_CHECK_LAUNCH("timestep_embedding");
+  return B200_OK;
+}
+
+extern "C" int b200_unet_input_im2col(const float* x, const float* sigma, void* cols, int B, int C, int H, int W,
+                                      int ldo, int reps, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && sigma && cols && B > 0 && C > 0 && H > 0 && W > 0 && ldo >= 9 * C && ldo % 8 == 0 && reps > 0,
+                 "unet_input_im2col: bad arguments");
+  const size_t total = (size_t)B * H * W * ldo;
+  DISPATCH_DTYPE(dtype, unet_input_im2col_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+                            x, sigma, cols, B, C, H, W, ldo, reps));
+  B200_CHECK_LAUNCH("unet_input_im2col");
+  return B200_OK;
+}
+
+extern "C" int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && out && pixels > 0 && ldx >= 3, "vae_postprocess: bad arguments");
+  DISPATCH_DTYPE(dtype, vae_post_kernel<BF><<<grid_for(pixels * 3, 256), 256, 0, (cudaStream_t)s>>>(x, out, pixels, ldx));
+  B200_CHECK_LAUNCH("vae_postprocess");
+  return B200_OK;
+}

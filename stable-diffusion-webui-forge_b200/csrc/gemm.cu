@@ -1,0 +1,486 @@
+// b200forge — persistent warp-specialised GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   C[M, N] = epilogue( A[M, K] * B[N, K]^T )        fp16 or bf16 operands, fp32 accumulation in TMEM
+//
+// One CTA per SM, static round-robin over 128 x BN output tiles (BN runtime, multiple of 32, <= 256):
+//   warp 0   TMA producer: A tile (128 x 64) and B tile (BN x 64) per k-chunk into a ring of smem stages
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage; tcgen05.commit
+//            releases the stage and, after the last chunk, publishes the TMEM accumulator
+//   warp 2   TMEM allocator (512 columns = two 256-column accumulator stages)
+//   warps 4-7 epilogue: tcgen05.ld the accumulator (thread = row), add bias / time-embedding row /
+//            residual, apply SiLU / GELU / GEGLU, convert and store — overlapped with the next tile's MMAs
+//
+// The A operand is fetched in one of two ways:
+//   mode 0  plain row-major [M, K] (optionally the channel concatenation of two matrices)
+//   mode 1  3x3 stride-1 pad-1 convolution on NHWC: k-chunk = (filter tap, 64-channel slice); the tile of
+//           128 output pixels is a (tile_n x tile_h x tile_w) box and the tap shifts the box by (ky-1, kx-1);
+//           TMA zero-fills the out-of-image part, which is exactly the convolution's zero padding.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+struct GemmKParams {
+  int M, N;
+  int num_k_chunks;
+  int mode;
+  int split_chunk;     // mode 0: first chunk served by source 2; mode 1: chunks of source 1 per tap
+  int chunks_per_tap;  // mode 1
+  int tile_w, tile_h, tile_n, tiles_w, tiles_h;
+  int BN, tiles_m, tiles_n, num_stages;
+  uint32_t idesc;
+  void* C;
+  int ldc;
+  const void* bias;
+  int bias_along_m;
+  const void* residual;
+  int ldr;
+  const void* rowvec;
+  int ld_rowvec;
+  int rows_per_vec;
+  int epilogue;
+};
+
+static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
+static constexpr int kThreads = 256;
+
+template <bool BF16>
+__device__ __forceinline__ void epi_store8(const GemmKParams& p, int m, int n, float (&x)[8]) {
+  // x: 8 consecutive output columns n..n+7 of row m, activation already applied
+  if (p.residual) {
+    uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) +
+                                              ((size_t)m * p.ldr + n) * 2);
+    float2 f;
+    f = unpack2<BF16>(r.x); x[0] += f.x; x[1] += f.y;
+    f = unpack2<BF16>(r.y); x[2] += f.x; x[3] += f.y;
+    f = unpack2<BF16>(r.z); x[4] += f.x; x[5] += f.y;
+    f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
+  }
+  uint4 o;
+  o.x = pack2<BF16>(x[0], x[1]);
+  o.y = pack2<BF16>(x[2], x[3]);
+  o.z = pack2<BF16>(x[4], x[5]);
+  o.w = pack2<BF16>(x[6], x[7]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.C) + ((size_t)m * p.ldc + n) * 2) = o;
+}
+
+template <bool BF16>
+__device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, float (&x)[8]) {
+  uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(base) + elem_off * 2));
+  float2 f;
+  f = unpack2<BF16>(r.x); x[0] += f.x; x[1] += f.y;
+  f = unpack2<BF16>(r.y); x[2] += f.x; x[3] += f.y;
+  f = unpack2<BF16>(r.z); x[4] += f.x; x[5] += f.y;
+  f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+            const __grid_constant__ CUtensorMap mapB, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.num_stages;
+  const int BN = p.BN;
+  const uint32_t b_tile_bytes = (uint32_t)BN * 128u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)S * kATileBytes;
+  const uint32_t bar_base = b_base + (uint32_t)S * b_tile_bytes;
+  // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM pointer slot
+  auto full_bar = [&](int i) { return bar_base + (uint32_t)i * 8u; };
+  auto empty_bar = [&](int i) { return bar_base + (uint32_t)(S + i) * 8u; };
+  auto tfull_bar = [&](int i) { return bar_base + (uint32_t)(2 * S + i) * 8u; };
+  auto tempty_bar = [&](int i) { return bar_base + (uint32_t)(2 * S + 2 + i) * 8u; };
+  const uint32_t tmem_slot = bar_base + (uint32_t)(2 * S + 4) * 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int nk = p.num_k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = (uint32_t)kATileBytes + b_tile_bytes;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = tile / p.tiles_m;
+      int cn = 0, ch = 0, cw = 0;
+      if (p.mode == 1) {
+        const int tpi = p.tiles_w * p.tiles_h;
+        const int img_grp = m_blk / tpi;
+        const int rem = m_blk - img_grp * tpi;
+        cn = img_grp * p.tile_n;
+        ch = (rem / p.tiles_w) * p.tile_h;
+        cw = (rem % p.tiles_w) * p.tile_w;
+      }
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t fb = full_bar(stage);
+        mbar_expect_tx(fb, tx_bytes);
+        const uint32_t a_dst = a_base + (uint32_t)stage * kATileBytes;
+        if (p.mode == 0) {
+          if (kc < p.split_chunk) tma_load_2d(a_dst, &mapA, fb, kc * 64, m_blk * 128);
+          else tma_load_2d(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
+        } else {
+          const int tap = kc / p.chunks_per_tap;
+          const int cc = kc - tap * p.chunks_per_tap;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
+          else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
+        }
+        tma_load_2d(b_base + (uint32_t)stage * b_tile_bytes, &mapB, fb, kc * 64, n_blk * BN);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc_sw128(a_base + (uint32_t)stage * kATileBytes, 0, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(b_base + (uint32_t)stage * b_tile_bytes, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // +32 bytes per 16-element k step inside the 128-byte swizzle atom (encoded >> 4)
+          umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = tile / p.tiles_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
+      const int m = m_blk * 128 + r;
+      const bool row_ok = m < p.M;
+      const int n0 = n_blk * BN;
+      float bias_m = 0.f;
+      if (p.bias && p.bias_along_m && row_ok) bias_m = ld1<BF16>(p.bias, m);
+      const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
+
+      if (p.epilogue == B200_EPI_GEGLU) {
+        const int half_bn = BN >> 1;
+        const int out_n0 = n_blk * half_bn;
+        for (int c = 0; c < half_bn; c += 32) {
+          uint32_t vx[32], vg[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, vx);
+          tmem_ld_32x32(t_addr + (uint32_t)(half_bn + c), vg);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int nx = n0 + c + g * 8;        // interleaved column of the x half
+              const int ng = nx + half_bn;          // matching gate column
+              if (ng < p.N) {
+                float x[8], gt[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  x[i] = __uint_as_float(vx[g * 8 + i]);
+                  gt[i] = __uint_as_float(vg[g * 8 + i]);
+                }
+                if (p.bias) {
+                  epi_add_vec8<BF16>(p.bias, (size_t)nx, x);
+                  epi_add_vec8<BF16>(p.bias, (size_t)ng, gt);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = x[i] * gelu_erf_f(gt[i]);
+                epi_store8<BF16>(p, m, out_n0 + c + g * 8, x);
+              }
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + c + g * 8;
+              if (n < p.N) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+                if (p.bias) {
+                  if (p.bias_along_m) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] += bias_m;
+                  } else {
+                    epi_add_vec8<BF16>(p.bias, (size_t)n, x);
+                  }
+                }
+                if (p.rowvec) epi_add_vec8<BF16>(p.rowvec, rv_off + (size_t)n, x);
+                if (p.epilogue == B200_EPI_SILU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) x[i] = silu_f(x[i]);
+                } else if (p.epilogue == B200_EPI_GELU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) x[i] = gelu_erf_f(x[i]);
+                }
+                epi_store8<BF16>(p, m, n, x);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static int pick_block_n(int N, int epilogue) {
+  const int step = (epilogue == B200_EPI_GEGLU) ? 64 : 32;
+  if (N >= 256) {
+    for (int bn = 256; bn >= 128; bn -= step)
+      if (N % bn == 0) return bn;
+    return 256;  // tail tile handled by TMA zero fill + guarded stores
+  }
+  int bn = (N + step - 1) / step * step;
+  return bn;
+}
+
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
+                       int dtype, cudaStream_t stream) {
+  const int stage_bytes = kATileBytes + p.BN * 128;
+  int S = (220 * 1024) / stage_bytes;
+  if (S > 8) S = 8;
+  if (S < 2) S = 2;
+  p.num_stages = S;
+  const size_t smem = (size_t)S * stage_bytes + 1024 + (2 * S + 4) * 8 + 16;
+  const int total = p.tiles_m * p.tiles_n;
+  int grid = num_sms();
+  if (grid <= 0) {
+    set_error("gemm: no device");
+    return B200_ENODEVICE;
+  }
+  if (grid > total) grid = total;
+  cudaError_t e;
+  if (dtype == B200_BF16) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("gemm: smem attr: %s", cudaGetErrorString(e)); return B200_ECUDA; }
+      attr_done = true;
+    }
+    gemm_kernel<true><<<grid, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      e = cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("gemm: smem attr: %s", cudaGetErrorString(e)); return B200_ECUDA; }
+      attr_done = true;
+    }
+    gemm_kernel<false><<<grid, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
+  }
+  B200_CHECK_LAUNCH("gemm");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s) {
+  B200_CHECK_ARG(A && B && C && d, "gemm: null argument");
+  B200_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape %d %d %d", d->M, d->N, d->K);
+  B200_CHECK_ARG(d->N % 8 == 0 && d->K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", d->N, d->K);
+  B200_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0 && d->ldc % 8 == 0, "gemm: leading dims must be multiples of 8");
+  B200_CHECK_ARG(d->dtype == B200_F16 || d->dtype == B200_BF16, "gemm: dtype");
+  B200_CHECK_ARG(!d->residual || d->ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
+  B200_CHECK_ARG(!d->rowvec || (d->rows_per_vec > 0 && d->ld_rowvec % 8 == 0), "gemm: rowvec layout");
+  int K1 = d->K, K2 = 0;
+  if (d->A2) {
+    K1 = d->K1;
+    K2 = d->K - d->K1;
+    B200_CHECK_ARG(K1 > 0 && K2 > 0 && K1 % 64 == 0 && d->lda2 % 8 == 0, "gemm: concat split K1=%d K=%d", K1, d->K);
+  }
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M;
+  p.N = d->N;
+  p.mode = 0;
+  const int chunks1 = (K1 + 63) / 64, chunks2 = (K2 + 63) / 64;
+  p.num_k_chunks = chunks1 + chunks2;
+  p.split_chunk = d->A2 ? chunks1 : p.num_k_chunks;
+  int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->N, d->epilogue);
+  const int bn_step = d->epilogue == B200_EPI_GEGLU ? 64 : 32;
+  B200_CHECK_ARG(bn % bn_step == 0 && bn <= 256, "gemm: block_n %d invalid", bn);
+  if (d->epilogue == B200_EPI_GEGLU)
+    B200_CHECK_ARG(d->N % bn == 0, "gemm: GEGLU needs N (%d) divisible by block_n (%d)", d->N, bn);
+  p.BN = bn;
+  p.tiles_m = (d->M + 127) / 128;
+  p.tiles_n = (d->N + bn - 1) / bn;
+  p.idesc = make_idesc_f16(128, bn, d->dtype == B200_BF16, false, false);
+  p.C = C;
+  p.ldc = d->ldc;
+  p.bias = d->bias;
+  p.bias_along_m = d->bias_along_m;
+  p.residual = d->residual;
+  p.ldr = d->ldr;
+  p.rowvec = d->rowvec;
+  p.ld_rowvec = d->ld_rowvec;
+  p.rows_per_vec = d->rows_per_vec > 0 ? d->rows_per_vec : 1;
+  p.epilogue = d->epilogue;
+
+  CUtensorMap mA, mA2, mB;
+  {
+    uint64_t dims[2] = {(uint64_t)K1, (uint64_t)d->M};
+    uint64_t str[1] = {(uint64_t)d->lda * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap(&mA, d->dtype, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  if (d->A2) {
+    uint64_t dims[2] = {(uint64_t)K2, (uint64_t)d->M};
+    uint64_t str[1] = {(uint64_t)d->lda2 * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap(&mA2, d->dtype, d->A2, 2, dims, str, box);
+    if (rc) return rc;
+  } else {
+    mA2 = mA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    uint64_t str[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    int rc = make_tmap(&mB, d->dtype, B, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  return launch_gemm(mA, mA2, mB, p, d->dtype, static_cast<cudaStream_t>(s));
+}
+
+extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y,
+                            const b200_conv3x3_desc* d, b200_stream_t s) {
+  B200_CHECK_ARG(x1 && w_packed && y && d, "conv3x3: null argument");
+  B200_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "conv3x3: bad shape");
+  B200_CHECK_ARG(d->C1 > 0 && d->C1 % 64 == 0 && d->C2 >= 0 && d->C2 % 64 == 0,
+                 "conv3x3: C1 (%d) / C2 (%d) must be multiples of 64 (use b200_im2col3x3 + b200_gemm otherwise)",
+                 d->C1, d->C2);
+  B200_CHECK_ARG((d->C2 == 0) == (x2 == nullptr), "conv3x3: x2 / C2 mismatch");
+  B200_CHECK_ARG(d->Cout % 8 == 0, "conv3x3: Cout must be a multiple of 8");
+  B200_CHECK_ARG(d->dtype == B200_F16 || d->dtype == B200_BF16, "conv3x3: dtype");
+  // output tile = tile_n images x tile_h rows x tile_w columns = 128 consecutive NHWC pixels
+  int tile_w = d->W < 128 ? d->W : 128;
+  B200_CHECK_ARG(128 % tile_w == 0 && d->W % tile_w == 0, "conv3x3: W=%d does not tile into 128-pixel rows", d->W);
+  int tile_h = 128 / tile_w;
+  if (tile_h > d->H) tile_h = d->H;
+  B200_CHECK_ARG(d->H % tile_h == 0 && (128 % (tile_w * tile_h)) == 0, "conv3x3: H=%d does not tile", d->H);
+  int tile_n = 128 / (tile_w * tile_h);
+  B200_CHECK_ARG(tile_n == 1 || (tile_w == d->W && tile_h == d->H), "conv3x3: tiling");
+  const int C = d->C1 + d->C2;
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->N * d->H * d->W;
+  p.N = d->Cout;
+  p.mode = 1;
+  p.chunks_per_tap = C / 64;
+  p.split_chunk = d->C1 / 64;
+  p.num_k_chunks = 9 * p.chunks_per_tap;
+  p.tile_w = tile_w;
+  p.tile_h = tile_h;
+  p.tile_n = tile_n;
+  p.tiles_w = d->W / tile_w;
+  p.tiles_h = d->H / tile_h;
+  int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, d->epilogue);
+  B200_CHECK_ARG(bn % 32 == 0 && bn <= 256, "conv3x3: block_n %d invalid", bn);
+  B200_CHECK_ARG(d->epilogue != B200_EPI_GEGLU, "conv3x3: GEGLU epilogue not supported");
+  p.BN = bn;
+  p.tiles_m = ((d->N + tile_n - 1) / tile_n) * p.tiles_w * p.tiles_h;
+  p.tiles_n = (d->Cout + bn - 1) / bn;
+  p.idesc = make_idesc_f16(128, bn, d->dtype == B200_BF16, false, false);
+  p.C = y;
+  p.ldc = d->Cout;
+  p.bias = d->bias;
+  p.residual = d->residual;
+  p.ldr = d->ldr;
+  B200_CHECK_ARG(!d->residual || d->ldr % 8 == 0, "conv3x3: ldr");
+  p.rowvec = d->temb;
+  p.ld_rowvec = d->ld_temb;
+  B200_CHECK_ARG(!d->temb || d->ld_temb % 8 == 0, "conv3x3: ld_temb");
+  p.rows_per_vec = d->H * d->W;
+  p.epilogue = d->epilogue;
+
+  CUtensorMap mA, mA2, mB;
+  auto make4 = [&](CUtensorMap* m, const void* base, int Csrc) {
+    uint64_t dims[4] = {(uint64_t)Csrc, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)Csrc * 2, (uint64_t)d->W * Csrc * 2, (uint64_t)d->H * d->W * Csrc * 2};
+    uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_n};
+    return make_tmap(m, d->dtype, base, 4, dims, str, box);
+  };
+  int rc = make4(&mA, x1, d->C1);
+  if (rc) return rc;
+  if (x2) {
+    rc = make4(&mA2, x2, d->C2);
+    if (rc) return rc;
+  } else {
+    mA2 = mA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)(9 * C), (uint64_t)d->Cout};
+    uint64_t str[1] = {(uint64_t)(9 * C) * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    rc = make_tmap(&mB, d->dtype, w_packed, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  return launch_gemm(mA, mA2, mB, p, d->dtype, static_cast<cudaStream_t>(s));
+}

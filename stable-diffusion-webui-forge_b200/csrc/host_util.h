@@ -1,0 +1,47 @@
+// b200forge — host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200forge.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+// cuTensorMapEncodeTiled fetched through the runtime so that the library has no link-time
+// dependency on libcuda.so (it must dlopen on a GPU-less build box).
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled tmap_encoder();
+
+// rank-N tiled tensor map over 16-bit elements, 128-byte swizzle, zero fill out of bounds.
+// dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
+int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
+
+#define B200_CHECK_ARG(cond, ...)  \
+  do {                             \
+    if (!(cond)) {                 \
+      b200::set_error(__VA_ARGS__); \
+      return B200_EINVAL;          \
+    }                              \
+  } while (0)
+
+#define B200_CHECK_LAUNCH(name)                                                  \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      b200::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+      return B200_ECUDA;                                                         \
+    }                                                                            \
+  } while (0)
+
+}  // namespace b200

@@ -1,0 +1,332 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, raw pointers + descriptors out.
+
+PyTorch is used for device memory and streams only; every function here enqueues exactly the
+hand-written sm_100a kernels of libb200forge.so on the current CUDA stream.  Nothing in this module
+falls back to a torch op — unsupported shapes raise `B200Error` (code B200_EUNSUPPORTED) so that the
+caller (the plug-in layer) can decide to hand the block back to Forge's own code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as _l
+from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER)  # noqa: F401
+
+LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return _l.B200_F16
+    if t.dtype == torch.bfloat16:
+        return _l.B200_BF16
+    raise TypeError(f"b200forge kernels take fp16/bf16 tensors, got {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rowmajor2d(t: torch.Tensor, name: str) -> None:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} / {t.stride()}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+         residual: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 1,
+         epilogue: int = EPI_NONE, a2: Optional[torch.Tensor] = None, bias_along_m: bool = False,
+         out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+    """out[M, N] = epi(cat(a, a2) @ w.T + bias + rowvec[row // rows_per_vec]) + residual.
+
+    a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
+    GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
+    """
+    _rowmajor2d(a, "a")
+    _rowmajor2d(w, "w")
+    M, K1 = a.shape
+    N, K = w.shape
+    if a2 is not None:
+        _rowmajor2d(a2, "a2")
+        assert a2.shape[0] == M and K1 + a2.shape[1] == K
+    else:
+        assert K1 == K, (a.shape, w.shape)
+    n_out = N // 2 if epilogue == EPI_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=a.dtype, device=a.device)
+    _rowmajor2d(out, "out")
+    assert out.shape[0] == M and out.shape[1] == n_out
+    d = _l.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldb, d.ldc = a.stride(0), w.stride(0), out.stride(0)
+    d.dtype = _dt(a)
+    d.epilogue = epilogue
+    d.block_n = block_n
+    d.bias = _p(bias)
+    d.bias_along_m = 1 if bias_along_m else 0
+    if residual is not None:
+        _rowmajor2d(residual, "residual")
+        d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
+    if rowvec is not None:
+        _rowmajor2d(rowvec, "rowvec")
+        d.rowvec, d.ld_rowvec, d.rows_per_vec = rowvec.data_ptr(), rowvec.stride(0), rows_per_vec
+    if a2 is not None:
+        d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), K1
+    _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    _count()
+    return out
+
+
+def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor], block_n: int = 256):
+    """Interleave GEGLU projection rows so each BN-wide output tile holds BN/2 value rows followed by
+    the matching BN/2 gate rows (reference layout: rows [0, I) value, [I, 2I) gate — unet.py:109-110)."""
+    two_i = w.shape[0]
+    inner = two_i // 2
+    half = block_n // 2
+    assert inner % half == 0, (inner, block_n)
+    idx = torch.arange(two_i, device=w.device).view(-1, block_n)
+    tile = idx // block_n
+    within = idx % block_n
+    src = torch.where(within < half, tile * half + within, inner + tile * half + (within - half)).reshape(-1)
+    wp = w.index_select(0, src).contiguous()
+    bp = b.index_select(0, src).contiguous() if b is not None else None
+    return wp, bp
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] (torch Conv2d) -> [Cout, 9*Cin] with k = (ky*3 + kx)*Cin + c."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
+
+
+def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+            x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            temb: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None,
+            block_n: int = 0) -> torch.Tensor:
+    """3x3/stride 1/pad 1 convolution on contiguous NHWC tensors; x2 is an optional second channel group."""
+    assert x1.dim() == 4 and x1.is_contiguous()
+    n, h, w_, c1 = x1.shape
+    c2 = 0
+    if x2 is not None:
+        assert x2.is_contiguous() and x2.shape[:3] == x1.shape[:3]
+        c2 = x2.shape[3]
+    cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 9 * (c1 + c2) and w_packed.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h, w_, cout), dtype=x1.dtype, device=x1.device)
+    assert out.is_contiguous()
+    d = _l.Conv3x3Desc()
+    d.N, d.H, d.W, d.C1, d.C2, d.Cout = n, h, w_, c1, c2, cout
+    d.dtype = _dt(x1)
+    d.epilogue = epilogue
+    d.block_n = block_n
+    d.bias = _p(bias)
+    if residual is not None:
+        assert residual.is_contiguous()
+        d.residual, d.ldr = residual.data_ptr(), residual.shape[-1]
+    if temb is not None:
+        _rowmajor2d(temb, "temb")
+        d.temb, d.ld_temb = temb.data_ptr(), temb.stride(0)
+    _l.check(_l.load().b200_conv3x3(x1.data_ptr(), _p(x2), w_packed.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B, Lq, H*Dh], k/v [B, Lk, H*Dh] (unit inner stride; may be column slices of a fused projection)."""
+    b, lq, hd = q.shape
+    lk = k.shape[1]
+    dh = hd // heads
+    for t in (q, k, v):
+        assert t.dim() == 3 and t.stride(2) == 1 and t.shape[2] == hd
+    if out is None:
+        out = torch.empty((b, lq, hd), dtype=q.dtype, device=q.device)
+    assert out.stride(2) == 1
+    d = _l.AttnDesc()
+    d.B, d.H, d.Lq, d.Lk, d.Dh = b, heads, lq, lk, dh
+    d.q_stride_b, d.q_stride_l = q.stride(0), q.stride(1)
+    d.k_stride_b, d.k_stride_l = k.stride(0), k.stride(1)
+    d.v_stride_b, d.v_stride_l = v.stride(0), v.stride(1)
+    d.o_stride_b, d.o_stride_l = out.stride(0), out.stride(1)
+    d.scale = float(scale if scale is not None else dh ** -0.5)
+    d.dtype = _dt(q)
+    _l.check(_l.load().b200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    _count()
+    return out
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
+              silu: bool = False, x2: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over the channel concat of NHWC tensors x1, x2 -> NHWC [.., C1+C2]."""
+    assert x1.is_contiguous()
+    n = x1.shape[0]
+    c1 = x1.shape[-1]
+    hw = x1.numel() // (n * c1)
+    c2 = 0
+    if x2 is not None:
+        assert x2.is_contiguous() and x2.shape[:-1] == x1.shape[:-1]
+        c2 = x2.shape[-1]
+    if sums is None:
+        sums = torch.empty((n, groups, 2), dtype=torch.float32, device=x1.device)
+    if out is None:
+        out = torch.empty(tuple(x1.shape[:-1]) + (c1 + c2,), dtype=x1.dtype, device=x1.device)
+    d = _l.GnDesc()
+    d.N, d.HW, d.C1, d.C2, d.groups, d.eps, d.silu, d.dtype = n, hw, c1, c2, groups, eps, 1 if silu else 0, _dt(x1)
+    L = _l.load()
+    st = _stream()
+    _l.check(L.b200_fill_zero(sums.data_ptr(), n * groups * 2 * 4, st))
+    _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), sums.data_ptr(), C.byref(d), st))
+    _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                    out.data_ptr(), C.byref(d), st))
+    _count(3)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(_l.load().b200_layernorm(x.data_ptr(), _p(gamma), _p(beta), out.data_ptr(), rows, c, eps, _dt(x), _stream()))
+    _count()
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dim() == 4 and x.is_contiguous()
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+    _l.check(_l.load().b200_upsample2x(x.data_ptr(), out.data_ptr(), n, h, w, c, _dt(x), _stream()))
+    _count()
+    return out
+
+
+def im2col3x3(x: torch.Tensor, *, stride: int = 1, pad_lo: int = 1, pad_hi: int = 1, ldo: Optional[int] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC -> [N*Ho*Wo, ldo] patch matrix, k = (ky*3+kx)*C + c, zero padded to ldo columns."""
+    assert x.dim() == 4 and x.is_contiguous()
+    n, h, w, c = x.shape
+    ho = (h + pad_lo + pad_hi - 3) // stride + 1
+    wo = (w + pad_lo + pad_hi - 3) // stride + 1
+    if ldo is None:
+        ldo = (9 * c + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((n * ho * wo, ldo), dtype=x.dtype, device=x.device)
+    _l.check(_l.load().b200_im2col3x3(x.data_ptr(), out.data_ptr(), n, h, w, c, stride, pad_lo, ho, wo, ldo, _dt(x),
+                                      _stream()))
+    _count()
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dim() == 4 and x.is_contiguous()
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    is_f32 = x.dtype == torch.float32
+    assert is_f32 or x.dtype == dtype
+    _l.check(_l.load().b200_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), n, c, h, w, 1 if is_f32 else 0, _dt(out), _stream()))
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: Optional[int] = None, out_dtype: Optional[torch.dtype] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x NHWC (channel stride ldx = x.shape[3]); keeps the first `channels` channels."""
+    assert x.dim() == 4 and x.is_contiguous()
+    n, h, w, ldx = x.shape
+    c = channels or ldx
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=out_dtype, device=x.device)
+    _l.check(_l.load().b200_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), n, c, h, w, ldx,
+                                         1 if out.dtype == torch.float32 else 0, _dt(x), _stream()))
+    _count()
+    return out
+
+
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(_l.load().b200_silu(x.data_ptr(), out.data_ptr(), x.numel(), _dt(x), _stream()))
+    _count()
+    return out
+
+
+def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
+    _rowmajor2d(x, "x")
+    _l.check(_l.load().b200_softmax_rows(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), scale, _dt(x), _stream()))
+    _count()
+    return x
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, dtype: torch.dtype, max_period: float = 10000.0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    if out is None:
+        out = torch.empty((t.shape[0], dim), dtype=dtype, device=t.device)
+    _l.check(_l.load().b200_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, _dt(out), _stream()))
+    _count()
+    return out
+
+
+def unet_input_im2col(x: torch.Tensor, sigma: torch.Tensor, dtype: torch.dtype, *, reps: int, ldo: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dtype == torch.float32 and x.is_contiguous() and sigma.dtype == torch.float32
+    b, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((reps * b * h * w, ldo), dtype=dtype, device=x.device)
+    _l.check(_l.load().b200_unet_input_im2col(x.data_ptr(), sigma.data_ptr(), out.data_ptr(), b, c, h, w, ldo, reps,
+                                              _dt(out), _stream()))
+    _count()
+    return out
+
+
+def sampler_step(x: torch.Tensor, eps: torch.Tensor, denoised: torch.Tensor, *, kind: int, sigma: float,
+                 cfg_scale: float, has_uncond: bool, dt: float = 0.0, noise: Optional[torch.Tensor] = None,
+                 noise_scale: float = 0.0, old_denoised: Optional[torch.Tensor] = None, c_x: float = 0.0,
+                 c_d: float = 0.0, c_old: float = 0.0, prediction: int = 0) -> None:
+    """In-place fused CFG + sampler update; eps is NHWC [(2|1)*B, H, W, ld] (uncond rows first)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and denoised.is_contiguous()
+    b, c, h, w = x.shape
+    assert eps.is_contiguous() and eps.shape[0] == (2 * b if has_uncond else b)
+    d = _l.StepDesc()
+    d.kind, d.B, d.C, d.H, d.W = kind, b, c, h, w
+    d.ld_eps = eps.shape[-1]
+    d.has_uncond = 1 if has_uncond else 0
+    d.prediction = prediction
+    d.sigma, d.cfg_scale, d.dt, d.noise_scale = sigma, cfg_scale, dt, noise_scale
+    d.c_x, d.c_d, d.c_old = c_x, c_d, c_old
+    d.eps_dtype = _dt(eps)
+    _l.check(_l.load().b200_sampler_step(x.data_ptr(), eps.data_ptr(), _p(noise), denoised.data_ptr(),
+                                         _p(old_denoised), C.byref(d), _stream()))
+    _count()
+
+
+def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC [B,H,W,ld>=3] -> fp32 NHWC [B,H,W,3] clamp((x+1)/2, 0, 1)."""
+    assert x.dim() == 4 and x.is_contiguous()
+    n, h, w, ld = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.float32, device=x.device)
+    _l.check(_l.load().b200_vae_postprocess(x.data_ptr(), out.data_ptr(), n * h * w, ld, _dt(x), _stream()))
+    _count()
+    return out

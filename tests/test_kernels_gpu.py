@@ -1,0 +1,321 @@
+"""GPU parity tests, kernel level: each C-ABI entry point against the oracle (oracle/ops.py, fp32) on
+the same seeded fp16/bf16-rounded inputs.  Tolerances: outputs are fp16/bf16 with fp32 accumulation,
+so the bound is one output rounding (2^-11 fp16, 2^-8 bf16 relative) plus accumulation-order noise.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import ops as O
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from b200forge import ops
+    return ops
+
+
+def _rand(*shape, dtype=torch.float16, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _tol(dtype):
+    return dict(rel_rms=2e-3) if dtype == torch.float16 else dict(rel_rms=1.2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 320, 320), (1232, 1280, 2048), (16, 1280, 320),
+                                   (4096, 640, 640), (300, 96, 200), (2048, 10240, 1280)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_plain(M, N, K, dtype):
+    if dtype == torch.bfloat16 and M * N * K > 1e9:
+        pytest.skip("large case covered in fp16")
+    ops = _ops()
+    a = _rand(M, K, dtype=dtype, seed=1)
+    w = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=2)
+    b = _rand(N, dtype=dtype, seed=3)
+    y = ops.gemm(a, w, b)
+    torch.cuda.synchronize()
+    ref = O.linear(a.float(), w.float(), b.float())
+    assert_close(f"gemm {M}x{N}x{K} {dtype}", y, ref, **_tol(dtype))
+
+
+def test_gemm_no_bias_strided_output():
+    ops = _ops()
+    M, N, K = 512, 640, 640
+    a = _rand(M, K, seed=4)
+    w = _rand(N, K, scale=K ** -0.5, seed=5)
+    buf = torch.zeros(M, 3 * N, dtype=torch.float16, device=DEV)
+    ops.gemm(a, w, out=buf[:, N:2 * N])
+    torch.cuda.synchronize()
+    assert_close("gemm strided out", buf[:, N:2 * N], O.linear(a.float(), w.float()), rel_rms=2e-3)
+    assert buf[:, :N].abs().max().item() == 0 and buf[:, 2 * N:].abs().max().item() == 0
+
+
+def test_gemm_residual_rowvec_silu():
+    ops = _ops()
+    M, N, K = 1024, 320, 1280
+    a = _rand(M, K, seed=6)
+    w = _rand(N, K, scale=K ** -0.5, seed=7)
+    b = _rand(N, seed=8)
+    res = _rand(M, N, seed=9)
+    rv = _rand(4, N, seed=10)
+    y = ops.gemm(a, w, b, residual=res, rowvec=rv, rows_per_vec=256, epilogue=ops.EPI_SILU)
+    torch.cuda.synchronize()
+    pre = O.linear(a.float(), w.float(), b.float()) + rv.float().repeat_interleave(256, dim=0)
+    ref = O.silu(pre) + res.float()
+    assert_close("gemm silu+rowvec+residual", y, ref, rel_rms=2e-3)
+
+
+def test_gemm_bias_along_m():
+    ops = _ops()
+    M, N, K = 512, 1024, 512
+    a = _rand(M, K, seed=11)
+    w = _rand(N, K, scale=K ** -0.5, seed=12)
+    b = _rand(M, seed=13)
+    y = ops.gemm(a, w, b, bias_along_m=True)
+    torch.cuda.synchronize()
+    assert_close("gemm bias_m", y, O.linear(a.float(), w.float()) + b.float()[:, None], rel_rms=2e-3)
+
+
+@pytest.mark.parametrize("C", [640, 1280])
+def test_gemm_geglu(C):
+    ops = _ops()
+    M = 1024
+    a = _rand(M, C, seed=14)
+    w = _rand(8 * C, C, scale=C ** -0.5, seed=15)
+    b = _rand(8 * C, seed=16, scale=0.1)
+    wp, bp = ops.pack_geglu(w, b, 256)
+    y = ops.gemm(a, wp, bp, epilogue=ops.EPI_GEGLU, block_n=256)
+    torch.cuda.synchronize()
+    assert_close(f"geglu C={C}", y, O.geglu(a.float(), w.float(), b.float()), rel_rms=3e-3)
+
+
+def test_gemm_concat_sources():
+    ops = _ops()
+    M, K1, K2, N = 1024, 640, 320, 640
+    a1 = _rand(M, K1, seed=17)
+    a2 = _rand(M, K2, seed=18)
+    w = _rand(N, K1 + K2, scale=(K1 + K2) ** -0.5, seed=19)
+    y = ops.gemm(a1, w, a2=a2)
+    torch.cuda.synchronize()
+    assert_close("gemm concat", y, O.linear(torch.cat([a1, a2], 1).float(), w.float()), rel_rms=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("N,H,W,C1,C2,Cout", [(2, 32, 32, 64, 0, 64), (2, 128, 128, 320, 0, 320),
+                                              (3, 64, 64, 640, 320, 640), (2, 32, 32, 1280, 1280, 1280),
+                                              (4, 8, 8, 1280, 0, 1280), (2, 16, 16, 128, 64, 320)])
+def test_conv3x3(N, H, W, C1, C2, Cout):
+    ops = _ops()
+    C = C1 + C2
+    x = _rand(N, C, H, W, seed=20)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=21)
+    b = _rand(Cout, seed=22)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    x1 = xn[..., :C1].contiguous()
+    x2 = xn[..., C1:].contiguous() if C2 else None
+    y = ops.conv3x3(x1, ops.pack_conv3x3(w), b, x2=x2)
+    torch.cuda.synchronize()
+    ref = O.conv2d(x.float(), w.float(), b.float()).permute(0, 2, 3, 1)
+    assert_close(f"conv3x3 {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3)
+
+
+def test_conv3x3_temb_residual():
+    ops = _ops()
+    N, H, W, C, Cout = 2, 64, 64, 320, 320
+    x = _rand(N, C, H, W, seed=23)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=24)
+    b = _rand(Cout, seed=25)
+    temb = _rand(N, Cout, seed=26)
+    res = _rand(N, H, W, Cout, seed=27)
+    y = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), b, temb=temb, residual=res)
+    torch.cuda.synchronize()
+    ref = O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + res.float()
+    assert_close("conv3x3 temb+residual", y, ref, rel_rms=2e-3)
+
+
+def test_conv_via_im2col_stride2_and_small_c():
+    ops = _ops()
+    # stride-2 downsample (backend/nn/unet.py:358-374)
+    N, H, W, C, Cout = 2, 64, 64, 320, 320
+    x = _rand(N, C, H, W, seed=28)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=29)
+    b = _rand(Cout, seed=30)
+    cols = ops.im2col3x3(x.permute(0, 2, 3, 1).contiguous(), stride=2)
+    y = ops.gemm(cols, ops.pack_conv3x3(w), b).view(N, H // 2, W // 2, Cout)
+    torch.cuda.synchronize()
+    ref = O.conv2d(x.float(), w.float(), b.float(), stride=2).permute(0, 2, 3, 1)
+    assert_close("conv s2 via im2col", y, ref, rel_rms=2e-3)
+    # 4-channel scalar path
+    x4 = _rand(2, 4, 32, 32, seed=31)
+    cols4 = ops.im2col3x3(x4.permute(0, 2, 3, 1).contiguous(), ldo=64)
+    ref4 = torch.nn.functional.unfold(x4.float(), 3, padding=1)  # [n, c*9, P] with k = c*9 + tap
+    ref4 = ref4.view(2, 4, 9, -1).permute(0, 3, 2, 1).reshape(2 * 32 * 32, 36)
+    torch.cuda.synchronize()
+    assert torch.equal(cols4[:, :36].float().cpu(), ref4.cpu())
+    assert cols4[:, 36:].abs().max().item() == 0
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Lq,Lk,Dh", [(2, 10, 4096, 4096, 64), (2, 20, 1024, 1024, 64), (2, 20, 1024, 77, 64),
+                                          (1, 10, 4096, 77, 64), (2, 4, 200, 333, 64), (1, 24, 1152, 1152, 128),
+                                          (2, 3, 130, 77, 128)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention(B, H, Lq, Lk, Dh, dtype):
+    ops = _ops()
+    q = _rand(B, Lq, H * Dh, dtype=dtype, seed=32)
+    k = _rand(B, Lk, H * Dh, dtype=dtype, seed=33)
+    v = _rand(B, Lk, H * Dh, dtype=dtype, seed=34)
+    o = ops.attention(q, k, v, H)
+    torch.cuda.synchronize()
+    ref = O.attention(q.float(), k.float(), v.float(), H)
+    tol = dict(rel_rms=3e-3) if dtype == torch.float16 else dict(rel_rms=1.5e-2)
+    assert_close(f"attention B{B} H{H} {Lq}x{Lk} d{Dh} {dtype}", o, ref, **tol)
+
+
+def test_attention_fused_qkv_views():
+    ops = _ops()
+    B, L, H, Dh = 2, 1024, 10, 64
+    C = H * Dh
+    qkv = _rand(B, L, 3 * C, seed=35)
+    o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    torch.cuda.synchronize()
+    ref = O.attention(qkv[:, :, :C].float(), qkv[:, :, C:2 * C].float(), qkv[:, :, 2 * C:].float(), H)
+    assert_close("attention fused qkv", o, ref, rel_rms=3e-3)
+
+
+def test_attention_peaked_logits():
+    # large-magnitude logits exercise the online-softmax rescaling path
+    ops = _ops()
+    B, L, H, Dh = 1, 512, 2, 64
+    q = _rand(B, L, H * Dh, seed=36, scale=4.0)
+    k = _rand(B, L, H * Dh, seed=37, scale=4.0)
+    v = _rand(B, L, H * Dh, seed=38)
+    o = ops.attention(q, k, v, H)
+    torch.cuda.synchronize()
+    assert_close("attention peaked", o, O.attention(q.float(), k.float(), v.float(), H), rel_rms=5e-3)
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("N,H,W,C1,C2", [(2, 32, 32, 320, 0), (2, 64, 64, 640, 320), (3, 16, 16, 1280, 1280),
+                                         (2, 128, 128, 320, 0), (1, 8, 8, 2560, 0)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm(N, H, W, C1, C2, silu):
+    ops = _ops()
+    C = C1 + C2
+    x = _rand(N, C, H, W, seed=39) * 2 + 0.5
+    g = _rand(C, seed=40) * 0.2 + 1
+    b = _rand(C, seed=41) * 0.2
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    x1 = xn[..., :C1].contiguous()
+    x2 = xn[..., C1:].contiguous() if C2 else None
+    y = ops.groupnorm(x1, g, b, eps=1e-5, silu=silu, x2=x2)
+    torch.cuda.synchronize()
+    ref = O.group_norm(x.float(), 32, g.float(), b.float(), 1e-5)
+    if silu:
+        ref = O.silu(ref)
+    assert_close(f"groupnorm {N}x{H}x{W} {C1}+{C2} silu={silu}", y, ref.permute(0, 2, 3, 1), max_abs=2e-2, rel_rms=1.5e-3)
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 640), (1000, 1280), (77, 320), (512, 3072)])
+def test_layernorm(rows, C):
+    ops = _ops()
+    x = _rand(rows, C, seed=42) * 3 + 1
+    g = _rand(C, seed=43) * 0.2 + 1
+    b = _rand(C, seed=44) * 0.2
+    y = ops.layernorm(x, g, b, 1e-5)
+    y2 = ops.layernorm(x, None, None, 1e-6)
+    torch.cuda.synchronize()
+    assert_close(f"layernorm {rows}x{C}", y, O.layer_norm(x.float(), g.float(), b.float(), 1e-5), rel_rms=1.5e-3)
+    assert_close(f"layernorm noaffine {rows}x{C}", y2, O.layer_norm(x.float(), None, None, 1e-6), rel_rms=1.5e-3)
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def test_layout_upsample_silu_temb():
+    ops = _ops()
+    x = _rand(2, 64, 16, 16, seed=45)
+    xn = ops.nchw_to_nhwc(x, torch.float16)
+    assert torch.equal(xn, x.permute(0, 2, 3, 1).contiguous())
+    xf = torch.randn(2, 4, 16, 16, device=DEV)
+    xh = ops.nchw_to_nhwc(xf, torch.float16)
+    assert torch.equal(xh, xf.permute(0, 2, 3, 1).contiguous().half())
+    back = ops.nhwc_to_nchw(xn, out_dtype=torch.float32)
+    assert torch.equal(back, x.float())
+    part = ops.nhwc_to_nchw(xn, channels=4)
+    assert torch.equal(part, x[:, :4])
+    up = ops.upsample2x(xn)
+    assert torch.equal(up, O.upsample_nearest2x(x).permute(0, 2, 3, 1).contiguous())
+    s = ops.silu(x)
+    assert_close("silu", s, O.silu(x.float()), rel_rms=1e-3)
+    t = torch.tensor([0.0, 1.0, 500.0, 999.0], device=DEV)
+    e = ops.timestep_embedding(t, 320, torch.float32 if False else torch.float16)
+    ref = O.timestep_embedding(t.cpu(), 320)
+    torch.cuda.synchronize()
+    assert_close("timestep_embedding", e, ref, max_abs=2e-3)
+
+
+def test_unet_input_im2col():
+    ops = _ops()
+    B, C, H, W = 2, 4, 16, 16
+    x = torch.randn(B, C, H, W, device=DEV)
+    sigma = torch.tensor([14.6, 0.5], device=DEV)
+    cols = ops.unet_input_im2col(x, sigma, torch.float16, reps=2, ldo=64)
+    torch.cuda.synchronize()
+    xc = (x / (sigma.view(-1, 1, 1, 1) ** 2 + 1.0) ** 0.5).half()
+    ref = torch.nn.functional.unfold(xc.float(), 3, padding=1).view(B, C, 9, -1).permute(0, 3, 2, 1).reshape(B * H * W, 36)
+    assert cols.shape == (2 * B * H * W, 64)
+    assert_close("unet_input_im2col", cols[:B * H * W, :36], ref, max_abs=1e-3)
+    assert torch.equal(cols[:B * H * W], cols[B * H * W:])
+    assert cols[:, 36:].abs().max().item() == 0
+
+
+def test_softmax_rows():
+    ops = _ops()
+    x = _rand(64, 4096, dtype=torch.bfloat16, seed=46) * 3
+    ref = torch.softmax(x.float() * 0.125, dim=-1)
+    ops.softmax_rows_(x, 0.125)
+    torch.cuda.synchronize()
+    assert_close("softmax_rows", x, ref, rel_rms=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ sampler step
+def test_sampler_step_euler_ancestral_and_dpmpp():
+    ops = _ops()
+    from oracle import sampling as S
+    B, C, H, W = 2, 4, 16, 16
+    g = torch.Generator().manual_seed(47)
+    x = torch.randn(B, C, H, W, generator=g)
+    eps = torch.randn(2 * B, H, W, 8, generator=g).half()
+    noise = torch.randn(B, C, H, W, generator=g)
+    sigma, sigma_next, cfg = 7.5, 5.0, 7.0
+    eps_nchw = eps[..., :C].permute(0, 3, 1, 2).float()
+    den_ref = S.cfg_denoised_eps(x, eps_nchw[:B], eps_nchw[B:], sigma, cfg)
+    x_ref = S.euler_ancestral_step(x, den_ref, sigma, sigma_next, noise, eta=1.0, s_noise=1.0)
+    sd, su = S.get_ancestral_step(sigma, sigma_next, 1.0)
+    xd = x.to(DEV).clone()
+    den = torch.empty_like(xd)
+    ops.sampler_step(xd, eps.to(DEV), den, kind=ops.STEP_EULER, sigma=sigma, cfg_scale=cfg, has_uncond=True,
+                     dt=sd - sigma, noise=noise.to(DEV), noise_scale=su)
+    torch.cuda.synchronize()
+    assert_close("sampler denoised", den, den_ref, max_abs=2e-5)
+    assert_close("sampler euler-a x", xd, x_ref, max_abs=2e-5)
+    # dpm++ 2m second-order step
+    old = torch.randn(B, C, H, W, generator=g)
+    sig_prev = 9.0
+    x_ref2 = S.dpmpp_2m_step(x, den_ref, old, sig_prev, sigma, sigma_next)
+    cx, cd, cold = S.dpmpp_2m_coeffs(sig_prev, sigma, sigma_next, has_old=True)
+    xd = x.to(DEV).clone()
+    oldd = old.to(DEV).clone()
+    ops.sampler_step(xd, eps.to(DEV), den, kind=ops.STEP_DPMPP_2M, sigma=sigma, cfg_scale=cfg, has_uncond=True,
+                     old_denoised=oldd, c_x=cx, c_d=cd, c_old=cold)
+    torch.cuda.synchronize()
+    assert_close("sampler dpmpp2m x", xd, x_ref2, max_abs=5e-5)
+    assert_close("sampler dpmpp2m old", oldd, den_ref, max_abs=2e-5)
