@@ -1,0 +1,53 @@
+"""ORACLE — test infrastructure only.
+
+LDM-format UNet / VAE configurations of the reference.  The reference obtains them from the third-party
+package `huggingface_guess` @ 84826248b49bb7ca754c73293299c4d4e23a548d (modules/launch_utils.py:397,404;
+imported at backend/loader.py:7,452), which is not vendored under /root/reference; the values below are
+restated from SURVEY.md §8c, which checked them against the vendored diffusers configs
+(backend/huggingface/*/unet/config.json via backend/misc/diffusers_state_dict.py:70-134) and the canonical
+parameter counts (SD1.5 859.5 M, SDXL 2567.5 M).
+
+`TINY_*` are reduced-width configurations with the same block structure, used for CPU-sized parity tests
+and golden vectors; every channel count stays a multiple of 64 so the same kernels are exercised.
+"""
+
+SD15 = dict(
+    in_channels=4, out_channels=4, model_channels=320, num_res_blocks=[2, 2, 2, 2], channel_mult=[1, 2, 4, 4],
+    transformer_depth=[1, 1, 1, 1, 1, 1, 0, 0], transformer_depth_output=[1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0],
+    transformer_depth_middle=1, num_heads=8, num_head_channels=-1, use_spatial_transformer=True,
+    use_linear_in_transformer=False, context_dim=768, adm_in_channels=None, num_classes=None,
+)
+
+SDXL = dict(
+    in_channels=4, out_channels=4, model_channels=320, num_res_blocks=[2, 2, 2], channel_mult=[1, 2, 4],
+    transformer_depth=[0, 0, 2, 2, 10, 10], transformer_depth_output=[0, 0, 0, 2, 2, 2, 10, 10, 10],
+    transformer_depth_middle=10, num_heads=-1, num_head_channels=64, use_spatial_transformer=True,
+    use_linear_in_transformer=True, context_dim=2048, adm_in_channels=2816, num_classes="sequential",
+)
+
+# same topology as SDXL (3 levels, linear proj, label_emb, head dim 64), 64/128/256 channels
+TINY_XL = dict(
+    in_channels=4, out_channels=4, model_channels=64, num_res_blocks=[2, 2, 2], channel_mult=[1, 2, 4],
+    transformer_depth=[0, 0, 1, 1, 2, 2], transformer_depth_output=[0, 0, 0, 1, 1, 1, 2, 2, 2],
+    transformer_depth_middle=2, num_heads=-1, num_head_channels=64, use_spatial_transformer=True,
+    use_linear_in_transformer=True, context_dim=128, adm_in_channels=96, num_classes="sequential",
+)
+
+# same topology as SD1.5 (4 levels, conv proj, no label_emb) but head dim 64 (the fused path's head dims)
+TINY_15 = dict(
+    in_channels=4, out_channels=4, model_channels=64, num_res_blocks=[1, 1, 1, 1], channel_mult=[1, 2, 4, 4],
+    transformer_depth=[1, 1, 1, 0], transformer_depth_output=[1, 1, 1, 1, 1, 1, 0, 0],
+    transformer_depth_middle=1, num_heads=-1, num_head_channels=64, use_spatial_transformer=True,
+    use_linear_in_transformer=False, context_dim=128, adm_in_channels=None, num_classes=None,
+)
+
+# SDXL VAE (backend/huggingface/stabilityai/stable-diffusion-xl-base-1.0/vae/config.json)
+VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
+VAE_SD15 = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                latent_channels=4, scaling_factor=0.18215, shift_factor=0.0)
+TINY_VAE = dict(in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+                latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
+
+CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny_xl": TINY_XL, "tiny_15": TINY_15}
+VAE_CONFIGS = {"sdxl": VAE_SDXL, "sd15": VAE_SD15, "tiny": TINY_VAE}

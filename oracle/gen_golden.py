@@ -1,0 +1,186 @@
+"""ORACLE tooling — generates tests/golden/*.pt by running the UNMODIFIED reference (imported from
+/root/reference through oracle/ref_import.py) on CPU fp32 with deterministic synthetic weights.
+
+    python -m oracle.gen_golden            # in the build container (needs /root/reference)
+
+The fixtures pin (a) the oracle restatement and (b) the CUDA path on the GPU box, where the reference tree
+does not exist.  Weights are not stored: `oracle.unet.random_state_dict(cfg, seed)` regenerates them
+bit-identically (CPU torch.Generator), and each fixture stores a checksum of the weights it was made with.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import configs as CF  # noqa: E402
+from oracle import ref_import  # noqa: E402
+from oracle import unet as OU  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sd_checksum(sd) -> float:
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def make_inputs(cfg, B, hw, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 4, hw, hw, generator=g)
+    ctx = torch.randn(B, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(B, cfg["adm_in_channels"], generator=g) if cfg.get("adm_in_channels") else None
+    return x, ctx, y
+
+
+def gen_unet(name: str, hw: int = 16):
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    cfg = CF.CONFIGS[name]
+    sd = OU.random_state_dict(cfg, seed=1)
+    m = RefUNet(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    x, ctx, y = make_inputs(cfg, 2, hw, seed=2)
+    t = torch.tensor([981.0, 23.0])
+    with torch.no_grad():
+        out = m(x, t, context=ctx, y=y, transformer_options={})
+    torch.save(dict(config=name, weight_seed=1, weight_checksum=sd_checksum(sd), x=x, t=t, context=ctx, y=y, out=out),
+               os.path.join(GOLD, f"unet_{name}.pt"))
+    print("unet", name, "out std", out.std().item())
+
+
+def gen_trajectories(name: str = "tiny_xl", hw: int = 16, steps: int = 6):
+    """Reference denoise loop: KModel.apply_model -> sampling_function_inner (CFG) -> k_diffusion sample_*."""
+    import k_diffusion.sampling as ks
+    from backend.modules.k_model import KModel
+    from backend.modules.k_prediction import Prediction
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    from backend.sampling.condition import compile_conditions
+    from backend.sampling.sampling_function import sampling_function_inner
+    from k_diffusion.external import ForgeScheduleLinker
+
+    # modules/sd_schedulers.py:10-15 replaces k_diffusion.sampling.to_d at import time; `modules` cannot be
+    # imported here (gradio etc. missing), so the same override is applied by hand.
+    ks.to_d = lambda x, sigma, denoised: (x - denoised) / sigma
+
+    cfg = CF.CONFIGS[name]
+    sd = OU.random_state_dict(cfg, seed=1)
+    unet = RefUNet(**cfg).eval()
+    unet.load_state_dict(sd, strict=True)
+    unet.storage_dtype = torch.float32
+    unet.computation_dtype = torch.float32
+    pred = Prediction(prediction_type="epsilon")
+    kmodel = KModel(unet, diffusers_scheduler=None, k_predictor=pred)
+    linker = ForgeScheduleLinker(pred)
+
+    B = 2
+    g = torch.Generator().manual_seed(7)
+    cond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g),
+                vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    uncond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g),
+                  vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    cond_c, uncond_c = compile_conditions(cond), compile_conditions(uncond)
+    cfg_scale = 7.0
+
+    class Wrap:  # what k-diffusion sees as `model`: CFGDenoiser minus UI glue (sd_samplers_cfg_denoiser.py:199)
+        class _Inner:
+            predictor = pred
+        inner_model = _Inner()
+
+        def __call__(self, x, sigma, **kw):
+            return sampling_function_inner(kmodel, x, sigma, uncond_c, cond_c, cfg_scale, {}, None)
+
+    seeds = [1000, 1001]
+    gens = [torch.Generator().manual_seed(s) for s in seeds]
+
+    def draw():  # modules/rng.py:167-177 ImageRNG.next(): one randn per image generator, stacked
+        return torch.stack([torch.randn((4, hw, hw), generator=gg) for gg in gens])
+
+    sig_auto = linker.get_sigmas(steps)                       # Euler / Euler a "Automatic" schedule
+    sig_karras = ks.get_sigmas_karras(steps, float(pred.sigma_min), float(pred.sigma_max))
+    out = dict(config=name, weight_seed=1, weight_checksum=sd_checksum(sd), cond=cond, uncond=uncond,
+               cfg_scale=cfg_scale, seeds=seeds, hw=hw, steps=steps, sigmas_auto=sig_auto, sigmas_karras=sig_karras)
+    with torch.no_grad():
+        noise0 = draw()
+        x0 = pred.noise_scaling(sig_auto[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+        out["noise0"] = noise0
+        out["x0"] = x0
+        step_noise = []
+
+        class Hijack:  # TorchHijack (modules/sd_samplers_common.py:214-235): randn_like -> ImageRNG.next
+            @staticmethod
+            def randn_like(x):
+                n = draw()
+                step_noise.append(n)
+                return n
+
+            def __getattr__(self, item):
+                return getattr(torch, item)
+
+        ks.torch = Hijack()
+        try:
+            dens = []
+            cb = lambda d: dens.append(d["denoised"].clone())  # noqa: E731
+            out["euler_a"] = ks.sample_euler_ancestral(Wrap(), x0.clone(), sig_auto, extra_args={}, callback=cb, disable=True)
+            out["euler_a_step_noise"] = torch.stack(step_noise)
+            out["euler_a_denoised0"] = dens[0]
+            out["euler_a_denoised_last"] = dens[-1]
+            step_noise.clear()
+            out["euler"] = ks.sample_euler(Wrap(), x0.clone(), sig_auto, extra_args={}, disable=True)
+            x0k = pred.noise_scaling(sig_karras[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+            out["x0_karras"] = x0k
+            out["dpmpp_2m"] = ks.sample_dpmpp_2m(Wrap(), x0k.clone(), sig_karras, extra_args={}, disable=True)
+        finally:
+            ks.torch = torch
+    torch.save(out, os.path.join(GOLD, f"traj_{name}.pt"))
+    print("traj", name, {k: float(v.std()) for k, v in out.items() if k in ("euler_a", "euler", "dpmpp_2m")})
+
+
+def gen_schedules():
+    import k_diffusion.sampling as ks
+    from backend.modules.k_prediction import Prediction
+    from k_diffusion.external import ForgeScheduleLinker
+    pred = Prediction(prediction_type="epsilon")
+    linker = ForgeScheduleLinker(pred)
+    probe = torch.tensor([14.6146, 10.0, 3.3, 1.0, 0.5, 0.1, 0.0292])
+    out = dict(sigmas=pred.sigmas.clone(), auto20=linker.get_sigmas(20), auto30=linker.get_sigmas(30),
+               karras30=ks.get_sigmas_karras(30, float(pred.sigma_min), float(pred.sigma_max)),
+               probe=probe, probe_timestep=pred.timestep(probe))
+    torch.save(out, os.path.join(GOLD, "schedules.pt"))
+    print("schedules sigma_min/max", float(pred.sigma_min), float(pred.sigma_max))
+
+
+def gen_vae(name: str = "tiny", hw: int = 16):
+    from backend.nn.vae import IntegratedAutoencoderKL
+    from oracle import vae as OV
+    cfg = CF.VAE_CONFIGS[name]
+    sd = OV.random_state_dict(cfg, seed=3)
+    m = IntegratedAutoencoderKL(**{k: v for k, v in cfg.items()}).eval()
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys, missing
+    assert all(k.startswith(("encoder.", "quant_conv.")) for k in missing.missing_keys), missing.missing_keys
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(2, cfg["latent_channels"], hw, hw, generator=g)
+    with torch.no_grad():
+        out = m.decode(m.process_out(z))
+    torch.save(dict(config=name, weight_seed=3, weight_checksum=sd_checksum(sd), z=z, out=out),
+               os.path.join(GOLD, f"vae_{name}.pt"))
+    print("vae", name, "out std", out.std().item())
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    ref_import.load()
+    which = sys.argv[1:] or ["unet", "traj", "sched", "vae"]
+    if "unet" in which:
+        gen_unet("tiny_xl")
+        gen_unet("tiny_15")
+    if "traj" in which:
+        gen_trajectories("tiny_xl")
+    if "sched" in which:
+        gen_schedules()
+    if "vae" in which:
+        gen_vae("tiny")

@@ -21,15 +21,16 @@ def make_sigmas_scaled_linear(linear_start: float = 0.00085, linear_end: float =
     betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=torch.float64) ** 2
     alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
     sigmas = ((1 - alphas_cumprod) / alphas_cumprod) ** 0.5
-    return sigmas.float()
+    return sigmas  # fp64; the reference registers sigmas.float() and sigmas.log().float() (log taken in fp64)
 
 
 class EpsPrediction:
     """backend/modules/k_prediction.py:113-167 (Prediction, prediction_type='epsilon', sigma_data=1)."""
 
     def __init__(self):
-        self.sigmas = make_sigmas_scaled_linear()
-        self.log_sigmas = self.sigmas.log()
+        s64 = make_sigmas_scaled_linear()
+        self.sigmas = s64.float()
+        self.log_sigmas = s64.log().float()
         self.sigma_data = 1.0
 
     @property

@@ -1,0 +1,154 @@
+"""Public API of the backend: the txt2img denoise job (what `StableDiffusionProcessingTxt2Img.sample` +
+`decode_latent_batch` do in the reference, modules/processing.py:1342-1428, 628-635) driven entirely through
+the sm_100a kernels.
+
+    pipe = Txt2ImgPipeline(unet_cfg, unet_state_dict, vae_cfg=..., vae_state_dict=...)
+    out = pipe.generate(cond, uncond, noise=..., steps=30, sampler="euler_a", cfg_scale=7.0)
+
+Inputs are the same objects the reference's sampler receives: conditioning dicts {"crossattn": [B,77,ctx],
+"vector": [B,adm]} (backend/sampling/condition.py:91-119), initial noise N(0,1) [B,4,h,w] (ImageRNG,
+modules/rng.py) and — for ancestral samplers — one noise tensor per step.  Host tensors are accepted
+(pinned or not) and copied in; the UNet forward is captured once per (batch, latent size) in a CUDA graph
+and replayed every step.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import ops, sampling
+from .unet_engine import UNetEngine
+
+
+class GraphedUNet:
+    """One CUDA graph of `UNetEngine.forward_sigma` for fixed shapes, with static input/output buffers."""
+
+    def __init__(self, engine: UNetEngine, batch: int, reps: int, hh: int, ww: int, n_ctx: int, use_graph: bool = True):
+        self.engine = engine
+        dev, dt = engine.device, engine.dtype
+        cfg = engine.cfg
+        n = batch * reps
+        self.x = torch.zeros((batch, cfg["in_channels"], hh, ww), dtype=torch.float32, device=dev)
+        self.sigma = torch.ones((batch,), dtype=torch.float32, device=dev)
+        self.timesteps = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.context = torch.zeros((n, n_ctx, cfg["context_dim"]), dtype=dt, device=dev)
+        self.y = torch.zeros((n, cfg["adm_in_channels"]), dtype=dt, device=dev) if engine.has_label else None
+        self.reps = reps
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.eps: Optional[torch.Tensor] = None
+        self.launches_per_forward = 0
+        if use_graph:
+            self._capture()
+
+    def _eager(self) -> torch.Tensor:
+        return self.engine.forward_sigma(self.x, self.sigma, self.timesteps, self.context, self.y, self.reps)
+
+    def _capture(self) -> None:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: first-call attribute setup, allocator pools
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = ops.LAUNCHES
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.eps = self._eager()
+        self.launches_per_forward = ops.LAUNCHES - before
+        self.graph = g
+
+    def __call__(self) -> torch.Tensor:
+        if self.graph is None:
+            before = ops.LAUNCHES
+            self.eps = self._eager()
+            self.launches_per_forward = ops.LAUNCHES - before
+        else:
+            self.graph.replay()
+            ops.LAUNCHES += self.launches_per_forward
+        return self.eps
+
+
+class Txt2ImgPipeline:
+    def __init__(self, unet_cfg: dict, unet_state_dict: Dict[str, torch.Tensor], *, vae_cfg: Optional[dict] = None,
+                 vae_state_dict: Optional[Dict[str, torch.Tensor]] = None, dtype: torch.dtype = torch.float16,
+                 vae_dtype: torch.dtype = torch.bfloat16, device="cuda", use_graph: bool = True):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.unet = UNetEngine(unet_cfg, unet_state_dict, dtype=dtype, device=device)
+        self.pred = sampling.Prediction()
+        self.use_graph = use_graph
+        self._graphs: Dict[tuple, GraphedUNet] = {}
+        self.vae = None
+        if vae_cfg is not None:
+            from .vae_engine import VAEDecoderEngine
+            self.vae = VAEDecoderEngine(vae_cfg, vae_state_dict, dtype=vae_dtype, device=device)
+
+    def _graph_for(self, batch, reps, hh, ww, n_ctx) -> GraphedUNet:
+        key = (batch, reps, hh, ww, n_ctx)
+        if key not in self._graphs:
+            self._graphs[key] = GraphedUNet(self.unet, batch, reps, hh, ww, n_ctx, self.use_graph)
+        return self._graphs[key]
+
+    @torch.no_grad()
+    def sample(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, *, steps: int = 30,
+               sampler: str = "euler_a", cfg_scale: float = 7.0, sigmas: Optional[torch.Tensor] = None,
+               step_noise: Optional[torch.Tensor] = None, eta: float = 1.0, s_noise: float = 1.0,
+               callback: Optional[Callable] = None) -> torch.Tensor:
+        """Returns the final latent [B,4,h,w] fp32 on the device.
+        noise: [B,4,h,w] N(0,1) (host or device).  step_noise: [steps-1 or more, B,4,h,w] for ancestral samplers
+        (row i is added after step i, matching the order in which ImageRNG.next() is drawn by the reference)."""
+        dev = self.device
+        b, c, hh, ww = noise.shape
+        has_uncond = uncond is not None and not abs(cfg_scale - 1.0) < 1e-9  # sampling_function.py:295-298
+        reps = 2 if has_uncond else 1
+        n_ctx = cond["crossattn"].shape[1]
+        gu = self._graph_for(b, reps, hh, ww, n_ctx)
+        if sigmas is None:
+            sigmas = sampling.make_sigmas(self.pred, sampler, steps)
+        sigmas = sigmas.float().cpu()
+        builder = sampling.SAMPLERS[sampler][0]
+        plan = builder(sigmas, eta, s_noise) if sampler == "euler_a" else builder(sigmas)
+
+        # ---- host -> device: conditioning, initial noise, per-step noise
+        def put(t, dtype):
+            return t.to(device=dev, dtype=dtype, non_blocking=True)
+
+        ctx = [cond["crossattn"]] if not has_uncond else [uncond["crossattn"], cond["crossattn"]]  # [uncond, cond]
+        gu.context.copy_(torch.cat([put(t, self.dtype) for t in ctx], 0))
+        if gu.y is not None:
+            ys = [cond["vector"]] if not has_uncond else [uncond["vector"], cond["vector"]]
+            gu.y.copy_(torch.cat([put(t, self.dtype) for t in ys], 0))
+        x = gu.x
+        # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: max_denoise, zero latent)
+        x.copy_(put(noise, torch.float32))
+        x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)))
+        sn_dev = put(step_noise, torch.float32) if step_noise is not None else None
+        # per-step scalar tables (sigma per image, UNet timestep = index of nearest log-sigma)
+        sig_tab = sigmas[:-1].to(dev).view(-1, 1).expand(-1, b).contiguous()
+        t_tab = self.pred.timestep(sigmas[:-1]).float().to(dev).view(-1, 1).expand(-1, b * reps).contiguous()
+
+        def eps_fn(i):
+            gu.sigma.copy_(sig_tab[i])
+            gu.timesteps.copy_(t_tab[i])
+            return gu()
+
+        noise_fn = (lambda i: sn_dev[i]) if sn_dev is not None else None
+        if sampling.SAMPLERS[sampler][2] and noise_fn is None:
+            raise ValueError(f"sampler {sampler} needs step_noise")
+        sampling.run_sampler(eps_fn, x, plan, cfg_scale=cfg_scale, has_uncond=has_uncond, noise_fn=noise_fn,
+                             callback=callback)
+        return x
+
+    @torch.no_grad()
+    def decode(self, latent: torch.Tensor) -> torch.Tensor:
+        """latent [B,4,h,w] fp32 -> images [B,H,W,3] fp32 in [0,1] (VAE.decode, backend/patcher/vae.py:128-155)."""
+        if self.vae is None:
+            raise RuntimeError("pipeline built without a VAE")
+        return self.vae.decode(latent)
+
+    @torch.no_grad()
+    def generate(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, **kw) -> torch.Tensor:
+        latent = self.sample(cond, uncond, noise, **kw)
+        return self.decode(latent) if self.vae is not None else latent

@@ -1,0 +1,296 @@
+"""Fused channels-last UNet forward for the LDM UNet of SD1.x / SDXL — the B200 replacement for
+`IntegratedUNet2DConditionModel.forward` (reference backend/nn/unet.py:696-763) on the plain txt2img path
+(no control / patches / block modifiers: the fast-path predicate of SURVEY.md §8b).
+
+The engine consumes a state dict with the reference's own parameter names, repacks the weights once
+(3x3 filters -> [Cout, 9*Cin], fused QKV / KV projections, GEGLU row interleave, all ResBlock
+time-embedding projections stacked into one matrix) and then runs the forward as a flat sequence of
+libb200forge launches on NHWC activations:
+
+  ResBlock            GN-stats -> GN-apply+SiLU(+concat) -> conv3x3(+bias +temb) -> GN -> conv3x3(+bias +skip)
+  SpatialTransformer  GN -> proj_in GEMM -> depth x [LN -> QKV GEMM -> attention -> out GEMM(+res)
+                                                      LN -> Q GEMM, KV GEMM(ctx) -> attention -> out GEMM(+res)
+                                                      LN -> GEGLU GEMM -> FF-out GEMM(+res)] -> proj_out GEMM(+res)
+  skip concat         never materialised: GN-apply, the 1x1 skip GEMM and the conv read both sources
+
+No torch operator runs on the data path; torch only provides buffers (`torch.empty`) and the stream.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import EPI_GEGLU, EPI_NONE, EPI_SILU
+
+SD = Dict[str, torch.Tensor]
+
+
+def unet_structure(cfg: dict):
+    """Block list of the LDM UNet for a config (mirrors the constructor order of backend/nn/unet.py:481-693):
+    ("conv"|"res"|"attn"|"down"|"up", prefix, ...)."""
+    mc = cfg["model_channels"]
+    nrb = cfg["num_res_blocks"]
+    cm = list(cfg["channel_mult"])
+    if isinstance(nrb, int):
+        nrb = len(cm) * [nrb]
+    td = list(cfg["transformer_depth"])
+    tdo = list(cfg["transformer_depth_output"])
+    nh, nhc = cfg["num_heads"], cfg["num_head_channels"]
+
+    def heads_of(ch):
+        return (nh, ch // nh) if nhc == -1 else (ch // nhc, nhc)
+
+    inp = [[("conv", "input_blocks.0.0", cfg["in_channels"], mc)]]
+    chans = [mc]
+    ch = mc
+    i = 1
+    for level, mult in enumerate(cm):
+        for _ in range(nrb[level]):
+            layers = [("res", f"input_blocks.{i}.0", ch, mult * mc)]
+            ch = mult * mc
+            depth = td.pop(0)
+            if depth > 0:
+                h, dh = heads_of(ch)
+                layers.append(("attn", f"input_blocks.{i}.1", ch, h, dh, depth))
+            inp.append(layers)
+            chans.append(ch)
+            i += 1
+        if level != len(cm) - 1:
+            inp.append([("down", f"input_blocks.{i}.0", ch)])
+            chans.append(ch)
+            i += 1
+    h, dh = heads_of(ch)
+    mid = [("res", "middle_block.0", ch, ch)]
+    if cfg["transformer_depth_middle"] >= 0:
+        mid += [("attn", "middle_block.1", ch, h, dh, cfg["transformer_depth_middle"]),
+                ("res", "middle_block.2", ch, ch)]
+    out = []
+    i = 0
+    for level, mult in list(enumerate(cm))[::-1]:
+        for k in range(nrb[level] + 1):
+            ich = chans.pop()
+            layers = [("res", f"output_blocks.{i}.0", ch + ich, mc * mult, ch, ich)]
+            ch = mc * mult
+            depth = tdo.pop()
+            j = 1
+            if depth > 0:
+                h, dh = heads_of(ch)
+                layers.append(("attn", f"output_blocks.{i}.{j}", ch, h, dh, depth))
+                j += 1
+            if level and k == nrb[level]:
+                layers.append(("up", f"output_blocks.{i}.{j}", ch))
+            out.append(layers)
+            i += 1
+    return dict(input=inp, middle=mid, output=out, out_ch=ch)
+
+
+class UNetEngine:
+    """Weights packed for the sm_100a kernels + the launch sequence of one forward."""
+
+    def __init__(self, cfg: dict, state_dict: SD, dtype: torch.dtype = torch.float16, device="cuda"):
+        self.cfg = dict(cfg)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.st = unet_structure(cfg)
+        self.mc = cfg["model_channels"]
+        self.ted = self.mc * 4
+        self.has_label = cfg.get("num_classes") is not None
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(state_dict)
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _t(self, t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=self.device, dtype=self.dtype).contiguous()
+
+    def _pack(self, sd: SD) -> None:
+        w = self.w
+        g = lambda k: self._t(sd[k])  # noqa: E731
+        for p in ("time_embed.0", "time_embed.2"):
+            w[p + ".w"], w[p + ".b"] = g(p + ".weight"), g(p + ".bias")
+        if self.has_label:
+            for p in ("label_emb.0.0", "label_emb.0.2"):
+                w[p + ".w"], w[p + ".b"] = g(p + ".weight"), g(p + ".bias")
+        emb_w, emb_b = [], []
+        self.emb_off: Dict[str, tuple] = {}
+        off = 0
+
+        def pack_layer(layer):
+            nonlocal off
+            kind, p = layer[0], layer[1]
+            if kind == "conv":  # conv_in: Cin=4 -> im2col K=36 padded to 64
+                wp = ops.pack_conv3x3(g(p + ".weight"))
+                kpad = torch.zeros((wp.shape[0], 64), dtype=self.dtype, device=self.device)
+                kpad[:, : wp.shape[1]] = wp
+                w[p + ".w"], w[p + ".b"] = kpad, g(p + ".bias")
+            elif kind == "res":
+                cin, cout = layer[2], layer[3]
+                for n in ("in_layers.0", "out_layers.0"):
+                    w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight"), g(f"{p}.{n}.bias")
+                w[p + ".conv1.w"], w[p + ".conv1.b"] = ops.pack_conv3x3(g(p + ".in_layers.2.weight")), g(p + ".in_layers.2.bias")
+                w[p + ".conv2.w"], w[p + ".conv2.b"] = ops.pack_conv3x3(g(p + ".out_layers.3.weight")), g(p + ".out_layers.3.bias")
+                emb_w.append(g(p + ".emb_layers.1.weight"))
+                emb_b.append(g(p + ".emb_layers.1.bias"))
+                self.emb_off[p] = (off, cout)
+                off += cout
+                if cin != cout:
+                    sw = g(p + ".skip_connection.weight")
+                    assert sw.shape[2] == 1, "3x3 skip convs (use_conv=True) are not used by SD/SDXL"
+                    w[p + ".skip.w"], w[p + ".skip.b"] = sw.reshape(cout, cin).contiguous(), g(p + ".skip_connection.bias")
+            elif kind == "attn":
+                ch, depth = layer[2], layer[5]
+                w[p + ".norm.g"], w[p + ".norm.b"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+                for n in ("proj_in", "proj_out"):
+                    w[f"{p}.{n}.w"] = g(f"{p}.{n}.weight").reshape(ch, ch).contiguous()
+                    w[f"{p}.{n}.b"] = g(f"{p}.{n}.bias")
+                for d in range(depth):
+                    q = f"{p}.transformer_blocks.{d}"
+                    for n in ("norm1", "norm2", "norm3"):
+                        w[f"{q}.{n}.g"], w[f"{q}.{n}.b"] = g(f"{q}.{n}.weight"), g(f"{q}.{n}.bias")
+                    w[q + ".attn1.qkv"] = torch.cat([g(f"{q}.attn1.to_q.weight"), g(f"{q}.attn1.to_k.weight"),
+                                                      g(f"{q}.attn1.to_v.weight")], 0).contiguous()
+                    w[q + ".attn2.q"] = g(f"{q}.attn2.to_q.weight")
+                    w[q + ".attn2.kv"] = torch.cat([g(f"{q}.attn2.to_k.weight"), g(f"{q}.attn2.to_v.weight")], 0).contiguous()
+                    for a in ("attn1", "attn2"):
+                        w[f"{q}.{a}.o.w"], w[f"{q}.{a}.o.b"] = g(f"{q}.{a}.to_out.0.weight"), g(f"{q}.{a}.to_out.0.bias")
+                    bn = 256 if (4 * ch) % 128 == 0 else 128
+                    w[q + ".ff1.w"], w[q + ".ff1.b"] = ops.pack_geglu(g(f"{q}.ff.net.0.proj.weight"),
+                                                                       g(f"{q}.ff.net.0.proj.bias"), bn)
+                    w[q + ".ff1.bn"] = bn
+                    w[q + ".ff2.w"], w[q + ".ff2.b"] = g(f"{q}.ff.net.2.weight"), g(f"{q}.ff.net.2.bias")
+            elif kind == "down":
+                w[p + ".w"], w[p + ".b"] = ops.pack_conv3x3(g(p + ".op.weight")), g(p + ".op.bias")
+            elif kind == "up":
+                w[p + ".w"], w[p + ".b"] = ops.pack_conv3x3(g(p + ".conv.weight")), g(p + ".conv.bias")
+
+        for blk in self.st["input"] + [self.st["middle"]] + self.st["output"]:
+            for layer in blk:
+                pack_layer(layer)
+        w["emb_all.w"] = torch.cat(emb_w, 0).contiguous()
+        w["emb_all.b"] = torch.cat(emb_b, 0).contiguous()
+        w["out.0.g"], w["out.0.b"] = g("out.0.weight"), g("out.0.bias")
+        ow = ops.pack_conv3x3(g("out.2.weight"))  # [4, 9*mc] -> pad to 8 output channels
+        co = ow.shape[0]
+        self.out_channels = co
+        owp = torch.zeros((8, ow.shape[1]), dtype=self.dtype, device=self.device)
+        owp[:co] = ow
+        obp = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        obp[:co] = g("out.2.bias")
+        w["out.2.w"], w["out.2.b"] = owp, obp
+
+    # ------------------------------------------------------------------------------------------ blocks
+    def _res(self, p: str, layer, x1: torch.Tensor, x2: Optional[torch.Tensor], temb_all: torch.Tensor) -> torch.Tensor:
+        w = self.w
+        cin, cout = layer[2], layer[3]
+        n, hh, ww, c1 = x1.shape
+        m = n * hh * ww
+        h = ops.groupnorm(x1, w[p + ".in_layers.0.g"], w[p + ".in_layers.0.b"], eps=1e-5, silu=True, x2=x2)
+        off, _ = self.emb_off[p]
+        h = ops.conv3x3(h, w[p + ".conv1.w"], w[p + ".conv1.b"], temb=temb_all[:, off:off + cout])
+        h = ops.groupnorm(h, w[p + ".out_layers.0.g"], w[p + ".out_layers.0.b"], eps=1e-5, silu=True)
+        if cin != cout:
+            skip = ops.gemm(x1.view(m, c1), w[p + ".skip.w"], w[p + ".skip.b"],
+                            a2=None if x2 is None else x2.view(m, x2.shape[-1])).view(n, hh, ww, cout)
+        else:
+            assert x2 is None
+            skip = x1
+        return ops.conv3x3(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
+
+    def _attn(self, p: str, layer, x: torch.Tensor, ctx2d: torch.Tensor, n_ctx: int) -> torch.Tensor:
+        w = self.w
+        ch, heads, depth = layer[2], layer[3], layer[5]
+        n, hh, ww, _ = x.shape
+        L = hh * ww
+        m = n * L
+        x2d = x.view(m, ch)
+        t = ops.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], eps=1e-6, silu=False).view(m, ch)
+        t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"])
+        for d in range(depth):
+            q = f"{p}.transformer_blocks.{d}"
+            # self attention
+            nrm = ops.layernorm(t, w[q + ".norm1.g"], w[q + ".norm1.b"])
+            qkv = ops.gemm(nrm, w[q + ".attn1.qkv"]).view(n, L, 3 * ch)
+            att = ops.attention(qkv[:, :, :ch], qkv[:, :, ch:2 * ch], qkv[:, :, 2 * ch:], heads)
+            ops.gemm(att.view(m, ch), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t)
+            # cross attention
+            nrm = ops.layernorm(t, w[q + ".norm2.g"], w[q + ".norm2.b"])
+            qq = ops.gemm(nrm, w[q + ".attn2.q"]).view(n, L, ch)
+            kv = ops.gemm(ctx2d, w[q + ".attn2.kv"]).view(n, n_ctx, 2 * ch)
+            att = ops.attention(qq, kv[:, :, :ch], kv[:, :, ch:], heads)
+            ops.gemm(att.view(m, ch), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t)
+            # feed-forward (GEGLU)
+            nrm = ops.layernorm(t, w[q + ".norm3.g"], w[q + ".norm3.b"])
+            gg = ops.gemm(nrm, w[q + ".ff1.w"], w[q + ".ff1.b"], epilogue=EPI_GEGLU, block_n=w[q + ".ff1.bn"])
+            ops.gemm(gg, w[q + ".ff2.w"], w[q + ".ff2.b"], residual=t, out=t)
+        out = ops.gemm(t, w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
+        return out.view(n, hh, ww, ch)
+
+    def _run(self, layers, h, h2, temb_all, ctx2d, n_ctx):
+        for layer in layers:
+            kind, p = layer[0], layer[1]
+            if kind == "res":
+                h = self._res(p, layer, h, h2, temb_all)
+                h2 = None
+            elif kind == "attn":
+                h = self._attn(p, layer, h, ctx2d, n_ctx)
+            elif kind == "down":
+                n, hh, ww, c = h.shape
+                cols = ops.im2col3x3(h, stride=2)
+                h = ops.gemm(cols, self.w[p + ".w"], self.w[p + ".b"]).view(n, hh // 2, ww // 2, c)
+            elif kind == "up":
+                h = ops.conv3x3(ops.upsample2x(h), self.w[p + ".w"], self.w[p + ".b"])
+        return h
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _embeddings(self, timesteps: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
+        w = self.w
+        t_emb = ops.timestep_embedding(timesteps, self.mc, self.dtype)
+        e = ops.gemm(t_emb, w["time_embed.0.w"], w["time_embed.0.b"], epilogue=EPI_SILU)
+        emb = ops.gemm(e, w["time_embed.2.w"], w["time_embed.2.b"])
+        if self.has_label:
+            assert y is not None
+            l1 = ops.gemm(y, w["label_emb.0.0.w"], w["label_emb.0.0.b"], epilogue=EPI_SILU)
+            ops.gemm(l1, w["label_emb.0.2.w"], w["label_emb.0.2.b"], residual=emb, out=emb)
+        # every ResBlock applies Linear(SiLU(emb)) (unet.py:412-415): one stacked GEMM for all of them
+        return ops.gemm(ops.silu(emb), w["emb_all.w"], w["emb_all.b"])
+
+    def forward_cols(self, cols: torch.Tensor, n: int, hh: int, ww: int, timesteps: torch.Tensor,
+                     context: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
+        """cols: conv_in im2col rows [n*hh*ww, 64]; returns eps NHWC [n, hh, ww, 8] (channels >= 4 are zero)."""
+        w = self.w
+        assert context.dtype == self.dtype and context.is_contiguous() and context.shape[0] == n
+        n_ctx = context.shape[1]
+        ctx2d = context.view(n * n_ctx, context.shape[2])
+        temb_all = self._embeddings(timesteps, y)
+        p0 = self.st["input"][0][0][1]
+        h = ops.gemm(cols, w[p0 + ".w"], w[p0 + ".b"]).view(n, hh, ww, self.mc)
+        hs = [h]
+        for layers in self.st["input"][1:]:
+            h = self._run(layers, h, None, temb_all, ctx2d, n_ctx)
+            hs.append(h)
+        h = self._run(self.st["middle"], h, None, temb_all, ctx2d, n_ctx)
+        for layers in self.st["output"]:
+            h = self._run(layers, h, hs.pop(), temb_all, ctx2d, n_ctx)
+        h = ops.groupnorm(h, w["out.0.g"], w["out.0.b"], eps=1e-5, silu=True)
+        return ops.conv3x3(h, w["out.2.w"], w["out.2.b"])
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
+                y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same contract as IntegratedUNet2DConditionModel.forward (unet.py:696): x NCHW [N,4,h,w] in the
+        computation dtype, timesteps [N], context [N,77,ctx], y [N,adm] -> NCHW [N,4,h,w]."""
+        n, c, hh, ww = x.shape
+        xn = ops.nchw_to_nhwc(x.to(self.dtype).contiguous(), self.dtype)
+        cols = ops.im2col3x3(xn, ldo=64)
+        eps = self.forward_cols(cols, n, hh, ww, timesteps.float().contiguous(), context.to(self.dtype).contiguous(),
+                                None if y is None else y.to(self.dtype).contiguous())
+        return ops.nhwc_to_nchw(eps, channels=self.out_channels, out_dtype=x.dtype)
+
+    def forward_sigma(self, x: torch.Tensor, sigma: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
+                      y: Optional[torch.Tensor], reps: int) -> torch.Tensor:
+        """KModel.apply_model's front half fused into the entry (k_model.py:27-36): x fp32 NCHW [B,4,h,w] is
+        scaled by 1/sqrt(sigma^2+1), cast, laid out channels-last and replicated `reps` times (cond/uncond
+        batch) in one pass.  Returns eps NHWC [reps*B, h, w, 8]."""
+        b, c, hh, ww = x.shape
+        cols = ops.unet_input_im2col(x, sigma, self.dtype, reps=reps, ldo=64)
+        return self.forward_cols(cols, reps * b, hh, ww, timesteps, context, y)
