@@ -145,7 +145,10 @@ int b200_upsample2x(const void* x, void* y, int N, int H, int W, int C, int dtyp
  * (1 for the UNet convs; 0 for the VAE encoder's asymmetric (0,1,0,1) pad). */
 int b200_im2col3x3(const void* x, void* out, int N, int H, int W, int C, int stride, int pad_lo, int Ho, int Wo,
                    int ldo, int dtype, b200_stream_t s);
-int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int in_is_f32, int dtype, b200_stream_t s);
+/* y[(n,h,w), c] = x[n,c,h,w] * scale for c < C, 0 for C <= c < ldy (channel padding for the TMA/GEMM paths);
+ * x is fp32 when in_is_f32 else dtype.  Used at the UNet/VAE entry (NCHW latents). */
+int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int ldy, float scale, int in_is_f32,
+                      int dtype, b200_stream_t s);
 int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int ldx, int out_is_f32, int dtype,
                       b200_stream_t s);
 /* y = silu(x) elementwise (SiLU in front of ResBlock.emb_layers, backend/nn/unet.py:412). */

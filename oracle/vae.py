@@ -1,0 +1,125 @@
+"""ORACLE — test infrastructure only (see oracle/ops.py header).
+
+Functional restatement of the reference VAE decode path: IntegratedAutoencoderKL.decode
+(backend/nn/vae.py:305-310) -> Decoder.forward (:248-271) with ResnetBlock (:99-115), AttnBlock (:127-137),
+Upsample (:43-57), plus the driver arithmetic of VAE.decode_inner (backend/patcher/vae.py:128-148) and
+process_out (backend/nn/vae.py:315-316).  State-dict keys are the reference's parameter names.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops as O
+
+SD = Dict[str, torch.Tensor]
+
+
+def _conv(sd, p, x, padding=1):
+    return O.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], padding=padding)
+
+
+def _gn(sd, p, x):
+    return O.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], 1e-6)  # Normalize(), vae.py:12-13
+
+
+def resnet_block(sd: SD, p: str, x):
+    """backend/nn/vae.py:99-115 with temb=None, dropout=0."""
+    h = _conv(sd, p + ".conv1", O.silu(_gn(sd, p + ".norm1", x)))
+    h = _conv(sd, p + ".conv2", O.silu(_gn(sd, p + ".norm2", h)))
+    if (p + ".nin_shortcut.weight") in sd:
+        x = _conv(sd, p + ".nin_shortcut", x, padding=0)
+    return x + h
+
+
+def attn_block(sd: SD, p: str, x):
+    """backend/nn/vae.py:127-137 + pytorch_attention_single_head_spatial (backend/attention.py:412-427):
+    single-head attention over the h*w positions with C-dim queries/keys/values."""
+    h_ = _gn(sd, p + ".norm", x)
+    q = _conv(sd, p + ".q", h_, padding=0)
+    k = _conv(sd, p + ".k", h_, padding=0)
+    v = _conv(sd, p + ".v", h_, padding=0)
+    b, c, hh, ww = q.shape
+    qt, kt, vt = (t.reshape(b, c, hh * ww).transpose(1, 2) for t in (q, k, v))  # [b, L, C]
+    out = O.attention(qt, kt, vt, heads=1)
+    out = out.transpose(1, 2).reshape(b, c, hh, ww)
+    return x + _conv(sd, p + ".proj_out", out, padding=0)
+
+
+def decoder_structure(cfg: dict):
+    boc = list(cfg["block_out_channels"])
+    ch = boc[0]
+    ch_mult = [c // ch for c in boc]
+    nres = len(ch_mult)
+    return ch, ch_mult, nres, cfg["layers_per_block"]
+
+
+def decode(sd: SD, cfg: dict, z: torch.Tensor) -> torch.Tensor:
+    """IntegratedAutoencoderKL.decode: post_quant_conv then Decoder.forward.  z is the *processed-out* latent."""
+    ch, ch_mult, nres, nrb = decoder_structure(cfg)
+    if "post_quant_conv.weight" in sd:
+        z = _conv(sd, "post_quant_conv", z, padding=0)
+    h = _conv(sd, "decoder.conv_in", z)
+    h = resnet_block(sd, "decoder.mid.block_1", h)
+    h = attn_block(sd, "decoder.mid.attn_1", h)
+    h = resnet_block(sd, "decoder.mid.block_2", h)
+    for lvl in reversed(range(nres)):
+        for j in range(nrb + 1):
+            h = resnet_block(sd, f"decoder.up.{lvl}.block.{j}", h)
+        if lvl != 0:
+            h = _conv(sd, f"decoder.up.{lvl}.upsample.conv", O.upsample_nearest2x(h))
+    h = O.silu(_gn(sd, "decoder.norm_out", h))
+    return _conv(sd, "decoder.conv_out", h)
+
+
+def decode_first_stage(sd: SD, cfg: dict, latent: torch.Tensor) -> torch.Tensor:
+    """process_out (vae.py:315-316) -> decode -> clamp((x+1)/2, 0, 1) -> NHWC  (patcher/vae.py:142,147).
+    Returns [B, H, W, 3] fp32 in [0, 1]."""
+    z = latent / cfg["scaling_factor"] + cfg.get("shift_factor", 0.0)
+    x = decode(sd, cfg, z)
+    return torch.clamp((x.float() + 1.0) / 2.0, min=0.0, max=1.0).movedim(1, -1)
+
+
+def random_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> SD:
+    """Synthetic decoder weights (+ post_quant_conv) with the reference's names; the encoder half is not on
+    the txt2img path and is left out."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+
+    def conv(p, cin, cout, k):
+        sd[p + ".weight"] = (torch.randn(cout, cin, k, k, generator=g) * (cin * k * k) ** -0.5).to(dtype)
+        sd[p + ".bias"] = (torch.randn(cout, generator=g) * 0.05).to(dtype)
+
+    def norm(p, c):
+        sd[p + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g)).to(dtype)
+        sd[p + ".bias"] = (0.05 * torch.randn(c, generator=g)).to(dtype)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cin, cout, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cin, cout, 1)
+
+    ch, ch_mult, nres, nrb = decoder_structure(cfg)
+    zc = cfg["latent_channels"]
+    conv("post_quant_conv", zc, zc, 1)
+    block_in = ch * ch_mult[-1]
+    conv("decoder.conv_in", zc, block_in, 3)
+    res("decoder.mid.block_1", block_in, block_in)
+    norm("decoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"decoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("decoder.mid.block_2", block_in, block_in)
+    for lvl in reversed(range(nres)):
+        block_out = ch * ch_mult[lvl]
+        for j in range(nrb + 1):
+            res(f"decoder.up.{lvl}.block.{j}", block_in, block_out)
+            block_in = block_out
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3)
+    norm("decoder.norm_out", block_in)
+    conv("decoder.conv_out", block_in, cfg["out_channels"], 3)
+    return sd

@@ -262,17 +262,21 @@ __global__ void im2col3x3_scalar_kernel(const uint16_t* __restrict__ x, uint16_t
 
 template <bool BF16>
 __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, int N, int C, int H, int W,
-                                    int in_is_f32) {
-  const size_t total = (size_t)N * H * W * C;
+                                    int ldy, float scale, int in_is_f32) {
+  const size_t total = (size_t)N * H * W * ldy;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    size_t t = i / C;
+    const int c = (int)(i % ldy);
+    size_t t = i / ldy;
     const int w = (int)(t % W);
     t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
-    const size_t src = (((size_t)n * C + c) * H + h) * W + w;
-    const float v = in_is_f32 ? reinterpret_cast<const float*>(x)[src] : ld1<BF16>(x, src);
+    float v = 0.f;
+    if (c < C) {
+      const size_t src = (((size_t)n * C + c) * H + h) * W + w;
+      v = in_is_f32 ? reinterpret_cast<const float*>(x)[src] : ld1<BF16>(x, src);
+      if (scale != 1.0f) v = v * scale;
+    }
     st1<BF16>(y, i, v);
   }
 }
@@ -518,12 +522,12 @@ extern "C" int b200_im2col3x3(const void* x, void* out, int N, int H, int W, int
   return B200_OK;
 }
 
-extern "C" int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int in_is_f32, int dtype,
-                                 b200_stream_t s) {
-  B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
-  const size_t total = (size_t)N * C * H * W;
-  DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W,
-                                                                                                  in_is_f32));
+extern "C" int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int ldy, float scale,
+                                 int in_is_f32, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && ldy >= C, "nchw_to_nhwc: bad arguments");
+  const size_t total = (size_t)N * ldy * H * W;
+  DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W, ldy,
+                                                                                                  scale, in_is_f32));
   B200_CHECK_LAUNCH("nchw_to_nhwc");
   return B200_OK;
 }

@@ -93,7 +93,7 @@ SIGNATURES = {
     "b200_fill_zero": (_i, [_vp, _sz, _vp]),
     "b200_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_im2col3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_silu": (_i, [_vp, _vp, _sz, _i, _vp]),
     "b200_softmax_rows": (_i, [_vp, _i, _i, _i, _f, _i, _vp]),

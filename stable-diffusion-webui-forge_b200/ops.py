@@ -235,14 +235,18 @@ def im2col3x3(x: torch.Tensor, *, stride: int = 1, pad_lo: int = 1, pad_hi: int 
     return out
 
 
-def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, *, ldy: Optional[int] = None, scale: float = 1.0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW (fp32 or `dtype`) -> NHWC `dtype` with optional scaling and zero channel padding to ldy."""
     assert x.dim() == 4 and x.is_contiguous()
     n, c, h, w = x.shape
+    ldy = ldy or c
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+        out = torch.empty((n, h, w, ldy), dtype=dtype, device=x.device)
     is_f32 = x.dtype == torch.float32
     assert is_f32 or x.dtype == dtype
-    _l.check(_l.load().b200_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), n, c, h, w, 1 if is_f32 else 0, _dt(out), _stream()))
+    _l.check(_l.load().b200_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), n, c, h, w, ldy, scale, 1 if is_f32 else 0,
+                                         _dt(out), _stream()))
     _count()
     return out
 

@@ -1,0 +1,147 @@
+"""Fused channels-last VAE decoder — the B200 replacement for the decode path
+`VAE.decode -> IntegratedAutoencoderKL.decode -> Decoder.forward` (reference backend/patcher/vae.py:128-155,
+backend/nn/vae.py:305-310, 248-271) in bf16 (the reference's VAE dtype on sm_80+, memory_management.py:193-199).
+
+Everything is the same kernel set as the UNet: GroupNorm stats/apply+SiLU, tiled implicit-GEMM conv3x3 with the
+residual add in its epilogue, GEMMs for the 1x1 convs.  The single-head Dh=C attention of the mid block
+(backend/nn/vae.py:118-137) runs as S = Q K^T (GEMM) -> row softmax -> O = S V (GEMM with V^T produced directly by
+the V projection with swapped operands), one image at a time.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops
+
+SD = Dict[str, torch.Tensor]
+
+
+class VAEDecoderEngine:
+    def __init__(self, cfg: dict, state_dict: SD, dtype: torch.dtype = torch.bfloat16, device="cuda"):
+        self.cfg = dict(cfg)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        boc = list(cfg["block_out_channels"])
+        self.ch = boc[0]
+        self.ch_mult = [c // self.ch for c in boc]
+        self.nres = len(boc)
+        self.nrb = cfg["layers_per_block"]
+        self.zc = cfg["latent_channels"]
+        self.scaling = float(cfg["scaling_factor"])
+        self.shift = float(cfg.get("shift_factor", 0.0) or 0.0)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(state_dict)
+
+    def _t(self, t):
+        return t.detach().to(device=self.device, dtype=self.dtype).contiguous()
+
+    def _pack(self, sd: SD) -> None:
+        w = self.w
+        g = lambda k: self._t(sd[k])  # noqa: E731
+        zc = self.zc
+        assert zc <= 8
+        # post_quant_conv 1x1 on the latent padded to 8 channels
+        pq = torch.zeros((8, 8), dtype=self.dtype, device=self.device)
+        pqb = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        if "post_quant_conv.weight" in sd:
+            pq[:zc, :zc] = g("post_quant_conv.weight").reshape(zc, zc)
+            pqb[:zc] = g("post_quant_conv.bias")
+        else:
+            pq[:zc, :zc] = torch.eye(zc, dtype=self.dtype, device=self.device)
+        w["pq.w"], w["pq.b"] = pq, pqb
+        # conv_in on 8-channel (zero padded) input via im2col: k = tap*8 + c
+        ci = g("decoder.conv_in.weight")  # [Cb, zc, 3, 3]
+        cb = ci.shape[0]
+        cip = torch.zeros((cb, 3, 3, 8), dtype=self.dtype, device=self.device)
+        cip[..., :zc] = ci.permute(0, 2, 3, 1)
+        w["conv_in.w"], w["conv_in.b"] = cip.reshape(cb, 72).contiguous(), g("decoder.conv_in.bias")
+
+        def res(p):
+            for n in ("norm1", "norm2"):
+                w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight"), g(f"{p}.{n}.bias")
+            for n in ("conv1", "conv2"):
+                w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = ops.pack_conv3x3(g(f"{p}.{n}.weight")), g(f"{p}.{n}.bias")
+            if f"{p}.nin_shortcut.weight" in sd:
+                sw = g(f"{p}.nin_shortcut.weight")
+                w[f"{p}.skip.w"], w[f"{p}.skip.b"] = sw.reshape(sw.shape[0], sw.shape[1]).contiguous(), g(f"{p}.nin_shortcut.bias")
+
+        res("decoder.mid.block_1")
+        res("decoder.mid.block_2")
+        p = "decoder.mid.attn_1"
+        w[p + ".norm.g"], w[p + ".norm.b"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+        for n in ("q", "k", "v", "proj_out"):
+            cw = g(f"{p}.{n}.weight")
+            w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = cw.reshape(cw.shape[0], cw.shape[1]).contiguous(), g(f"{p}.{n}.bias")
+        for lvl in range(self.nres):
+            for j in range(self.nrb + 1):
+                res(f"decoder.up.{lvl}.block.{j}")
+            if lvl != 0:
+                q = f"decoder.up.{lvl}.upsample.conv"
+                w[q + ".w"], w[q + ".b"] = ops.pack_conv3x3(g(q + ".weight")), g(q + ".bias")
+        w["norm_out.g"], w["norm_out.b"] = g("decoder.norm_out.weight"), g("decoder.norm_out.bias")
+        co = ops.pack_conv3x3(g("decoder.conv_out.weight"))  # [3, 9*ch] -> pad to 8 rows
+        cop = torch.zeros((8, co.shape[1]), dtype=self.dtype, device=self.device)
+        cop[: co.shape[0]] = co
+        cob = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        cob[: co.shape[0]] = g("decoder.conv_out.bias")
+        w["conv_out.w"], w["conv_out.b"] = cop, cob
+
+    # ------------------------------------------------------------------------------------------ blocks
+    def _res(self, p: str, x: torch.Tensor) -> torch.Tensor:
+        w = self.w
+        n, hh, ww, cin = x.shape
+        h = ops.groupnorm(x, w[p + ".norm1.g"], w[p + ".norm1.b"], eps=1e-6, silu=True)
+        h = ops.conv3x3(h, w[p + ".conv1.w"], w[p + ".conv1.b"])
+        h = ops.groupnorm(h, w[p + ".norm2.g"], w[p + ".norm2.b"], eps=1e-6, silu=True)
+        if (p + ".skip.w") in w:
+            cout = w[p + ".skip.w"].shape[0]
+            skip = ops.gemm(x.view(-1, cin), w[p + ".skip.w"], w[p + ".skip.b"]).view(n, hh, ww, cout)
+        else:
+            skip = x
+        return ops.conv3x3(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
+
+    def _attn(self, p: str, x: torch.Tensor) -> torch.Tensor:
+        w = self.w
+        n, hh, ww, c = x.shape
+        L = hh * ww
+        x2d = x.view(n * L, c)
+        hn = ops.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], eps=1e-6, silu=False).view(n, L, c)
+        q = ops.gemm(hn.view(n * L, c), w[p + ".q.w"], w[p + ".q.b"]).view(n, L, c)
+        k = ops.gemm(hn.view(n * L, c), w[p + ".k.w"], w[p + ".k.b"]).view(n, L, c)
+        o = torch.empty((n, L, c), dtype=self.dtype, device=self.device)
+        s = torch.empty((L, L), dtype=self.dtype, device=self.device)
+        vt = torch.empty((c, L), dtype=self.dtype, device=self.device)
+        for b in range(n):
+            ops.gemm(w[p + ".v.w"], hn[b], w[p + ".v.b"], bias_along_m=True, out=vt)  # V^T [C, L]
+            ops.gemm(q[b], k[b], out=s)                                               # S = Q K^T [L, L]
+            ops.softmax_rows_(s, c ** -0.5)
+            ops.gemm(s, vt, out=o[b])                                                 # O = P V [L, C]
+        out = ops.gemm(o.view(n * L, c), w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
+        return out.view(n, hh, ww, c)
+
+    # ------------------------------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def decode(self, latent: torch.Tensor) -> torch.Tensor:
+        """latent fp32 NCHW [B, zc, h, w] (sampler output) -> fp32 NHWC [B, 8h, 8w, 3] in [0, 1]."""
+        w = self.w
+        assert latent.dtype == torch.float32 and self.shift == 0.0
+        latent = latent.contiguous()
+        n, zc, hh, ww = latent.shape
+        z = ops.nchw_to_nhwc(latent, self.dtype, ldy=8, scale=1.0 / self.scaling)  # process_out (vae.py:315-316)
+        z = ops.gemm(z.view(-1, 8), w["pq.w"], w["pq.b"]).view(n, hh, ww, 8)
+        cols = ops.im2col3x3(z, ldo=72)
+        h = ops.gemm(cols, w["conv_in.w"], w["conv_in.b"]).view(n, hh, ww, -1)
+        h = self._res("decoder.mid.block_1", h)
+        h = self._attn("decoder.mid.attn_1", h)
+        h = self._res("decoder.mid.block_2", h)
+        for lvl in reversed(range(self.nres)):
+            for j in range(self.nrb + 1):
+                h = self._res(f"decoder.up.{lvl}.block.{j}", h)
+            if lvl != 0:
+                q = f"decoder.up.{lvl}.upsample.conv"
+                h = ops.conv3x3(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
+        h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
+        h = ops.conv3x3(h, w["conv_out.w"], w["conv_out.b"])
+        return ops.vae_postprocess(h)
