@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 diffusion backend (BASELINE.json: SDXL-base 1024x1024, 30 Euler-a
+steps, batch 8 per GPU, images/sec; UNet ms/step).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+One bench "step" = one complete txt2img batch: initial latent -> 30 x (UNet forward at batch 16 [uncond|cond] +
+fused CFG/Euler-a update) -> VAE decode of 8 images.  Data is synthetic: random-init SDXL UNet/VAE weights of the
+reference architecture, N(0,1) latents/noise, N(0,1) conditioning.
+
+Printed JSON (one line, rank 0):
+  value      images/sec over all ranks, inputs resident in HBM when the timed region starts
+  e2e        the same job through the public API (Txt2ImgPipeline.generate) fed from pinned HOST buffers, with the
+             host->device copies and the device->host read of the images inside the timed region
+  roofline   the dominant kernel family (tcgen05 GEMM/implicit-GEMM conv): algorithmic FLOPs / CUDA-event time of
+             its launches in one instrumented (eager, un-graphed) job step, against the measured dense peak
+  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample (N=1, rank 0)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "images_per_sec_sdxl_1024_euler_a_30steps_batch8"
+UNIT = "images/s"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        peaks.update({k: p[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in p})
+        peaks["source"] = "measured"
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = []
+        reasons = set()
+        mx = 0.0
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [v for v in sm if v > 500] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_sample(latent_hw: int, threads: int):
+    """Oracle port (the reference's CPU arithmetic: ATen fp32) on a bounded sample: ONE SDXL UNet forward of one
+    sample at the benchmark's latent size.  Returns seconds per forward."""
+    from oracle import configs as CF
+    from oracle import unet as OU
+    torch.set_num_threads(threads)
+    cfg = CF.SDXL
+    sd = OU.random_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, latent_hw, latent_hw, generator=g)
+    ctx = torch.randn(1, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(1, cfg["adm_in_channels"], generator=g)
+    t = torch.tensor([500.0])
+
+    def fwd():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            OU.unet_forward(sd, cfg, x, t, ctx, y)
+            return time.perf_counter() - t0
+    return fwd
+
+
+def images_per_sec_from_forward(sec_per_sample_forward: float, steps: int = 30) -> float:
+    # one image = `steps` sampler steps x 2 UNet sample-forwards (cond + uncond); VAE decode excluded (favours the CPU)
+    return 1.0 / (2 * steps * sec_per_sample_forward)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fwd = cpu_baseline_sample(128, threads)
+    for _ in range(args.warmup if args.warmup is not None else 1):
+        fwd()
+    k = args.steps if args.steps is not None else 2
+    times = [fwd() for _ in range(k)]
+    sec = sum(times) / len(times)
+    val = images_per_sec_from_forward(sec)
+    sample = ("per bench step: 1 SDXL UNet sample-forward (batch 1, latent 128x128, fp32, oracle port = the reference's "
+              "ATen CPU path) of the 480 forwards (8 images x 30 steps x cond+uncond) in one batch; images/s = 1/(60*t_fwd)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": k,
+            "warmup": args.warmup if args.warmup is not None else 1, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SDXL-base 1024x1024 Euler-a 30 steps batch 8 (CPU sample: one UNet sample-forward)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def gpu_reference_unet_ms(batch: int, hw: int, iters: int = 3):
+    """Context number (not the graded reference arm): the oracle port — the same ATen calls the reference makes
+    (F.conv2d / F.linear / F.group_norm / SDPA) — in fp16 on this GPU, UNet forward at the benchmark batch."""
+    from oracle import configs as CF
+    from oracle import unet as OU
+    from b200forge import synthetic
+    cfg = CF.SDXL
+    sd = synthetic.random_unet_state_dict(cfg, device="cuda", dtype=torch.float16, seed=0)
+    x = torch.randn(batch, 4, hw, hw, device="cuda", dtype=torch.float16)
+    ctx = torch.randn(batch, 77, cfg["context_dim"], device="cuda", dtype=torch.float16)
+    y = torch.randn(batch, cfg["adm_in_channels"], device="cuda", dtype=torch.float16)
+    t = torch.full((batch,), 500.0, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            OU.unet_forward(sd, cfg, x, t, ctx, y)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            OU.unet_forward(sd, cfg, x, t, ctx, y)
+        e.record()
+        torch.cuda.synchronize()
+    del sd
+    torch.cuda.empty_cache()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--sampler_steps", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    K = args.steps if args.steps is not None else 3
+    W = args.warmup if args.warmup is not None else 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    from b200forge import lib, ops, synthetic
+    from b200forge.pipeline import Txt2ImgPipeline
+    lib.check(lib.load().b200_device_ok())
+    peaks = load_peaks()
+
+    B, S = args.batch, args.sampler_steps
+    hw = args.size // 8
+    ucfg, vcfg = synthetic.SDXL, synthetic.VAE_SDXL
+    usd = synthetic.random_unet_state_dict(ucfg, device=dev, dtype=torch.float16, seed=0)
+    vsd = synthetic.random_vae_decoder_state_dict(vcfg, device=dev, dtype=torch.bfloat16, seed=1)
+    pipe = Txt2ImgPipeline(ucfg, usd, vae_cfg=vcfg, vae_state_dict=vsd, dtype=torch.float16, device=dev)
+    del usd, vsd
+
+    # ---- synthetic job inputs (pinned host copies for the e2e leg, device copies for the resident leg)
+    seeds = [1000 + rank * B + i for i in range(B)]  # contiguous-by-seed sharding: results independent of N
+    gens = [torch.Generator().manual_seed(s) for s in seeds]
+
+    def draw():
+        return torch.stack([torch.randn((4, hw, hw), generator=g) for g in gens])
+
+    g0 = torch.Generator().manual_seed(7)
+    host = {
+        "noise": draw().pin_memory(),
+        "step_noise": torch.stack([draw() for _ in range(S - 1)]).pin_memory(),
+        "cond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
+                 "vector": torch.randn(B, ucfg["adm_in_channels"], generator=g0).half().pin_memory()},
+        "uncond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
+                   "vector": torch.randn(B, ucfg["adm_in_channels"], generator=g0).half().pin_memory()},
+    }
+    devin = {"noise": host["noise"].to(dev), "step_noise": host["step_noise"].to(dev),
+             "cond": {k: v.to(dev) for k, v in host["cond"].items()},
+             "uncond": {k: v.to(dev) for k, v in host["uncond"].items()}}
+    h2d = (host["noise"].numel() * 4 + host["step_noise"].numel() * 4 +
+           sum(v.numel() * 2 for v in host["cond"].values()) + sum(v.numel() * 2 for v in host["uncond"].values()))
+    out_host = torch.empty((B, args.size, args.size, 3), dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * 4
+    gathered = [torch.empty((B, args.size, args.size, 3), dtype=torch.float32, device=dev) for _ in range(world)] \
+        if (dist is not None and rank == 0) else None
+
+    def job(inp):
+        img = pipe.generate(inp["cond"], inp["uncond"], inp["noise"], steps=S, sampler="euler_a", cfg_scale=7.0,
+                            step_noise=inp["step_noise"])
+        return img
+
+    def finish(img):
+        # multi-GPU: the only collective on the path — gather of the finished images to rank 0
+        if dist is not None:
+            dist.gather(img, gathered, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) * 1e-3
+
+    def step_resident():
+        finish(job(devin))
+
+    def step_e2e():
+        img = job(host)
+        finish(img)
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the device->host read of the step's result
+
+    for _ in range(W):
+        step_resident()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    l0 = ops.LAUNCHES
+    sec = timed(step_resident, K)
+    launches = ops.LAUNCHES - l0
+    step_e2e()
+    sec_e2e = timed(step_e2e, K)
+    clk = clocks.stop()
+
+    total_images = B * world * K
+    value = total_images / sec
+    e2e_value = total_images / sec_e2e
+
+    # ---- UNet ms/step and the per-kernel-family roofline from one instrumented eager denoise step + VAE decode
+    unet_ms = None
+    roof = None
+    fam = {}
+    if rank == 0:
+        gu = next(iter(pipe._graphs.values()))
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(10):
+            gu()
+        e_.record()
+        torch.cuda.synchronize()
+        unet_ms = s_.elapsed_time(e_) / 10
+        ops.PROFILE = []
+        gu._eager()
+        pipe.decode(torch.randn(B, 4, hw, hw, device=dev) * 0.13025)
+        torch.cuda.synchronize()
+        for name, fl, by, s2, e2 in ops.PROFILE:
+            d = fam.setdefault(name, {"launches": 0, "flops": 0.0, "bytes": 0.0, "ms": 0.0})
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+            d["ms"] += s2.elapsed_time(e2)
+        ops.PROFILE = None
+        tens = {"launches": 0, "flops": 0.0, "ms": 0.0}
+        for name in ("gemm", "conv3x3"):
+            if name in fam:
+                for k in tens:
+                    tens[k] += fam[name][k]
+        ach = tens["flops"] / (tens["ms"] * 1e-3) / 1e12 if tens["ms"] > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"kernel": "b200::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3; 1 UNet forward @batch 16 + VAE decode)",
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                "launches": tens["launches"], "avg_launch_ms": tens["ms"] / max(1, tens["launches"]),
+                "flops_per_launch_avg": tens["flops"] / max(1, tens["launches"])}
+        for name, d in fam.items():
+            d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+            d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+
+    cpu_base = None
+    gpu_ref_ms = None
+    if rank == 0 and world == 1:
+        if not args.no_gpu_reference:
+            try:
+                gpu_ref_ms = gpu_reference_unet_ms(2 * B, hw)
+            except Exception as ex:  # context number only
+                gpu_ref_ms = f"failed: {type(ex).__name__}"
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            fwd = cpu_baseline_sample(hw, threads)
+            t = fwd()
+            cpu_base = {"value": images_per_sec_from_forward(t, S), "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": (f"1 SDXL UNet sample-forward (batch 1, latent {hw}x{hw}, fp32 ATen via the oracle port) "
+                                   f"= {t:.2f} s; images/s = 1/(2*{S}*t), VAE decode excluded")}
+
+    if rank == 0:
+        flops_per_image = 2 * S * synthetic.UNET_GFLOP_PER_SAMPLE["sdxl@128"] * 1e9 + \
+            synthetic.VAE_GFLOP_PER_IMAGE["sdxl@1024"] * 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 (UNet) / bf16 (VAE), fp32 accumulate and sampler state", "data": "synthetic",
+            "config": {"workload": f"SDXL-base {args.size}x{args.size} txt2img, Euler-a {S} steps, CFG 7, batch {B}/GPU "
+                                   f"(UNet batch {2 * B}), VAE decode included; 1 bench step = 1 batch of {B} images/GPU",
+                       "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of images only)",
+                       "l2": "working set (5.1 GB weights + activations) >> 126 MB L2; no explicit flush",
+                       "roofline_pass": "separate instrumented eager pass after the timed region (graph replays cannot be bracketed)"},
+            "unet_ms_per_step": unet_ms,
+            "unet_roofline_ms_per_step": 2 * B * synthetic.UNET_GFLOP_PER_SAMPLE["sdxl@128"] * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
+            "flop_roofline_frac_whole_job": value / world * flops_per_image / (peaks["bf16_tflops_sustained"] * 1e12),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": roof,
+            "kernel_families": fam,
+            "cpu_baseline": cpu_base,
+            "gpu_reference_unet_ms_per_step": gpu_ref_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,27 @@ from . import lib as _l
 from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER)  # noqa: F401
 
 LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
+PROFILE = None  # set to a list to record (family, algorithmic flops, algorithmic bytes, start_evt, end_evt) per call
+
+
+class _prof:
+    """CUDA-event bracket around one library call on the launching stream (bench.py roofline accounting)."""
+
+    def __init__(self, family: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.family, self.flops, self.nbytes = family, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            PROFILE.append((self.family, self.flops, self.nbytes, self.s, e))
+        return False
 
 
 def _count(n: int = 1) -> None:
@@ -83,7 +104,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.rowvec, d.ld_rowvec, d.rows_per_vec = rowvec.data_ptr(), rowvec.stride(0), rows_per_vec
     if a2 is not None:
         d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), K1
-    _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    with _prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
+        _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
 
@@ -139,7 +161,8 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     if temb is not None:
         _rowmajor2d(temb, "temb")
         d.temb, d.ld_temb = temb.data_ptr(), temb.stride(0)
-    _l.check(_l.load().b200_conv3x3(x1.data_ptr(), _p(x2), w_packed.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    with _prof("conv3x3", 2.0 * n * h * w_ * cout * 9 * (c1 + c2), 2.0 * (n * h * w_ * (c1 + c2 + cout) + cout * 9 * (c1 + c2))):
+        _l.check(_l.load().b200_conv3x3(x1.data_ptr(), _p(x2), w_packed.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
 
@@ -163,7 +186,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, 
     d.o_stride_b, d.o_stride_l = out.stride(0), out.stride(1)
     d.scale = float(scale if scale is not None else dh ** -0.5)
     d.dtype = _dt(q)
-    _l.check(_l.load().b200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    with _prof("attention", 4.0 * b * heads * lq * lk * dh, 2.0 * b * hd * (2 * lq + 2 * lk)):
+        _l.check(_l.load().b200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
 
@@ -188,10 +212,11 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     d.N, d.HW, d.C1, d.C2, d.groups, d.eps, d.silu, d.dtype = n, hw, c1, c2, groups, eps, 1 if silu else 0, _dt(x1)
     L = _l.load()
     st = _stream()
-    _l.check(L.b200_fill_zero(sums.data_ptr(), n * groups * 2 * 4, st))
-    _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), sums.data_ptr(), C.byref(d), st))
-    _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                    out.data_ptr(), C.byref(d), st))
+    with _prof("groupnorm", 0.0, 2.0 * 3 * n * hw * (c1 + c2)):
+        _l.check(L.b200_fill_zero(sums.data_ptr(), n * groups * 2 * 4, st))
+        _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), sums.data_ptr(), C.byref(d), st))
+        _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                        out.data_ptr(), C.byref(d), st))
     _count(3)
     return out
 
@@ -203,7 +228,8 @@ def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[tor
     rows = x.numel() // c
     if out is None:
         out = torch.empty_like(x)
-    _l.check(_l.load().b200_layernorm(x.data_ptr(), _p(gamma), _p(beta), out.data_ptr(), rows, c, eps, _dt(x), _stream()))
+    with _prof("layernorm", 0.0, 2.0 * 2 * rows * c):
+        _l.check(_l.load().b200_layernorm(x.data_ptr(), _p(gamma), _p(beta), out.data_ptr(), rows, c, eps, _dt(x), _stream()))
     _count()
     return out
 
