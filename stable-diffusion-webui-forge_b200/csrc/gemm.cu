@@ -2,7 +2,12 @@
 //
 //   C[M, N] = epilogue( A[M, K] * B[N, K]^T )        fp16 or bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA per SM, static round-robin over 128 x BN output tiles (BN runtime, multiple of 32, <= 256):
+// Two builds of the same kernel:
+//   CG = 1  one CTA per SM, 128 x BN tiles (tcgen05.mma cta_group::1, M = 128)
+//   CG = 2  CTA pairs (cluster of 2) cooperate on 256 x BN tiles (cta_group::2, M = 256): each CTA loads its own
+//           128 A rows and HALF of the B tile, the pair's tensor cores read both halves — 1.5x fewer shared-memory
+//           and L2 bytes per FLOP than CG = 1, which is what lifts the kernel off the smem-bandwidth ceiling.
+// One CTA per SM, static round-robin over output tiles (BN runtime, multiple of 32, <= 256):
 //   warp 0   TMA producer: A tile (128 x 64) and B tile (BN x 64) per k-chunk into a ring of smem stages
 //   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage; tcgen05.commit
 //            releases the stage and, after the last chunk, publishes the TMEM accumulator
@@ -17,6 +22,7 @@
 //           TMA zero-fills the out-of-image part, which is exactly the convolution's zero padding.
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -74,15 +80,19 @@ __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, 
   f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
 }
 
-template <bool BF16>
+template <bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
             const __grid_constant__ CUtensorMap mapB, const GemmKParams p) {
+  // CG == 2: launched with cluster dims (2,1,1); rank 0 of each pair is the MMA leader.
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair (or CTA) index
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.num_stages;
   const int BN = p.BN;
-  const uint32_t b_tile_bytes = (uint32_t)BN * 128u;
+  const uint32_t b_tile_bytes = (uint32_t)(BN / CG) * 128u;  // CG == 2: this CTA holds half of the B tile
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)S * kATileBytes;
   const uint32_t bar_base = b_base + (uint32_t)S * b_tile_bytes;
@@ -103,36 +113,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(full_bar(i), 1);
+      mbar_init(full_bar(i), CG);  // CG == 2: one arrival per CTA's producer, bytes of both CTAs
       mbar_init(empty_bar(i), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 128);
+      mbar_init(tempty_bar(i), 128 * CG);
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, 512);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_mu = (p.tiles_m + CG - 1) / CG;  // M tiles per unit: a pair covers two adjacent 128-row tiles
+  const int total_tiles = tiles_mu * p.tiles_n;
   const int nk = p.num_k_chunks;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = (uint32_t)kATileBytes + b_tile_bytes;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.tiles_m;
-      const int n_blk = tile / p.tiles_m;
+    const uint32_t tx_bytes = ((uint32_t)kATileBytes + b_tile_bytes) * CG;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
+      const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
+      const int n_blk = tile / tiles_mu;
       int cn = 0, ch = 0, cw = 0;
       if (p.mode == 1) {
         const int tpi = p.tiles_w * p.tiles_h;
@@ -145,28 +161,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t fb = full_bar(stage);
-        mbar_expect_tx(fb, tx_bytes);
         const uint32_t a_dst = a_base + (uint32_t)stage * kATileBytes;
-        if (p.mode == 0) {
-          if (kc < p.split_chunk) tma_load_2d(a_dst, &mapA, fb, kc * 64, m_blk * 128);
-          else tma_load_2d(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
+        const uint32_t b_dst = b_base + (uint32_t)stage * b_tile_bytes;
+        if constexpr (CG == 1) {
+          mbar_expect_tx(fb, tx_bytes);
+          if (p.mode == 0) {
+            if (kc < p.split_chunk) tma_load_2d(a_dst, &mapA, fb, kc * 64, m_blk * 128);
+            else tma_load_2d(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
+          } else {
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
+            else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
+          }
+          tma_load_2d(b_dst, &mapB, fb, kc * 64, n_blk * BN);
         } else {
-          const int tap = kc / p.chunks_per_tap;
-          const int cc = kc - tap * p.chunks_per_tap;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
-          else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
+          // both CTAs' loads complete on the leader's barrier; the leader arms it for the pair's bytes
+          if (cta_rank == 0) mbar_expect_tx(fb, tx_bytes);
+          else mbar_arrive_remote(fb, 0);
+          if (p.mode == 0) {
+            if (kc < p.split_chunk) tma_load_2d_cg2(a_dst, &mapA, fb, kc * 64, m_blk * 128);
+            else tma_load_2d_cg2(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
+          } else {
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            if (cc < p.split_chunk) tma_load_4d_cg2(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
+            else tma_load_4d_cg2(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
+          }
+          tma_load_2d_cg2(b_dst, &mapB, fb, kc * 64, n_blk * BN + (int)cta_rank * (BN / 2));
         }
-        tma_load_2d(b_base + (uint32_t)stage * b_tile_bytes, &mapB, fb, kc * 64, n_blk * BN);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair leader only)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -180,12 +214,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // +32 bytes per 16-element k step inside the 128-byte swizzle atom (encoded >> 4)
-          umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          if constexpr (CG == 2)
+            umma_f16_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          else
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));
+        if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));
+      if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -193,9 +230,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % p.tiles_m;
-      const int n_blk = tile / p.tiles_m;
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+      const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
+      const int n_blk = tile / tiles_mu;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -275,15 +312,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      else mbar_arrive(tempty_bar(acc));
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -299,41 +337,79 @@ static int pick_block_n(int N, int epilogue) {
   return bn;
 }
 
-static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
-                       int dtype, cudaStream_t stream) {
-  const int stage_bytes = kATileBytes + p.BN * 128;
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_CG");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool BF16, int CG>
+static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
+                         cudaStream_t stream) {
+  const int stage_bytes = kATileBytes + (p.BN / CG) * 128;
   int S = (220 * 1024) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) S = 2;
   p.num_stages = S;
   const size_t smem = (size_t)S * stage_bytes + 1024 + (2 * S + 4) * 8 + 16;
-  const int total = p.tiles_m * p.tiles_n;
-  int grid = num_sms();
-  if (grid <= 0) {
+  const int total = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+  int units = num_sms() / CG;
+  if (units <= 0) {
     set_error("gemm: no device");
     return B200_ENODEVICE;
   }
-  if (grid > total) grid = total;
-  cudaError_t e;
-  if (dtype == B200_BF16) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) { set_error("gemm: smem attr: %s", cudaGetErrorString(e)); return B200_ECUDA; }
-      attr_done = true;
+  if (units > total) units = total;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BF16, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("gemm: smem attr: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
     }
-    gemm_kernel<true><<<grid, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
+    attr_done = true;
+  }
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(units * 2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG>, mapA, mapA2, mapB, p);
+    if (e != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
   } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      e = cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) { set_error("gemm: smem attr: %s", cudaGetErrorString(e)); return B200_ECUDA; }
-      attr_done = true;
-    }
-    gemm_kernel<false><<<grid, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
+    gemm_kernel<BF16, CG><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
   }
   B200_CHECK_LAUNCH("gemm");
   return B200_OK;
+}
+
+// The B tensor map's box height depends on the cluster mode, so the mode is decided before the maps are built.
+static int gemm_cg(const GemmKParams& p) { return (use_pair_kernel() && p.tiles_m >= 2 && p.BN % 32 == 0) ? 2 : 1; }
+
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
+                       int dtype, int cg, cudaStream_t stream) {
+  if (cg == 2) {
+    p.idesc = make_idesc_f16(256, p.BN, dtype == B200_BF16, false, false);
+    return dtype == B200_BF16 ? launch_gemm_t<true, 2>(mapA, mapA2, mapB, p, stream)
+                              : launch_gemm_t<false, 2>(mapA, mapA2, mapB, p, stream);
+  }
+  p.idesc = make_idesc_f16(128, p.BN, dtype == B200_BF16, false, false);
+  return dtype == B200_BF16 ? launch_gemm_t<true, 1>(mapA, mapA2, mapB, p, stream)
+                            : launch_gemm_t<false, 1>(mapA, mapA2, mapB, p, stream);
 }
 
 }  // namespace b200
@@ -399,14 +475,15 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   } else {
     mA2 = mA;
   }
+  const int cg = gemm_cg(p);
   {
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     uint64_t str[1] = {(uint64_t)d->ldb * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(bn / cg)};
     int rc = make_tmap(&mB, d->dtype, B, 2, dims, str, box);
     if (rc) return rc;
   }
-  return launch_gemm(mA, mA2, mB, p, d->dtype, static_cast<cudaStream_t>(s));
+  return launch_gemm(mA, mA2, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
 }
 
 extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y,
@@ -475,12 +552,13 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   } else {
     mA2 = mA;
   }
+  const int cg = gemm_cg(p);
   {
     uint64_t dims[2] = {(uint64_t)(9 * C), (uint64_t)d->Cout};
     uint64_t str[1] = {(uint64_t)(9 * C) * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(bn / cg)};
     rc = make_tmap(&mB, d->dtype, w_packed, 2, dims, str, box);
     if (rc) return rc;
   }
-  return launch_gemm(mA, mA2, mB, p, d->dtype, static_cast<cudaStream_t>(s));
+  return launch_gemm(mA, mA2, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
 }
