@@ -41,6 +41,7 @@ struct GemmKParams {
   int bias_along_m;
   const void* residual;
   int ldr;
+  int n_out;  // output columns (N, or N/2 for GEGLU)
   const void* rowvec;
   int ld_rowvec;
   int rows_per_vec;
@@ -49,26 +50,8 @@ struct GemmKParams {
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
 static constexpr int kThreads = 256;
-
-template <bool BF16>
-__device__ __forceinline__ void epi_store8(const GemmKParams& p, int m, int n, float (&x)[8]) {
-  // x: 8 consecutive output columns n..n+7 of row m, activation already applied
-  if (p.residual) {
-    uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) +
-                                              ((size_t)m * p.ldr + n) * 2);
-    float2 f;
-    f = unpack2<BF16>(r.x); x[0] += f.x; x[1] += f.y;
-    f = unpack2<BF16>(r.y); x[2] += f.x; x[3] += f.y;
-    f = unpack2<BF16>(r.z); x[4] += f.x; x[5] += f.y;
-    f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
-  }
-  uint4 o;
-  o.x = pack2<BF16>(x[0], x[1]);
-  o.y = pack2<BF16>(x[2], x[3]);
-  o.z = pack2<BF16>(x[4], x[5]);
-  o.w = pack2<BF16>(x[6], x[7]);
-  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.C) + ((size_t)m * p.ldc + n) * 2) = o;
-}
+static constexpr uint32_t kStageBufs = 4;          // epilogue staging tiles (128 rows x 32 cols, 64B swizzle)
+static constexpr uint32_t kStageBufBytes = 128 * 64;
 
 template <bool BF16>
 __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, float (&x)[8]) {
@@ -83,7 +66,8 @@ __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, 
 template <bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-            const __grid_constant__ CUtensorMap mapB, const GemmKParams p) {
+            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+            const GemmKParams p) {
   // CG == 2: launched with cluster dims (2,1,1); rank 0 of each pair is the MMA leader.
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair (or CTA) index
@@ -95,7 +79,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const uint32_t b_tile_bytes = (uint32_t)(BN / CG) * 128u;  // CG == 2: this CTA holds half of the B tile
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)S * kATileBytes;
-  const uint32_t bar_base = b_base + (uint32_t)S * b_tile_bytes;
+  const uint32_t stg_base = b_base + (uint32_t)S * b_tile_bytes;  // 1024-aligned: every tile size is a multiple of 1 KB
+  const uint32_t bar_base = stg_base + kStageBufs * kStageBufBytes;
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM pointer slot
   auto full_bar = [&](int i) { return bar_base + (uint32_t)i * 8u; };
   auto empty_bar = [&](int i) { return bar_base + (uint32_t)(S + i) * 8u; };
@@ -110,6 +95,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -226,9 +212,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // Per 32-column chunk: TMEM -> registers -> (bias, temb row, activation, residual) -> fp16/bf16 ->
+    // 64B-swizzled staging tile in smem -> one TMA store (coalesced, clipped at the matrix edge).
     const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
+    const int epi_tid = (int)threadIdx.x - 128;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t sw = (uint32_t)(r >> 1) & 3u;
+    uint32_t chunk_ctr = 0;
+    const bool geglu = p.epilogue == B200_EPI_GEGLU;
+    const int ncols_out = geglu ? (BN >> 1) : BN;
     int it = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
@@ -240,81 +233,102 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
       const int m = m_blk * 128 + r;
       const bool row_ok = m < p.M;
-      const int n0 = n_blk * BN;
+      const int n0 = n_blk * BN;            // first accumulator column of this tile (weight row index)
+      const int out_n0 = n_blk * ncols_out; // first output column
       float bias_m = 0.f;
       if (p.bias && p.bias_along_m && row_ok) bias_m = ld1<BF16>(p.bias, m);
       const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
 
-      if (p.epilogue == B200_EPI_GEGLU) {
-        const int half_bn = BN >> 1;
-        const int out_n0 = n_blk * half_bn;
-        for (int c = 0; c < half_bn; c += 32) {
-          uint32_t vx[32], vg[32];
-          tmem_ld_32x32(t_addr + (uint32_t)c, vx);
-          tmem_ld_32x32(t_addr + (uint32_t)(half_bn + c), vg);
+      for (int c = 0; c < ncols_out; c += 32, ++chunk_ctr) {
+        const uint32_t buf = stg_base + (chunk_ctr % kStageBufs) * kStageBufBytes;
+        if (epi_tid == 0) bulk_wait_group_read<kStageBufs - 1>();  // the store that last used `buf` has read it
+        named_bar_sync(1, 128);
+        uint32_t v[32];
+        float x[32];
+        tmem_ld_32x32(t_addr + (uint32_t)c, v);
+        if (geglu) {
+          uint32_t vg[32];
+          tmem_ld_32x32(t_addr + (uint32_t)(ncols_out + c), vg);
           tmem_ld_wait();
-          if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int nx = n0 + c + g * 8;        // interleaved column of the x half
-              const int ng = nx + half_bn;          // matching gate column
-              if (ng < p.N) {
-                float x[8], gt[8];
+          for (int g = 0; g < 4; ++g) {
+            const int nx = n0 + c + g * 8;   // interleaved weight row of the value half
+            const int ng = nx + ncols_out;   // matching gate row
+            float xv[8], gt[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  x[i] = __uint_as_float(vx[g * 8 + i]);
-                  gt[i] = __uint_as_float(vg[g * 8 + i]);
-                }
-                if (p.bias) {
-                  epi_add_vec8<BF16>(p.bias, (size_t)nx, x);
-                  epi_add_vec8<BF16>(p.bias, (size_t)ng, gt);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = x[i] * gelu_erf_f(gt[i]);
-                epi_store8<BF16>(p, m, out_n0 + c + g * 8, x);
-              }
+            for (int i = 0; i < 8; ++i) {
+              xv[i] = __uint_as_float(v[g * 8 + i]);
+              gt[i] = __uint_as_float(vg[g * 8 + i]);
             }
+            if (p.bias && ng < p.N) {
+              epi_add_vec8<BF16>(p.bias, (size_t)nx, xv);
+              epi_add_vec8<BF16>(p.bias, (size_t)ng, gt);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i] * gelu_erf_f(gt[i]);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c + g * 8;
+            float xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
+            if (n < p.N) {
+              if (p.bias) {
+                if (p.bias_along_m) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) xv[i] += bias_m;
+                } else {
+                  epi_add_vec8<BF16>(p.bias, (size_t)n, xv);
+                }
+              }
+              if (p.rowvec && row_ok) epi_add_vec8<BF16>(p.rowvec, rv_off + (size_t)n, xv);
+            }
+            if (p.epilogue == B200_EPI_SILU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xv[i] = silu_f(xv[i]);
+            } else if (p.epilogue == B200_EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xv[i] = gelu_erf_f(xv[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
           }
         }
-      } else {
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (row_ok) {
+        const uint32_t row_smem = buf + (uint32_t)r * 64u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n0 + c + g * 8;
-              if (n < p.N) {
-                float x[8];
+        for (int g = 0; g < 4; ++g) {
+          const int n = out_n0 + c + g * 8;
+          if (p.residual && row_ok && n < p.n_out) {
+            float xv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-                if (p.bias) {
-                  if (p.bias_along_m) {
+            for (int i = 0; i < 8; ++i) xv[i] = x[g * 8 + i];
+            epi_add_vec8<BF16>(p.residual, (size_t)m * p.ldr + n, xv);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] += bias_m;
-                  } else {
-                    epi_add_vec8<BF16>(p.bias, (size_t)n, x);
-                  }
-                }
-                if (p.rowvec) epi_add_vec8<BF16>(p.rowvec, rv_off + (size_t)n, x);
-                if (p.epilogue == B200_EPI_SILU) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) x[i] = silu_f(x[i]);
-                } else if (p.epilogue == B200_EPI_GELU) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) x[i] = gelu_erf_f(x[i]);
-                }
-                epi_store8<BF16>(p, m, n, x);
-              }
-            }
+            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
           }
+          const uint32_t o0 = pack2<BF16>(x[g * 8 + 0], x[g * 8 + 1]);
+          const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
+          const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
+          const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
+          const uint32_t addr = row_smem + ((((uint32_t)g) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          tma_store_2d(&mapC, buf, out_n0 + c, m_blk * 128);
+          bulk_commit_group();
         }
       }
       tc_fence_before();
       if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
       else mbar_arrive(tempty_bar(acc));
     }
+    if (epi_tid == 0) bulk_wait_group_read<0>();  // staging smem must outlive the last store's reads
   }
 
   tc_fence_before();
@@ -347,14 +361,15 @@ static bool use_pair_kernel() {
 }
 
 template <bool BF16, int CG>
-static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
-                         cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
+                         const CUtensorMap& mapC, GemmKParams& p, cudaStream_t stream) {
   const int stage_bytes = kATileBytes + (p.BN / CG) * 128;
-  int S = (220 * 1024) / stage_bytes;
+  const int staging = (int)(kStageBufs * kStageBufBytes);
+  int S = (222 * 1024 - staging) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) S = 2;
   p.num_stages = S;
-  const size_t smem = (size_t)S * stage_bytes + 1024 + (2 * S + 4) * 8 + 16;
+  const size_t smem = (size_t)S * stage_bytes + staging + 1024 + (2 * S + 4) * 8 + 16;
   const int total = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
   int units = num_sms() / CG;
   if (units <= 0) {
@@ -385,13 +400,13 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG>, mapA, mapA2, mapB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG>, mapA, mapA2, mapB, mapC, p);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return B200_ECUDA;
     }
   } else {
-    gemm_kernel<BF16, CG><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, p);
+    gemm_kernel<BF16, CG><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, mapC, p);
   }
   B200_CHECK_LAUNCH("gemm");
   return B200_OK;
@@ -402,14 +417,23 @@ static int gemm_cg(const GemmKParams& p) { return (use_pair_kernel() && p.tiles_
 
 static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
                        int dtype, int cg, cudaStream_t stream) {
+  // output map: [M, n_out] row-major, 32-column x 128-row store boxes, 64-byte swizzle
+  CUtensorMap mapC;
+  {
+    uint64_t dims[2] = {(uint64_t)p.n_out, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)p.ldc * 2};
+    uint32_t box[2] = {32, 128};
+    int rc = make_tmap(&mapC, dtype, p.C, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
   if (cg == 2) {
     p.idesc = make_idesc_f16(256, p.BN, dtype == B200_BF16, false, false);
-    return dtype == B200_BF16 ? launch_gemm_t<true, 2>(mapA, mapA2, mapB, p, stream)
-                              : launch_gemm_t<false, 2>(mapA, mapA2, mapB, p, stream);
+    return dtype == B200_BF16 ? launch_gemm_t<true, 2>(mapA, mapA2, mapB, mapC, p, stream)
+                              : launch_gemm_t<false, 2>(mapA, mapA2, mapB, mapC, p, stream);
   }
   p.idesc = make_idesc_f16(128, p.BN, dtype == B200_BF16, false, false);
-  return dtype == B200_BF16 ? launch_gemm_t<true, 1>(mapA, mapA2, mapB, p, stream)
-                            : launch_gemm_t<false, 1>(mapA, mapA2, mapB, p, stream);
+  return dtype == B200_BF16 ? launch_gemm_t<true, 1>(mapA, mapA2, mapB, mapC, p, stream)
+                            : launch_gemm_t<false, 1>(mapA, mapA2, mapB, mapC, p, stream);
 }
 
 }  // namespace b200
@@ -453,6 +477,7 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.bias_along_m = d->bias_along_m;
   p.residual = d->residual;
   p.ldr = d->ldr;
+  p.n_out = d->epilogue == B200_EPI_GEGLU ? d->N / 2 : d->N;
   p.rowvec = d->rowvec;
   p.ld_rowvec = d->ld_rowvec;
   p.rows_per_vec = d->rows_per_vec > 0 ? d->rows_per_vec : 1;
@@ -530,6 +555,7 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   p.bias = d->bias;
   p.residual = d->residual;
   p.ldr = d->ldr;
+  p.n_out = d->Cout;
   B200_CHECK_ARG(!d->residual || d->ldr % 8 == 0, "conv3x3: ldr");
   p.rowvec = d->temb;
   p.ld_rowvec = d->ld_temb;

@@ -37,7 +37,7 @@ PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -69,7 +69,7 @@ int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uin
   }
   CUresult r = enc(out, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
               (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);

@@ -25,7 +25,8 @@ PFN_tmapEncodeTiled tmap_encoder();
 // rank-N tiled tensor map over 16-bit elements, 128-byte swizzle, zero fill out of bounds.
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
 int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box);
+              const uint64_t* strides_bytes, const uint32_t* box,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 #define B200_CHECK_ARG(cond, ...)  \
   do {                             \
