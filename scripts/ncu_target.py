@@ -1,0 +1,47 @@
+"""Tiny launcher for ncu captures: runs a handful of representative kernels once each (after one warm-up)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from b200forge import ops
+
+DEV = "cuda"
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+
+
+def gemm(M, N, K):
+    a = torch.randn(M, K, device=DEV, dtype=torch.float16)
+    w = torch.randn(N, K, device=DEV, dtype=torch.float16) * K ** -0.5
+    b = torch.randn(N, device=DEV, dtype=torch.float16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    for _ in range(2):
+        ops.gemm(a, w, b, out=out)
+    torch.cuda.synchronize()
+
+
+def conv(N, H, W, C, Co):
+    x = torch.randn(N, H, W, C, device=DEV, dtype=torch.float16)
+    w = torch.randn(Co, 9 * C, device=DEV, dtype=torch.float16) * (9 * C) ** -0.5
+    b = torch.randn(Co, device=DEV, dtype=torch.float16)
+    out = torch.empty(N, H, W, Co, device=DEV, dtype=torch.float16)
+    for _ in range(2):
+        ops.conv3x3(x, w, b, out=out)
+    torch.cuda.synchronize()
+
+
+def attn(B, H, Lq, Lk, Dh):
+    q = torch.randn(B, Lq, H * Dh, device=DEV, dtype=torch.float16)
+    k = torch.randn(B, Lk, H * Dh, device=DEV, dtype=torch.float16)
+    v = torch.randn(B, Lk, H * Dh, device=DEV, dtype=torch.float16)
+    out = torch.empty_like(q)
+    for _ in range(2):
+        ops.attention(q, k, v, H, out=out)
+    torch.cuda.synchronize()
+
+
+if which == "gemm":
+    gemm(16384, 10240, 1280)
+    gemm(65536, 5120, 640)
+    conv(16, 128, 128, 320, 320)
+elif which == "attn":
+    attn(16, 10, 4096, 4096, 64)
+    attn(16, 20, 1024, 1024, 64)

@@ -50,8 +50,8 @@ struct GemmKParams {
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
 static constexpr int kThreads = 256;
-static constexpr uint32_t kStageBufs = 4;          // epilogue staging tiles (128 rows x 32 cols, 64B swizzle)
-static constexpr uint32_t kStageBufBytes = 128 * 64;
+static constexpr uint32_t kStageBufs = 4;          // one private epilogue staging tile per epilogue warp
+static constexpr uint32_t kStageBufBytes = 32 * 64;  // 32 rows x 32 cols (64 B, swizzled)
 
 template <bool BF16>
 __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, float (&x)[8]) {
@@ -213,13 +213,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // Per 32-column chunk: TMEM -> registers -> (bias, temb row, activation, residual) -> fp16/bf16 ->
-    // 64B-swizzled staging tile in smem -> one TMA store (coalesced, clipped at the matrix edge).
+    // warp-private 64B-swizzled staging tile in smem -> coalesced full-sector global stores.
     const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
-    const int epi_tid = (int)threadIdx.x - 128;
+    const uint32_t my_stg = stg_base + (uint32_t)quad * 2048u;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t sw = (uint32_t)(r >> 1) & 3u;
-    uint32_t chunk_ctr = 0;
+    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
     const int ncols_out = geglu ? (BN >> 1) : BN;
     int it = 0;
@@ -239,10 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (p.bias && p.bias_along_m && row_ok) bias_m = ld1<BF16>(p.bias, m);
       const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
 
-      for (int c = 0; c < ncols_out; c += 32, ++chunk_ctr) {
-        const uint32_t buf = stg_base + (chunk_ctr % kStageBufs) * kStageBufBytes;
-        if (epi_tid == 0) bulk_wait_group_read<kStageBufs - 1>();  // the store that last used `buf` has read it
-        named_bar_sync(1, 128);
+      for (int c = 0; c < ncols_out; c += 32) {
         uint32_t v[32];
         float x[32];
         tmem_ld_32x32(t_addr + (uint32_t)c, v);
@@ -297,7 +293,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
           }
         }
-        const uint32_t row_smem = buf + (uint32_t)r * 64u;
+        // stage this warp's 32 rows x 64 B in its private (64B-swizzled) smem tile, then write them out as
+        // full 32-byte sectors: each store instruction covers 8 rows x 64 contiguous bytes
+        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int n = out_n0 + c + g * 8;
@@ -313,22 +311,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
           const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
           const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
-          const uint32_t addr = row_smem + ((((uint32_t)g) ^ sw) << 4);
+          const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
                        : "memory");
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_store_2d(&mapC, buf, out_n0 + c, m_blk * 128);
-          bulk_commit_group();
+        __syncwarp();
+        {
+          const int piece = lane & 3;
+          const int col = out_n0 + c + piece * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rl = j * 8 + (lane >> 2);
+            const uint32_t addr = my_stg + (uint32_t)rl * 64u + ((((uint32_t)piece) ^ (((uint32_t)rl >> 1) & 3u)) << 4);
+            uint32_t o0, o1, o2, o3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
+            const int mm = m_blk * 128 + quad * 32 + rl;
+            if (mm < p.M && col < p.n_out) {
+              uint4 o = make_uint4(o0, o1, o2, o3);
+              *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.C) + ((size_t)mm * p.ldc + col) * 2) = o;
+            }
+          }
         }
       }
       tc_fence_before();
       if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
       else mbar_arrive(tempty_bar(acc));
     }
-    if (epi_tid == 0) bulk_wait_group_read<0>();  // staging smem must outlive the last store's reads
   }
 
   tc_fence_before();
