@@ -63,6 +63,21 @@ __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, 
   f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
 }
 
+template <bool BF16>
+__device__ __forceinline__ void add_u4(const uint4& r, float (&x)[8]) {
+  float2 f;
+  f = unpack2<BF16>(r.x); x[0] += f.x; x[1] += f.y;
+  f = unpack2<BF16>(r.y); x[2] += f.x; x[3] += f.y;
+  f = unpack2<BF16>(r.z); x[4] += f.x; x[5] += f.y;
+  f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
+}
+template <bool BF16>
+__device__ __forceinline__ void add_smem8(uint32_t addr, float (&x)[8]) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  add_u4<BF16>(r, x);
+}
+
 template <bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -80,7 +95,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)S * kATileBytes;
   const uint32_t stg_base = b_base + (uint32_t)S * b_tile_bytes;  // 1024-aligned: every tile size is a multiple of 1 KB
-  const uint32_t bar_base = stg_base + kStageBufs * kStageBufBytes;
+  const uint32_t bar_base = stg_base + kStageBufs * kStageBufBytes + 1024u;  // + per-tile bias row
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM pointer slot
   auto full_bar = [&](int i) { return bar_base + (uint32_t)i * 8u; };
   auto empty_bar = [&](int i) { return bar_base + (uint32_t)(S + i) * 8u; };
@@ -217,6 +232,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
     const uint32_t my_stg = stg_base + (uint32_t)quad * 2048u;
+    const uint32_t bias_smem = stg_base + 4u * 2048u;  // 256 halfs
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
@@ -237,8 +253,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       float bias_m = 0.f;
       if (p.bias && p.bias_along_m && row_ok) bias_m = ld1<BF16>(p.bias, m);
       const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
+      // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
+      const bool col_bias = p.bias && !p.bias_along_m;
+      if (col_bias) {
+        named_bar_sync(1, 128);  // every warp is done with the previous tile's bias
+        const int e0 = (int)(threadIdx.x - 128) * 8;
+        if (e0 < BN) {
+          uint4 bv = make_uint4(0, 0, 0, 0);
+          if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.bias) + (size_t)(n0 + e0) * 2));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 2u), "r"(bv.x), "r"(bv.y),
+                       "r"(bv.z), "r"(bv.w)
+                       : "memory");
+        }
+        named_bar_sync(1, 128);
+      }
 
       for (int c = 0; c < ncols_out; c += 32) {
+        // issue this chunk's global operand loads first so their latency overlaps the TMEM read
+        uint4 rv[4], rs[4];
+        const bool has_rv = p.rowvec && row_ok && !geglu;
+        const bool has_rs = p.residual && row_ok;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rv[g] = make_uint4(0, 0, 0, 0);
+          rs[g] = make_uint4(0, 0, 0, 0);
+          const int n = n0 + c + g * 8;
+          const int no = out_n0 + c + g * 8;
+          if (has_rv && n < p.N)
+            rv[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.rowvec) + (rv_off + (size_t)n) * 2));
+          if (has_rs && no < p.n_out)
+            rs[g] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)m * p.ldr + no) * 2);
+        }
         uint32_t v[32];
         float x[32];
         tmem_ld_32x32(t_addr + (uint32_t)c, v);
@@ -248,17 +293,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int nx = n0 + c + g * 8;   // interleaved weight row of the value half
-            const int ng = nx + ncols_out;   // matching gate row
             float xv[8], gt[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               xv[i] = __uint_as_float(v[g * 8 + i]);
               gt[i] = __uint_as_float(vg[g * 8 + i]);
             }
-            if (p.bias && ng < p.N) {
-              epi_add_vec8<BF16>(p.bias, (size_t)nx, xv);
-              epi_add_vec8<BF16>(p.bias, (size_t)ng, gt);
+            if (col_bias) {
+              add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
+              add_smem8<BF16>(bias_smem + (uint32_t)(ncols_out + c + g * 8) * 2u, gt);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i] * gelu_erf_f(gt[i]);
@@ -267,21 +310,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c + g * 8;
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
-            if (n < p.N) {
-              if (p.bias) {
-                if (p.bias_along_m) {
+            if (col_bias) add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
+            else if (p.bias) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) xv[i] += bias_m;
-                } else {
-                  epi_add_vec8<BF16>(p.bias, (size_t)n, xv);
-                }
-              }
-              if (p.rowvec && row_ok) epi_add_vec8<BF16>(p.rowvec, rv_off + (size_t)n, xv);
+              for (int i = 0; i < 8; ++i) xv[i] += bias_m;
             }
+            if (has_rv) add_u4<BF16>(rv[g], xv);
             if (p.epilogue == B200_EPI_SILU) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) xv[i] = silu_f(xv[i]);
@@ -298,12 +335,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int n = out_n0 + c + g * 8;
-          if (p.residual && row_ok && n < p.n_out) {
+          if (has_rs) {
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xv[i] = x[g * 8 + i];
-            epi_add_vec8<BF16>(p.residual, (size_t)m * p.ldr + n, xv);
+            add_u4<BF16>(rs[g], xv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
           }
@@ -372,7 +408,7 @@ template <bool BF16, int CG>
 static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                          const CUtensorMap& mapC, GemmKParams& p, cudaStream_t stream) {
   const int stage_bytes = kATileBytes + (p.BN / CG) * 128;
-  const int staging = (int)(kStageBufs * kStageBufBytes);
+  const int staging = (int)(kStageBufs * kStageBufBytes) + 1024;
   int S = (222 * 1024 - staging) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) S = 2;
