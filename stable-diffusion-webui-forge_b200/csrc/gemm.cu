@@ -49,8 +49,9 @@ struct GemmKParams {
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
-static constexpr int kThreads = 256;
-static constexpr uint32_t kStageBufs = 4;          // one private epilogue staging tile per epilogue warp
+static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
+static constexpr int kEpiThreads = 256;
+static constexpr uint32_t kStageBufs = 8;          // one private epilogue staging tile per epilogue warp
 static constexpr uint32_t kStageBufBytes = 32 * 64;  // 32 rows x 32 cols (64 B, swizzled)
 
 template <bool BF16>
@@ -119,7 +120,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 128 * CG);
+      mbar_init(tempty_bar(i), kEpiThreads * CG);
     }
     mbar_fence_init();
   }
@@ -229,10 +230,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // ------------------------------------------------------------------ epilogue
     // Per 32-column chunk: TMEM -> registers -> (bias, temb row, activation, residual) -> fp16/bf16 ->
     // warp-private 64B-swizzled staging tile in smem -> coalesced full-sector global stores.
-    const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
+    const int quad = warp & 3;          // the TMEM lane quadrant this warp may access
+    const int chalf = (warp - 4) >> 2;  // the two warps of a quadrant take alternate 32-column chunks
     const int r = quad * 32 + lane;
-    const uint32_t my_stg = stg_base + (uint32_t)quad * 2048u;
-    const uint32_t bias_smem = stg_base + 4u * 2048u;  // 256 halfs
+    const uint32_t my_stg = stg_base + (uint32_t)(warp - 4) * 2048u;
+    const uint32_t bias_smem = stg_base + kStageBufs * kStageBufBytes;  // 256 halfs
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
@@ -256,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
       const bool col_bias = p.bias && !p.bias_along_m;
       if (col_bias) {
-        named_bar_sync(1, 128);  // every warp is done with the previous tile's bias
+        named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias
         const int e0 = (int)(threadIdx.x - 128) * 8;
         if (e0 < BN) {
           uint4 bv = make_uint4(0, 0, 0, 0);
@@ -265,10 +267,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                        "r"(bv.z), "r"(bv.w)
                        : "memory");
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
       }
 
-      for (int c = 0; c < ncols_out; c += 32) {
+      for (int c = chalf * 32; c < ncols_out; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
         uint4 rv[4], rs[4];
         const bool has_rv = p.rowvec && row_ok && !geglu;
