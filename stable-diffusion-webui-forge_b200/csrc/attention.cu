@@ -14,6 +14,7 @@
 // overlaps the other's MMAs; QK_{j+1} is also issued while softmax_j's O fold is still running.
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -278,6 +279,9 @@ static int launch_attn(const CUtensorMap& mQ, const CUtensorMap& mK, const CUten
 
 }  // namespace b200
 
+namespace b200 {
+int attention64_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
+}
 using namespace b200;
 
 extern "C" int b200_attention(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d,
@@ -294,6 +298,14 @@ extern "C" int b200_attention(const void* q, const void* k, const void* v, void*
                      d->v_stride_b % 8 == 0 && d->o_stride_b % 8 == 0,
                  "attention: strides must be multiples of 8 elements");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output not 16-byte aligned");
+  if (d->Dh == 64) {
+    static int use_old = -1;
+    if (use_old < 0) {
+      const char* e = getenv("B200_ATTN_V1");
+      use_old = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!use_old) return attention64_dispatch(q, k, v, o, d, static_cast<cudaStream_t>(s));
+  }
   AttnKParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;

@@ -1,0 +1,363 @@
+// b200forge — head-dim-64 attention forward, the SDXL / SD2.x shape (every SDXL attention has Dh = 64).
+//
+// At Dh = 64 the kernel is bound by the exponentials, not the MMAs (128x128 exps per tile-block on a 16/clk MUFU
+// = 1024 cycles vs 512 MMA cycles), so the design goal is to keep the MUFU pipe busy all the time:
+//   * one CTA per SM works on TWO 128-query tiles; two softmax warpgroups (4 warps each, thread = query row)
+//     ping-pong, so one group's exponentials overlap the other group's QK^T / PV MMAs;
+//   * O stays in TMEM and accumulates across key blocks (tcgen05.mma accumulate) — no per-block read-back.
+//     The softmax reference max is only advanced when a row's block max exceeds it by more than 2^8
+//     ("lazy rescale"): then, and only then, the warp rescales its O rows in TMEM (tcgen05.ld/st);
+//   * tcgen05 executes MMAs in issue order, so "S_{j+1} is ready" already implies "PV_j has retired": the only
+//     barriers are S-full, P-full and the final O-full per tile, plus the K/V ring.
+// TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384).
+// smem: Q 2x16 KB | K/V ring 4x16 KB | P 2x32 KB (reused as the output staging tile at the end).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+struct Attn64Params {
+  int B, H, Lq, Lk;
+  int BKV, n_kv, q_tiles;  // q_tiles: 256-query CTA tiles
+  float scale_log2;
+  void* O;
+  long long o_stride_b, o_stride_l;
+  uint32_t idesc_qk, idesc_pv;
+};
+
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
+static constexpr int kRingSlots = 4;
+static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
+
+template <bool BF16>
+__global__ void __launch_bounds__(384, 1)
+attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+              const __grid_constant__ CUtensorMap mapV, const Attn64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base;                       // 2 tiles
+  const uint32_t ring_smem = base + 2 * kTile;        // 4 tiles
+  const uint32_t p_smem = ring_smem + kRingSlots * kTile;  // 2 x (2 atoms)
+  const uint32_t bar_base = p_smem + 4 * kTile;
+  const uint32_t q_full = bar_base;
+  auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
+  auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kRingSlots + i); };
+  auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * kRingSlots + t); };
+  auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * kRingSlots + t); };
+  auto o_final = [&](int t) { return bar_base + 8u * (5 + 2 * kRingSlots + t); };
+  const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * kRingSlots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int h = (blockIdx.x / p.q_tiles) % p.H;
+  const int b = blockIdx.x / (p.q_tiles * p.H);
+  const int q0 = qt * 256;
+  const int BKV = p.BKV;
+  const int n_kv = p.n_kv;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kRingSlots; ++i) {
+      mbar_init(ring_full(i), 1);
+      mbar_init(ring_empty(i), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(s_full(t), 1);
+      mbar_init(p_full(t), 128);
+      mbar_init(o_final(t), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    mbar_expect_tx(q_full, 2u * kTile);
+    tma_load_3d(q_smem, &mapQ, q_full, h * 64, q0, b);
+    tma_load_3d(q_smem + kTile, &mapQ, q_full, h * 64, q0 + 128, b);
+    const uint32_t kv_bytes = (uint32_t)BKV * 128u;
+    for (int idx = 0; idx < 2 * n_kv; ++idx) {  // even: K_{idx/2}, odd: V_{idx/2}
+      const int slot = idx % kRingSlots;
+      const uint32_t phase = (uint32_t)(idx / kRingSlots) & 1u;
+      mbar_wait(ring_empty(slot), phase ^ 1u);
+      mbar_expect_tx(ring_full(slot), kv_bytes);
+      tma_load_3d(ring_smem + slot * kTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    auto wait_full = [&](int idx) {
+      mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
+      tc_fence_after();
+    };
+    auto issue_qk = [&](int idx, int t) {  // S_t = Q_t K^T
+      const uint32_t k_smem = ring_smem + (idx % kRingSlots) * kTile;
+      const uint32_t qs = q_smem + t * kTile;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base + (uint32_t)t * 128u, make_smem_desc_sw128(qs + k * 32u, 0, 1024),
+                 make_smem_desc_sw128(k_smem + k * 32u, 0, 1024), p.idesc_qk, k != 0 ? 1u : 0u);
+      umma_commit(s_full(t));
+    };
+    mbar_wait(q_full, 0);
+    wait_full(0);
+    issue_qk(0, 0);
+    issue_qk(0, 1);
+    umma_commit(ring_empty(0));
+    const int ksteps = BKV >> 4;
+    for (int j = 0; j < n_kv; ++j) {
+      const int vidx = 2 * j + 1, kidx = 2 * j + 2;
+      wait_full(vidx);
+      const uint32_t v_smem = ring_smem + (vidx % kRingSlots) * kTile;
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full(t), (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t ps = p_smem + t * 2 * kTile;
+        const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(ps + (uint32_t)(kk >> 2) * kTile + (uint32_t)(kk & 3) * 32u, 0, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
+          umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        if (t == 1) umma_commit(ring_empty(vidx % kRingSlots));
+        if (j + 1 < n_kv) {
+          if (t == 0) wait_full(kidx);
+          issue_qk(kidx, t);
+          if (t == 1) umma_commit(ring_empty(kidx % kRingSlots));
+        } else {
+          umma_commit(o_final(t));
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax warpgroups (t = tile)
+    const int t = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row inside the tile
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + (uint32_t)t * 128u + lane_addr;
+    const uint32_t o_addr = tmem_base + 256u + (uint32_t)t * 64u + lane_addr;
+    const uint32_t p_tile = p_smem + (uint32_t)t * 2 * kTile;
+    const uint32_t p_row = p_tile + (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const float sl2 = p.scale_log2;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      int nvalid = p.Lk - j * BKV;
+      if (nvalid > BKV) nvalid = BKV;
+      mbar_wait(s_full(t), (uint32_t)j & 1u);
+      tc_fence_after();
+      // pass 1: block max of this row
+      float mx = -INFINITY;
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 32 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_blk = mx * sl2;
+      if (j == 0) {
+        m_ref = m_blk;
+      } else {
+        const bool need = m_blk > m_ref + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // S_j full => PV_{j-1} retired (in-order tensor pipe): O in TMEM is stable, rescale it in place
+          const float alpha = need ? ex2a(m_ref - m_blk) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(o_addr + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(o_addr + (uint32_t)c, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_ref = m_blk;
+        }
+      }
+      // pass 2: p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand)
+      float rs0 = 0.f, rs1 = 0.f;
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (c + 32 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2a(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+            const float p1 = ex2a(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
+            rs0 += p0;
+            rs1 += p1;
+            pk[i >> 1] = pack2<BF16>(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[i]), sl2, -m_ref)) : 0.f;
+            const float p1 = (c + i + 1 < nvalid) ? ex2a(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref)) : 0.f;
+            rs0 += p0;
+            rs1 += p1;
+            pk[i >> 1] = pack2<BF16>(p0, p1);
+          }
+        }
+        const uint32_t atom_off = (uint32_t)(c >> 6) * kTile;
+        const uint32_t chunk0 = (uint32_t)(c & 63) >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c + g * 8 < BKV) {
+            const uint32_t addr = p_row + atom_off + (((chunk0 + g) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                         "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
+                         : "memory");
+          }
+        }
+      }
+      l_run += rs0 + rs1;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full(t));
+    }
+
+    // ---- output: O_t / l -> fp16 -> warp-private staging (the P tile is free now) -> coalesced stores
+    mbar_wait(o_final(t), 0);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const uint32_t stg = p_tile + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(o_addr + (uint32_t)c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t o0 = pack2<BF16>(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+        const uint32_t o1 = pack2<BF16>(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+        const uint32_t o2 = pack2<BF16>(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+        const uint32_t o3 = pack2<BF16>(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;  // 16B chunk index inside the 128B row
+        const uint32_t addr = stg + (uint32_t)lane * 128u + ((chunk ^ (uint32_t)(lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      }
+    }
+    __syncwarp();
+    {
+      const int piece = lane & 7;
+      char* obase = reinterpret_cast<char*>(p.O) + ((size_t)b * p.o_stride_b + (size_t)h * 64) * 2;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int rl = jj * 4 + (lane >> 3);
+        const uint32_t addr = stg + (uint32_t)rl * 128u + ((((uint32_t)piece) ^ (uint32_t)(rl & 7)) << 4);
+        uint32_t o0, o1, o2, o3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
+        const int q = q0 + t * 128 + quad * 32 + rl;
+        if (q < p.Lq)
+          *reinterpret_cast<uint4*>(obase + ((size_t)q * p.o_stride_l + piece * 8) * 2) = make_uint4(o0, o1, o2, o3);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool BF16>
+static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64Params& p,
+                         cudaStream_t stream) {
+  const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("attention64: smem attr: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
+    attr_done = true;
+  }
+  const int grid = p.q_tiles * p.H * p.B;
+  attn64_kernel<BF16><<<grid, 384, smem, stream>>>(mQ, mK, mV, p);
+  B200_CHECK_LAUNCH("attention64");
+  return B200_OK;
+}
+
+// called from b200_attention (attention.cu) for Dh == 64
+int attention64_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+  Attn64Params p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B;
+  p.H = d->H;
+  p.Lq = d->Lq;
+  p.Lk = d->Lk;
+  p.BKV = d->Lk >= 128 ? 128 : ((d->Lk + 15) / 16) * 16;
+  p.n_kv = (d->Lk + p.BKV - 1) / p.BKV;
+  p.q_tiles = (d->Lq + 255) / 256;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.O = o;
+  p.o_stride_b = d->o_stride_b;
+  p.o_stride_l = d->o_stride_l;
+  const bool bf = d->dtype == B200_BF16;
+  p.idesc_qk = make_idesc_f16(128, p.BKV, bf, false, false);
+  p.idesc_pv = make_idesc_f16(128, 64, bf, false, true);
+  const uint64_t cols = (uint64_t)d->H * 64;
+  CUtensorMap mQ, mK, mV;
+  auto make3 = [&](CUtensorMap* m, const void* base, int L, long long sl, long long sb, int rows) {
+    uint64_t dims[3] = {cols, (uint64_t)L, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)sl * 2, (uint64_t)sb * 2};
+    uint32_t box[3] = {64, (uint32_t)rows, 1};
+    return make_tmap(m, d->dtype, base, 3, dims, str, box);
+  };
+  int rc = make3(&mQ, q, d->Lq, d->q_stride_l, d->q_stride_b, 128);
+  if (rc) return rc;
+  rc = make3(&mK, k, d->Lk, d->k_stride_l, d->k_stride_b, p.BKV);
+  if (rc) return rc;
+  rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
+  if (rc) return rc;
+  return bf ? launch_attn64<true>(mQ, mK, mV, p, st) : launch_attn64<false>(mQ, mK, mV, p, st);
+}
+
+}  // namespace b200
