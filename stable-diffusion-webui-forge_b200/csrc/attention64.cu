@@ -7,8 +7,10 @@
 //   * O stays in TMEM and accumulates across key blocks (tcgen05.mma accumulate) — no per-block read-back.
 //     The softmax reference max is only advanced when a row's block max exceeds it by more than 2^8
 //     ("lazy rescale"): then, and only then, the warp rescales its O rows in TMEM (tcgen05.ld/st);
-//   * tcgen05 executes MMAs in issue order, so "S_{j+1} is ready" already implies "PV_j has retired": the only
-//     barriers are S-full, P-full and the final O-full per tile, plus the K/V ring.
+//   * a softmax thread pulls its whole S row (128 fp32) into registers with one TMEM round trip and releases S
+//     immediately, so QK_{j+1} runs underneath the exponentials of block j; PV_j follows when P_j is staged.
+//     Barriers per tile: S-full, S-consumed, P-full, PV-done (+ the K/V ring).  The softmax warpgroups take
+//     216 registers each via setmaxnreg, the control warps drop to 56.
 // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384).
 // smem: Q 2x16 KB | K/V ring 4x16 KB | P 2x32 KB (reused as the output staging tile at the end).
 #include "common.cuh"
@@ -63,8 +65,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kRingSlots + i); };
   auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * kRingSlots + t); };
   auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * kRingSlots + t); };
-  auto o_final = [&](int t) { return bar_base + 8u * (5 + 2 * kRingSlots + t); };
-  const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * kRingSlots);
+  auto pv_done = [&](int t) { return bar_base + 8u * (5 + 2 * kRingSlots + t); };
+  auto s_cons = [&](int t) { return bar_base + 8u * (7 + 2 * kRingSlots + t); };
+  const uint32_t tmem_slot = bar_base + 8u * (9 + 2 * kRingSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +90,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     for (int t = 0; t < 2; ++t) {
       mbar_init(s_full(t), 1);
       mbar_init(p_full(t), 128);
-      mbar_init(o_final(t), 1);
+      mbar_init(pv_done(t), 1);
+      mbar_init(s_cons(t), 128);
     }
     mbar_fence_init();
   }
@@ -101,6 +105,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, 2u * kTile);
@@ -137,6 +143,16 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const int ksteps = BKV >> 4;
     for (int j = 0; j < n_kv; ++j) {
       const int vidx = 2 * j + 1, kidx = 2 * j + 2;
+      // QK_{j+1} as soon as the softmax threads have pulled S_j into registers (runs under their exps)
+      if (j + 1 < n_kv) {
+        wait_full(kidx);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(s_cons(t), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_qk(kidx, t);
+        }
+        umma_commit(ring_empty(kidx % kRingSlots));
+      }
       wait_full(vidx);
       const uint32_t v_smem = ring_smem + (vidx % kRingSlots) * kTile;
       for (int t = 0; t < 2; ++t) {
@@ -149,17 +165,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
           umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
         }
-        if (t == 1) umma_commit(ring_empty(vidx % kRingSlots));
-        if (j + 1 < n_kv) {
-          if (t == 0) wait_full(kidx);
-          issue_qk(kidx, t);
-          if (t == 1) umma_commit(ring_empty(kidx % kRingSlots));
-        } else {
-          umma_commit(o_final(t));
-        }
+        umma_commit(pv_done(t));
       }
+      umma_commit(ring_empty(vidx % kRingSlots));
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax warpgroups (t = tile)
     const int t = (warp - 4) >> 2;
     const int quad = warp & 3;
@@ -178,79 +190,70 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       if (nvalid > BKV) nvalid = BKV;
       mbar_wait(s_full(t), (uint32_t)j & 1u);
       tc_fence_after();
-      // pass 1: block max of this row
+      // the whole S row -> registers in one TMEM round trip, then hand S back to the tensor core
+      uint32_t v[128];
+      tmem_ld_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld_32x32(s_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_32x32(s_addr + 64u, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld_32x32(s_addr + 96u, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_cons(t));
+      const bool full_blk = nvalid == 128;
       float mx = -INFINITY;
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (c + 32 <= nvalid) {
+      if (full_blk) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 128; ++i)
+          if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       const float m_blk = mx * sl2;
+      // PV_{j-1} must have retired before O is rescaled and before P is overwritten
+      if (j > 0) {
+        mbar_wait(pv_done(t), (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
       if (j == 0) {
         m_ref = m_blk;
       } else {
         const bool need = m_blk > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          // S_j full => PV_{j-1} retired (in-order tensor pipe): O in TMEM is stable, rescale it in place
           const float alpha = need ? ex2a(m_ref - m_blk) : 1.0f;
 #pragma unroll
           for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(o_addr + (uint32_t)c, v);
+            uint32_t w[32];
+            tmem_ld_32x32(o_addr + (uint32_t)c, w);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(o_addr + (uint32_t)c, v);
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+            tmem_st_32x32(o_addr + (uint32_t)c, w);
           }
           tmem_st_wait();
           l_run *= alpha;
           if (need) m_ref = m_blk;
         }
       }
-      // pass 2: p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand)
+      // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand)
       float rs0 = 0.f, rs1 = 0.f;
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + (uint32_t)c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (c + 32 <= nvalid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2a(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
-            const float p1 = ex2a(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
-            rs0 += p0;
-            rs1 += p1;
-            pk[i >> 1] = pack2<BF16>(p0, p1);
-          }
-        } else {
+      for (int c = 0; c < 128; c += 8) {
+        if (c < BKV) {
+          float pe[8];
+          if (full_blk) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[i]), sl2, -m_ref)) : 0.f;
-            const float p1 = (c + i + 1 < nvalid) ? ex2a(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref)) : 0.f;
-            rs0 += p0;
-            rs1 += p1;
-            pk[i >> 1] = pack2<BF16>(p0, p1);
-          }
-        }
-        const uint32_t atom_off = (uint32_t)(c >> 6) * kTile;
-        const uint32_t chunk0 = (uint32_t)(c & 63) >> 3;
+            for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, -m_ref));
+          } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (c + g * 8 < BKV) {
-            const uint32_t addr = p_row + atom_off + (((chunk0 + g) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
-                         "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
-                         : "memory");
+            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[c + i]), sl2, -m_ref)) : 0.f;
           }
+          rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
+          rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+          const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7]))
+                       : "memory");
         }
       }
       l_run += rs0 + rs1;
@@ -260,7 +263,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     }
 
     // ---- output: O_t / l -> fp16 -> warp-private staging (the P tile is free now) -> coalesced stores
-    mbar_wait(o_final(t), 0);
+    mbar_wait(pv_done(t), (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const uint32_t stg = p_tile + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
