@@ -184,6 +184,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+    if (t == 1) named_bar_arrive(2, 256);  // warpgroup 0 takes the first turn on the MUFU
 
     for (int j = 0; j < n_kv; ++j) {
       int nvalid = p.Lk - j * BKV;
@@ -235,27 +236,40 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           if (need) m_ref = m_blk;
         }
       }
-      // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand)
+      // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand).
+      // The two warpgroups take turns on this MUFU-bound phase (named-barrier hand-off) so that one group's
+      // exponentials overlap the other group's TMEM loads / max / stores instead of both fighting for the MUFU.
+      named_bar_sync(2 + t, 256);
       float rs0 = 0.f, rs1 = 0.f;
+      const float nm = -m_ref;
+      if (full_blk) {
 #pragma unroll
-      for (int c = 0; c < 128; c += 8) {
-        if (c < BKV) {
+        for (int c = 0; c < 128; c += 8) {
           float pe[8];
-          if (full_blk) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, -m_ref));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[c + i]), sl2, -m_ref)) : 0.f;
-          }
+          for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm));
           rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
           rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
           const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
-                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7]))
-                       : "memory");
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) {
+          if (c < BKV) {
+            float pe[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
+            rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
+            rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+            const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                         "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+          }
         }
       }
+      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
       l_run += rs0 + rs1;
       fence_proxy_async_smem();
       tc_fence_before();
