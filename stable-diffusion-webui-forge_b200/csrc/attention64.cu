@@ -237,39 +237,35 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
       }
       // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand).
-      // The two warpgroups take turns on this MUFU-bound phase (named-barrier hand-off) so that one group's
-      // exponentials overlap the other group's TMEM loads / max / stores instead of both fighting for the MUFU.
+      // The two warpgroups take turns on the MUFU (named-barrier hand-off): one group's 128 back-to-back
+      // exponentials overlap the other group's TMEM loads / max / conversions / stores.
       named_bar_sync(2 + t, 256);
-      float rs0 = 0.f, rs1 = 0.f;
       const float nm = -m_ref;
+      // stage A (MUFU-exclusive): all exponentials of the row, in place, nothing consumes them yet
       if (full_blk) {
 #pragma unroll
-        for (int c = 0; c < 128; c += 8) {
+        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(ex2a(fmaf(__uint_as_float(v[i]), sl2, nm)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          v[i] = (i < nvalid) ? __float_as_uint(ex2a(fmaf(__uint_as_float(v[i]), sl2, nm))) : 0u;
+      }
+      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
+      // stage B (overlaps the other group's stage A): row sum, convert, stage P
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        if (c < BKV) {
           float pe[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm));
+          for (int i = 0; i < 8; ++i) pe[i] = __uint_as_float(v[c + i]);
           rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
           rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
           const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
                        "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
         }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 128; c += 8) {
-          if (c < BKV) {
-            float pe[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
-            rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
-            rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
-            const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
-                         "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
-          }
-        }
       }
-      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
       l_run += rs0 + rs1;
       fence_proxy_async_smem();
       tc_fence_before();
