@@ -94,6 +94,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores() -> int:
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count() reports
+    the host's cores even inside a CPU-limited container, which would oversubscribe the ATen thread pool)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline_sample(latent_hw: int, threads: int):
     """Oracle port (the reference's CPU arithmetic: ATen fp32) on a bounded sample: ONE SDXL UNet forward of one
     sample at the benchmark's latent size.  Returns seconds per forward."""
@@ -125,7 +142,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     fwd = cpu_baseline_sample(128, threads)
     for _ in range(args.warmup if args.warmup is not None else 1):
         fwd()
@@ -345,7 +362,7 @@ def main():
             except Exception as ex:  # context number only
                 gpu_ref_ms = f"failed: {type(ex).__name__}"
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = usable_cores()
             fwd = cpu_baseline_sample(hw, threads)
             t = fwd()
             cpu_base = {"value": images_per_sec_from_forward(t, S), "unit": UNIT, "cores": threads, "kind": "port",
