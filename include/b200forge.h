@@ -200,6 +200,16 @@ typedef struct {
 int b200_sampler_step(float* x, const void* eps, const float* noise, float* denoised, float* old_denoised,
                       const b200_step_desc* d, b200_stream_t s);
 
+/* The update alone, for samplers installed under an unmodified CFGDenoiser (plug point P4): `denoised` is what
+ * the model callable returned (fp32 NCHW).  Same scalars as b200_sampler_step; eps-related fields are ignored. */
+int b200_sampler_update(float* x, const float* denoised, const float* noise, float* old_denoised,
+                        const b200_step_desc* d, b200_stream_t s);
+
+/* KModel.apply_model tail for the model_function_wrapper plug point (backend/modules/k_model.py:45-46,
+ * backend/modules/k_prediction.py:81-92): denoised[n,c,h,w] = x - eps*sigma_n from the channels-last UNet output. */
+int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, float* out, int N, int C, int H, int W,
+                         int ld_eps, int prediction, int eps_dtype, b200_stream_t s);
+
 /* VAE post-decode: clamp((x+1)/2, 0, 1) NHWC (dtype) -> fp32 NHWC [B,H,W,3]
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);

@@ -1,0 +1,123 @@
+"""Plug point P4 — k-diffusion sampler functions with the reference's exact call contract
+(k_diffusion/sampling.py:119-137 sample_euler, :140-159 sample_euler_ancestral, :648-671 sample_dpmpp_2m):
+
+    fn(model, x, sigmas, extra_args=None, callback=None, disable=None, ...) -> x
+
+`model` is whatever Forge passes (CFGDenoiser.forward, modules/sd_samplers_cfg_denoiser.py:156-228) and is called
+unchanged; what changes is the per-step arithmetic around it: the reference evaluates 4-8 tiny fp32 tensor kernels
+plus 2-3 device->host syncs per step on 0-dim GPU sigmas, here the schedule is read to the host ONCE and each step's
+update is a single `b200_sampler_update` launch.  Contract details that are preserved:
+  * `callback({'x','i','sigma','sigma_hat','denoised'})` every step with the pre-update x (drives progress/interrupt);
+  * noise is drawn through k-diffusion's module-global `torch.randn_like` (TorchHijack -> ImageRNG.next(),
+    modules/sd_samplers_common.py:214-235) in the same order and count as the reference — sample_euler draws one
+    (unused when s_churn = 0) tensor per step, sample_euler_ancestral draws only while sigma_next > 0;
+  * `modules/sd_schedulers.py:10-15` to_d override: d = (x - denoised) / sigma.
+Cases outside the fused path (s_churn > 0, Flux rectified-flow variant) defer to `reference_*` when the plug-in
+recorded the originals, else raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import lib as _l
+from . import ops, sampling
+
+reference_sample_euler = None
+reference_sample_euler_ancestral = None
+reference_sample_dpmpp_2m = None
+
+
+def _randn_like(x):
+    try:  # k-diffusion's own (possibly hijacked) torch handle keeps the per-image seeded RNG stream
+        import k_diffusion.sampling as ks  # type: ignore
+        return ks.torch.randn_like(x)
+    except Exception:
+        return torch.randn_like(x)
+
+
+def _host_sigmas(sigmas):
+    return [float(v) for v in sigmas.detach().float().cpu().tolist()]
+
+
+def _fusable(x):
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+
+
+def _prep(x):
+    return x if x.is_contiguous() else x.contiguous()
+
+
+@torch.no_grad()
+def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0.,
+                 s_tmax=float('inf'), s_noise=1.):
+    if s_churn > 0 or not _fusable(x):
+        if reference_sample_euler is None:
+            raise _l.B200Error(_l.E_UNSUPPORTED, "sample_euler: s_churn > 0 / non-CUDA-fp32 latents need the reference sampler")
+        return reference_sample_euler(model, x, sigmas, extra_args, callback, disable, s_churn, s_tmin, s_tmax, s_noise)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = _host_sigmas(sigmas)
+    plan = sampling.plan_euler(sig)
+    x = _prep(x).clone()
+    for i, st in enumerate(plan):
+        _randn_like(x)  # the reference draws eps every step even when gamma == 0 (sampling.py:126): keep the RNG stream aligned
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        ops.sampler_update(x, _prep(denoised.float()), kind=ops.STEP_EULER, sigma=st.sigma, dt=st.dt)
+    return x
+
+
+@torch.no_grad()
+def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
+                           noise_sampler=None):
+    is_flux = False
+    try:
+        from backend.modules.k_prediction import PredictionFlux  # type: ignore
+        is_flux = isinstance(model.inner_model.predictor, PredictionFlux)
+    except Exception:
+        pass
+    if is_flux or not _fusable(x):
+        if reference_sample_euler_ancestral is None:
+            raise _l.B200Error(_l.E_UNSUPPORTED, "sample_euler_ancestral: rectified-flow / non-CUDA-fp32 case needs the reference sampler")
+        return reference_sample_euler_ancestral(model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    extra_args = {} if extra_args is None else extra_args
+    if noise_sampler is None:
+        noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731  (default_noise_sampler, sampling.py:63-64)
+    s_in = x.new_ones([x.shape[0]])
+    sig = _host_sigmas(sigmas)
+    plan = sampling.plan_euler_ancestral(sig, eta, s_noise)
+    x = _prep(x).clone()
+    for i, st in enumerate(plan):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        noise = None
+        if sig[i + 1] > 0:
+            noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+        ops.sampler_update(x, _prep(denoised.float()), kind=ops.STEP_EULER, sigma=st.sigma, dt=st.dt, noise=noise,
+                           noise_scale=st.noise_scale if noise is not None else 0.0)
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=None):
+    if not _fusable(x):
+        if reference_sample_dpmpp_2m is None:
+            raise _l.B200Error(_l.E_UNSUPPORTED, "sample_dpmpp_2m: non-CUDA-fp32 latents need the reference sampler")
+        return reference_sample_dpmpp_2m(model, x, sigmas, extra_args, callback, disable)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = _host_sigmas(sigmas)
+    plan = sampling.plan_dpmpp_2m(sig)
+    x = _prep(x).clone()
+    old = torch.zeros_like(x)
+    for i, st in enumerate(plan):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        ops.sampler_update(x, _prep(denoised.float()), kind=ops.STEP_DPMPP_2M, sigma=max(st.sigma, 1e-30), old_denoised=old,
+                           c_x=st.c_x, c_d=st.c_d, c_old=st.c_old)
+    return x

@@ -360,3 +360,32 @@ def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     _l.check(_l.load().b200_vae_postprocess(x.data_ptr(), out.data_ptr(), n * h * w, ld, _dt(x), _stream()))
     _count()
     return out
+
+
+def sampler_update(x: torch.Tensor, denoised: torch.Tensor, *, kind: int, sigma: float, dt: float = 0.0,
+                   noise: Optional[torch.Tensor] = None, noise_scale: float = 0.0,
+                   old_denoised: Optional[torch.Tensor] = None, c_x: float = 0.0, c_d: float = 0.0,
+                   c_old: float = 0.0) -> None:
+    """In-place sampler update from an already CFG-combined `denoised` (fp32, same shape as x)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and denoised.dtype == torch.float32 and denoised.is_contiguous()
+    b, c, h, w = x.shape
+    d = _l.StepDesc()
+    d.kind, d.B, d.C, d.H, d.W = kind, b, c, h, w
+    d.sigma, d.dt, d.noise_scale = sigma, dt, noise_scale
+    d.c_x, d.c_d, d.c_old = c_x, c_d, c_old
+    _l.check(_l.load().b200_sampler_update(x.data_ptr(), denoised.data_ptr(), _p(noise), _p(old_denoised), C.byref(d),
+                                           _stream()))
+    _count()
+
+
+def eps_to_denoised(x: torch.Tensor, eps: torch.Tensor, sigma: torch.Tensor, prediction: int = 0,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 NCHW [N,C,H,W], eps NHWC [N,H,W,ld] (fp16/bf16), sigma fp32 [N] -> denoised fp32 NCHW."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous() and sigma.dtype == torch.float32
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(_l.load().b200_eps_to_denoised(x.data_ptr(), eps.data_ptr(), sigma.data_ptr(), out.data_ptr(), n, c, h, w,
+                                            eps.shape[-1], prediction, _dt(eps), _stream()))
+    _count()
+    return out

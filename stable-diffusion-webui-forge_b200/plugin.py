@@ -1,0 +1,197 @@
+"""Binding of the B200 backend to stable-diffusion-webui-forge's own plug points.
+
+    import b200forge.plugin as b200
+    b200.install()                       # inside a running Forge process, after `initialize_forge()`
+
+Nothing above `backend/` changes: `modules/processing.py` and `modules/sd_samplers_cfg_denoiser.py` keep calling
+`attention_function`, `model.apply_model` (through `model_function_wrapper`), the `k_diffusion.sampling.sample_*`
+names and `VAE.decode` exactly as before.
+
+Fast-path predicate (reference hooks that the fused forward cannot honour => the call goes to the reference code):
+  transformer_options has no patches / patches_replace / block_modifiers / block_inner_modifiers /
+  group_norm_wrapper; control is None; no c_concat; epsilon prediction; fp16/bf16 computation dtype; CUDA sm_100.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Any, Callable, Dict, Optional
+
+import torch
+
+from . import attention as b200_attention
+from . import k_samplers, ops
+from .unet_engine import UNetEngine
+
+_BLOCKING_KEYS = ("patches", "patches_replace", "block_modifiers", "block_inner_modifiers", "group_norm_wrapper")
+# modules that imported attention_function *by value* (backend/nn/unet.py:5, nn/flux.py:11, nn/chroma.py:10, nn/vae.py:3)
+_ATTENTION_IMPORTERS = ("backend.nn.unet", "backend.nn.flux", "backend.nn.chroma", "backend.nn.mmditx")
+_installed: Dict[str, Any] = {}
+
+
+def fast_path_ok(c: dict) -> bool:
+    """True when the conditioning dict of one apply_model call can be served by the fused forward."""
+    to = c.get("transformer_options") or {}
+    for k in _BLOCKING_KEYS:
+        v = to.get(k)
+        if v:
+            return False
+    if c.get("control") is not None or c.get("c_concat") is not None:
+        return False
+    return c.get("c_crossattn") is not None
+
+
+# ------------------------------------------------------------------------------------------------- P1 attention
+def install_attention(modules: Optional[dict] = None) -> None:
+    """Rebind `attention_function` (+ the single-head VAE variant) in backend.attention and in every module that
+    imported it by value; the originals are kept as the fallback for masks / unsupported head dims."""
+    mods = sys.modules if modules is None else modules
+    ba = mods.get("backend.attention")
+    if ba is None:
+        raise RuntimeError("backend.attention is not imported — call install() from inside Forge")
+    if "attention" not in _installed:
+        _installed["attention"] = (ba.attention_function, ba.attention_function_single_head_spatial)
+    b200_attention.fallback, b200_attention.fallback_single_head = _installed["attention"]
+    ba.attention_function = b200_attention.attention_function
+    ba.attention_function_single_head_spatial = b200_attention.attention_function_single_head_spatial
+    for name in _ATTENTION_IMPORTERS:
+        m = mods.get(name)
+        if m is not None and hasattr(m, "attention_function"):
+            m.attention_function = b200_attention.attention_function
+    v = mods.get("backend.nn.vae")
+    if v is not None and hasattr(v, "attention_function_single_head_spatial"):
+        v.attention_function_single_head_spatial = b200_attention.attention_function_single_head_spatial
+
+
+def uninstall_attention(modules: Optional[dict] = None) -> None:
+    mods = sys.modules if modules is None else modules
+    if "attention" not in _installed:
+        return
+    fn, fn1 = _installed.pop("attention")
+    ba = mods.get("backend.attention")
+    if ba is not None:
+        ba.attention_function, ba.attention_function_single_head_spatial = fn, fn1
+    for name in _ATTENTION_IMPORTERS:
+        m = mods.get(name)
+        if m is not None and hasattr(m, "attention_function"):
+            m.attention_function = fn
+    v = mods.get("backend.nn.vae")
+    if v is not None and hasattr(v, "attention_function_single_head_spatial"):
+        v.attention_function_single_head_spatial = fn1
+    b200_attention.fallback = b200_attention.fallback_single_head = None
+
+
+# ------------------------------------------------------------------------------------------------- P2 operators
+def install_operations(modules: Optional[dict] = None) -> None:
+    """Make `using_forge_operations(operations=None)` (backend/loader.py:159) build models from B200Operations:
+    the default operator set is looked up as `backend.operations.ForgeOperations` at call time (:447-453)."""
+    from .operations import B200Operations
+    mods = sys.modules if modules is None else modules
+    bo = mods.get("backend.operations")
+    if bo is None:
+        raise RuntimeError("backend.operations is not imported")
+    if "operations" not in _installed:
+        _installed["operations"] = bo.ForgeOperations
+    base = _installed["operations"]
+    # keep every Forge-specific attribute (lazy weights, manual cast...) of the ops we do not replace
+    merged = type("B200ForgeOperations", (base,), {k: getattr(B200Operations, k) for k in ("Linear", "Conv2d", "GroupNorm", "LayerNorm")})
+    bo.ForgeOperations = merged
+
+
+# ------------------------------------------------------------------------------------------------- P3 whole model
+class UNetWrapper:
+    """`model_options['model_function_wrapper']` (reference backend/sampling/sampling_function.py:270-273):
+    wrapper(apply_model_fn, {"input": x fp32 [N,4,h,w], "timestep": sigma [N], "c": {...}, "cond_or_uncond": [...]})
+    -> denoised fp32 [N,4,h,w].  Serves the call from the fused channels-last forward when `fast_path_ok`, else
+    calls `apply_model_fn(input, timestep, **c)` (the reference path) unchanged."""
+
+    def __init__(self, engine: UNetEngine, predictor):
+        self.engine = engine
+        self.predictor = predictor  # backend.modules.k_prediction.Prediction (for .timestep and .prediction_type)
+        self.calls_fast = 0
+        self.calls_reference = 0
+
+    def __call__(self, apply_model_fn: Callable, args: dict):
+        x, sigma, c = args["input"], args["timestep"], args["c"]
+        ptype = getattr(self.predictor, "prediction_type", "epsilon")
+        if (not fast_path_ok(c) or not x.is_cuda or x.dtype != torch.float32 or ptype not in ("epsilon", "v_prediction")
+                or (self.engine.has_label and c.get("y") is None)):
+            self.calls_reference += 1
+            return apply_model_fn(x, sigma, **c)
+        self.calls_fast += 1
+        eng = self.engine
+        x = x.contiguous()
+        sigma = sigma.float().contiguous()
+        t = self.predictor.timestep(sigma).float().contiguous()           # k_model.py:35
+        ctx = c["c_crossattn"].to(eng.dtype).contiguous()                  # k_model.py:36
+        y = c.get("y")
+        y = None if y is None else y.to(eng.dtype).contiguous()
+        eps = eng.forward_sigma(x, sigma, t, ctx, y, reps=1)                # k_model.py:27,34 fused into the entry
+        return ops.eps_to_denoised(x, eps, sigma, prediction=1 if ptype == "v_prediction" else 0)  # k_model.py:45-46
+
+
+def install_unet_wrapper(unet_patcher, engine: Optional[UNetEngine] = None) -> UNetWrapper:
+    """Attach the fused forward to a Forge `UnetPatcher` (backend/patcher/unet.py) through its own setter
+    `set_model_unet_function_wrapper` (backend/patcher/base.py:146-147)."""
+    kmodel = unet_patcher.model
+    dm = kmodel.diffusion_model
+    if engine is None:
+        cfg = dict(dm.config) if hasattr(dm, "config") else None
+        if cfg is None:
+            raise ValueError("pass engine=UNetEngine(cfg, state_dict) — the module carries no config")
+        engine = UNetEngine(cfg, dm.state_dict(), dtype=kmodel.computation_dtype, device=unet_patcher.load_device)
+    w = UNetWrapper(engine, kmodel.predictor)
+    unet_patcher.set_model_unet_function_wrapper(w)
+    return w
+
+
+# ------------------------------------------------------------------------------------------------- P4 samplers
+def install_samplers(modules: Optional[dict] = None) -> None:
+    """Replace k_diffusion.sampling.sample_euler / sample_euler_ancestral / sample_dpmpp_2m: the sampler table
+    (modules/sd_samplers_kdiffusion.py:14-41) resolves them by getattr at sampler construction (:76)."""
+    mods = sys.modules if modules is None else modules
+    ks = mods.get("k_diffusion.sampling")
+    if ks is None:
+        raise RuntimeError("k_diffusion.sampling is not imported")
+    if "samplers" not in _installed:
+        _installed["samplers"] = (ks.sample_euler, ks.sample_euler_ancestral, ks.sample_dpmpp_2m)
+    (k_samplers.reference_sample_euler, k_samplers.reference_sample_euler_ancestral,
+     k_samplers.reference_sample_dpmpp_2m) = _installed["samplers"]
+    ks.sample_euler = k_samplers.sample_euler
+    ks.sample_euler_ancestral = k_samplers.sample_euler_ancestral
+    ks.sample_dpmpp_2m = k_samplers.sample_dpmpp_2m
+
+
+# ------------------------------------------------------------------------------------------------- P5 VAE
+class VAEDecodeWrapper:
+    """`model_options['model_vae_decode_wrapper']` (reference backend/patcher/vae.py:150-155):
+    wrapper(decode_inner_fn, samples_in [B,4,h,w]) -> images [B,H,W,3] fp32 in [0,1] on the output device.
+    NB: Forge hands this wrapper the *processed-out* latent (engine.decode_first_stage divides by the scaling factor
+    first, diffusion_engine/sdxl.py:134-138), so the engine is driven with scaling 1."""
+
+    def __init__(self, vae_engine, output_device=None):
+        self.engine = vae_engine
+        self.output_device = output_device
+
+    def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
+        if not samples_in.is_cuda:
+            return decode_inner_fn(samples_in)
+        scaling = self.engine.scaling
+        try:
+            self.engine.scaling = 1.0
+            img = self.engine.decode(samples_in.float().contiguous())
+        finally:
+            self.engine.scaling = scaling
+        return img if self.output_device is None else img.to(self.output_device)
+
+
+def install(modules: Optional[dict] = None, attention: bool = True, samplers: bool = True, operations: bool = False) -> None:
+    """One call from inside Forge.  The per-checkpoint hooks (install_unet_wrapper, VAEDecodeWrapper) are attached when
+    a model is loaded, e.g. from a `script_callbacks.on_model_loaded` callback."""
+    from . import lib
+    lib.check(lib.load().b200_device_ok())
+    if attention:
+        install_attention(modules)
+    if samplers:
+        install_samplers(modules)
+    if operations:
+        install_operations(modules)

@@ -1,0 +1,189 @@
+"""CPU tests of the host-side logic: C-ABI surface, plug-in binding, sampler plans, request sharding (gloo, 2 ranks)."""
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+
+from oracle import ref_import
+from oracle import sampling as S
+from tests.util import assert_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from b200forge import lib
+    hdr = open(os.path.join(ROOT, "include", "b200forge.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = lib.load()  # binds argtypes for every entry of SIGNATURES; AttributeError if a symbol is missing
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in b200forge.h but not exported"
+    assert declared == set(lib.SIGNATURES), (declared ^ set(lib.SIGNATURES))
+    assert L.b200_version() >= 100
+    assert isinstance(L.b200_last_error(), bytes)
+
+
+def test_no_gpu_calls_fail_loudly():
+    from b200forge import lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.load().b200_device_ok() != 0
+    with pytest.raises(Exception):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.float16), torch.zeros(8, 8, dtype=torch.float16))
+
+
+def test_sampler_plans_match_oracle_scalars():
+    from b200forge import sampling as BS
+    pred = BS.Prediction()
+    op = S.EpsPrediction()
+    assert torch.equal(pred.sigmas, op.sigmas) and torch.equal(pred.log_sigmas, op.log_sigmas)
+    assert torch.equal(BS.get_sigmas_uniform(pred, 30), S.get_sigmas_uniform(op, 30))
+    assert torch.equal(BS.get_sigmas_karras(30, pred.sigma_min, pred.sigma_max),
+                       S.get_sigmas_karras(30, float(op.sigma_min), float(op.sigma_max)))
+    sig = BS.get_sigmas_uniform(pred, 12)
+    for st, (a, b) in zip(BS.plan_euler_ancestral(sig), zip(sig[:-1], sig[1:])):
+        sd, su = S.get_ancestral_step(float(a), float(b), 1.0)
+        assert abs(st.dt - (sd - float(a))) <= 2e-6 * max(1.0, abs(st.dt))
+        assert abs(st.noise_scale - (su if float(b) > 0 else 0.0)) <= 2e-6 * max(1.0, su)
+    sk = BS.get_sigmas_karras(12, pred.sigma_min, pred.sigma_max)
+    plan = BS.plan_dpmpp_2m(sk)
+    for i, st in enumerate(plan):
+        cx, cd, co = S.dpmpp_2m_coeffs(float(sk[i - 1]) if i > 0 else None, float(sk[i]), float(sk[i + 1]), has_old=i > 0)
+        for got, ref in ((st.c_x, cx), (st.c_d, cd), (st.c_old, co)):
+            assert abs(got - ref) <= 1e-5 * max(1.0, abs(ref)), (i, got, ref)
+    ts = pred.timestep(sig[:-1])
+    assert torch.equal(ts, op.timestep(sig[:-1]))
+
+
+def test_fast_path_predicate():
+    from b200forge import plugin
+    ctx = torch.zeros(2, 77, 8)
+    assert plugin.fast_path_ok({"c_crossattn": ctx, "transformer_options": {}})
+    assert plugin.fast_path_ok({"c_crossattn": ctx, "transformer_options": {"patches": {}, "cond_or_uncond": [1, 0]}})
+    assert not plugin.fast_path_ok({"c_crossattn": ctx, "transformer_options": {"patches": {"attn1_patch": [lambda *a: a]}}})
+    assert not plugin.fast_path_ok({"c_crossattn": ctx, "transformer_options": {"block_modifiers": [lambda *a: a]}})
+    assert not plugin.fast_path_ok({"c_crossattn": ctx, "control": object(), "transformer_options": {}})
+    assert not plugin.fast_path_ok({"transformer_options": {}})
+
+
+def _fake_forge_modules():
+    ba = types.ModuleType("backend.attention")
+    ba.attention_function = lambda q, k, v, heads, mask=None, attn_precision=None, skip_reshape=False: ("ref", q.shape)
+    ba.attention_function_single_head_spatial = lambda q, k, v: ("ref1", q.shape)
+    un = types.ModuleType("backend.nn.unet")
+    un.attention_function = ba.attention_function
+    va = types.ModuleType("backend.nn.vae")
+    va.attention_function_single_head_spatial = ba.attention_function_single_head_spatial
+    ks = types.ModuleType("k_diffusion.sampling")
+    ks.sample_euler = lambda *a, **k: "ref_euler"
+    ks.sample_euler_ancestral = lambda *a, **k: "ref_euler_a"
+    ks.sample_dpmpp_2m = lambda *a, **k: "ref_dpmpp"
+    return {"backend.attention": ba, "backend.nn.unet": un, "backend.nn.vae": va, "k_diffusion.sampling": ks}
+
+
+def test_plugin_rebinds_and_restores_attention():
+    from b200forge import attention as A
+    from b200forge import plugin
+    mods = _fake_forge_modules()
+    orig = mods["backend.attention"].attention_function
+    plugin.install_attention(mods)
+    try:
+        assert mods["backend.attention"].attention_function is A.attention_function
+        assert mods["backend.nn.unet"].attention_function is A.attention_function  # imported-by-value copy rebound too
+        assert mods["backend.nn.vae"].attention_function_single_head_spatial is A.attention_function_single_head_spatial
+        # a CPU fp32 call is outside the fused path -> handed to the reference function, not emulated
+        q = torch.zeros(1, 4, 64)
+        assert A.attention_function(q, q, q, 1) == ("ref", q.shape)
+        assert A.attention_function(q.half(), q.half(), q.half(), 1, mask=torch.zeros(4, 4)) == ("ref", q.shape)
+    finally:
+        plugin.uninstall_attention(mods)
+    assert mods["backend.attention"].attention_function is orig and mods["backend.nn.unet"].attention_function is orig
+    from b200forge.lib import B200Error
+    with pytest.raises(B200Error):  # standalone: no reference to defer to -> loud error
+        A.attention_function(torch.zeros(1, 4, 64), torch.zeros(1, 4, 64), torch.zeros(1, 4, 64), 1)
+
+
+def test_plugin_installs_samplers_and_defers_unsupported_cases():
+    from b200forge import k_samplers, plugin
+    mods = _fake_forge_modules()
+    plugin.install_samplers(mods)
+    ks = mods["k_diffusion.sampling"]
+    assert ks.sample_euler is k_samplers.sample_euler and ks.sample_dpmpp_2m is k_samplers.sample_dpmpp_2m
+    x = torch.zeros(1, 4, 8, 8)  # CPU latent: not the fused path
+    assert ks.sample_euler(None, x, torch.tensor([1.0, 0.0])) == "ref_euler"
+    assert ks.sample_euler_ancestral(None, x, torch.tensor([1.0, 0.0])) == "ref_euler_a"
+    assert ks.sample_dpmpp_2m(None, x, torch.tensor([1.0, 0.0])) == "ref_dpmpp"
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_plugin_binds_into_the_real_reference_modules():
+    """With the actual reference imported: the names Forge's UNet/VAE call resolve to the B200 functions after
+    install(), and CPU calls (outside the fused path) still produce the reference's own results."""
+    ref_import.load()
+    import backend.attention as ba
+    import backend.nn.unet as bu
+    from b200forge import attention as A
+    from b200forge import plugin
+    plugin.install_attention()
+    try:
+        assert bu.attention_function is A.attention_function and ba.attention_function is A.attention_function
+        q = torch.randn(2, 16, 128)
+        out = bu.attention_function(q, q, q, 2)
+        from oracle import ops as O
+        assert_close("deferred attention == reference", out, O.attention(q, q, q, 2), max_abs=1e-5)
+    finally:
+        plugin.uninstall_attention()
+    assert bu.attention_function.__name__ == "attention_pytorch"
+
+
+def test_operations_class_surface_and_cpu_deferral():
+    from b200forge.operations import B200Operations
+    for name in ("Linear", "Conv1d", "Conv2d", "Conv3d", "ConvTranspose1d", "ConvTranspose2d", "ConvTranspose3d",
+                 "GroupNorm", "LayerNorm", "Embedding"):  # backend/operations.py:455
+        assert hasattr(B200Operations, name)
+    lin = B200Operations.Linear(16, 8)
+    ref = torch.nn.Linear(16, 8)
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(3, 16)
+    assert torch.equal(lin(x), ref(x))  # fp32 CPU input: stock torch module semantics
+    conv = B200Operations.Conv2d(8, 8, 3, padding=1)
+    assert conv(torch.randn(1, 8, 4, 4)).shape == (1, 8, 4, 4)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from b200forge import dist as D
+    seeds = D.shard_seeds(1000, 4, rank, world)
+    img = torch.tensor(seeds, dtype=torch.float32).view(4, 1, 1, 1).expand(4, 2, 2, 3).contiguous()
+    out = D.gather_to_rank0(img)
+    if rank == 0:
+        q.put((seeds, out[:, 0, 0, 0].tolist()))
+    else:
+        assert out is None
+        q.put((seeds, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_request_sharding_and_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gathered = [r[1] for r in res if r[1] is not None][0]
+    assert gathered == [1000.0 + i for i in range(8)]  # contiguous-by-seed, independent of the number of ranks
+    assert sorted(sum((r[0] for r in res), [])) == list(range(1000, 1008))
