@@ -239,17 +239,20 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand).
       // The two warpgroups take turns on the MUFU (named-barrier hand-off): one group's 128 back-to-back
       // exponentials overlap the other group's TMEM loads / max / conversions / stores.
-      named_bar_sync(2 + t, 256);
       const float nm = -m_ref;
-      // stage A (MUFU-exclusive): all exponentials of the row, in place, nothing consumes them yet
+      // pre-scale outside the MUFU-exclusive window: t_i = s_i*scale*log2e - m_ref (FMA pipe only)
       if (full_blk) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(ex2a(fmaf(__uint_as_float(v[i]), sl2, nm)));
+        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), sl2, nm));
       } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          v[i] = (i < nvalid) ? __float_as_uint(ex2a(fmaf(__uint_as_float(v[i]), sl2, nm))) : 0u;
+          v[i] = (i < nvalid) ? __float_as_uint(fmaf(__uint_as_float(v[i]), sl2, nm)) : 0xff800000u;  // -inf -> exp2 = 0
       }
+      named_bar_sync(2 + t, 256);
+      // stage A (MUFU-exclusive): 128 back-to-back exponentials, in place, nothing consumes them yet
+#pragma unroll
+      for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(ex2a(__uint_as_float(v[i])));
       if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
       // stage B (overlaps the other group's stage A): row sum, convert, stage P
       float rs0 = 0.f, rs1 = 0.f;
