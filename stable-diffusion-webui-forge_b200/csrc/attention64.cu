@@ -24,13 +24,33 @@ struct Attn64Params {
   float scale_log2;
   void* O;
   long long o_stride_b, o_stride_l;
-  uint32_t idesc_qk, idesc_pv;
+  uint32_t idesc_qk, idesc_pv, idesc_l;
 };
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// two exponentials per MUFU op on packed 16-bit lanes: P is consumed as fp16/bf16 by the PV MMA anyway, and
+// the row sum is taken by the tensor core from the same rounded values (ones-column MMA), so the softmax stays
+// self-consistent.  Halves the MUFU work that bounds this kernel.
+template <bool BF16>
+__device__ __forceinline__ uint32_t ex2_pack(float a, float b) {
+  uint32_t r;
+  if constexpr (BF16) {
+    asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  } else {
+    asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  }
+  return r;
+}
+__device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -59,7 +79,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   const uint32_t q_smem = base;                       // 2 tiles
   const uint32_t ring_smem = base + 2 * kTile;        // 4 tiles
   const uint32_t p_smem = ring_smem + kRingSlots * kTile;  // 2 x (2 atoms)
-  const uint32_t bar_base = p_smem + 4 * kTile;
+  const uint32_t ones_smem = p_smem + 4 * kTile;  // 16 rows x 128 k, every element 1.0: B operand of the row-sum MMA
+  const uint32_t bar_base = ones_smem + 4096;
   const uint32_t q_full = bar_base;
   auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
   auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kRingSlots + i); };
@@ -98,6 +119,11 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if (warp == 3) {
+    const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+    for (int i = lane; i < 1024; i += 32) asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_smem + 4u * i), "r"(one2) : "memory");
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -164,6 +190,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           const uint64_t adesc = make_smem_desc_sw128(ps + (uint32_t)(kk >> 2) * kTile + (uint32_t)(kk & 3) * 32u, 0, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
           umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          // row sums: L_t[128 x 16] += P[128 x 16k] * ones[16 x 16k]^T  (column 0 is read back at the end)
+          const uint64_t odesc = make_smem_desc_sw128(ones_smem + (uint32_t)(kk >> 2) * 2048u + (uint32_t)(kk & 3) * 32u, 0, 1024);
+          umma_f16(tmem_base + 384u + (uint32_t)t * 16u, adesc, odesc, p.idesc_l, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(pv_done(t));
       }
@@ -183,7 +212,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t p_row = p_tile + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
-    float m_ref = -INFINITY, l_run = 0.f;
+    const uint32_t l_addr = tmem_base + 384u + (uint32_t)t * 16u + lane_addr;
+    float m_ref = -INFINITY;
     if (t == 1) named_bar_arrive(2, 256);  // warpgroup 0 takes the first turn on the MUFU
 
     for (int j = 0; j < n_kv; ++j) {
@@ -231,8 +261,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
             tmem_st_32x32(o_addr + (uint32_t)c, w);
           }
+          {
+            uint32_t lv;
+            tmem_ld_32x32_x1(l_addr, lv);
+            tmem_ld_wait();
+            tmem_st_32x32_x1(l_addr, __float_as_uint(__uint_as_float(lv) * alpha));
+          }
           tmem_st_wait();
-          l_run *= alpha;
           if (need) m_ref = m_blk;
         }
       }
@@ -240,36 +275,28 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       // The two warpgroups take turns on the MUFU (named-barrier hand-off): one group's 128 back-to-back
       // exponentials overlap the other group's TMEM loads / max / conversions / stores.
       const float nm = -m_ref;
-      // pre-scale outside the MUFU-exclusive window: t_i = s_i*scale*log2e - m_ref (FMA pipe only)
-      if (full_blk) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), sl2, nm));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          v[i] = (i < nvalid) ? __float_as_uint(fmaf(__uint_as_float(v[i]), sl2, nm)) : 0xff800000u;  // -inf -> exp2 = 0
-      }
+      // exp phase (the two warpgroups take turns on the MUFU): t = s*scale*log2e - m_ref in fp32, rounded to the
+      // operand precision, two exponentials per MUFU op, straight into the swizzled P tile
       named_bar_sync(2 + t, 256);
-      // stage A (MUFU-exclusive): 128 back-to-back exponentials, in place, nothing consumes them yet
-#pragma unroll
-      for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(ex2a(__uint_as_float(v[i])));
-      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
-      // stage B (overlaps the other group's stage A): row sum, convert, stage P
-      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 128; c += 8) {
         if (c < BKV) {
-          float pe[8];
+          uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pe[i] = __uint_as_float(v[c + i]);
-          rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
-          rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+          for (int i = 0; i < 4; ++i) {
+            float t0 = fmaf(__uint_as_float(v[c + 2 * i]), sl2, nm);
+            float t1 = fmaf(__uint_as_float(v[c + 2 * i + 1]), sl2, nm);
+            if (!full_blk) {
+              if (c + 2 * i >= nvalid) t0 = -INFINITY;
+              if (c + 2 * i + 1 >= nvalid) t1 = -INFINITY;
+            }
+            pk[i] = ex2_pack<BF16>(t0, t1);
+          }
           const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
-                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]));
         }
       }
-      l_run += rs0 + rs1;
+      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(t));
@@ -278,7 +305,10 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // ---- output: O_t / l -> fp16 -> warp-private staging (the P tile is free now) -> coalesced stores
     mbar_wait(pv_done(t), (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
+    uint32_t lsum;
+    tmem_ld_32x32_x1(l_addr, lsum);
+    tmem_ld_wait();
+    const float inv = 1.0f / __uint_as_float(lsum);
     const uint32_t stg = p_tile + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
     __syncwarp();
 #pragma unroll
@@ -325,7 +355,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 template <bool BF16>
 static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64Params& p,
                          cudaStream_t stream) {
-  const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 1024 + 256;
+  const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 4096 + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -359,6 +389,7 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   const bool bf = d->dtype == B200_BF16;
   p.idesc_qk = make_idesc_f16(128, p.BKV, bf, false, false);
   p.idesc_pv = make_idesc_f16(128, 64, bf, false, true);
+  p.idesc_l = make_idesc_f16(128, 16, bf, false, false);
   const uint64_t cols = (uint64_t)d->H * 64;
   CUtensorMap mQ, mK, mV;
   auto make3 = [&](CUtensorMap* m, const void* base, int L, long long sl, long long sb, int rows) {
