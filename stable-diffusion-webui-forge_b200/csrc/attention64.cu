@@ -106,7 +106,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < kRingSlots; ++i) {
       mbar_init(ring_full(i), 1);
-      mbar_init(ring_empty(i), 1);
+      mbar_init(ring_empty(i), 2);  // both tiles' issuers release a K/V slot
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(s_full(t), 1);
@@ -132,7 +132,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, 2u * kTile);
@@ -146,56 +146,66 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_expect_tx(ring_full(slot), kv_bytes);
       tma_load_3d(ring_smem + slot * kTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if ((warp == 1 || warp == 3) && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 3 -> tile 1
+    // One issuing thread per query tile, so neither tile's events queue behind the other's.  At these small MMA
+    // shapes (N = 64 / 128, 32-64 clk each) the issue path itself is the critical resource: descriptors are built
+    // once and advanced by constants, the k loops are unrolled.
+    const int t = warp >> 1;  // 0 or 1
+    const uint32_t s_tmem = tmem_base + (uint32_t)t * 128u;
+    const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
+    const uint32_t l_tmem = tmem_base + 384u + (uint32_t)t * 16u;
+    const uint64_t qdesc = make_smem_desc_sw128(q_smem + t * kTile, 0, 1024);
+    const uint64_t pdesc = make_smem_desc_sw128(p_smem + t * 2 * kTile, 0, 1024);
+    const uint64_t odesc = make_smem_desc_sw128(ones_smem, 0, 1024);
+    const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);       // + slot * (kTile >> 4)
+    const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kTile, 1024);   // MN-major V
+    const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv, idesc_l = p.idesc_l;
     auto wait_full = [&](int idx) {
       mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
       tc_fence_after();
     };
-    auto issue_qk = [&](int idx, int t) {  // S_t = Q_t K^T
-      const uint32_t k_smem = ring_smem + (idx % kRingSlots) * kTile;
-      const uint32_t qs = q_smem + t * kTile;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + (uint32_t)t * 128u, make_smem_desc_sw128(qs + k * 32u, 0, 1024),
-                 make_smem_desc_sw128(k_smem + k * 32u, 0, 1024), p.idesc_qk, k != 0 ? 1u : 0u);
+    auto issue_qk = [&](int idx) {  // S_t = Q_t K^T
+      const uint64_t kd = kdesc0 + (uint64_t)((idx % kRingSlots) * (kTile >> 4));
+      umma_f16(s_tmem, qdesc, kd, idesc_qk, 0u);
+      umma_f16(s_tmem, qdesc + 2, kd + 2, idesc_qk, 1u);
+      umma_f16(s_tmem, qdesc + 4, kd + 4, idesc_qk, 1u);
+      umma_f16(s_tmem, qdesc + 6, kd + 6, idesc_qk, 1u);
       umma_commit(s_full(t));
+      umma_commit(ring_empty(idx % kRingSlots));
     };
     mbar_wait(q_full, 0);
     wait_full(0);
-    issue_qk(0, 0);
-    issue_qk(0, 1);
-    umma_commit(ring_empty(0));
+    issue_qk(0);
     const int ksteps = BKV >> 4;
     for (int j = 0; j < n_kv; ++j) {
       const int vidx = 2 * j + 1, kidx = 2 * j + 2;
-      // QK_{j+1} as soon as the softmax threads have pulled S_j into registers (runs under their exps)
-      if (j + 1 < n_kv) {
+      if (j + 1 < n_kv) {  // QK_{j+1} runs underneath the exponentials of block j
         wait_full(kidx);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(s_cons(t), (uint32_t)j & 1u);
-          tc_fence_after();
-          issue_qk(kidx, t);
-        }
-        umma_commit(ring_empty(kidx % kRingSlots));
+        mbar_wait(s_cons(t), (uint32_t)j & 1u);
+        tc_fence_after();
+        issue_qk(kidx);
       }
       wait_full(vidx);
-      const uint32_t v_smem = ring_smem + (vidx % kRingSlots) * kTile;
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(p_full(t), (uint32_t)j & 1u);
-        tc_fence_after();
-        const uint32_t ps = p_smem + t * 2 * kTile;
-        const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(ps + (uint32_t)(kk >> 2) * kTile + (uint32_t)(kk & 3) * 32u, 0, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
-          umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
-          // row sums: L_t[128 x 16] += P[128 x 16k] * ones[16 x 16k]^T  (column 0 is read back at the end)
-          const uint64_t odesc = make_smem_desc_sw128(ones_smem + (uint32_t)(kk >> 2) * 2048u + (uint32_t)(kk & 3) * 32u, 0, 1024);
-          umma_f16(tmem_base + 384u + (uint32_t)t * 16u, adesc, odesc, p.idesc_l, (j | kk) != 0 ? 1u : 0u);
+      mbar_wait(p_full(t), (uint32_t)j & 1u);
+      tc_fence_after();
+      const uint64_t vd = vdesc0 + (uint64_t)((vidx % kRingSlots) * (kTile >> 4));
+      const uint32_t acc0 = j != 0 ? 1u : 0u;
+      if (ksteps == 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t ad = pdesc + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2);
+          umma_f16(o_tmem, ad, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+          umma_f16(l_tmem, ad, odesc + (uint64_t)((kk >> 2) * (2048 >> 4) + (kk & 3) * 2), idesc_l, kk ? 1u : acc0);
         }
-        umma_commit(pv_done(t));
+      } else {
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t ad = pdesc + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2);
+          umma_f16(o_tmem, ad, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+          umma_f16(l_tmem, ad, odesc + (uint64_t)((kk >> 2) * (2048 >> 4) + (kk & 3) * 2), idesc_l, kk ? 1u : acc0);
+        }
       }
+      umma_commit(pv_done(t));
       umma_commit(ring_empty(vidx % kRingSlots));
     }
   }
