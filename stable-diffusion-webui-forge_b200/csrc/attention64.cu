@@ -1,16 +1,18 @@
 // b200forge — head-dim-64 attention forward, the SDXL / SD2.x shape (every SDXL attention has Dh = 64).
 //
-// One CTA per SM works on TWO 128-query tiles; per tile one MMA-issuing thread and one softmax warpgroup
-// (4 warps, thread = query row):
-//   QK_j (S_t in TMEM) -> softmax_j: whole S row to registers in one TMEM round trip, lazy running max,
-//   P = exp2(.) computed two-per-MUFU-op in the operand precision and written back OVER S in TMEM
-//   -> PV_j as a TS-mode MMA (A = P from tensor memory, B = [V_j | ones] straight from the [key, Dh] tile as an
-//   MN-major operand) accumulating O_t and the row sums in TMEM across key blocks -> QK_{j+1} ...
-// The other tile's MMAs fill the tensor pipe while this tile is in its softmax.  The tensor pipe executes in issue
-// order, so "S_{j+1} full" implies "PV_j retired": O is rescaled in place (tcgen05.ld/st) only when a row's block
-// max exceeds the reference max by 2^8.  No P round trip through shared memory, no row-sum FADDs, no O read-back.
-// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0|l0 [256,336)  O1|l1 [336,416).
-// smem: Q 2x16 KB | K/V ring 4x16 KB | ones 16 KB.
+// At Dh = 64 the kernel is bound by the exponentials, not the MMAs (128x128 exps per tile-block on a 16/clk MUFU
+// = 1024 cycles vs 512 MMA cycles), so the design goal is to keep the MUFU pipe busy all the time:
+//   * one CTA per SM works on TWO 128-query tiles; two softmax warpgroups (4 warps each, thread = query row)
+//     ping-pong, so one group's exponentials overlap the other group's QK^T / PV MMAs;
+//   * O stays in TMEM and accumulates across key blocks (tcgen05.mma accumulate) — no per-block read-back.
+//     The softmax reference max is only advanced when a row's block max exceeds it by more than 2^8
+//     ("lazy rescale"): then, and only then, the warp rescales its O rows in TMEM (tcgen05.ld/st);
+//   * a softmax thread pulls its whole S row (128 fp32) into registers with one TMEM round trip and releases S
+//     immediately, so QK_{j+1} runs underneath the exponentials of block j; PV_j follows when P_j is staged.
+//     Barriers per tile: S-full, S-consumed, P-full, PV-done (+ the K/V ring).  The softmax warpgroups take
+//     216 registers each via setmaxnreg, the control warps drop to 56.
+// TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384).
+// smem: Q 2x16 KB | K/V ring 4x16 KB | P 2x32 KB (reused as the output staging tile at the end).
 #include "common.cuh"
 #include "host_util.h"
 
@@ -22,33 +24,13 @@ struct Attn64Params {
   float scale_log2;
   void* O;
   long long o_stride_b, o_stride_l;
-  uint32_t idesc_qk, idesc_pv, idesc_l;
+  uint32_t idesc_qk, idesc_pv;
 };
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// two exponentials per MUFU op on packed 16-bit lanes: P is consumed as fp16/bf16 by the PV MMA anyway, and
-// the row sum is taken by the tensor core from the same rounded values (ones-column MMA), so the softmax stays
-// self-consistent.  Halves the MUFU work that bounds this kernel.
-template <bool BF16>
-__device__ __forceinline__ uint32_t ex2_pack(float a, float b) {
-  uint32_t r;
-  if constexpr (BF16) {
-    asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}" : "=r"(r) : "f"(a), "f"(b));
-  } else {
-    asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}" : "=r"(r) : "f"(a), "f"(b));
-  }
-  return r;
-}
-__device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x32_x1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -68,34 +50,24 @@ static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
 static constexpr int kRingSlots = 4;
 static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
 
-// D[tmem] (+)= A[tmem] * B[smem desc]: the P operand of P.V is read straight from tensor memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 template <bool BF16>
 __global__ void __launch_bounds__(384, 1)
 attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const Attn64Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = base;                              // 2 tiles (reused as output staging at the end)
-  const uint32_t ring_smem = base + 2 * kTile;               // 4 K/V tiles
-  const uint32_t ones_smem = ring_smem + kRingSlots * kTile; // [128 keys][64] of 1.0: second MN atom of the PV B operand
-  const uint32_t bar_base = ones_smem + kTile;
+  const uint32_t q_smem = base;                       // 2 tiles
+  const uint32_t ring_smem = base + 2 * kTile;        // 4 tiles
+  const uint32_t p_smem = ring_smem + kRingSlots * kTile;  // 2 x (2 atoms)
+  const uint32_t bar_base = p_smem + 4 * kTile;
   const uint32_t q_full = bar_base;
   auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
   auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kRingSlots + i); };
   auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * kRingSlots + t); };
   auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * kRingSlots + t); };
-  auto o_final = [&](int t) { return bar_base + 8u * (5 + 2 * kRingSlots + t); };
-  const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * kRingSlots);
+  auto pv_done = [&](int t) { return bar_base + 8u * (5 + 2 * kRingSlots + t); };
+  auto s_cons = [&](int t) { return bar_base + 8u * (7 + 2 * kRingSlots + t); };
+  const uint32_t tmem_slot = bar_base + 8u * (9 + 2 * kRingSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,24 +85,19 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < kRingSlots; ++i) {
       mbar_init(ring_full(i), 1);
-      mbar_init(ring_empty(i), 2);  // both tiles' issuers release a K/V slot
+      mbar_init(ring_empty(i), 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(s_full(t), 1);
       mbar_init(p_full(t), 128);
-      mbar_init(o_final(t), 1);
+      mbar_init(pv_done(t), 1);
+      mbar_init(s_cons(t), 128);
     }
     mbar_fence_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
-  }
-  if (warp >= 4) {  // fill the ones tile (every element 1.0, so the swizzle is irrelevant)
-    const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
-    for (int i = (int)threadIdx.x - 128; i < kTile / 16; i += 256)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_smem + 16u * i), "r"(one2) : "memory");
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -139,7 +106,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, 2u * kTile);
@@ -153,104 +120,107 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_expect_tx(ring_full(slot), kv_bytes);
       tma_load_3d(ring_smem + slot * kTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
     }
-  } else if ((warp == 1 || warp == 3) && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 3 -> tile 1
-    // Per tile the chain is  QK_j -> softmax_j (P written over S in TMEM) -> PV_j -> QK_{j+1} ...; the tensor pipe
-    // runs in issue order, so QK_{j+1} cannot overwrite P_j before PV_j has consumed it, and "S_{j+1} full"
-    // implies "O holds blocks <= j".  The other tile's MMAs fill the pipe while this tile is in its softmax.
-    const int t = warp >> 1;
-    const uint32_t s_tmem = tmem_base + (uint32_t)t * 128u;   // S_t; P_t aliases its first 64 columns
-    const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 80u;  // O_t [64] | row sums [16]
-    const uint64_t qdesc = make_smem_desc_sw128(q_smem + t * kTile, 0, 1024);
-    const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
-    const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
     auto wait_full = [&](int idx) {
       mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
       tc_fence_after();
     };
-    auto issue_qk = [&](int idx) {
-      const uint64_t kd = kdesc0 + (uint64_t)((idx % kRingSlots) * (kTile >> 4));
-      umma_f16(s_tmem, qdesc, kd, idesc_qk, 0u);
-      umma_f16(s_tmem, qdesc + 2, kd + 2, idesc_qk, 1u);
-      umma_f16(s_tmem, qdesc + 4, kd + 4, idesc_qk, 1u);
-      umma_f16(s_tmem, qdesc + 6, kd + 6, idesc_qk, 1u);
+    auto issue_qk = [&](int idx, int t) {  // S_t = Q_t K^T
+      const uint32_t k_smem = ring_smem + (idx % kRingSlots) * kTile;
+      const uint32_t qs = q_smem + t * kTile;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base + (uint32_t)t * 128u, make_smem_desc_sw128(qs + k * 32u, 0, 1024),
+                 make_smem_desc_sw128(k_smem + k * 32u, 0, 1024), p.idesc_qk, k != 0 ? 1u : 0u);
       umma_commit(s_full(t));
-      umma_commit(ring_empty(idx % kRingSlots));
     };
     mbar_wait(q_full, 0);
     wait_full(0);
-    issue_qk(0);
+    issue_qk(0, 0);
+    issue_qk(0, 1);
+    umma_commit(ring_empty(0));
     const int ksteps = BKV >> 4;
     for (int j = 0; j < n_kv; ++j) {
       const int vidx = 2 * j + 1, kidx = 2 * j + 2;
-      wait_full(vidx);
-      mbar_wait(p_full(t), (uint32_t)j & 1u);
-      tc_fence_after();
-      // B = [V_j | ones]: 64 value columns from the ring slot (MN-major), 16 more from the ones tile via LBO
-      const uint32_t v_addr = ring_smem + (uint32_t)(vidx % kRingSlots) * kTile;
-      const uint64_t vd = make_smem_desc_sw128(v_addr, ones_smem - v_addr, 1024);
-      const uint32_t acc0 = j != 0 ? 1u : 0u;
-      if (ksteps == 8) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ts(o_tmem, s_tmem + (uint32_t)kk * 8u, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
-      } else {
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_f16_ts(o_tmem, s_tmem + (uint32_t)kk * 8u, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
-      }
-      umma_commit(ring_empty(vidx % kRingSlots));
+      // QK_{j+1} as soon as the softmax threads have pulled S_j into registers (runs under their exps)
       if (j + 1 < n_kv) {
         wait_full(kidx);
-        issue_qk(kidx);
-      } else {
-        umma_commit(o_final(t));
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(s_cons(t), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_qk(kidx, t);
+        }
+        umma_commit(ring_empty(kidx % kRingSlots));
       }
+      wait_full(vidx);
+      const uint32_t v_smem = ring_smem + (vidx % kRingSlots) * kTile;
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full(t), (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t ps = p_smem + t * 2 * kTile;
+        const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(ps + (uint32_t)(kk >> 2) * kTile + (uint32_t)(kk & 3) * 32u, 0, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
+          umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done(t));
+      }
+      umma_commit(ring_empty(vidx % kRingSlots));
     }
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ------------------------------------------------------------------ softmax warpgroups (t = tile, thread = row)
+    // ------------------------------------------------------------------ softmax warpgroups (t = tile)
     const int t = (warp - 4) >> 2;
     const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row inside the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + (uint32_t)t * 128u + lane_addr;
-    const uint32_t o_addr = tmem_base + 256u + (uint32_t)t * 80u + lane_addr;
+    const uint32_t o_addr = tmem_base + 256u + (uint32_t)t * 64u + lane_addr;
+    const uint32_t p_tile = p_smem + (uint32_t)t * 2 * kTile;
+    const uint32_t p_row = p_tile + (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
-    float m_ref = -INFINITY;
+    float m_ref = -INFINITY, l_run = 0.f;
+    if (t == 1) named_bar_arrive(2, 256);  // warpgroup 0 takes the first turn on the MUFU
 
     for (int j = 0; j < n_kv; ++j) {
       int nvalid = p.Lk - j * BKV;
       if (nvalid > BKV) nvalid = BKV;
       mbar_wait(s_full(t), (uint32_t)j & 1u);
       tc_fence_after();
+      // the whole S row -> registers in one TMEM round trip, then hand S back to the tensor core
       uint32_t v[128];
       tmem_ld_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld_32x32(s_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tmem_ld_32x32(s_addr + 64u, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
       tmem_ld_32x32(s_addr + 96u, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_cons(t));
       const bool full_blk = nvalid == 128;
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx = -INFINITY;
       if (full_blk) {
 #pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
-          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-        }
+        for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
       } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+          if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      const float m_blk = mx * sl2;
+      // PV_{j-1} must have retired before O is rescaled and before P is overwritten
+      if (j > 0) {
+        mbar_wait(pv_done(t), (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
       if (j == 0) {
         m_ref = m_blk;
       } else {
         const bool need = m_blk > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          // S_j full => PV_{j-1} retired (in-order tensor pipe): rescale O and the row sums in place
           const float alpha = need ? ex2a(m_ref - m_blk) : 1.0f;
 #pragma unroll
           for (int c = 0; c < 64; c += 32) {
@@ -261,57 +231,69 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
             tmem_st_32x32(o_addr + (uint32_t)c, w);
           }
-          {
-            uint32_t lv;
-            tmem_ld_32x32_x1(o_addr + 64u, lv);
-            tmem_ld_wait();
-            tmem_st_32x32_x1(o_addr + 64u, __float_as_uint(__uint_as_float(lv) * alpha));
-          }
+          tmem_st_wait();
+          l_run *= alpha;
           if (need) m_ref = m_blk;
         }
       }
-      // P = exp2(s*scale*log2e - m_ref) in the operand precision (2 per MUFU op), written over S in TMEM:
-      // column c of P_t holds keys (2c, 2c+1) -> the K-major A operand of the TS-mode P.V MMA
+      // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand).
+      // The two warpgroups take turns on this MUFU-bound phase (named-barrier hand-off) so that one group's
+      // exponentials overlap the other group's TMEM loads / max / stores instead of both fighting for the MUFU.
+      named_bar_sync(2 + t, 256);
+      float rs0 = 0.f, rs1 = 0.f;
       const float nm = -m_ref;
-      uint32_t pk[64];
+      if (full_blk) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float t0 = fmaf(__uint_as_float(v[2 * i]), sl2, nm);
-        float t1 = fmaf(__uint_as_float(v[2 * i + 1]), sl2, nm);
-        if (!full_blk) {
-          if (2 * i >= nvalid) t0 = -INFINITY;
-          if (2 * i + 1 >= nvalid) t1 = -INFINITY;
+        for (int c = 0; c < 128; c += 8) {
+          float pe[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm));
+          rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
+          rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+          const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
         }
-        pk[i] = ex2_pack<BF16>(t0, t1);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) {
+          if (c < BKV) {
+            float pe[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
+            rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
+            rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+            const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                         "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+          }
+        }
       }
-      tmem_st_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-      tmem_st_32x32(s_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-      tmem_st_wait();
+      if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
+      l_run += rs0 + rs1;
+      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(t));
     }
 
-    // ---- output: O_t / l -> fp16 -> warp-private staging (the Q tile is free now) -> coalesced stores
-    mbar_wait(o_final(t), 0);
+    // ---- output: O_t / l -> fp16 -> warp-private staging (the P tile is free now) -> coalesced stores
+    mbar_wait(pv_done(t), (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
-    uint32_t lsum;
-    tmem_ld_32x32_x1(o_addr + 64u, lsum);
-    tmem_ld_wait();
-    const float inv = 1.0f / __uint_as_float(lsum);
-    const uint32_t stg = q_smem + (uint32_t)t * kTile + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    const float inv = 1.0f / l_run;
+    const uint32_t stg = p_tile + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
-      uint32_t w[32];
-      tmem_ld_32x32(o_addr + (uint32_t)c, w);
+      uint32_t v[32];
+      tmem_ld_32x32(o_addr + (uint32_t)c, v);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint32_t o0 = pack2<BF16>(__uint_as_float(w[g * 8 + 0]) * inv, __uint_as_float(w[g * 8 + 1]) * inv);
-        const uint32_t o1 = pack2<BF16>(__uint_as_float(w[g * 8 + 2]) * inv, __uint_as_float(w[g * 8 + 3]) * inv);
-        const uint32_t o2 = pack2<BF16>(__uint_as_float(w[g * 8 + 4]) * inv, __uint_as_float(w[g * 8 + 5]) * inv);
-        const uint32_t o3 = pack2<BF16>(__uint_as_float(w[g * 8 + 6]) * inv, __uint_as_float(w[g * 8 + 7]) * inv);
-        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;
+        const uint32_t o0 = pack2<BF16>(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+        const uint32_t o1 = pack2<BF16>(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+        const uint32_t o2 = pack2<BF16>(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+        const uint32_t o3 = pack2<BF16>(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;  // 16B chunk index inside the 128B row
         const uint32_t addr = stg + (uint32_t)lane * 128u + ((chunk ^ (uint32_t)(lane & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
       }
@@ -344,7 +326,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 template <bool BF16>
 static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64Params& p,
                          cudaStream_t stream) {
-  const size_t smem = (size_t)kTile * (2 + kRingSlots + 1) + 1024 + 256;
+  const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -377,8 +359,7 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   p.o_stride_l = d->o_stride_l;
   const bool bf = d->dtype == B200_BF16;
   p.idesc_qk = make_idesc_f16(128, p.BKV, bf, false, false);
-  p.idesc_pv = make_idesc_f16(128, 80, bf, false, true);  // N = 64 value columns + 16 row-sum columns
-  p.idesc_l = 0;
+  p.idesc_pv = make_idesc_f16(128, 64, bf, false, true);
   const uint64_t cols = (uint64_t)d->H * 64;
   CUtensorMap mQ, mK, mV;
   auto make3 = [&](CUtensorMap* m, const void* base, int L, long long sl, long long sb, int rows) {
