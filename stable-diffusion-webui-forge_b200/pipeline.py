@@ -35,6 +35,8 @@ class GraphedUNet:
         self.context = torch.zeros((n, n_ctx, cfg["context_dim"]), dtype=dt, device=dev)
         self.y = torch.zeros((n, cfg["adm_in_channels"]), dtype=dt, device=dev) if engine.has_label else None
         self.reps = reps
+        # cross-attention K|V projections of the (per-job constant) context: filled once per job, read by the graph
+        self.kv_cache = engine.alloc_kv_cache(n, n_ctx)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.eps: Optional[torch.Tensor] = None
         self.launches_per_forward = 0
@@ -42,7 +44,15 @@ class GraphedUNet:
             self._capture()
 
     def _eager(self) -> torch.Tensor:
-        return self.engine.forward_sigma(self.x, self.sigma, self.timesteps, self.context, self.y, self.reps)
+        return self.engine.forward_sigma(self.x, self.sigma, self.timesteps, self.context, self.y, self.reps,
+                                         kv_cache=self.kv_cache)
+
+    def set_context(self, context: torch.Tensor, y: Optional[torch.Tensor]) -> None:
+        """New conditioning for a job: copy in, then project K|V of every cross-attention layer once."""
+        self.context.copy_(context)
+        if self.y is not None:
+            self.y.copy_(y)
+        self.engine.fill_kv_cache(self.context, self.kv_cache)
 
     def _capture(self) -> None:
         side = torch.cuda.Stream()
@@ -116,10 +126,11 @@ class Txt2ImgPipeline:
             return t.to(device=dev, dtype=dtype, non_blocking=True)
 
         ctx = [cond["crossattn"]] if not has_uncond else [uncond["crossattn"], cond["crossattn"]]  # [uncond, cond]
-        gu.context.copy_(torch.cat([put(t, self.dtype) for t in ctx], 0))
+        yv = None
         if gu.y is not None:
             ys = [cond["vector"]] if not has_uncond else [uncond["vector"], cond["vector"]]
-            gu.y.copy_(torch.cat([put(t, self.dtype) for t in ys], 0))
+            yv = torch.cat([put(t, self.dtype) for t in ys], 0)
+        gu.set_context(torch.cat([put(t, self.dtype) for t in ctx], 0), yv)
         x = gu.x
         # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: max_denoise, zero latent)
         x.copy_(put(noise, torch.float32))

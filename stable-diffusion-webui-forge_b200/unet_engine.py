@@ -197,7 +197,27 @@ class UNetEngine:
             skip = x1
         return ops.conv3x3(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
 
-    def _attn(self, p: str, layer, x: torch.Tensor, ctx2d: torch.Tensor, n_ctx: int) -> torch.Tensor:
+    # ---- cross-attention K/V: the text context is constant over the sampler steps of a job, so its projections
+    # (reference: to_k / to_v recomputed in every CrossAttention.forward, unet.py:148-152) are loop-invariant.
+    def cross_kv_layers(self):
+        out = []
+        for blk in self.st["input"] + [self.st["middle"]] + self.st["output"]:
+            for layer in blk:
+                if layer[0] == "attn":
+                    for d in range(layer[5]):
+                        out.append((f"{layer[1]}.transformer_blocks.{d}", layer[2]))
+        return out
+
+    def alloc_kv_cache(self, n: int, n_ctx: int) -> Dict[str, torch.Tensor]:
+        return {q: torch.empty((n * n_ctx, 2 * ch), dtype=self.dtype, device=self.device) for q, ch in self.cross_kv_layers()}
+
+    def fill_kv_cache(self, context: torch.Tensor, cache: Dict[str, torch.Tensor]) -> None:
+        """One fused K|V projection GEMM per cross-attention layer, once per job."""
+        ctx2d = context.view(-1, context.shape[-1])
+        for q, _ in self.cross_kv_layers():
+            ops.gemm(ctx2d, self.w[q + ".attn2.kv"], out=cache[q])
+
+    def _attn(self, p: str, layer, x: torch.Tensor, ctx2d: torch.Tensor, n_ctx: int, kv_cache=None) -> torch.Tensor:
         w = self.w
         ch, heads, depth = layer[2], layer[3], layer[5]
         n, hh, ww, _ = x.shape
@@ -216,7 +236,7 @@ class UNetEngine:
             # cross attention
             nrm = ops.layernorm(t, w[q + ".norm2.g"], w[q + ".norm2.b"])
             qq = ops.gemm(nrm, w[q + ".attn2.q"]).view(n, L, ch)
-            kv = ops.gemm(ctx2d, w[q + ".attn2.kv"]).view(n, n_ctx, 2 * ch)
+            kv = (kv_cache[q] if kv_cache is not None else ops.gemm(ctx2d, w[q + ".attn2.kv"])).view(n, n_ctx, 2 * ch)
             att = ops.attention(qq, kv[:, :, :ch], kv[:, :, ch:], heads)
             ops.gemm(att.view(m, ch), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t)
             # feed-forward (GEGLU)
@@ -226,14 +246,14 @@ class UNetEngine:
         out = ops.gemm(t, w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, ch)
 
-    def _run(self, layers, h, h2, temb_all, ctx2d, n_ctx):
+    def _run(self, layers, h, h2, temb_all, ctx2d, n_ctx, kv_cache=None):
         for layer in layers:
             kind, p = layer[0], layer[1]
             if kind == "res":
                 h = self._res(p, layer, h, h2, temb_all)
                 h2 = None
             elif kind == "attn":
-                h = self._attn(p, layer, h, ctx2d, n_ctx)
+                h = self._attn(p, layer, h, ctx2d, n_ctx, kv_cache)
             elif kind == "down":
                 n, hh, ww, c = h.shape
                 cols = ops.im2col3x3(h, stride=2)
@@ -256,7 +276,7 @@ class UNetEngine:
         return ops.gemm(ops.silu(emb), w["emb_all.w"], w["emb_all.b"])
 
     def forward_cols(self, cols: torch.Tensor, n: int, hh: int, ww: int, timesteps: torch.Tensor,
-                     context: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
+                     context: torch.Tensor, y: Optional[torch.Tensor], kv_cache=None) -> torch.Tensor:
         """cols: conv_in im2col rows [n*hh*ww, 64]; returns eps NHWC [n, hh, ww, 8] (channels >= 4 are zero)."""
         w = self.w
         assert context.dtype == self.dtype and context.is_contiguous() and context.shape[0] == n
@@ -267,11 +287,11 @@ class UNetEngine:
         h = ops.gemm(cols, w[p0 + ".w"], w[p0 + ".b"]).view(n, hh, ww, self.mc)
         hs = [h]
         for layers in self.st["input"][1:]:
-            h = self._run(layers, h, None, temb_all, ctx2d, n_ctx)
+            h = self._run(layers, h, None, temb_all, ctx2d, n_ctx, kv_cache)
             hs.append(h)
-        h = self._run(self.st["middle"], h, None, temb_all, ctx2d, n_ctx)
+        h = self._run(self.st["middle"], h, None, temb_all, ctx2d, n_ctx, kv_cache)
         for layers in self.st["output"]:
-            h = self._run(layers, h, hs.pop(), temb_all, ctx2d, n_ctx)
+            h = self._run(layers, h, hs.pop(), temb_all, ctx2d, n_ctx, kv_cache)
         h = ops.groupnorm(h, w["out.0.g"], w["out.0.b"], eps=1e-5, silu=True)
         return ops.conv3x3(h, w["out.2.w"], w["out.2.b"])
 
@@ -287,10 +307,10 @@ class UNetEngine:
         return ops.nhwc_to_nchw(eps, channels=self.out_channels, out_dtype=x.dtype)
 
     def forward_sigma(self, x: torch.Tensor, sigma: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
-                      y: Optional[torch.Tensor], reps: int) -> torch.Tensor:
+                      y: Optional[torch.Tensor], reps: int, kv_cache=None) -> torch.Tensor:
         """KModel.apply_model's front half fused into the entry (k_model.py:27-36): x fp32 NCHW [B,4,h,w] is
         scaled by 1/sqrt(sigma^2+1), cast, laid out channels-last and replicated `reps` times (cond/uncond
         batch) in one pass.  Returns eps NHWC [reps*B, h, w, 8]."""
         b, c, hh, ww = x.shape
         cols = ops.unet_input_im2col(x, sigma, self.dtype, reps=reps, ldo=64)
-        return self.forward_cols(cols, reps * b, hh, ww, timesteps, context, y)
+        return self.forward_cols(cols, reps * b, hh, ww, timesteps, context, y, kv_cache)
