@@ -38,7 +38,21 @@ def attn(B, H, Lq, Lk, Dh):
     torch.cuda.synchronize()
 
 
-if which == "gemm":
+def gn(N, H, W, C):
+    x = torch.randn(N, H, W, C, device=DEV, dtype=torch.float16)
+    g = torch.randn(C, device=DEV, dtype=torch.float16)
+    b = torch.randn(C, device=DEV, dtype=torch.float16)
+    for _ in range(2):
+        ops.groupnorm(x, g, b, silu=True)
+    torch.cuda.synchronize()
+
+
+if which == "all":
+    gemm(16384, 10240, 1280)
+    conv(16, 128, 128, 320, 320)
+    attn(16, 10, 4096, 4096, 64)
+    gn(16, 128, 128, 320)
+elif which == "gemm":
     gemm(16384, 10240, 1280)
     gemm(65536, 5120, 640)
     conv(16, 128, 128, 320, 320)
