@@ -279,6 +279,13 @@ __device__ __forceinline__ void st1(void* p, size_t i, float v) {
   else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// one MUFU op instead of two (ex2 + rcp): sigmoid(x) = 0.5 + 0.5*tanh(x/2).  Used where the SiLU is applied to
+// every element of a large activation and the kernel would otherwise be MUFU- rather than HBM-bound (ncu: XU 59 %).
+__device__ __forceinline__ float silu_fast_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 }  // namespace b200

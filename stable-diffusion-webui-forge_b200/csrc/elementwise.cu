@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float t = fmaf(v[i], a[i], b[i]);
-        v[i] = silu ? silu_f(t) : t;
+        v[i] = silu ? silu_fast_f(t) : t;
       }
       store8<BF16>(y, ((size_t)n * HW + px) * C + c, v);
     }
