@@ -153,8 +153,9 @@ int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int ld
                       b200_stream_t s);
 /* y = silu(x) elementwise (SiLU in front of ResBlock.emb_layers, backend/nn/unet.py:412). */
 int b200_silu(const void* x, void* y, size_t n, int dtype, b200_stream_t s);
-/* Row softmax in place on [rows, cols] with scale (VAE single-head attention, backend/nn/vae.py:118-137). */
-int b200_softmax_rows(void* x, int rows, int cols, int ld, float scale, int dtype, b200_stream_t s);
+/* Row softmax in place on [rows, cols] with scale; columns >= valid_cols are treated as masked and written as 0
+ * (VAE single-head attention, backend/nn/vae.py:118-137; generic head dims with padded key counts). */
+int b200_softmax_rows(void* x, int rows, int cols, int valid_cols, int ld, float scale, int dtype, b200_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * UNet entry: sinusoidal timestep embedding (backend/nn/unet.py:55-67) -> [B, dim] in dtype,

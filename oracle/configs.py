@@ -41,6 +41,10 @@ TINY_15 = dict(
     use_linear_in_transformer=False, context_dim=128, adm_in_channels=None, num_classes=None,
 )
 
+# SD1.5-style head split (num_heads fixed -> head dims 8/16/32 here, 40/80/160 at full width): exercises the
+# head-dim padding of the fused path
+TINY_15H = dict(TINY_15, num_heads=8, num_head_channels=-1)
+
 # SDXL VAE (backend/huggingface/stabilityai/stable-diffusion-xl-base-1.0/vae/config.json)
 VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
@@ -49,5 +53,5 @@ VAE_SD15 = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512
 TINY_VAE = dict(in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
 
-CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny_xl": TINY_XL, "tiny_15": TINY_15}
+CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny_xl": TINY_XL, "tiny_15": TINY_15, "tiny_15h": TINY_15H}
 VAE_CONFIGS = {"sdxl": VAE_SDXL, "sd15": VAE_SD15, "tiny": TINY_VAE}

@@ -178,6 +178,7 @@ if __name__ == "__main__":
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
+        gen_unet("tiny_15h")
     if "traj" in which:
         gen_trajectories("tiny_xl")
     if "sched" in which:

@@ -348,7 +348,7 @@ __global__ void unet_input_im2col_kernel(const float* __restrict__ x, const floa
 }
 
 template <bool BF16>
-__global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2) {
+__global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2, int valid) {
   // one CTA per row; cols up to 64K
   const int row = blockIdx.x;
   __shared__ float red[32];
@@ -358,7 +358,8 @@ __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, in
     float v[8];
     load8<BF16>(base, (size_t)c, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+    for (int i = 0; i < 8; ++i)
+      if (c + i < valid) mx = fmaxf(mx, v[i]);
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -371,7 +372,8 @@ __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, in
     float v[8];
     load8<BF16>(base, (size_t)c, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += exp2f((v[i] - mx) * scale_log2);
+    for (int i = 0; i < 8; ++i)
+      if (c + i < valid) s += exp2f((v[i] - mx) * scale_log2);
   }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -383,7 +385,7 @@ __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, in
     float v[8];
     load8<BF16>(base, (size_t)c, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = exp2f((v[i] - mx) * scale_log2) * inv;
+    for (int i = 0; i < 8; ++i) v[i] = (c + i < valid) ? exp2f((v[i] - mx) * scale_log2) * inv : 0.f;
     store8<BF16>(base, (size_t)c, v);
   }
 }
@@ -549,10 +551,12 @@ extern "C" int b200_silu(const void* x, void* y, size_t n, int dtype, b200_strea
   return B200_OK;
 }
 
-extern "C" int b200_softmax_rows(void* x, int rows, int cols, int ld, float scale, int dtype, b200_stream_t s) {
-  B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "softmax_rows: bad arguments");
+extern "C" int b200_softmax_rows(void* x, int rows, int cols, int valid_cols, int ld, float scale, int dtype,
+                                 b200_stream_t s) {
+  B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && valid_cols > 0 && valid_cols <= cols,
+                 "softmax_rows: bad arguments");
   DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(x, rows, cols, ld,
-                                                                                  scale * 1.4426950408889634f));
+                                                                                  scale * 1.4426950408889634f, valid_cols));
   B200_CHECK_LAUNCH("softmax_rows");
   return B200_OK;
 }

@@ -192,6 +192,28 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, 
     return out
 
 
+def attention_generic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, scale: float,
+                      valid_keys: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Any head dim (multiple of 8), any key count padded to a multiple of 8 (`valid_keys` real ones): per (batch, head)
+    S = Q K^T (GEMM) -> masked row softmax -> O = P V (GEMM against V^T).  Used for SD1.5's Dh = 160 levels
+    (64 / 256 tokens), where a dedicated flash kernel is not worth its shared-memory footprint."""
+    b, lq, hd = q.shape
+    lk = k.shape[1]
+    dh = hd // heads
+    assert dh % 8 == 0 and lk % 8 == 0 and all(t.stride(2) == 1 for t in (q, k, v))
+    if out is None:
+        out = torch.empty((b, lq, hd), dtype=q.dtype, device=q.device)
+    s = torch.empty((lq, lk), dtype=q.dtype, device=q.device)
+    for i in range(b):
+        vt = transpose_rows(v[i])  # V^T [H*dh, Lk]
+        for h in range(heads):
+            sl = slice(h * dh, (h + 1) * dh)
+            gemm(q[i, :, sl], k[i, :, sl], out=s)
+            softmax_rows_(s, scale, valid_keys)
+            gemm(s, vt[sl], out=out[i, :, sl])
+    return out
+
+
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
               silu: bool = False, x2: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -292,6 +314,17 @@ def nhwc_to_nchw(x: torch.Tensor, channels: Optional[int] = None, out_dtype: Opt
     return out
 
 
+def transpose_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[L, C] (unit inner stride, any row stride) -> contiguous [C, L]; the NHWC->NCHW kernel with H = L, W = 1."""
+    _rowmajor2d(x, "x")
+    L, c = x.shape
+    if out is None:
+        out = torch.empty((c, L), dtype=x.dtype, device=x.device)
+    _l.check(_l.load().b200_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), 1, c, L, 1, x.stride(0), 0, _dt(x), _stream()))
+    _count()
+    return out
+
+
 def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert x.is_contiguous()
     if out is None:
@@ -301,9 +334,10 @@ def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
-def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
+def softmax_rows_(x: torch.Tensor, scale: float, valid_cols: Optional[int] = None) -> torch.Tensor:
     _rowmajor2d(x, "x")
-    _l.check(_l.load().b200_softmax_rows(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), scale, _dt(x), _stream()))
+    _l.check(_l.load().b200_softmax_rows(x.data_ptr(), x.shape[0], x.shape[1], valid_cols or x.shape[1], x.stride(0),
+                                         scale, _dt(x), _stream()))
     _count()
     return x
 

@@ -98,6 +98,7 @@ class UNetEngine:
         self.ted = self.mc * 4
         self.has_label = cfg.get("num_classes") is not None
         self.w: Dict[str, torch.Tensor] = {}
+        self.head_pad: Dict[str, tuple] = {}
         self._pack(state_dict)
 
     # ------------------------------------------------------------------------------------------ packing
@@ -144,16 +145,37 @@ class UNetEngine:
                 for n in ("proj_in", "proj_out"):
                     w[f"{p}.{n}.w"] = g(f"{p}.{n}.weight").reshape(ch, ch).contiguous()
                     w[f"{p}.{n}.b"] = g(f"{p}.{n}.bias")
+                heads, dh = layer[3], layer[4]
+                # head dims the flash kernels do not take natively (SD1.5: 40 / 80) are zero-padded to 64 / 128 inside
+                # the packed projection weights: q.k^T and the kept output columns are unchanged; Dh > 128 (SD1.5: 160)
+                # runs through the GEMM-softmax-GEMM path
+                dp = dh if dh in (64, 128) else (64 if dh < 64 else (128 if dh < 128 else dh))
+                self.head_pad[p] = (dh, dp)
+
+                def pad_rows(wt):  # [H*dh, K] -> [H*dp, K]
+                    if dp == dh:
+                        return wt
+                    o = torch.zeros((heads * dp, wt.shape[1]), dtype=wt.dtype, device=wt.device)
+                    o.view(heads, dp, -1)[:, :dh] = wt.view(heads, dh, -1)
+                    return o
+
+                def pad_cols(wt):  # [C, H*dh] -> [C, H*dp]
+                    if dp == dh:
+                        return wt
+                    o = torch.zeros((wt.shape[0], heads * dp), dtype=wt.dtype, device=wt.device)
+                    o.view(-1, heads, dp)[:, :, :dh] = wt.view(-1, heads, dh)
+                    return o
+
                 for d in range(depth):
                     q = f"{p}.transformer_blocks.{d}"
                     for n in ("norm1", "norm2", "norm3"):
                         w[f"{q}.{n}.g"], w[f"{q}.{n}.b"] = g(f"{q}.{n}.weight"), g(f"{q}.{n}.bias")
-                    w[q + ".attn1.qkv"] = torch.cat([g(f"{q}.attn1.to_q.weight"), g(f"{q}.attn1.to_k.weight"),
-                                                      g(f"{q}.attn1.to_v.weight")], 0).contiguous()
-                    w[q + ".attn2.q"] = g(f"{q}.attn2.to_q.weight")
-                    w[q + ".attn2.kv"] = torch.cat([g(f"{q}.attn2.to_k.weight"), g(f"{q}.attn2.to_v.weight")], 0).contiguous()
+                    w[q + ".attn1.qkv"] = torch.cat([pad_rows(g(f"{q}.attn1.to_q.weight")), pad_rows(g(f"{q}.attn1.to_k.weight")),
+                                                      pad_rows(g(f"{q}.attn1.to_v.weight"))], 0).contiguous()
+                    w[q + ".attn2.q"] = pad_rows(g(f"{q}.attn2.to_q.weight")).contiguous()
+                    w[q + ".attn2.kv"] = torch.cat([pad_rows(g(f"{q}.attn2.to_k.weight")), pad_rows(g(f"{q}.attn2.to_v.weight"))], 0).contiguous()
                     for a in ("attn1", "attn2"):
-                        w[f"{q}.{a}.o.w"], w[f"{q}.{a}.o.b"] = g(f"{q}.{a}.to_out.0.weight"), g(f"{q}.{a}.to_out.0.bias")
+                        w[f"{q}.{a}.o.w"], w[f"{q}.{a}.o.b"] = pad_cols(g(f"{q}.{a}.to_out.0.weight")).contiguous(), g(f"{q}.{a}.to_out.0.bias")
                     bn = 256 if (4 * ch) % 128 == 0 else 128
                     w[q + ".ff1.w"], w[q + ".ff1.b"] = ops.pack_geglu(g(f"{q}.ff.net.0.proj.weight"),
                                                                        g(f"{q}.ff.net.0.proj.bias"), bn)
@@ -204,18 +226,25 @@ class UNetEngine:
         for blk in self.st["input"] + [self.st["middle"]] + self.st["output"]:
             for layer in blk:
                 if layer[0] == "attn":
+                    dh, dp = self.head_pad[layer[1]]
                     for d in range(layer[5]):
-                        out.append((f"{layer[1]}.transformer_blocks.{d}", layer[2]))
+                        out.append((f"{layer[1]}.transformer_blocks.{d}", layer[3] * dp))
         return out
 
+    def _kv_buffer(self, n: int, n_ctx: int, width: int) -> torch.Tensor:
+        # 8 zeroed slack rows: the GEMM-softmax-GEMM path reads the key count rounded up to a multiple of 8
+        buf = torch.empty((n * n_ctx + 8, 2 * width), dtype=self.dtype, device=self.device)
+        ops._l.check(ops._l.load().b200_fill_zero(buf[n * n_ctx:].data_ptr(), 8 * 2 * width * 2, ops._stream()))
+        return buf
+
     def alloc_kv_cache(self, n: int, n_ctx: int) -> Dict[str, torch.Tensor]:
-        return {q: torch.empty((n * n_ctx, 2 * ch), dtype=self.dtype, device=self.device) for q, ch in self.cross_kv_layers()}
+        return {q: self._kv_buffer(n, n_ctx, cw) for q, cw in self.cross_kv_layers()}
 
     def fill_kv_cache(self, context: torch.Tensor, cache: Dict[str, torch.Tensor]) -> None:
         """One fused K|V projection GEMM per cross-attention layer, once per job."""
         ctx2d = context.view(-1, context.shape[-1])
         for q, _ in self.cross_kv_layers():
-            ops.gemm(ctx2d, self.w[q + ".attn2.kv"], out=cache[q])
+            ops.gemm(ctx2d, self.w[q + ".attn2.kv"], out=cache[q][: ctx2d.shape[0]])
 
     def _attn(self, p: str, layer, x: torch.Tensor, ctx2d: torch.Tensor, n_ctx: int, kv_cache=None) -> torch.Tensor:
         w = self.w
@@ -226,19 +255,38 @@ class UNetEngine:
         x2d = x.view(m, ch)
         t = ops.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], eps=1e-6, silu=False).view(m, ch)
         t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"])
+        dh, dp = self.head_pad[p]
+        cw = heads * dp          # width of the (head-padded) q / k / v / attention-output tensors
+        scale = dh ** -0.5
+        flash = dp in (64, 128)
+        nk8 = (n_ctx + 7) // 8 * 8
         for d in range(depth):
             q = f"{p}.transformer_blocks.{d}"
             # self attention
             nrm = ops.layernorm(t, w[q + ".norm1.g"], w[q + ".norm1.b"])
-            qkv = ops.gemm(nrm, w[q + ".attn1.qkv"]).view(n, L, 3 * ch)
-            att = ops.attention(qkv[:, :, :ch], qkv[:, :, ch:2 * ch], qkv[:, :, 2 * ch:], heads)
-            ops.gemm(att.view(m, ch), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t)
+            qkv = ops.gemm(nrm, w[q + ".attn1.qkv"]).view(n, L, 3 * cw)
+            if flash:
+                att = ops.attention(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
+            else:
+                att = ops.attention_generic(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
+            ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t)
             # cross attention
             nrm = ops.layernorm(t, w[q + ".norm2.g"], w[q + ".norm2.b"])
-            qq = ops.gemm(nrm, w[q + ".attn2.q"]).view(n, L, ch)
-            kv = (kv_cache[q] if kv_cache is not None else ops.gemm(ctx2d, w[q + ".attn2.kv"])).view(n, n_ctx, 2 * ch)
-            att = ops.attention(qq, kv[:, :, :ch], kv[:, :, ch:], heads)
-            ops.gemm(att.view(m, ch), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t)
+            qq = ops.gemm(nrm, w[q + ".attn2.q"]).view(n, L, cw)
+            if kv_cache is not None:
+                kvb = kv_cache[q]
+            else:
+                kvb = self._kv_buffer(n, n_ctx, cw)
+                ops.gemm(ctx2d, w[q + ".attn2.kv"], out=kvb[: n * n_ctx])
+            if flash:
+                kv = kvb[: n * n_ctx].view(n, n_ctx, 2 * cw)
+                att = ops.attention(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale)
+            else:
+                # key count rounded up to 8: the extra rows belong to the next image (or the zeroed slack) and are
+                # masked by the softmax (valid_keys), so they contribute exactly 0
+                kv = kvb.as_strided((n, nk8, 2 * cw), (n_ctx * 2 * cw, 2 * cw, 1))
+                att = ops.attention_generic(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale, valid_keys=n_ctx)
+            ops.gemm(att.view(m, cw), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t)
             # feed-forward (GEGLU)
             nrm = ops.layernorm(t, w[q + ".norm3.g"], w[q + ".norm3.b"])
             gg = ops.gemm(nrm, w[q + ".ff1.w"], w[q + ".ff1.b"], epilogue=EPI_GEGLU, block_n=w[q + ".ff1.bn"])

@@ -24,7 +24,7 @@ def _sd_checksum(sd):
     return float(sum(v.double().abs().sum() for v in sd.values()))
 
 
-@pytest.mark.parametrize("name", ["tiny_xl", "tiny_15"])
+@pytest.mark.parametrize("name", ["tiny_xl", "tiny_15", "tiny_15h"])
 def test_unet_oracle_matches_reference_golden(name):
     g = _gold(f"unet_{name}.pt")
     cfg = CF.CONFIGS[name]

@@ -32,7 +32,7 @@ def _engine(name, seed, dtype=torch.float16):
     return UNetEngine(cfg, sd, dtype=dtype, device=DEV), cfg, sd
 
 
-@pytest.mark.parametrize("name", ["tiny_xl", "tiny_15"])
+@pytest.mark.parametrize("name", ["tiny_xl", "tiny_15", "tiny_15h"])
 def test_unet_forward_vs_reference_golden(name):
     g = _gold(f"unet_{name}.pt")
     eng, cfg, sd = _engine(name, g["weight_seed"])
@@ -60,8 +60,6 @@ def test_unet_forward_bf16():
 def test_unet_full_width_vs_oracle_fp32(name, hw, batch):
     """Full-width SDXL / SD1.5 UNet (real channel counts and depths) on a small latent, against the oracle in fp32
     on the GPU (TF32 off) with the same fp16-rounded weights."""
-    if name == "sd15":
-        pytest.skip("SD1.5 head dims 40/80/160 are routed to the reference attention (next round)")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     cfg = CF.CONFIGS[name]
@@ -73,7 +71,7 @@ def test_unet_full_width_vs_oracle_fp32(name, hw, batch):
     ctx = torch.randn(batch, 77, cfg["context_dim"], generator=g).half().to(DEV)
     y = torch.randn(batch, cfg["adm_in_channels"], generator=g).half().to(DEV) if cfg["adm_in_channels"] else None
     t = torch.tensor([800.0, 100.0][:batch], device=DEV)
-    out = eng.forward(x, t, ctx, y)
+    out = eng.forward(x, t, ctx, y)  # sd15: head dims 40 / 80 (padded to 64 / 128) and 160 (GEMM-softmax-GEMM path)
     torch.cuda.synchronize()
     sd32 = {k: v.float().to(DEV) for k, v in sd.items()}
     with torch.no_grad():
