@@ -346,7 +346,10 @@ def main():
         peak = peaks["bf16_tflops_sustained"]
         roof = {"kernel": "b200::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3; 1 UNet forward @batch 16 + VAE decode)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                # dram__bytes_read+write of one representative launch from the committed `ncu --set full` capture
+                # (profiles/ncu_r1_summary.md): gemm M=16384 N=10240 K=1280, algorithmic bytes 403.7 MB
+                "traffic": 475.2e6, "traffic_launch": "gemm M=16384 N=10240 K=1280 fp16 (algorithmic 403.7e6 B, 429.5e9 FLOP)",
+                "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                 "launches": tens["launches"], "avg_launch_ms": tens["ms"] / max(1, tens["launches"]),
                 "flops_per_launch_avg": tens["flops"] / max(1, tens["launches"])}
         for name, d in fam.items():
