@@ -62,6 +62,16 @@ typedef struct {
   const void* A2;     /* second A source or NULL */
   int lda2;
   int K1;
+  /* LayerNorm folded into the GEMM (replaces F.layer_norm + F.linear, backend/nn/unet.py:171-175 with operations.py:323-329):
+   * A holds the un-normalised rows, B = W.diag(gamma); y = rstd_m*(acc - mean_m*ln_c[n]) + ln_d[n] with
+   * ln_c = rowsum(B) and ln_d = W.beta (+ bias), both fp32 [N]; ln_stats [M,2] = (sum, sum of squares) of each A row. */
+  const float* ln_stats;
+  const float* ln_c;
+  const float* ln_d;
+  float ln_eps;
+  /* when set, the epilogue accumulates (sum, sum of squares) of every output row into row_stats_out [M,2]
+   * (zeroed by the caller) — the ln_stats of the next GEMM, so no separate LayerNorm pass touches HBM. */
+  float* row_stats_out;
 } b200_gemm_desc;
 
 int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);

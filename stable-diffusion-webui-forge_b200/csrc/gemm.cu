@@ -46,6 +46,13 @@ struct GemmKParams {
   int ld_rowvec;
   int rows_per_vec;
   int epilogue;
+  // LayerNorm folded into the GEMM (A is the *un-normalised* activation, B is W.diag(gamma)):
+  //   y = rstd[m] * (acc - mean[m] * ln_c[n]) + ln_d[n],  ln_c = rowsum(W.diag(gamma)),  ln_d = W.beta (+ bias)
+  const float* ln_stats;  // [M, 2] (sum, sum of squares) of each A row, produced by the previous GEMM's epilogue
+  const float* ln_c;
+  const float* ln_d;
+  float ln_inv_k, ln_eps;
+  float* row_stats_out;   // [M, 2]: this GEMM accumulates (sum, sumsq) of its own output rows (caller zeroes it)
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
@@ -79,6 +86,17 @@ __device__ __forceinline__ void add_smem8(uint32_t addr, float (&x)[8]) {
   add_u4<BF16>(r, x);
 }
 
+// x[i] = rstd * (x[i] - mean * c[col+i]) + d[col+i]   (c, d: fp32 rows of the current tile in smem)
+__device__ __forceinline__ void ln_apply8(uint32_t c_smem, uint32_t d_smem, int col, float mean, float rstd, float (&x)[8]) {
+  float cv[8], dv[8];
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cv[0]), "=f"(cv[1]), "=f"(cv[2]), "=f"(cv[3]) : "r"(c_smem + 4u * col));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cv[4]), "=f"(cv[5]), "=f"(cv[6]), "=f"(cv[7]) : "r"(c_smem + 4u * col + 16u));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dv[0]), "=f"(dv[1]), "=f"(dv[2]), "=f"(dv[3]) : "r"(d_smem + 4u * col));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dv[4]), "=f"(dv[5]), "=f"(dv[6]), "=f"(dv[7]) : "r"(d_smem + 4u * col + 16u));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = fmaf(rstd, fmaf(-mean, cv[i], x[i]), dv[i]);
+}
+
 template <bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -96,7 +114,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)S * kATileBytes;
   const uint32_t stg_base = b_base + (uint32_t)S * b_tile_bytes;  // 1024-aligned: every tile size is a multiple of 1 KB
-  const uint32_t bar_base = stg_base + kStageBufs * kStageBufBytes + 1024u;  // + per-tile bias row
+  const uint32_t bar_base = stg_base + kStageBufs * kStageBufBytes + 1024u + 2048u;  // + bias row + LN c/d rows
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM pointer slot
   auto full_bar = [&](int i) { return bar_base + (uint32_t)i * 8u; };
   auto empty_bar = [&](int i) { return bar_base + (uint32_t)(S + i) * 8u; };
@@ -235,6 +253,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int r = quad * 32 + lane;
     const uint32_t my_stg = stg_base + (uint32_t)(warp - 4) * 2048u;
     const uint32_t bias_smem = stg_base + kStageBufs * kStageBufBytes;  // 256 halfs
+    const uint32_t lnc_smem = bias_smem + 1024u;                        // 256 floats
+    const uint32_t lnd_smem = lnc_smem + 1024u;                         // 256 floats
+    const bool ln = p.ln_stats != nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
@@ -257,10 +278,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
       // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
       const bool col_bias = p.bias && !p.bias_along_m;
-      if (col_bias) {
-        named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ln && row_ok) {
+        const float s1 = p.ln_stats[2 * (size_t)m], s2 = p.ln_stats[2 * (size_t)m + 1];
+        ln_mean = s1 * p.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
+      if (col_bias || ln) {
+        named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias / LN rows
         const int e0 = (int)(threadIdx.x - 128) * 8;
-        if (e0 < BN) {
+        if (ln) {
+          const int e = (int)threadIdx.x - 128;
+          if (e < BN) {
+            const bool ok = n0 + e < p.N;
+            const float cv = ok ? __ldg(p.ln_c + n0 + e) : 0.f, dv = ok ? __ldg(p.ln_d + n0 + e) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnc_smem + 4u * e), "f"(cv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnd_smem + 4u * e), "f"(dv) : "memory");
+          }
+        }
+        if (col_bias && e0 < BN) {
           uint4 bv = make_uint4(0, 0, 0, 0);
           if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.bias) + (size_t)(n0 + e0) * 2));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 2u), "r"(bv.x), "r"(bv.y),
@@ -301,6 +338,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               xv[i] = __uint_as_float(v[g * 8 + i]);
               gt[i] = __uint_as_float(vg[g * 8 + i]);
             }
+            if (ln) {
+              ln_apply8(lnc_smem, lnd_smem, c + g * 8, ln_mean, ln_rstd, xv);
+              ln_apply8(lnc_smem, lnd_smem, ncols_out + c + g * 8, ln_mean, ln_rstd, gt);
+            }
             if (col_bias) {
               add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
               add_smem8<BF16>(bias_smem + (uint32_t)(ncols_out + c + g * 8) * 2u, gt);
@@ -315,6 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
+            if (ln) ln_apply8(lnc_smem, lnd_smem, c + g * 8, ln_mean, ln_rstd, xv);
             if (col_bias) add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
             else if (p.bias) {
 #pragma unroll
@@ -349,6 +391,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
           const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
           const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
+          if (p.row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // statistics of the values as stored (rounded)
+            const float2 f0 = unpack2<BF16>(o0), f1 = unpack2<BF16>(o1), f2 = unpack2<BF16>(o2), f3 = unpack2<BF16>(o3);
+            st_sum += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+            st_sq += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) +
+                     ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+          }
           const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
                        : "memory");
@@ -370,6 +418,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             }
           }
         }
+      }
+      if (p.row_stats_out && row_ok) {
+        atomicAdd(p.row_stats_out + 2 * (size_t)m, st_sum);
+        atomicAdd(p.row_stats_out + 2 * (size_t)m + 1, st_sq);
       }
       tc_fence_before();
       if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -410,7 +462,7 @@ template <bool BF16, int CG>
 static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                          const CUtensorMap& mapC, GemmKParams& p, cudaStream_t stream) {
   const int stage_bytes = kATileBytes + (p.BN / CG) * 128;
-  const int staging = (int)(kStageBufs * kStageBufBytes) + 1024;
+  const int staging = (int)(kStageBufs * kStageBufBytes) + 1024 + 2048;
   int S = (222 * 1024 - staging) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) S = 2;
@@ -528,6 +580,13 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.ld_rowvec = d->ld_rowvec;
   p.rows_per_vec = d->rows_per_vec > 0 ? d->rows_per_vec : 1;
   p.epilogue = d->epilogue;
+  p.ln_stats = d->ln_stats;
+  p.ln_c = d->ln_c;
+  p.ln_d = d->ln_d;
+  p.ln_inv_k = 1.0f / (float)d->K;
+  p.ln_eps = d->ln_eps;
+  p.row_stats_out = d->row_stats_out;
+  B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2), "gemm: LayerNorm folding needs ln_c and ln_d (single A source)");
 
   CUtensorMap mA, mA2, mB;
   {

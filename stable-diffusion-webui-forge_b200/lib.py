@@ -36,6 +36,8 @@ class GemmDesc(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int),
         ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int), ("rows_per_vec", C.c_int),
         ("A2", C.c_void_p), ("lda2", C.c_int), ("K1", C.c_int),
+        ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_d", C.c_void_p), ("ln_eps", C.c_float),
+        ("row_stats_out", C.c_void_p),
     ]
 
 

@@ -68,11 +68,14 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          residual: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 1,
          epilogue: int = EPI_NONE, a2: Optional[torch.Tensor] = None, bias_along_m: bool = False,
-         out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, block_n: int = 0, ln: Optional[tuple] = None,
+         row_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M, N] = epi(cat(a, a2) @ w.T + bias + rowvec[row // rows_per_vec]) + residual.
 
     a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
     GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
+    ln = (stats [M,2] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
+    see `fold_layernorm`).  row_stats_out [M,2] fp32 (zeroed): receives (sum, sumsq) of the output rows.
     """
     _rowmajor2d(a, "a")
     _rowmajor2d(w, "w")
@@ -104,6 +107,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.rowvec, d.ld_rowvec, d.rows_per_vec = rowvec.data_ptr(), rowvec.stride(0), rows_per_vec
     if a2 is not None:
         d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), K1
+    if ln is not None:
+        st, lc, ld_, eps = ln
+        assert st.dtype == torch.float32 and st.shape == (M, 2) and st.is_contiguous()
+        assert lc.dtype == torch.float32 and ld_.dtype == torch.float32 and lc.numel() == N and ld_.numel() == N
+        d.ln_stats, d.ln_c, d.ln_d, d.ln_eps = st.data_ptr(), lc.data_ptr(), ld_.data_ptr(), eps
+    if row_stats_out is not None:
+        assert row_stats_out.dtype == torch.float32 and row_stats_out.shape == (M, 2) and row_stats_out.is_contiguous()
+        d.row_stats_out = row_stats_out.data_ptr()
     with _prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
         _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
@@ -124,6 +135,24 @@ def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor], block_n: int = 256):
     wp = w.index_select(0, src).contiguous()
     bp = b.index_select(0, src).contiguous() if b is not None else None
     return wp, bp
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm -> Linear as one GEMM on the raw rows:  LN(x) W^T + b = rstd (x (W.gamma)^T - mean c) + d,
+    c = rowsum(W.gamma), d = W beta + b.  Returns (W.gamma in the weight dtype, c fp32, d fp32); c is summed from the
+    *rounded* folded weight so that it cancels exactly against what the tensor core multiplies."""
+    wf = (w.float() * gamma.float()[None, :]).to(w.dtype).contiguous()
+    c = wf.float().sum(dim=1).contiguous()
+    d = (w.float() @ beta.float())
+    if b is not None:
+        d = d + b.float()
+    return wf, c, d.contiguous()
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_contiguous()
+    _l.check(_l.load().b200_fill_zero(t.data_ptr(), t.numel() * t.element_size(), _stream()))
+    return t
 
 
 def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:

@@ -168,17 +168,23 @@ class UNetEngine:
 
                 for d in range(depth):
                     q = f"{p}.transformer_blocks.{d}"
-                    for n in ("norm1", "norm2", "norm3"):
-                        w[f"{q}.{n}.g"], w[f"{q}.{n}.b"] = g(f"{q}.{n}.weight"), g(f"{q}.{n}.bias")
-                    w[q + ".attn1.qkv"] = torch.cat([pad_rows(g(f"{q}.attn1.to_q.weight")), pad_rows(g(f"{q}.attn1.to_k.weight")),
-                                                      pad_rows(g(f"{q}.attn1.to_v.weight"))], 0).contiguous()
-                    w[q + ".attn2.q"] = pad_rows(g(f"{q}.attn2.to_q.weight")).contiguous()
+                    # LayerNorm (norm1/2/3, eps 1e-5) is folded into the GEMM that consumes it: weight <- W.gamma,
+                    # epilogue y = rstd*(acc - mean*c) + d with the row statistics produced by the previous GEMM
+                    gam = {n: g(f"{q}.{n}.weight") for n in ("norm1", "norm2", "norm3")}
+                    bet = {n: g(f"{q}.{n}.bias") for n in ("norm1", "norm2", "norm3")}
+                    qkv_w = torch.cat([pad_rows(g(f"{q}.attn1.to_q.weight")), pad_rows(g(f"{q}.attn1.to_k.weight")),
+                                       pad_rows(g(f"{q}.attn1.to_v.weight"))], 0).contiguous()
+                    w[q + ".attn1.qkv"], w[q + ".attn1.qkv.c"], w[q + ".attn1.qkv.d"] = ops.fold_layernorm(qkv_w, None, gam["norm1"], bet["norm1"])
+                    w[q + ".attn2.q"], w[q + ".attn2.q.c"], w[q + ".attn2.q.d"] = ops.fold_layernorm(
+                        pad_rows(g(f"{q}.attn2.to_q.weight")).contiguous(), None, gam["norm2"], bet["norm2"])
                     w[q + ".attn2.kv"] = torch.cat([pad_rows(g(f"{q}.attn2.to_k.weight")), pad_rows(g(f"{q}.attn2.to_v.weight"))], 0).contiguous()
                     for a in ("attn1", "attn2"):
                         w[f"{q}.{a}.o.w"], w[f"{q}.{a}.o.b"] = pad_cols(g(f"{q}.{a}.to_out.0.weight")).contiguous(), g(f"{q}.{a}.to_out.0.bias")
                     bn = 256 if (4 * ch) % 128 == 0 else 128
-                    w[q + ".ff1.w"], w[q + ".ff1.b"] = ops.pack_geglu(g(f"{q}.ff.net.0.proj.weight"),
-                                                                       g(f"{q}.ff.net.0.proj.bias"), bn)
+                    f1w, f1c, f1d = ops.fold_layernorm(g(f"{q}.ff.net.0.proj.weight"), g(f"{q}.ff.net.0.proj.bias"),
+                                                       gam["norm3"], bet["norm3"])
+                    w[q + ".ff1.w"], w[q + ".ff1.c"] = ops.pack_geglu(f1w, f1c, bn)   # same row interleave for c and d
+                    _, w[q + ".ff1.d"] = ops.pack_geglu(f1w, f1d, bn)
                     w[q + ".ff1.bn"] = bn
                     w[q + ".ff2.w"], w[q + ".ff2.b"] = g(f"{q}.ff.net.2.weight"), g(f"{q}.ff.net.2.bias")
             elif kind == "down":
@@ -254,7 +260,8 @@ class UNetEngine:
         m = n * L
         x2d = x.view(m, ch)
         t = ops.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], eps=1e-6, silu=False).view(m, ch)
-        t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"])
+        st1, st2, st3 = (torch.empty((m, 2), dtype=torch.float32, device=self.device) for _ in range(3))
+        t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"], row_stats_out=ops.zero_(st1))
         dh, dp = self.head_pad[p]
         cw = heads * dp          # width of the (head-padded) q / k / v / attention-output tensors
         scale = dh ** -0.5
@@ -263,16 +270,14 @@ class UNetEngine:
         for d in range(depth):
             q = f"{p}.transformer_blocks.{d}"
             # self attention
-            nrm = ops.layernorm(t, w[q + ".norm1.g"], w[q + ".norm1.b"])
-            qkv = ops.gemm(nrm, w[q + ".attn1.qkv"]).view(n, L, 3 * cw)
+            qkv = ops.gemm(t, w[q + ".attn1.qkv"], ln=(st1, w[q + ".attn1.qkv.c"], w[q + ".attn1.qkv.d"], 1e-5)).view(n, L, 3 * cw)
             if flash:
                 att = ops.attention(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
             else:
                 att = ops.attention_generic(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
-            ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t)
+            ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t, row_stats_out=ops.zero_(st2))
             # cross attention
-            nrm = ops.layernorm(t, w[q + ".norm2.g"], w[q + ".norm2.b"])
-            qq = ops.gemm(nrm, w[q + ".attn2.q"]).view(n, L, cw)
+            qq = ops.gemm(t, w[q + ".attn2.q"], ln=(st2, w[q + ".attn2.q.c"], w[q + ".attn2.q.d"], 1e-5)).view(n, L, cw)
             if kv_cache is not None:
                 kvb = kv_cache[q]
             else:
@@ -286,11 +291,12 @@ class UNetEngine:
                 # masked by the softmax (valid_keys), so they contribute exactly 0
                 kv = kvb.as_strided((n, nk8, 2 * cw), (n_ctx * 2 * cw, 2 * cw, 1))
                 att = ops.attention_generic(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale, valid_keys=n_ctx)
-            ops.gemm(att.view(m, cw), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t)
+            ops.gemm(att.view(m, cw), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t, row_stats_out=ops.zero_(st3))
             # feed-forward (GEGLU)
-            nrm = ops.layernorm(t, w[q + ".norm3.g"], w[q + ".norm3.b"])
-            gg = ops.gemm(nrm, w[q + ".ff1.w"], w[q + ".ff1.b"], epilogue=EPI_GEGLU, block_n=w[q + ".ff1.bn"])
-            ops.gemm(gg, w[q + ".ff2.w"], w[q + ".ff2.b"], residual=t, out=t)
+            gg = ops.gemm(t, w[q + ".ff1.w"], None, epilogue=EPI_GEGLU, block_n=w[q + ".ff1.bn"],
+                          ln=(st3, w[q + ".ff1.c"], w[q + ".ff1.d"], 1e-5))
+            ops.gemm(gg, w[q + ".ff2.w"], w[q + ".ff2.b"], residual=t, out=t,
+                     row_stats_out=ops.zero_(st1) if d + 1 < depth else None)
         out = ops.gemm(t, w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, ch)
 

@@ -319,3 +319,39 @@ def test_sampler_step_euler_ancestral_and_dpmpp():
     torch.cuda.synchronize()
     assert_close("sampler dpmpp2m x", xd, x_ref2, max_abs=5e-5)
     assert_close("sampler dpmpp2m old", oldd, den_ref, max_abs=2e-5)
+
+
+def test_gemm_layernorm_fold_and_row_stats():
+    """LayerNorm -> Linear as one GEMM on the raw rows (stats from the producer's epilogue) vs the oracle's
+    layer_norm + linear; also the GEGLU variant used by the transformer feed-forward."""
+    ops = _ops()
+    M, C, N = 1024, 640, 1280
+    x_in = _rand(M, C, seed=50)
+    w0 = _rand(C, C, scale=C ** -0.5, seed=51)
+    res = _rand(M, C, seed=52) * 2 + 0.7
+    # producer: t = x_in @ w0^T + res, with row statistics of t taken in its epilogue
+    stats = torch.zeros(M, 2, device=DEV)
+    t = ops.gemm(x_in, w0, residual=res, row_stats_out=stats)
+    torch.cuda.synchronize()
+    tf = t.float()
+    assert_close("row stats sum", stats[:, 0], tf.sum(1), rel_rms=1e-5)
+    assert_close("row stats sumsq", stats[:, 1], (tf * tf).sum(1), rel_rms=1e-5)
+    gamma = (_rand(C, seed=53) * 0.2 + 1)
+    beta = _rand(C, seed=54) * 0.2
+    w1 = _rand(N, C, scale=C ** -0.5, seed=55)
+    b1 = _rand(N, seed=56)
+    wf, c, d = ops.fold_layernorm(w1, b1, gamma, beta)
+    y = ops.gemm(t, wf, None, ln=(stats, c, d, 1e-5))
+    torch.cuda.synchronize()
+    ref = O.linear(O.layer_norm(tf, gamma.float(), beta.float(), 1e-5), w1.float(), b1.float())
+    assert_close("LN folded into GEMM", y, ref, rel_rms=3e-3)
+    # GEGLU consumer
+    w2 = _rand(8 * C, C, scale=C ** -0.5, seed=57)
+    b2 = _rand(8 * C, seed=58, scale=0.1)
+    wf2, c2, d2 = ops.fold_layernorm(w2, b2, gamma, beta)
+    wp, cp = ops.pack_geglu(wf2, c2, 256)
+    _, dp = ops.pack_geglu(wf2, d2, 256)
+    g = ops.gemm(t, wp, None, epilogue=ops.EPI_GEGLU, block_n=256, ln=(stats, cp, dp, 1e-5))
+    torch.cuda.synchronize()
+    refg = O.geglu(O.layer_norm(tf, gamma.float(), beta.float(), 1e-5), w2.float(), b2.float())
+    assert_close("LN folded into GEGLU GEMM", g, refg, rel_rms=4e-3)
