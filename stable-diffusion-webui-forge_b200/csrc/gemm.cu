@@ -391,11 +391,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
           const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
           const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
-          if (p.row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // statistics of the values as stored (rounded)
-            const float2 f0 = unpack2<BF16>(o0), f1 = unpack2<BF16>(o1), f2 = unpack2<BF16>(o2), f3 = unpack2<BF16>(o3);
-            st_sum += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-            st_sq += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) +
-                     ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+          if (p.row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              st_sum += x[g * 8 + i];
+              st_sq = fmaf(x[g * 8 + i], x[g * 8 + i], st_sq);
+            }
           }
           const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
