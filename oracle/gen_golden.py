@@ -171,10 +171,31 @@ def gen_vae(name: str = "tiny", hw: int = 16):
     print("vae", name, "out std", out.std().item())
 
 
+def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128):
+    """Reference Flux transformer (backend/nn/flux.py) on CPU fp32, distilled-guidance input included."""
+    from backend.nn.flux import IntegratedFluxTransformer2DModel
+    from oracle import flux as OF
+    cfg = OF.CONFIGS[name]
+    sd = OF.random_state_dict(cfg, seed=5)
+    m = IntegratedFluxTransformer2DModel(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, cfg["in_channels"], hw, hw, generator=g)
+    ctx = torch.randn(2, txt_len, cfg["context_in_dim"], generator=g)
+    y = torch.randn(2, cfg["vec_in_dim"], generator=g)
+    t = torch.tensor([0.93, 0.12])
+    guidance = torch.tensor([3.5, 3.5])
+    with torch.no_grad():
+        out = m(x, t, ctx, y, guidance)
+    torch.save(dict(config=name, weight_seed=5, weight_checksum=sd_checksum(sd), x=x, t=t, context=ctx, y=y,
+                    guidance=guidance, out=out), os.path.join(GOLD, "flux_tiny.pt"))
+    print("flux", name, "out std", out.std().item())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "sched", "vae"]
+    which = sys.argv[1:] or ["unet", "traj", "sched", "vae", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -185,3 +206,5 @@ if __name__ == "__main__":
         gen_schedules()
     if "vae" in which:
         gen_vae("tiny")
+    if "flux" in which:
+        gen_flux()

@@ -152,3 +152,27 @@ def test_structure_reproduces_reference_parameter_counts():
         st = OU.structure(cfg)
         n_res = sum(1 for blk in st["input"] + [st["middle"]] + st["output"] for l in blk if l[0] == "res")
         assert sum(1 for k in keys if k.endswith("emb_layers.1.weight")) == n_res
+
+
+def test_flux_oracle_matches_reference_golden():
+    """oracle/flux.py against tests/golden/flux_tiny.pt (imported reference IntegratedFluxTransformer2DModel, CPU fp32)."""
+    from oracle import flux as OF
+    g = _gold("flux_tiny.pt")
+    cfg = OF.CONFIGS[g["config"]]
+    sd = OF.random_state_dict(cfg, seed=g["weight_seed"])
+    assert abs(_sd_checksum(sd) - g["weight_checksum"]) <= 1e-6 * g["weight_checksum"]
+    with torch.no_grad():
+        out = OF.flux_forward(sd, cfg, g["x"], g["t"], g["context"], g["y"], g["guidance"])
+    assert_close("oracle flux tiny vs reference golden", out, g["out"], max_abs=5e-5)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_flux_dev_parameter_count():
+    """The restated Flux.1-dev config reproduces the canonical 11.90 B parameters."""
+    ref_import.load()
+    from backend.nn.flux import IntegratedFluxTransformer2DModel
+    from oracle import flux as OF
+    with torch.device("meta"):
+        m = IntegratedFluxTransformer2DModel(**OF.FLUX_DEV)
+    n = sum(p.numel() for p in m.parameters())
+    assert 11.89e9 < n < 11.91e9, n
