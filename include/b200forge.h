@@ -31,7 +31,8 @@ enum {
   B200_EPI_NONE = 0,
   B200_EPI_SILU = 1,  /* y = silu(acc + bias) */
   B200_EPI_GEGLU = 2, /* weight rows pre-interleaved per BN tile: y[:, j] = (x_j + b) * gelu_erf(gate_j + b) */
-  B200_EPI_GELU = 3   /* y = gelu_erf(acc + bias) */
+  B200_EPI_GELU = 3,  /* y = gelu_erf(acc + bias) */
+  B200_EPI_GELU_TANH = 4 /* y = gelu_tanh(acc + bias)  (nn.GELU(approximate="tanh"), backend/nn/flux.py:193,202,280) */
 };
 
 int b200_version(void);
@@ -72,6 +73,17 @@ typedef struct {
   /* when set, the epilogue accumulates (sum, sum of squares) of every output row into row_stats_out [M,2]
    * (zeroed by the caller) — the ln_stats of the next GEMM, so no separate LayerNorm pass touches HBM. */
   float* row_stats_out;
+  /* Two row segments with their own weights — Flux DoubleStreamBlock (backend/nn/flux.py:206-264) keeps txt and img
+   * tokens in one joint [B, L_txt + L_img, C] activation: rows with (m % seg_period) < seg_split use B / bias / rowvec,
+   * the others B2 / bias2 / rowvec2 (same shapes and leading dimensions).  seg_period, seg_split multiples of 256.
+   * B2 = NULL: one weight set (all other fields of this block ignored). */
+  const void* B2;
+  const void* bias2;
+  const void* rowvec2;
+  int seg_period, seg_split;
+  int rowvec_mul; /* rowvec multiplies instead of adds: y = residual + rowvec * (acc + bias)  (modulation gate, flux.py:252-258,300) */
+  int act_col0;   /* the activation applies to output columns >= act_col0 (multiple of block_n); SingleStreamBlock.linear1
+                     = [qkv | mlp] with GELU on the mlp part only (flux.py:289-298) */
 } b200_gemm_desc;
 
 int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);
@@ -224,6 +236,35 @@ int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, fl
 /* VAE post-decode: clamp((x+1)/2, 0, 1) NHWC (dtype) -> fp32 NHWC [B,H,W,3]
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flux (DiT) path — backend/nn/flux.py.  Token activations are [rows, C]; a joint activation holds, for every
+ * sample, `seg_split` txt rows followed by img rows (`seg_period` rows per sample); segment 0 = txt, 1 = img.
+ */
+
+/* Modulated LayerNorm: y = (1 + scale_g[b]) * LayerNorm(x, no affine, eps) + shift_g[b]
+ * (flux.py:211-212,232-233,255,259 DoubleStreamBlock; :287 SingleStreamBlock; :319 LastLayer).
+ * shift/scale: row b of a [B, ld_mod] matrix (the Modulation output chunk).  shift1 = NULL: one parameter set. */
+int b200_adaln(const void* x, void* y, int rows, int C, float eps, const void* shift0, const void* scale0,
+               const void* shift1, const void* scale1, int ld_mod, int seg_period, int seg_split, int dtype,
+               b200_stream_t s);
+
+/* QKNorm + rotary embedding, in place on the q and k thirds of a fused QKV projection row [3, H, Dh] (row stride ld):
+ * t = rms_norm(x, eps) * scale, then rotation of adjacent pairs by (cos, sin)[row % seg_period]
+ * (flux.py:128-139 QKNorm; :15-18, :45-51 apply_rope).  cos_t / sin_t: fp32 [seg_period, Dh/2] (EmbedND, :75-89).
+ * Dh = 128 only (else B200_EUNSUPPORTED). */
+int b200_qk_norm_rope(void* qkv, int rows, int H, int Dh, int ld, const void* q_scale0, const void* k_scale0,
+                      const void* q_scale1, const void* k_scale1, const float* cos_t, const float* sin_t, int seg_period,
+                      int seg_split, float eps, int dtype, b200_stream_t s);
+
+/* 2x2 patchify: x NCHW [B, C, H, W] (fp32 if in_is_f32 else dtype) -> tokens [B*(H/2)*(W/2), ld], feature c*4 + ph*2 + pw
+ * (flux.py:398-399; even H, W only: the circular-pad branch returns B200_EUNSUPPORTED). */
+int b200_flux_patchify(const void* x, void* tokens, int B, int C, int H, int W, int ld, int in_is_f32, int dtype,
+                       b200_stream_t s);
+/* inverse (flux.py:412): tokens -> NCHW fp32 [B, C, H, W] if out_nchw_f32 else NHWC [B, H, W, C] in dtype
+ * (the layout b200_sampler_step reads). */
+int b200_flux_unpatchify(const void* tokens, void* out, int B, int C, int H, int W, int ld, int out_nchw_f32, int dtype,
+                         b200_stream_t s);
 
 #ifdef __cplusplus
 }

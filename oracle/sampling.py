@@ -243,3 +243,42 @@ def image_rng_noise(shape, seeds, device="cpu"):
         return torch.stack([torch.randn(shape, generator=g, device=device) for g in gens])
 
     return draw(), draw
+
+
+# --------------------------------------------------------------------------------------------- Flux (flow matching)
+# PredictionFlux (backend/modules/k_prediction.py:285-322) builds its sigma table with two helpers of the third-party
+# package `diffusers` (not vendored under /root/reference, not installed here; Forge pins diffusers==0.31.0 in
+# requirements_versions.txt): pipelines.flux.pipeline_flux.calculate_shift and
+# FlowMatchEulerDiscreteScheduler.time_shift.  Both are restated from the published algorithm — PARITY UNPINNED for the
+# table itself (no reference output to compare against in this container); everything downstream of the table
+# (simple_scheduler, the Euler update, `const` prediction) follows reference code that is present.
+def flux_calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                         max_shift: float = 1.15) -> float:
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b
+
+
+def flux_sigma_table(seq_len: int = 4096, pseudo_timestep_range: int = 10000, mu=None) -> torch.Tensor:
+    """k_prediction.py:292-301: sigmas = time_shift(mu, 1.0, arange(1, N+1)/N), time_shift = e^mu / (e^mu + (1/t - 1))."""
+    if mu is None:
+        mu = flux_calculate_shift(seq_len)
+    t = torch.arange(1, pseudo_timestep_range + 1, 1) / pseudo_timestep_range
+    return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** 1.0)
+
+
+def simple_scheduler(n: int, table: torch.Tensor) -> torch.Tensor:
+    """modules/sd_schedulers.py:81-87 (the default scheduler Forge selects for Flux)."""
+    ss = len(table) / n
+    sigs = [float(table[-(1 + int(x * ss))]) for x in range(n)]
+    return torch.FloatTensor(sigs + [0.0])
+
+
+def const_noise_scaling(sigma, noise, latent):
+    """k_prediction.py:94-96 for prediction_type 'const'."""
+    return sigma * noise + (1.0 - sigma) * latent
+
+
+def const_denoised(x, model_output, sigma):
+    """k_prediction.py:81-92 'const' branch: model_input - model_output * sigma (calculate_input is the identity, :74-76)."""
+    return x - model_output * sigma

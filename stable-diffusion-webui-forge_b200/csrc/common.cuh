@@ -287,5 +287,13 @@ __device__ __forceinline__ float silu_fast_f(float x) {
   return x * fmaf(0.5f, t, 0.5f);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), MUFU.TANH (rel. error ~2^-11)
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
 }  // namespace b200

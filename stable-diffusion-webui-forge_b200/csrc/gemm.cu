@@ -53,6 +53,13 @@ struct GemmKParams {
   const float* ln_d;
   float ln_inv_k, ln_eps;
   float* row_stats_out;   // [M, 2]: this GEMM accumulates (sum, sumsq) of its own output rows (caller zeroes it)
+  // two row segments with their own weights (Flux double-stream blocks: txt rows and img rows of one joint
+  // [B, L_txt + L_img, C] activation): rows with (m % seg_period) >= seg_split use mapB2 / bias2 / rowvec2.
+  int seg_period, seg_split;
+  const void* bias2;
+  const void* rowvec2;
+  int rowvec_mul;  // rowvec multiplies (per-sample gate) instead of being added
+  int act_col0;    // the activation applies to output columns >= act_col0 only
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
@@ -80,6 +87,14 @@ __device__ __forceinline__ void add_u4(const uint4& r, float (&x)[8]) {
   f = unpack2<BF16>(r.w); x[6] += f.x; x[7] += f.y;
 }
 template <bool BF16>
+__device__ __forceinline__ void mul_u4(const uint4& r, float (&x)[8]) {
+  float2 f;
+  f = unpack2<BF16>(r.x); x[0] *= f.x; x[1] *= f.y;
+  f = unpack2<BF16>(r.y); x[2] *= f.x; x[3] *= f.y;
+  f = unpack2<BF16>(r.z); x[4] *= f.x; x[5] *= f.y;
+  f = unpack2<BF16>(r.w); x[6] *= f.x; x[7] *= f.y;
+}
+template <bool BF16>
 __device__ __forceinline__ void add_smem8(uint32_t addr, float (&x)[8]) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -97,12 +112,18 @@ __device__ __forceinline__ void ln_apply8(uint32_t c_smem, uint32_t d_smem, int 
   for (int i = 0; i < 8; ++i) x[i] = fmaf(rstd, fmaf(-mean, cv[i], x[i]), dv[i]);
 }
 
-template <bool BF16, int CG>
+// FEAT selects the epilogue build so that each caller only carries the state it uses (the epilogue sits at the
+// 168-register cap):  bit 0 (LNS) LayerNorm folding + output row statistics (UNet transformer blocks),
+// bit 1 (EXT) the Flux-path features (row segments with two weight sets, multiplicative rowvec, partial activation,
+// tanh GELU).  Convolutions and plain linears run the FEAT = 0 build.
+template <bool BF16, int CG, int FEAT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
             const GemmKParams p) {
   // CG == 2: launched with cluster dims (2,1,1); rank 0 of each pair is the MMA leader.
+  constexpr bool LNS = (FEAT & 1) != 0;
+  constexpr bool EXT = (FEAT & 2) != 0;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair (or CTA) index
   const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -129,7 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapB);
-    tma_prefetch_desc(&mapC);
+    tma_prefetch_desc(&mapB2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -169,6 +190,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
       const int n_blk = tile / tiles_mu;
+      // a pair's 256 rows never straddle a segment boundary (host-checked), so the weight set is per tile
+      const CUtensorMap* mb = (EXT && p.seg_period && ((tile % tiles_mu) * (CG * 128)) % p.seg_period >= p.seg_split) ? &mapB2 : &mapB;
       int cn = 0, ch = 0, cw = 0;
       if (p.mode == 1) {
         const int tpi = p.tiles_w * p.tiles_h;
@@ -195,7 +218,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d(b_dst, &mapB, fb, kc * 64, n_blk * BN);
+          tma_load_2d(b_dst, mb, fb, kc * 64, n_blk * BN);
         } else {
           // both CTAs' loads complete on the leader's barrier; the leader arms it for the pair's bytes
           if (cta_rank == 0) mbar_expect_tx(fb, tx_bytes);
@@ -210,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (cc < p.split_chunk) tma_load_4d_cg2(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d_cg2(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d_cg2(b_dst, &mapB, fb, kc * 64, n_blk * BN + (int)cta_rank * (BN / 2));
+          tma_load_2d_cg2(b_dst, mb, fb, kc * 64, n_blk * BN + (int)cta_rank * (BN / 2));
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -255,7 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t bias_smem = stg_base + kStageBufs * kStageBufBytes;  // 256 halfs
     const uint32_t lnc_smem = bias_smem + 1024u;                        // 256 floats
     const uint32_t lnd_smem = lnc_smem + 1024u;                         // 256 floats
-    const bool ln = p.ln_stats != nullptr;
+    const bool ln = LNS && p.ln_stats != nullptr;
+    float* const row_stats_out = LNS ? p.row_stats_out : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
@@ -273,11 +297,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const bool row_ok = m < p.M;
       const int n0 = n_blk * BN;            // first accumulator column of this tile (weight row index)
       const int out_n0 = n_blk * ncols_out; // first output column
+      const bool seg1 = EXT && p.seg_period && ((tile % tiles_mu) * (CG * 128)) % p.seg_period >= p.seg_split;
+      const void* const bias_p = seg1 ? p.bias2 : p.bias;
+      const void* const rowvec_p = seg1 ? p.rowvec2 : p.rowvec;
+      const bool act_on = !EXT || n0 >= p.act_col0;
       float bias_m = 0.f;
-      if (p.bias && p.bias_along_m && row_ok) bias_m = ld1<BF16>(p.bias, m);
-      const size_t rv_off = (p.rowvec && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
+      if (bias_p && p.bias_along_m && row_ok) bias_m = ld1<BF16>(bias_p, m);
+      const size_t rv_off = (rowvec_p && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
       // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
-      const bool col_bias = p.bias && !p.bias_along_m;
+      const bool col_bias = bias_p && !p.bias_along_m;
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (ln && row_ok) {
         const float s1 = p.ln_stats[2 * (size_t)m], s2 = p.ln_stats[2 * (size_t)m + 1];
@@ -299,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         if (col_bias && e0 < BN) {
           uint4 bv = make_uint4(0, 0, 0, 0);
-          if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.bias) + (size_t)(n0 + e0) * 2));
+          if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bias_p) + (size_t)(n0 + e0) * 2));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 2u), "r"(bv.x), "r"(bv.y),
                        "r"(bv.z), "r"(bv.w)
                        : "memory");
@@ -310,7 +338,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       for (int c = chalf * 32; c < ncols_out; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
         uint4 rv[4], rs[4];
-        const bool has_rv = p.rowvec && row_ok && !geglu;
+        const bool has_rv = rowvec_p && row_ok && !geglu;
         const bool has_rs = p.residual && row_ok;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -319,7 +347,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const int n = n0 + c + g * 8;
           const int no = out_n0 + c + g * 8;
           if (has_rv && n < p.N)
-            rv[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.rowvec) + (rv_off + (size_t)n) * 2));
+            rv[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(rowvec_p) + (rv_off + (size_t)n) * 2));
           if (has_rs && no < p.n_out)
             rs[g] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)m * p.ldr + no) * 2);
         }
@@ -358,17 +386,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
             if (ln) ln_apply8(lnc_smem, lnd_smem, c + g * 8, ln_mean, ln_rstd, xv);
             if (col_bias) add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
-            else if (p.bias) {
+            else if (bias_p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) xv[i] += bias_m;
             }
-            if (has_rv) add_u4<BF16>(rv[g], xv);
-            if (p.epilogue == B200_EPI_SILU) {
+            if (has_rv) {
+              if (EXT && p.rowvec_mul) mul_u4<BF16>(rv[g], xv);
+              else add_u4<BF16>(rv[g], xv);
+            }
+            if (act_on) {
+              if (p.epilogue == B200_EPI_SILU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xv[i] = silu_f(xv[i]);
-            } else if (p.epilogue == B200_EPI_GELU) {
+                for (int i = 0; i < 8; ++i) xv[i] = silu_f(xv[i]);
+              } else if (p.epilogue == B200_EPI_GELU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xv[i] = gelu_erf_f(xv[i]);
+                for (int i = 0; i < 8; ++i) xv[i] = gelu_erf_f(xv[i]);
+              } else if (EXT && p.epilogue == B200_EPI_GELU_TANH) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xv[i] = gelu_tanh_f(xv[i]);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
@@ -391,7 +427,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
           const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
           const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
-          if (p.row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm
+          if (row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               st_sum += x[g * 8 + i];
@@ -420,9 +456,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         }
       }
-      if (p.row_stats_out && row_ok) {
-        atomicAdd(p.row_stats_out + 2 * (size_t)m, st_sum);
-        atomicAdd(p.row_stats_out + 2 * (size_t)m + 1, st_sq);
+      if (row_stats_out && row_ok) {
+        atomicAdd(row_stats_out + 2 * (size_t)m, st_sum);
+        atomicAdd(row_stats_out + 2 * (size_t)m + 1, st_sq);
       }
       tc_fence_before();
       if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -459,9 +495,9 @@ static bool use_pair_kernel() {
   return v == 1;
 }
 
-template <bool BF16, int CG>
+template <bool BF16, int CG, int FEAT>
 static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
-                         const CUtensorMap& mapC, GemmKParams& p, cudaStream_t stream) {
+                         const CUtensorMap& mapB2, GemmKParams& p, cudaStream_t stream) {
   const int stage_bytes = kATileBytes + (p.BN / CG) * 128;
   const int staging = (int)(kStageBufs * kStageBufBytes) + 1024 + 2048;
   int S = (222 * 1024 - staging) / stage_bytes;
@@ -478,7 +514,7 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
   if (units > total) units = total;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BF16, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BF16, CG, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("gemm: smem attr: %s", cudaGetErrorString(e));
       return B200_ECUDA;
@@ -499,13 +535,13 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG>, mapA, mapA2, mapB, mapC, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG, FEAT>, mapA, mapA2, mapB, mapB2, p);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return B200_ECUDA;
     }
   } else {
-    gemm_kernel<BF16, CG><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, mapC, p);
+    gemm_kernel<BF16, CG, FEAT><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, mapB2, p);
   }
   B200_CHECK_LAUNCH("gemm");
   return B200_OK;
@@ -514,25 +550,29 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
 // The B tensor map's box height depends on the cluster mode, so the mode is decided before the maps are built.
 static int gemm_cg(const GemmKParams& p) { return (use_pair_kernel() && p.tiles_m >= 2 && p.BN % 32 == 0) ? 2 : 1; }
 
-static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB, GemmKParams& p,
-                       int dtype, int cg, cudaStream_t stream) {
-  // output map: [M, n_out] row-major, 32-column x 128-row store boxes, 64-byte swizzle
-  CUtensorMap mapC;
-  {
-    uint64_t dims[2] = {(uint64_t)p.n_out, (uint64_t)p.M};
-    uint64_t str[1] = {(uint64_t)p.ldc * 2};
-    uint32_t box[2] = {32, 128};
-    int rc = make_tmap(&mapC, dtype, p.C, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-  }
+template <int FEAT>
+static int launch_gemm_e(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
+                         const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
   if (cg == 2) {
     p.idesc = make_idesc_f16(256, p.BN, dtype == B200_BF16, false, false);
-    return dtype == B200_BF16 ? launch_gemm_t<true, 2>(mapA, mapA2, mapB, mapC, p, stream)
-                              : launch_gemm_t<false, 2>(mapA, mapA2, mapB, mapC, p, stream);
+    return dtype == B200_BF16 ? launch_gemm_t<true, 2, FEAT>(mapA, mapA2, mapB, mapB2, p, stream)
+                              : launch_gemm_t<false, 2, FEAT>(mapA, mapA2, mapB, mapB2, p, stream);
   }
   p.idesc = make_idesc_f16(128, p.BN, dtype == B200_BF16, false, false);
-  return dtype == B200_BF16 ? launch_gemm_t<true, 1>(mapA, mapA2, mapB, mapC, p, stream)
-                            : launch_gemm_t<false, 1>(mapA, mapA2, mapB, mapC, p, stream);
+  return dtype == B200_BF16 ? launch_gemm_t<true, 1, FEAT>(mapA, mapA2, mapB, mapB2, p, stream)
+                            : launch_gemm_t<false, 1, FEAT>(mapA, mapA2, mapB, mapB2, p, stream);
+}
+
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
+                       const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
+  const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH;
+  const bool lns = p.ln_stats != nullptr || p.row_stats_out != nullptr;
+  switch ((lns ? 1 : 0) | (ext ? 2 : 0)) {
+    case 0: return launch_gemm_e<0>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
+    case 1: return launch_gemm_e<1>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
+    case 2: return launch_gemm_e<2>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
+    default: return launch_gemm_e<3>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
+  }
 }
 
 }  // namespace b200
@@ -588,8 +628,24 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.ln_eps = d->ln_eps;
   p.row_stats_out = d->row_stats_out;
   B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2), "gemm: LayerNorm folding needs ln_c and ln_d (single A source)");
+  p.rowvec_mul = d->rowvec_mul;
+  p.act_col0 = d->act_col0;
+  B200_CHECK_ARG(d->act_col0 >= 0 && d->act_col0 % bn == 0, "gemm: act_col0 (%d) must be a multiple of block_n (%d)", d->act_col0, bn);
+  if (d->B2) {
+    // tiles of 256 rows (CTA pairs) must not straddle a segment boundary
+    B200_CHECK_ARG(d->seg_period > 0 && d->seg_split > 0 && d->seg_split < d->seg_period && d->seg_period % 256 == 0 &&
+                       d->seg_split % 256 == 0 && d->M % d->seg_period == 0,
+                   "gemm: row segments (period %d, split %d) must be multiples of 256 rows", d->seg_period, d->seg_split);
+    B200_CHECK_ARG(!d->ln_stats && !d->bias_along_m, "gemm: row segments exclude LayerNorm folding and bias_along_m");
+    p.seg_period = d->seg_period;
+    p.seg_split = d->seg_split;
+    p.bias2 = d->bias2;
+    p.rowvec2 = d->rowvec2;
+    B200_CHECK_ARG((d->bias != nullptr) == (d->bias2 != nullptr) && (d->rowvec != nullptr) == (d->rowvec2 != nullptr),
+                   "gemm: both row segments need the same set of epilogue operands");
+  }
 
-  CUtensorMap mA, mA2, mB;
+  CUtensorMap mA, mA2, mB, mB2;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)d->M};
     uint64_t str[1] = {(uint64_t)d->lda * 2};
@@ -613,8 +669,14 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
     uint32_t box[2] = {64, (uint32_t)(bn / cg)};
     int rc = make_tmap(&mB, d->dtype, B, 2, dims, str, box);
     if (rc) return rc;
+    if (d->B2) {
+      rc = make_tmap(&mB2, d->dtype, d->B2, 2, dims, str, box);
+      if (rc) return rc;
+    } else {
+      mB2 = mB;
+    }
   }
-  return launch_gemm(mA, mA2, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
+  return launch_gemm(mA, mA2, mB, mB2, p, d->dtype, cg, static_cast<cudaStream_t>(s));
 }
 
 extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y,
@@ -692,5 +754,5 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
     rc = make_tmap(&mB, d->dtype, w_packed, 2, dims, str, box);
     if (rc) return rc;
   }
-  return launch_gemm(mA, mA2, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
+  return launch_gemm(mA, mA2, mB, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
 }

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb200forge.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 B200_F16, B200_BF16 = 0, 1
-EPI_NONE, EPI_SILU, EPI_GEGLU, EPI_GELU = 0, 1, 2, 3
+EPI_NONE, EPI_SILU, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH = 0, 1, 2, 3, 4
 STEP_EULER, STEP_DPMPP_2M = 0, 1
 E_UNSUPPORTED = -2
 
@@ -38,6 +38,8 @@ class GemmDesc(C.Structure):
         ("A2", C.c_void_p), ("lda2", C.c_int), ("K1", C.c_int),
         ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_d", C.c_void_p), ("ln_eps", C.c_float),
         ("row_stats_out", C.c_void_p),
+        ("B2", C.c_void_p), ("bias2", C.c_void_p), ("rowvec2", C.c_void_p),
+        ("seg_period", C.c_int), ("seg_split", C.c_int), ("rowvec_mul", C.c_int), ("act_col0", C.c_int),
     ]
 
 
@@ -105,6 +107,10 @@ SIGNATURES = {
     "b200_vae_postprocess": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "b200_sampler_update": (_i, [_vp, _vp, _vp, _vp, C.POINTER(StepDesc), _vp]),
     "b200_eps_to_denoised": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_adaln": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200_qk_norm_rope": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "b200_flux_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_flux_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _l
-from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER)  # noqa: F401
+from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER)  # noqa: F401
 
 LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
 PROFILE = None  # set to a list to record (family, algorithmic flops, algorithmic bytes, start_evt, end_evt) per call
@@ -69,13 +69,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 1,
          epilogue: int = EPI_NONE, a2: Optional[torch.Tensor] = None, bias_along_m: bool = False,
          out: Optional[torch.Tensor] = None, block_n: int = 0, ln: Optional[tuple] = None,
-         row_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         row_stats_out: Optional[torch.Tensor] = None, rowvec_mul: bool = False, act_col0: int = 0,
+         seg: Optional[tuple] = None) -> torch.Tensor:
     """out[M, N] = epi(cat(a, a2) @ w.T + bias + rowvec[row // rows_per_vec]) + residual.
 
     a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
     GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
     ln = (stats [M,2] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
     see `fold_layernorm`).  row_stats_out [M,2] fp32 (zeroed): receives (sum, sumsq) of the output rows.
+    rowvec_mul: out = residual + rowvec * (acc + bias) (modulation gate).  act_col0: the activation applies to output
+    columns >= act_col0.  seg = (period, split, w2, bias2, rowvec2): rows with (m % period) >= split use the second
+    weight set (Flux double-stream blocks on the joint [txt | img] activation).
     """
     _rowmajor2d(a, "a")
     _rowmajor2d(w, "w")
@@ -115,6 +119,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if row_stats_out is not None:
         assert row_stats_out.dtype == torch.float32 and row_stats_out.shape == (M, 2) and row_stats_out.is_contiguous()
         d.row_stats_out = row_stats_out.data_ptr()
+    d.rowvec_mul = 1 if rowvec_mul else 0
+    d.act_col0 = act_col0
+    if seg is not None:
+        period, split, w2, bias2, rowvec2 = seg
+        _rowmajor2d(w2, "w2")
+        assert w2.shape == w.shape and w2.stride(0) == w.stride(0)
+        assert rowvec2 is None or rowvec2.stride(0) == rowvec.stride(0)
+        d.B2, d.bias2, d.rowvec2 = w2.data_ptr(), _p(bias2), _p(rowvec2)
+        d.seg_period, d.seg_split = period, split
     with _prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
         _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
@@ -389,6 +402,80 @@ def unet_input_im2col(x: torch.Tensor, sigma: torch.Tensor, dtype: torch.dtype, 
         out = torch.empty((reps * b * h * w, ldo), dtype=dtype, device=x.device)
     _l.check(_l.load().b200_unet_input_im2col(x.data_ptr(), sigma.data_ptr(), out.data_ptr(), b, c, h, w, ldo, reps,
                                               _dt(out), _stream()))
+    _count()
+    return out
+
+
+def adaln(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, *, eps: float = 1e-6,
+          shift1: Optional[torch.Tensor] = None, scale1: Optional[torch.Tensor] = None, seg_period: int = 0,
+          seg_split: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(1 + scale[b]) * LayerNorm(x) + shift[b] on [rows, C]; shift/scale are [B, C] views (row stride free, shared)
+    of the Modulation output; rows of sample b are [b*seg_period, (b+1)*seg_period), the first seg_split of them use
+    (shift, scale), the rest (shift1, scale1)."""
+    _rowmajor2d(x, "x")
+    assert x.is_contiguous()
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape
+    ld = shift.stride(0)
+    for t in (shift, scale, shift1, scale1):
+        assert t is None or (t.stride(-1) == 1 and t.stride(0) == ld and t.shape[1] == Cc)
+    if seg_period <= 0:
+        assert rows % shift.shape[0] == 0
+        seg_period = rows // shift.shape[0]
+        seg_split = seg_period
+    with _prof("adaln", 0.0, 4.0 * rows * Cc):
+        _l.check(_l.load().b200_adaln(x.data_ptr(), out.data_ptr(), rows, Cc, eps, shift.data_ptr(), scale.data_ptr(),
+                                      _p(shift1), _p(scale1), ld, seg_period, seg_split, _dt(x), _stream()))
+    _count()
+    return out
+
+
+def qk_norm_rope_(qkv: torch.Tensor, heads: int, q_scale: torch.Tensor, k_scale: torch.Tensor, cos: torch.Tensor,
+                  sin: torch.Tensor, *, q_scale1: Optional[torch.Tensor] = None, k_scale1: Optional[torch.Tensor] = None,
+                  seg_split: int = 0, eps: float = 1e-6) -> torch.Tensor:
+    """In place on the q and k thirds of qkv [rows, >= 3*heads*128]: RMSNorm * scale, then RoPE with the fp32 tables
+    cos/sin [seg_period, 64] indexed by row % seg_period."""
+    _rowmajor2d(qkv, "qkv")
+    assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+    assert cos.shape == sin.shape and cos.shape[1] == 64
+    rows = qkv.shape[0]
+    period = cos.shape[0]
+    assert rows % period == 0
+    with _prof("qk_norm_rope", 0.0, 4.0 * rows * 2 * heads * 128):
+        _l.check(_l.load().b200_qk_norm_rope(qkv.data_ptr(), rows, heads, 128, qkv.stride(0), q_scale.data_ptr(),
+                                             k_scale.data_ptr(), _p(q_scale1), _p(k_scale1), cos.data_ptr(), sin.data_ptr(),
+                                             period, seg_split if q_scale1 is not None else period, eps, _dt(qkv), _stream()))
+    _count()
+    return qkv
+
+
+def flux_patchify(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x NCHW [B, C, H, W] (fp32 or `dtype`) -> tokens [B*(H/2)*(W/2), 4C] in `dtype`."""
+    assert x.is_contiguous() and x.dim() == 4 and x.dtype in (torch.float32, dtype)
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((B * (H // 2) * (W // 2), 4 * Cc), dtype=dtype, device=x.device)
+    _rowmajor2d(out, "out")
+    with _prof("flux_patchify", 0.0, x.numel() * (x.element_size() + 2.0)):
+        _l.check(_l.load().b200_flux_patchify(x.data_ptr(), out.data_ptr(), B, Cc, H, W, out.stride(0),
+                                              1 if x.dtype == torch.float32 else 0, _dt(out), _stream()))
+    _count()
+    return out
+
+
+def flux_unpatchify(tokens: torch.Tensor, B: int, Cc: int, H: int, W: int, *, nchw_f32: bool,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tokens [B*(H/2)*(W/2), >= 4C] -> NCHW fp32 [B, C, H, W] (nchw_f32) or NHWC [B, H, W, C] in the tokens' dtype."""
+    _rowmajor2d(tokens, "tokens")
+    if out is None:
+        out = (torch.empty((B, Cc, H, W), dtype=torch.float32, device=tokens.device) if nchw_f32
+               else torch.empty((B, H, W, Cc), dtype=tokens.dtype, device=tokens.device))
+    assert out.is_contiguous()
+    with _prof("flux_unpatchify", 0.0, B * Cc * H * W * (2.0 + out.element_size())):
+        _l.check(_l.load().b200_flux_unpatchify(tokens.data_ptr(), out.data_ptr(), B, Cc, H, W, tokens.stride(0),
+                                                1 if nchw_f32 else 0, _dt(tokens), _stream()))
     _count()
     return out
 

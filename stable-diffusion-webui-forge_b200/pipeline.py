@@ -163,3 +163,95 @@ class Txt2ImgPipeline:
     def generate(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, **kw) -> torch.Tensor:
         latent = self.sample(cond, uncond, noise, **kw)
         return self.decode(latent) if self.vae is not None else latent
+
+
+class GraphedFlux:
+    """One CUDA graph of `FluxEngine.forward_nhwc` for fixed shapes, with static input/output buffers."""
+
+    def __init__(self, engine, batch: int, hh: int, ww: int, n_txt: int, use_graph: bool = True):
+        self.engine = engine
+        dev, dt, cfg = engine.device, engine.dtype, engine.cfg
+        self.x = torch.zeros((batch, cfg["in_channels"], hh, ww), dtype=torch.float32, device=dev)
+        self.t = torch.ones((batch,), dtype=torch.float32, device=dev)
+        self.guidance = torch.full((batch,), 3.5, dtype=torch.float32, device=dev)
+        self.context = torch.zeros((batch, n_txt, cfg["context_in_dim"]), dtype=dt, device=dev)
+        self.y = torch.zeros((batch, cfg["vec_in_dim"]), dtype=dt, device=dev)
+        self.out = torch.zeros((batch, hh, ww, cfg["in_channels"]), dtype=dt, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_forward = 0
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._eager()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            before = ops.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eager()
+            self.launches_per_forward = ops.LAUNCHES - before
+            self.graph = g
+
+    def _eager(self) -> torch.Tensor:
+        return self.engine.forward_nhwc(self.x, self.t, self.context, self.y,
+                                        self.guidance if self.engine.guidance_embed else None, out=self.out)
+
+    def __call__(self) -> torch.Tensor:
+        if self.graph is None:
+            before = ops.LAUNCHES
+            self._eager()
+            self.launches_per_forward = ops.LAUNCHES - before
+        else:
+            self.graph.replay()
+            ops.LAUNCHES += self.launches_per_forward
+        return self.out
+
+
+class FluxTxt2ImgPipeline:
+    """Flux txt2img denoise job: what the reference runs through KModel.apply_model with PredictionFlux
+    (backend/modules/k_model.py:25-46, k_prediction.py:285-322), CFG scale 1 (distilled guidance enters the model as an
+    embedding, backend/diffusion_engine/flux.py), Euler over the "Simple" schedule.  One fused launch per sampler step."""
+
+    def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], *, dtype: torch.dtype = torch.bfloat16, device="cuda",
+                 use_graph: bool = True):
+        from .flux_engine import FluxEngine
+        self.device, self.dtype = torch.device(device), dtype
+        self.model = FluxEngine(cfg, state_dict, dtype=dtype, device=device)
+        self.use_graph = use_graph
+        self._graphs: Dict[tuple, GraphedFlux] = {}
+
+    def _graph_for(self, batch, hh, ww, n_txt) -> GraphedFlux:
+        key = (batch, hh, ww, n_txt)
+        if key not in self._graphs:
+            self._graphs[key] = GraphedFlux(self.model, batch, hh, ww, n_txt, self.use_graph)
+        return self._graphs[key]
+
+    @torch.no_grad()
+    def sample(self, cond: dict, noise: torch.Tensor, *, steps: int = 20, guidance: float = 3.5,
+               sigmas: Optional[torch.Tensor] = None, callback: Optional[Callable] = None) -> torch.Tensor:
+        """cond = {"crossattn": [B, Lt, ctx] (T5), "vector": [B, vec] (pooled CLIP)}; noise [B, 16, h, w] N(0,1).
+        Returns the final latent [B, 16, h, w] fp32 on the device."""
+        dev = self.device
+        b, c, hh, ww = noise.shape
+        gf = self._graph_for(b, hh, ww, cond["crossattn"].shape[1])
+        if sigmas is None:
+            pred = sampling.FluxPrediction(seq_len=(hh // 2) * (ww // 2))
+            sigmas = sampling.get_sigmas_simple(pred.sigmas, steps)
+        sigmas = sigmas.float().cpu()
+        plan = sampling.plan_euler(sigmas)
+        gf.context.copy_(cond["crossattn"].to(device=dev, dtype=self.dtype, non_blocking=True))
+        gf.y.copy_(cond["vector"].to(device=dev, dtype=self.dtype, non_blocking=True))
+        gf.guidance.fill_(float(guidance))
+        x = gf.x
+        x.copy_(noise.to(device=dev, dtype=torch.float32, non_blocking=True))
+        x.mul_(float(sigmas[0]))  # 'const' noise_scaling with a zero latent (k_prediction.py:94-96)
+        sig_tab = sigmas[:-1].to(dev).view(-1, 1).expand(-1, b).contiguous()
+
+        def model_fn(i):
+            gf.t.copy_(sig_tab[i])  # PredictionFlux.timestep(sigma) = sigma (k_prediction.py:311-312)
+            return gf()
+
+        sampling.run_sampler(model_fn, x, plan, cfg_scale=1.0, has_uncond=False, callback=callback)
+        return x

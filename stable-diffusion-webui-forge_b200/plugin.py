@@ -144,6 +144,57 @@ def install_unet_wrapper(unet_patcher, engine: Optional[UNetEngine] = None) -> U
     return w
 
 
+class FluxWrapper:
+    """The same plug point (P3) for Flux: KModel.apply_model with PredictionFlux ('const': model input = x, timestep =
+    sigma, denoised = x - sigma * output; backend/modules/k_model.py:25-46, k_prediction.py:74-92,285-322) served by
+    the fused DiT forward.  `c` carries c_crossattn (T5 states), y (pooled CLIP) and guidance
+    (backend/diffusion_engine/flux.py:92)."""
+
+    def __init__(self, engine, predictor):
+        self.engine = engine
+        self.predictor = predictor
+        self.calls_fast = 0
+        self.calls_reference = 0
+
+    def __call__(self, apply_model_fn: Callable, args: dict):
+        x, sigma, c = args["input"], args["timestep"], args["c"]
+        eng = self.engine
+        ok = (fast_path_ok(c) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+              and getattr(self.predictor, "prediction_type", None) == "const" and c.get("c_concat") is None
+              and c.get("y") is not None and (x.shape[2] | x.shape[3]) % 2 == 0
+              and (c.get("guidance") is not None or not eng.guidance_embed))
+        if not ok:
+            self.calls_reference += 1
+            return apply_model_fn(x, sigma, **c)
+        self.calls_fast += 1
+        x = x.contiguous()
+        sigma = sigma.float().contiguous()
+        t = self.predictor.timestep(sigma).float().contiguous()
+        g = c.get("guidance")
+        out = eng.forward_nhwc(x, t, c["c_crossattn"].to(eng.dtype).contiguous(), c["y"].to(eng.dtype).contiguous(),
+                               None if g is None else g.to(x.device).float().contiguous())
+        return ops.eps_to_denoised(x, out, sigma, prediction=0)  # x - sigma * v
+
+
+def install_flux_wrapper(unet_patcher, engine=None) -> FluxWrapper:
+    """Attach the fused Flux forward to a Forge `UnetPatcher` whose model is a KModel around
+    IntegratedFluxTransformer2DModel (backend/diffusion_engine/flux.py)."""
+    from .flux_engine import FluxEngine
+    kmodel = unet_patcher.model
+    dm = kmodel.diffusion_model
+    if engine is None:
+        cfg = dict(dm.config) if hasattr(dm, "config") else None
+        if cfg is None:
+            raise ValueError("pass engine=FluxEngine(cfg, state_dict) — the module carries no config")
+        keys = ("in_channels", "vec_in_dim", "context_in_dim", "hidden_size", "mlp_ratio", "num_heads", "depth",
+                "depth_single_blocks", "axes_dim", "theta", "qkv_bias", "guidance_embed")
+        engine = FluxEngine({k: cfg[k] for k in keys}, dm.state_dict(), dtype=kmodel.computation_dtype,
+                            device=unet_patcher.load_device)
+    w = FluxWrapper(engine, kmodel.predictor)
+    unet_patcher.set_model_unet_function_wrapper(w)
+    return w
+
+
 # ------------------------------------------------------------------------------------------------- P4 samplers
 def install_samplers(modules: Optional[dict] = None) -> None:
     """Replace k_diffusion.sampling.sample_euler / sample_euler_ancestral / sample_dpmpp_2m: the sampler table

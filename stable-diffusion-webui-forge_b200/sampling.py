@@ -57,6 +57,45 @@ class Prediction:
         return noise if latent_image is None else noise + latent_image
 
 
+class FluxPrediction:
+    """PredictionFlux (backend/modules/k_prediction.py:285-322): prediction type 'const' (model input = x, denoised =
+    x - sigma * output, timestep = sigma) over a 10000-entry sigma table shifted by mu.  mu and the shift come from the
+    third-party `diffusers` helpers the reference imports (calculate_shift, FlowMatchEulerDiscreteScheduler.time_shift),
+    restated here from their published form."""
+
+    def __init__(self, seq_len: int = 4096, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                 max_shift: float = 1.15, pseudo_timestep_range: int = 10000, mu: Optional[float] = None):
+        if mu is None:
+            m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+            mu = seq_len * m + (base_shift - m * base_seq_len)
+        self.mu = mu
+        t = torch.arange(1, pseudo_timestep_range + 1, 1) / pseudo_timestep_range
+        self.sigmas = math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** 1.0)
+
+    @property
+    def sigma_min(self) -> float:
+        return float(self.sigmas[0])
+
+    @property
+    def sigma_max(self) -> float:
+        return float(self.sigmas[-1])
+
+    def timestep(self, sigma: torch.Tensor) -> torch.Tensor:
+        return sigma
+
+    def noise_scaling(self, sigma, noise, latent_image=None, max_denoise: bool = False):
+        out = sigma * noise
+        if latent_image is not None:
+            out = out + (1.0 - sigma) * latent_image
+        return out
+
+
+def get_sigmas_simple(table: torch.Tensor, n: int) -> torch.Tensor:
+    """"Simple" scheduler (modules/sd_schedulers.py:81-87), Forge's default for Flux."""
+    ss = len(table) / n
+    return torch.tensor([float(table[-(1 + int(x * ss))]) for x in range(n)] + [0.0], dtype=torch.float32)
+
+
 def get_sigmas_uniform(pred: Prediction, n: int) -> torch.Tensor:
     """ForgeScheduleLinker.get_sigmas (k_diffusion/external.py:62-67): 'Automatic' for Euler / Euler a."""
     t = torch.linspace(len(pred.sigmas) - 1, 0, n)

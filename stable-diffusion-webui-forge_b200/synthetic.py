@@ -142,3 +142,50 @@ def random_vae_decoder_state_dict(cfg: dict, device="cuda", dtype=torch.bfloat16
     g.norm("decoder.norm_out", block_in)
     g.conv("decoder.conv_out", block_in, cfg["out_channels"], 3)
     return g.sd
+
+
+FLUX_DEV = dict(in_channels=16, vec_in_dim=768, context_in_dim=4096, hidden_size=3072, mlp_ratio=4.0, num_heads=24,
+                depth=19, depth_single_blocks=38, axes_dim=[16, 56, 56], theta=10000, qkv_bias=True, guidance_embed=True)
+
+
+def random_flux_state_dict(cfg: dict, device="cuda", dtype=torch.bfloat16, seed: int = 2) -> Dict[str, torch.Tensor]:
+    """Random Flux transformer weights with the reference's parameter names (backend/nn/flux.py:326-353), generated on
+    the device (Flux.1-dev: 11.9 B parameters = 23.8 GB in bf16).  Modulation weights are scaled down so (1 + scale)
+    stays near 1 and the gates near 0.1-0.3: the residual stream keeps O(1) magnitude through 57 blocks."""
+    g = _Gen(torch.device(device), dtype, seed)
+    hs, H = cfg["hidden_size"], cfg["num_heads"]
+    D = hs // H
+    mlp = int(hs * cfg["mlp_ratio"])
+
+    def lin(p, cin, cout, bias=True, wscale=1.0, bmean=0.0):
+        g.sd[p + ".weight"] = g._randn(cout, cin, scale=wscale * cin ** -0.5)
+        if bias:
+            g.sd[p + ".bias"] = (bmean + g._randn(cout, scale=0.05).float()).to(dtype)
+
+    def qknorm(p):
+        g.sd[p + ".query_norm.scale"] = (1.0 + g._randn(D, scale=0.1).float()).to(dtype)
+        g.sd[p + ".key_norm.scale"] = (1.0 + g._randn(D, scale=0.1).float()).to(dtype)
+
+    lin("img_in", cfg["in_channels"] * 4, hs)
+    for name, cin in [("time_in", 256), ("vector_in", cfg["vec_in_dim"])] + ([("guidance_in", 256)] if cfg["guidance_embed"] else []):
+        lin(name + ".in_layer", cin, hs)
+        lin(name + ".out_layer", hs, hs)
+    lin("txt_in", cfg["context_in_dim"], hs)
+    for i in range(cfg["depth"]):
+        p = f"double_blocks.{i}"
+        for s in ("img", "txt"):
+            lin(f"{p}.{s}_mod.lin", hs, 6 * hs, wscale=0.3, bmean=0.1)
+            lin(f"{p}.{s}_attn.qkv", hs, 3 * hs, bias=cfg["qkv_bias"])
+            qknorm(f"{p}.{s}_attn.norm")
+            lin(f"{p}.{s}_attn.proj", hs, hs)
+            lin(f"{p}.{s}_mlp.0", hs, mlp)
+            lin(f"{p}.{s}_mlp.2", mlp, hs)
+    for i in range(cfg["depth_single_blocks"]):
+        p = f"single_blocks.{i}"
+        lin(p + ".linear1", hs, 3 * hs + mlp)
+        lin(p + ".linear2", hs + mlp, hs)
+        qknorm(p + ".norm")
+        lin(p + ".modulation.lin", hs, 3 * hs, wscale=0.3, bmean=0.1)
+    lin("final_layer.linear", hs, 4 * cfg["in_channels"])
+    lin("final_layer.adaLN_modulation.1", hs, 2 * hs, wscale=0.3)
+    return g.sd

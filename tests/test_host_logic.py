@@ -187,3 +187,24 @@ def test_request_sharding_and_gather_world2_gloo():
     gathered = [r[1] for r in res if r[1] is not None][0]
     assert gathered == [1000.0 + i for i in range(8)]  # contiguous-by-seed, independent of the number of ranks
     assert sorted(sum((r[0] for r in res), [])) == list(range(1000, 1008))
+
+
+def test_flux_schedule_matches_oracle_and_known_values():
+    """Product FluxPrediction / Simple scheduler vs the oracle restatement, plus closed-form anchors: mu(4096) = 1.15,
+    mu(256) = 0.5, sigma table ends at exactly 1, time_shift(mu, t=0.5) = e^mu / (e^mu + 1)."""
+    import math
+
+    import torch
+
+    from b200forge import sampling as S
+    from oracle import sampling as OS
+    p = S.FluxPrediction()
+    assert abs(p.mu - 1.15) < 1e-12 and abs(S.FluxPrediction(seq_len=256).mu - 0.5) < 1e-12
+    assert abs(OS.flux_calculate_shift(1024) - (0.5 + (1.15 - 0.5) * (1024 - 256) / (4096 - 256))) < 1e-12
+    assert torch.equal(p.sigmas, OS.flux_sigma_table()) and float(p.sigmas[-1]) == 1.0
+    assert abs(float(p.sigmas[4999]) - math.exp(1.15) / (math.exp(1.15) + 1.0)) < 1e-6
+    for n in (4, 20, 28):
+        a, b = S.get_sigmas_simple(p.sigmas, n), OS.simple_scheduler(n, OS.flux_sigma_table())
+        assert torch.equal(a, b) and float(a[0]) == 1.0 and float(a[-1]) == 0.0 and bool((a[:-1] > a[1:]).all())
+    noise = torch.randn(2, 16, 4, 4)
+    assert torch.equal(p.noise_scaling(1.0, noise), OS.const_noise_scaling(1.0, noise, torch.zeros_like(noise)))
