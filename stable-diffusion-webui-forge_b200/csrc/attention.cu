@@ -281,6 +281,7 @@ static int launch_attn(const CUtensorMap& mQ, const CUtensorMap& mK, const CUten
 
 namespace b200 {
 int attention64_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
+int attention128_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
 }
 using namespace b200;
 
@@ -298,12 +299,13 @@ extern "C" int b200_attention(const void* q, const void* k, const void* v, void*
                      d->v_stride_b % 8 == 0 && d->o_stride_b % 8 == 0,
                  "attention: strides must be multiples of 8 elements");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output not 16-byte aligned");
+  static int use_old = -1;
+  if (use_old < 0) {
+    const char* e = getenv("B200_ATTN_V1");
+    use_old = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (d->Dh == 128 && !use_old && d->Lk > 128) return attention128_dispatch(q, k, v, o, d, static_cast<cudaStream_t>(s));
   if (d->Dh == 64) {
-    static int use_old = -1;
-    if (use_old < 0) {
-      const char* e = getenv("B200_ATTN_V1");
-      use_old = (e && e[0] == '1') ? 1 : 0;
-    }
     // a single key block (cross-attention, Lk = 77) is latency- not throughput-bound: the one-tile kernel below keeps
     // two CTAs resident per SM and measured faster there (97 vs 125 us at B=16, H=10, Lq=4096)
     if (!use_old && d->Lk > 128) return attention64_dispatch(q, k, v, o, d, static_cast<cudaStream_t>(s));
