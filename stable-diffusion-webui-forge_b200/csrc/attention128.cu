@@ -42,12 +42,6 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 
 }  // namespace a128
 using namespace a128;
@@ -165,6 +159,7 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (elect_one()) umma_commit(ring_empty(0));
     __syncwarp();
     const int ksteps = BKV >> 4;
+#pragma unroll 1
     for (int j = 0; j < n_kv; ++j) {
       const int vidx = 2 * j + 1, kidx = 2 * j + 2;
       if (j + 1 < n_kv) {  // QK_{j+1} as soon as the softmax threads hold S_j in registers

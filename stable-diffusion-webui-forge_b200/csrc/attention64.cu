@@ -15,6 +15,7 @@
 // smem: Q 2x16 KB | K/V ring 4x16 KB | P 2x32 KB (reused as the output staging tile at the end).
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -50,7 +51,9 @@ static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
 static constexpr int kRingSlots = 4;
 static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
 
-template <bool BF16>
+// ELECT: the MMA-issue warp runs converged with one elected lane (descriptors in uniform registers) instead of a
+// lane-0 branch.  The lane-0 build is kept for A/B measurements (B200_ATTN64_ISSUE=lane0).
+template <bool BF16, bool ELECT>
 __global__ void __launch_bounds__(384, 1)
 attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const Attn64Params p) {
@@ -106,7 +109,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");  // 4 x (168 - 72) released = 8 x (216 - 168) taken by the softmax warps
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     mbar_expect_tx(q_full, 2u * kTile);
@@ -120,7 +123,78 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_expect_tx(ring_full(slot), kv_bytes);
       tma_load_3d(ring_smem + slot * kTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (ELECT && warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the warp stays converged and one
+    // elected lane issues, so every descriptor below lives in uniform registers (a lane-0 branch costs ~75 clk per
+    // tcgen05.mma in register-to-uniform moves; at N = 64 an MMA is only 32 clk of tensor time)
+    const uint64_t qdesc0 = make_smem_desc_sw128(q_smem, 0, 1024);
+    const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
+    const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kTile, 1024);  // MN-major V
+    const uint64_t pdesc0 = make_smem_desc_sw128(p_smem, 0, 1024);
+    const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+    auto wait_full = [&](int idx) {
+      mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
+      tc_fence_after();
+    };
+    auto issue_qk = [&](int idx, int t) {  // S_t = Q_t K^T
+      const uint64_t kd = kdesc0 + (uint64_t)((idx % kRingSlots) * (kTile >> 4));
+      const uint64_t qd = qdesc0 + (uint64_t)(t * (kTile >> 4));
+      const uint32_t s_tmem = tmem_base + (uint32_t)t * 128u;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(s_full(t));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    wait_full(0);
+    issue_qk(0, 0);
+    issue_qk(0, 1);
+    if (elect_one()) umma_commit(ring_empty(0));
+    __syncwarp();
+    const int ksteps = BKV >> 4;
+#pragma unroll 1
+    for (int j = 0; j < n_kv; ++j) {
+      const int vidx = 2 * j + 1, kidx = 2 * j + 2;
+      // QK_{j+1} as soon as the softmax threads have pulled S_j into registers (runs under their exps)
+      if (j + 1 < n_kv) {
+        wait_full(kidx);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(s_cons(t), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_qk(kidx, t);
+        }
+        if (elect_one()) umma_commit(ring_empty(kidx % kRingSlots));
+        __syncwarp();
+      }
+      wait_full(vidx);
+      const uint64_t vd = vdesc0 + (uint64_t)((vidx % kRingSlots) * (kTile >> 4));
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full(t), (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint64_t pd = pdesc0 + (uint64_t)(t * 2 * (kTile >> 4));
+        const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
+        const uint32_t acc0 = j != 0 ? 1u : 0u;
+        if (elect_one()) {
+          if (ksteps == 8) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_f16(o_tmem, pd + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2), vd + (uint64_t)(kk * (2048 >> 4)),
+                       idesc_pv, kk ? 1u : acc0);
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_f16(o_tmem, pd + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2), vd + (uint64_t)(kk * (2048 >> 4)),
+                       idesc_pv, kk ? 1u : acc0);
+          }
+          umma_commit(pv_done(t));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(ring_empty(vidx % kRingSlots));
+      __syncwarp();
+    }
+  } else if (!ELECT && warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     auto wait_full = [&](int idx) {
       mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
@@ -323,13 +397,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   }
 }
 
-template <bool BF16>
+template <bool BF16, bool ELECT>
 static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64Params& p,
                          cudaStream_t stream) {
   const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("attention64: smem attr: %s", cudaGetErrorString(e));
       return B200_ECUDA;
@@ -337,7 +411,7 @@ static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUt
     attr_done = true;
   }
   const int grid = p.q_tiles * p.H * p.B;
-  attn64_kernel<BF16><<<grid, 384, smem, stream>>>(mQ, mK, mV, p);
+  attn64_kernel<BF16, ELECT><<<grid, 384, smem, stream>>>(mQ, mK, mV, p);
   B200_CHECK_LAUNCH("attention64");
   return B200_OK;
 }
@@ -374,7 +448,14 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   if (rc) return rc;
   rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
   if (rc) return rc;
-  return bf ? launch_attn64<true>(mQ, mK, mV, p, st) : launch_attn64<false>(mQ, mK, mV, p, st);
+  static int mode = -1;  // B200_ATTN64_ISSUE = elect | lane0 forces one build (A/B measurements)
+  if (mode < 0) {
+    const char* e = getenv("B200_ATTN64_ISSUE");
+    mode = !e ? 0 : (e[0] == 'e' ? 1 : 2);
+  }
+  const bool elect = mode != 2;  // measured: 611 vs 601 TF/s at L = 4096, 498 vs 484 at L = 1024
+  if (elect) return bf ? launch_attn64<true, true>(mQ, mK, mV, p, st) : launch_attn64<false, true>(mQ, mK, mV, p, st);
+  return bf ? launch_attn64<true, false>(mQ, mK, mV, p, st) : launch_attn64<false, false>(mQ, mK, mV, p, st);
 }
 
 }  // namespace b200

@@ -134,6 +134,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp.  Issuing tcgen05 / TMA instructions from `if (elect_one())` inside warp-uniform control
+// flow (instead of an `if (lane == 0)` branch) lets the compiler keep descriptors in uniform registers: measured
+// ~75 clk -> a few clk per tcgen05.mma.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // mbarrier arrives once every tcgen05 op issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -238,11 +238,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (pair leader only)
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair leader only): the warp stays
+    // converged and one elected lane issues, so descriptors are computed in uniform registers
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    const uint64_t adesc0 = make_smem_desc_sw128(a_base, 0, 1024);
+    const uint64_t bdesc0 = make_smem_desc_sw128(b_base, 0, 1024);
+    const uint32_t idesc = p.idesc;
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -252,20 +256,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(a_base + (uint32_t)stage * kATileBytes, 0, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(b_base + (uint32_t)stage * b_tile_bytes, 0, 1024);
+        const uint64_t adesc = adesc0 + (uint64_t)(((uint32_t)stage * kATileBytes) >> 4);
+        const uint64_t bdesc = bdesc0 + (uint64_t)(((uint32_t)stage * b_tile_bytes) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // +32 bytes per 16-element k step inside the 128-byte swizzle atom (encoded >> 4)
-          if constexpr (CG == 2)
-            umma_f16_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
-          else
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // +32 bytes per 16-element k step inside the 128-byte swizzle atom (encoded >> 4)
+            if constexpr (CG == 2)
+              umma_f16_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          if (kc == nk - 1) {
+            if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+          }
         }
-        if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue

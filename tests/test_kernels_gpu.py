@@ -334,8 +334,9 @@ def test_gemm_layernorm_fold_and_row_stats():
     t = ops.gemm(x_in, w0, residual=res, row_stats_out=stats)
     torch.cuda.synchronize()
     tf = t.float()
-    assert_close("row stats sum", stats[:, 0], tf.sum(1), rel_rms=1e-5)
-    assert_close("row stats sumsq", stats[:, 1], (tf * tf).sum(1), rel_rms=1e-5)
+    # the statistics are accumulated from the fp32 values before they are rounded to fp16 for the store
+    assert_close("row stats sum", stats[:, 0], tf.sum(1), rel_rms=2e-4)
+    assert_close("row stats sumsq", stats[:, 1], (tf * tf).sum(1), rel_rms=2e-4)
     gamma = (_rand(C, seed=53) * 0.2 + 1)
     beta = _rand(C, seed=54) * 0.2
     w1 = _rand(N, C, scale=C ** -0.5, seed=55)
