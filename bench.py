@@ -188,6 +188,145 @@ def gpu_reference_unet_ms(batch: int, hw: int, iters: int = 3):
     return s.elapsed_time(e) / iters
 
 
+def run_flux(args):
+    """BASELINE.json configs[4]: Flux.1-dev (DiT) 1024x1024, 20 Euler steps over the Simple schedule, batch 4 per GPU, bf16,
+    distilled guidance 3.5 (CFG 1).  Same contract as the default line; the roofline object is the attention kernel's
+    (the config asks for the attention-kernel roofline)."""
+    K = args.steps if args.steps is not None else 3
+    W = args.warmup if args.warmup is not None else 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    from b200forge import lib, ops, synthetic
+    from b200forge.pipeline import FluxTxt2ImgPipeline
+    lib.check(lib.load().b200_device_ok())
+    peaks = load_peaks()
+    B = args.batch if args.batch != 8 else 4
+    S = args.sampler_steps if args.sampler_steps != 30 else 20
+    hw, Lt = args.size // 8, 256
+    cfg = synthetic.FLUX_DEV
+    sd = synthetic.random_flux_state_dict(cfg, device=dev)
+    pipe = FluxTxt2ImgPipeline(cfg, sd, device=dev)
+    del sd
+    torch.cuda.empty_cache()
+    gens = [torch.Generator().manual_seed(1000 + rank * B + i) for i in range(B)]
+    g0 = torch.Generator().manual_seed(7)
+    host = {"noise": torch.stack([torch.randn((16, hw, hw), generator=g) for g in gens]).pin_memory(),
+            "cond": {"crossattn": torch.randn(B, Lt, cfg["context_in_dim"], generator=g0).bfloat16().pin_memory(),
+                     "vector": torch.randn(B, cfg["vec_in_dim"], generator=g0).bfloat16().pin_memory()}}
+    devin = {"noise": host["noise"].to(dev), "cond": {k: v.to(dev) for k, v in host["cond"].items()}}
+    h2d = host["noise"].numel() * 4 + sum(v.numel() * 2 for v in host["cond"].values())
+    out_host = torch.empty((B, 16, hw, hw), dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * 4
+    gathered = [torch.empty((B, 16, hw, hw), dtype=torch.float32, device=dev) for _ in range(world)] \
+        if (dist is not None and rank == 0) else None
+
+    def job(inp):
+        return pipe.sample(inp["cond"], inp["noise"], steps=S, guidance=3.5)
+
+    def finish(lat):
+        if dist is not None:
+            dist.gather(lat, gathered, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) * 1e-3
+
+    def step_resident():
+        finish(job(devin))
+
+    def step_e2e():
+        lat = job(host)
+        finish(lat)
+        out_host.copy_(lat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(W):
+        step_resident()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    l0 = ops.LAUNCHES
+    sec = timed(step_resident, K)
+    launches = ops.LAUNCHES - l0
+    step_e2e()
+    sec_e2e = timed(step_e2e, K)
+    clk = clocks.stop()
+    value = B * world * K / sec
+    e2e_value = B * world * K / sec_e2e
+    fam, fwd_ms, roof = {}, None, None
+    if rank == 0:
+        gf = next(iter(pipe._graphs.values()))
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(5):
+            gf()
+        e_.record()
+        torch.cuda.synchronize()
+        fwd_ms = s_.elapsed_time(e_) / 5
+        ops.PROFILE = []
+        gf._eager()
+        torch.cuda.synchronize()
+        for name, fl, by, s2, e2 in ops.PROFILE:
+            d = fam.setdefault(name, {"launches": 0, "flops": 0.0, "bytes": 0.0, "ms": 0.0})
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+            d["ms"] += s2.elapsed_time(e2)
+        ops.PROFILE = None
+        for d in fam.values():
+            d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+            d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        at = fam.get("attention", {"launches": 0, "flops": 0.0, "ms": 1.0})
+        ach = at["flops"] / (at["ms"] * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"kernel": "b200::attn128_kernel (joint txt+img attention, 24 heads x 128, 4352 tokens, batch %d)" % B,
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)", "launches": at["launches"],
+                "avg_launch_ms": at["ms"] / max(1, at["launches"]), "flops_per_launch_avg": at["flops"] / max(1, at["launches"])}
+        gflop = synthetic.FLUX_GFLOP_PER_SAMPLE
+        line = {"metric": "images_per_sec_flux_dev_1024_euler_20steps_batch4", "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16, fp32 accumulate and sampler state", "data": "synthetic",
+                "config": {"workload": f"Flux.1-dev {args.size}x{args.size} txt2img (transformer only: latent out), Euler {S} steps, "
+                                       f"Simple schedule, distilled guidance 3.5, batch {B}/GPU, {Lt} T5 tokens; 1 bench step = 1 batch",
+                           "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of latents only)",
+                           "l2": "working set (23.8 GB weights) >> 126 MB L2; no explicit flush"},
+                "transformer_ms_per_step": fwd_ms,
+                "transformer_roofline_ms_per_step": B * gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
+                "flop_roofline_frac_whole_job": value / world * S * gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernel_families": fam, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,12 +336,17 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--sampler_steps", type=int, default=30)
+    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux"],
+                    help="sdxl = BASELINE.json's headline config (default); flux = configs[4]: Flux.1-dev 1024x1024, 20 steps, batch 4, bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
 
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload == "flux":
+        run_flux(args)
         return
 
     K = args.steps if args.steps is not None else 3

@@ -29,6 +29,7 @@ VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512
 # modules with torch.utils.flop_counter
 UNET_GFLOP_PER_SAMPLE = {"sdxl@128": 6761.2, "sd15@64": 803.3}
 VAE_GFLOP_PER_IMAGE = {"sdxl@1024": 10470.4}
+FLUX_GFLOP_PER_SAMPLE = 69466.6  # Flux.1-dev forward at 4096 img + 256 txt tokens
 
 
 class _Gen:
