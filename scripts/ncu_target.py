@@ -28,10 +28,10 @@ def conv(N, H, W, C, Co):
     torch.cuda.synchronize()
 
 
-def attn(B, H, Lq, Lk, Dh):
-    q = torch.randn(B, Lq, H * Dh, device=DEV, dtype=torch.float16)
-    k = torch.randn(B, Lk, H * Dh, device=DEV, dtype=torch.float16)
-    v = torch.randn(B, Lk, H * Dh, device=DEV, dtype=torch.float16)
+def attn(B, H, Lq, Lk, Dh, dtype=torch.float16):
+    q = torch.randn(B, Lq, H * Dh, device=DEV, dtype=dtype)
+    k = torch.randn(B, Lk, H * Dh, device=DEV, dtype=dtype)
+    v = torch.randn(B, Lk, H * Dh, device=DEV, dtype=dtype)
     out = torch.empty_like(q)
     for _ in range(2):
         ops.attention(q, k, v, H, out=out)
@@ -51,6 +51,7 @@ if which == "all":
     gemm(16384, 10240, 1280)
     conv(16, 128, 128, 320, 320)
     attn(16, 10, 4096, 4096, 64)
+    attn(4, 24, 4352, 4352, 128, torch.bfloat16)  # Flux.1-dev joint attention
     gn(16, 128, 128, 320)
 elif which == "gemm":
     gemm(16384, 10240, 1280)

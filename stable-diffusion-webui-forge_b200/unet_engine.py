@@ -8,9 +8,16 @@ time-embedding projections stacked into one matrix) and then runs the forward as
 libb200forge launches on NHWC activations:
 
   ResBlock            GN-stats -> GN-apply+SiLU(+concat) -> conv3x3(+bias +temb) -> GN -> conv3x3(+bias +skip)
-  SpatialTransformer  GN -> proj_in GEMM -> depth x [LN -> QKV GEMM -> attention -> out GEMM(+res)
-                                                      LN -> Q GEMM, KV GEMM(ctx) -> attention -> out GEMM(+res)
-                                                      LN -> GEGLU GEMM -> FF-out GEMM(+res)] -> proj_out GEMM(+res)
+  SpatialTransformer  GN -> proj_in GEMM -> depth x [QKV GEMM(LN1 folded) -> attention -> out GEMM(+res, row stats)
+                                                      Q GEMM(LN2 folded), K|V from the per-job cache -> attention
+                                                                                          -> out GEMM(+res, row stats)
+                                                      GEGLU GEMM(LN3 folded) -> FF-out GEMM(+res, row stats)]
+                      -> proj_out GEMM(+res)
+  LayerNorm           never a kernel: gamma is folded into the consumer GEMM's weights, mean / rstd are applied in its
+                      epilogue from row sums that the producer GEMM's epilogue accumulated (ops.fold_layernorm)
+  cross-attention K|V projected once per job from the constant context (fill_kv_cache), not once per step
+  head dims           40 / 80 (SD1.5) zero-padded to 64 / 128 in the packed projections; 160 through
+                      GEMM -> softmax_rows -> GEMM (ops.attention_generic)
   skip concat         never materialised: GN-apply, the 1x1 skip GEMM and the conv read both sources
 
 No torch operator runs on the data path; torch only provides buffers (`torch.empty`) and the stream.
