@@ -237,6 +237,17 @@ int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, fl
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
 
+/* VAE encode entry: pixels NHWC fp32 [pixels, 3] in [0, 1] -> [pixels, 8] in dtype, channels 0-2 = 2x - 1, 3-7 = 0
+ * (backend/patcher/vae.py:177: `(2. * pixel_samples - 1.).to(vae_dtype)`; padded to 8 channels for the conv_in im2col). */
+int b200_vae_preprocess(const float* x, void* out, size_t pixels, int dtype, b200_stream_t s);
+
+/* DiagonalGaussianDistribution.sample() / .mode() (backend/nn/vae.py:16-32) on channels-last moments [N, H*W, ld]
+ * (mean = channels [0, C), logvar = [C, 2C)):  out NCHW fp32 [N, C, H*W] = (mean + exp(0.5*clamp(logvar,-30,20))*noise)*scale;
+ * noise (fp32, NCHW like out) may be NULL -> the mode.  scale = 1 for VAE.encode, the latent scaling factor for
+ * process_in (backend/nn/vae.py:312-313). */
+int b200_vae_posterior(const void* moments, const float* noise, float* out, int N, int C, int HW, int ld, float scale,
+                       int dtype, b200_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * Flux (DiT) path — backend/nn/flux.py.  Token activations are [rows, C]; a joint activation holds, for every
  * sample, `seg_split` txt rows followed by img rows (`seg_period` rows per sample); segment 0 = txt, 1 = img.

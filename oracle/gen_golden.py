@@ -171,6 +171,32 @@ def gen_vae(name: str = "tiny", hw: int = 16):
     print("vae", name, "out std", out.std().item())
 
 
+def gen_vae_encode(name: str = "tiny", hw: int = 64):
+    """Reference IntegratedAutoencoderKL.encode (backend/nn/vae.py:293-303): moments via a `regulation` hook, and the
+    default .sample() with the global CPU generator seeded (the reference draws torch.randn(mean.shape) there)."""
+    from backend.nn.vae import IntegratedAutoencoderKL
+    from oracle import vae as OV
+    cfg = CF.VAE_CONFIGS[name]
+    sd = OV.random_encoder_state_dict(cfg, seed=8)
+    m = IntegratedAutoencoderKL(**{k: v for k, v in cfg.items()}).eval()
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys, missing
+    assert all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing.missing_keys), missing.missing_keys
+    g = torch.Generator().manual_seed(9)
+    pixels = torch.rand(2, hw, hw, 3, generator=g)                       # NHWC in [0, 1], what VAE.encode receives
+    x = 2.0 * pixels.movedim(-1, 1) - 1.0                                # patcher/vae.py:177
+    with torch.no_grad():
+        mean, logvar = m.encode(x, regulation=lambda p: (p.mean, p.logvar))
+        torch.manual_seed(1234)
+        sample = m.encode(x)
+        torch.manual_seed(1234)
+        noise = torch.randn(mean.shape)
+    latent = m.process_in(sample)
+    torch.save(dict(config=name, weight_seed=8, weight_checksum=sd_checksum(sd), pixels=pixels, mean=mean, logvar=logvar,
+                    noise=noise, sample=sample, latent=latent), os.path.join(GOLD, f"vae_enc_{name}.pt"))
+    print("vae encode", name, "mean std", mean.std().item(), "logvar mean", logvar.mean().item())
+
+
 def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: str = "flux_tiny.pt"):
     """Reference Flux transformer (backend/nn/flux.py) on CPU fp32, distilled-guidance input included."""
     from backend.nn.flux import IntegratedFluxTransformer2DModel
@@ -195,7 +221,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "sched", "vae", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "sched", "vae", "vae_enc", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -206,6 +232,8 @@ if __name__ == "__main__":
         gen_schedules()
     if "vae" in which:
         gen_vae("tiny")
+    if "vae_enc" in which:
+        gen_vae_encode("tiny")
     if "flux" in which:
         gen_flux()                                                  # 64 img + 128 txt tokens: per-stream GEMM launches
         gen_flux(hw=32, txt_len=256, fname="flux_tiny_seg.pt")      # 256 + 256 tokens: two-segment GEMM path

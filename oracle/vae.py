@@ -123,3 +123,83 @@ def random_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> SD:
     norm("decoder.norm_out", block_in)
     conv("decoder.conv_out", block_in, cfg["out_channels"], 3)
     return sd
+
+
+# ------------------------------------------------------------------------------------------------- encoder
+def encode_moments(sd: SD, cfg: dict, x: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward (backend/nn/vae.py:180-200) + quant_conv (:293-297): x NCHW in [-1, 1] -> moments [B, 2*zc, h, w].
+    Downsample = pad (0,1,0,1) then conv3x3 stride 2 pad 0 (:61-73)."""
+    ch, ch_mult, nres, nrb = decoder_structure(cfg)
+    h = _conv(sd, "encoder.conv_in", x)
+    for lvl in range(nres):
+        for j in range(nrb):
+            h = resnet_block(sd, f"encoder.down.{lvl}.block.{j}", h)
+        if lvl != nres - 1:
+            p = f"encoder.down.{lvl}.downsample.conv"
+            h = torch.nn.functional.conv2d(torch.nn.functional.pad(h, (0, 1, 0, 1)), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = resnet_block(sd, "encoder.mid.block_1", h)
+    h = attn_block(sd, "encoder.mid.attn_1", h)
+    h = resnet_block(sd, "encoder.mid.block_2", h)
+    h = _conv(sd, "encoder.conv_out", O.silu(_gn(sd, "encoder.norm_out", h)))
+    if "quant_conv.weight" in sd:
+        h = _conv(sd, "quant_conv", h, padding=0)
+    return h
+
+
+def posterior(moments: torch.Tensor, noise=None):
+    """DiagonalGaussianDistribution (vae.py:16-32): returns mean + std * noise (noise None -> mode)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean if noise is None else mean + torch.exp(0.5 * logvar) * noise
+
+
+def encode_first_stage(sd: SD, cfg: dict, pixels_nhwc: torch.Tensor, noise=None) -> torch.Tensor:
+    """VAE.encode_inner (backend/patcher/vae.py:162-184): pixels NHWC in [0, 1] -> 2x-1 -> encode -> sample, float;
+    then process_in (backend/nn/vae.py:312-313) as the diffusion engines apply it (diffusion_engine/sdxl.py:128-132)."""
+    x = 2.0 * pixels_nhwc.movedim(-1, 1) - 1.0
+    z = posterior(encode_moments(sd, cfg, x), noise).float()
+    return (z - cfg.get("shift_factor", 0.0)) * cfg["scaling_factor"]
+
+
+def random_encoder_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> SD:
+    """Synthetic encoder weights (+ quant_conv) with the reference's names (a separate generator so the decoder fixtures
+    keep their weights)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+
+    def conv(p, cin, cout, k):
+        sd[p + ".weight"] = (torch.randn(cout, cin, k, k, generator=g) * (cin * k * k) ** -0.5).to(dtype)
+        sd[p + ".bias"] = (torch.randn(cout, generator=g) * 0.05).to(dtype)
+
+    def norm(p, c):
+        sd[p + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g)).to(dtype)
+        sd[p + ".bias"] = (0.05 * torch.randn(c, generator=g)).to(dtype)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cin, cout, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cin, cout, 1)
+
+    ch, ch_mult, nres, nrb = decoder_structure(cfg)
+    zc = cfg["latent_channels"]
+    conv("encoder.conv_in", cfg["in_channels"], ch, 3)
+    block_in = ch
+    for lvl in range(nres):
+        block_out = ch * ch_mult[lvl]
+        for j in range(nrb):
+            res(f"encoder.down.{lvl}.block.{j}", block_in, block_out)
+            block_in = block_out
+        if lvl != nres - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", block_in, 2 * zc, 3)
+    conv("quant_conv", 2 * zc, 2 * zc, 1)
+    return sd

@@ -402,6 +402,41 @@ __global__ void vae_post_kernel(const void* __restrict__ x, float* __restrict__ 
   }
 }
 
+// VAE encode entry: pixels NHWC fp32 [pixels, 3] in [0, 1] -> [pixels, 8] in dtype, channels 0-2 = 2x - 1, 3-7 = 0
+// (backend/patcher/vae.py:177 `2. * pixel_samples - 1.` then the cast to the VAE dtype)
+template <bool BF16>
+__global__ void vae_pre_kernel(const float* __restrict__ x, void* __restrict__ out, size_t pixels) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (size_t)gridDim.x * blockDim.x) {
+    const float r = 2.f * x[i * 3] - 1.f, g = 2.f * x[i * 3 + 1] - 1.f, b = 2.f * x[i * 3 + 2] - 1.f;
+    uint4 o;
+    o.x = pack2<BF16>(r, g);
+    o.y = pack2<BF16>(b, 0.f);
+    o.z = 0u;
+    o.w = 0u;
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// DiagonalGaussianDistribution (backend/nn/vae.py:16-32) on the channels-last moments [N, H, W, ld] (mean = channels
+// [0, C), logvar = [C, 2C)): out NCHW fp32 = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale; noise = null -> mode()
+template <bool BF16>
+__global__ void vae_posterior_kernel(const void* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ out,
+                                     int N, int C, int HW, int ld, float scale) {
+  const size_t total = (size_t)N * C * HW;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(t % HW);
+    const int c = (int)((t / HW) % C);
+    const int n = (int)(t / ((size_t)HW * C));
+    const size_t m = ((size_t)n * HW + hw) * ld;
+    float v = ld1<BF16>(mom, m + c);
+    if (noise) {
+      const float lv = fminf(fmaxf(ld1<BF16>(mom, m + C + c), -30.f), 20.f);
+      v = fmaf(__expf(0.5f * lv), noise[t], v);
+    }
+    out[t] = v * scale;
+  }
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = (size_t)num_sms() * 16;
@@ -586,5 +621,21 @@ extern "C" int b200_vae_postprocess(const void* x, float* out, size_t pixels, in
   B200_CHECK_ARG(x && out && pixels > 0 && ldx >= 3, "vae_postprocess: bad arguments");
   DISPATCH_DTYPE(dtype, vae_post_kernel<BF><<<grid_for(pixels * 3, 256), 256, 0, (cudaStream_t)s>>>(x, out, pixels, ldx));
   B200_CHECK_LAUNCH("vae_postprocess");
+  return B200_OK;
+}
+
+extern "C" int b200_vae_preprocess(const float* x, void* out, size_t pixels, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && out && pixels > 0, "vae_preprocess: bad arguments");
+  DISPATCH_DTYPE(dtype, vae_pre_kernel<BF><<<grid_for(pixels, 256), 256, 0, (cudaStream_t)s>>>(x, out, pixels));
+  B200_CHECK_LAUNCH("vae_preprocess");
+  return B200_OK;
+}
+
+extern "C" int b200_vae_posterior(const void* moments, const float* noise, float* out, int N, int C, int HW, int ld,
+                                  float scale, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(moments && out && N > 0 && C > 0 && HW > 0 && ld >= 2 * C, "vae_posterior: bad arguments");
+  DISPATCH_DTYPE(dtype, vae_posterior_kernel<BF><<<grid_for((size_t)N * C * HW, 256), 256, 0, (cudaStream_t)s>>>(
+                            moments, noise, out, N, C, HW, ld, scale));
+  B200_CHECK_LAUNCH("vae_posterior");
   return B200_OK;
 }

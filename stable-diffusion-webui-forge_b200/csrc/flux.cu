@@ -40,33 +40,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------------------------------ modulated LayerNorm
 // y = (1 + scale[b]) * LayerNorm(x) + shift[b]   (no affine, flux.py:188,190,279,313 with 211-212,232-233,255,259,287)
-// one warp per row; the row lives in registers (NV vectors of 8 per lane), variance by the two-pass formula.
+// one 128-thread block per row; the row lives in registers (NV vectors of 8 per thread), variance by the two-pass
+// formula, block reductions through shared memory.
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();  // sh may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
 template <bool BF16, int NV>
-__global__ void __launch_bounds__(256) adaln_kernel(const void* __restrict__ x, void* __restrict__ y, int rows, int C,
+__global__ void __launch_bounds__(128) adaln_kernel(const void* __restrict__ x, void* __restrict__ y, int rows, int C,
                                                     float eps, const void* __restrict__ shift0,
                                                     const void* __restrict__ scale0, const void* __restrict__ shift1,
                                                     const void* __restrict__ scale1, int ld_mod, int seg_period,
                                                     int seg_split) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
   const int nvec = C >> 3;
   float v[NV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int cv = lane + 32 * i;
+    const int cv = threadIdx.x + 128 * i;
     if (cv < nvec) {
       ld8<BF16>(x, (size_t)row * C + (size_t)cv * 8, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
   }
-  const float mean = warp_sum(s) / (float)C;
+  const float mean = block_sum_128(s, sh) / (float)C;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    if (lane + 32 * i < nvec) {
+    if (threadIdx.x + 128 * i < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = v[i][j] - mean;
@@ -74,18 +83,18 @@ __global__ void __launch_bounds__(256) adaln_kernel(const void* __restrict__ x, 
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const float rstd = rsqrtf(block_sum_128(q, sh) / (float)C + eps);
   const int b = row / seg_period;
   const bool g1 = (row - b * seg_period) >= seg_split;
-  const void* sh = g1 ? shift1 : shift0;
-  const void* sc = g1 ? scale1 : scale0;
+  const void* shp = g1 ? shift1 : shift0;
+  const void* scp = g1 ? scale1 : scale0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int cv = lane + 32 * i;
+    const int cv = threadIdx.x + 128 * i;
     if (cv < nvec) {
       float a[8], c[8], o[8];
-      ld8<BF16>(sh, (size_t)b * ld_mod + (size_t)cv * 8, a);
-      ld8<BF16>(sc, (size_t)b * ld_mod + (size_t)cv * 8, c);
+      ld8<BF16>(shp, (size_t)b * ld_mod + (size_t)cv * 8, a);
+      ld8<BF16>(scp, (size_t)b * ld_mod + (size_t)cv * 8, c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(1.0f + c[j], (v[i][j] - mean) * rstd, a[j]);
       st8<BF16>(y, (size_t)row * C + (size_t)cv * 8, o);
@@ -239,16 +248,13 @@ extern "C" int b200_adaln(const void* x, void* y, int rows, int C, float eps, co
   B200_CHECK_ARG(dtype == B200_F16 || dtype == B200_BF16, "adaln: dtype");
   if (seg_period <= 0) { seg_period = rows; seg_split = rows; }
   if (!shift1) { shift1 = shift0; scale1 = scale0; }
-  const int nv = (C / 8 + 31) / 32;
-  const int grid = (rows + 7) / 8;
+  const int nv = (C / 8 + 127) / 128;
 #define ADALN_LAUNCH(NV) \
-  DISPATCH_BF(dtype, (adaln_kernel<BF, NV><<<grid, 256, 0, (cudaStream_t)s>>>(x, y, rows, C, eps, shift0, scale0, shift1, scale1, ld_mod, seg_period, seg_split)))
+  DISPATCH_BF(dtype, (adaln_kernel<BF, NV><<<rows, 128, 0, (cudaStream_t)s>>>(x, y, rows, C, eps, shift0, scale0, shift1, scale1, ld_mod, seg_period, seg_split)))
   if (nv <= 1) ADALN_LAUNCH(1);
   else if (nv <= 2) ADALN_LAUNCH(2);
-  else if (nv <= 4) ADALN_LAUNCH(4);
-  else if (nv <= 8) ADALN_LAUNCH(8);
-  else if (nv <= 12) ADALN_LAUNCH(12);
-  else ADALN_LAUNCH(16);
+  else if (nv <= 3) ADALN_LAUNCH(3);
+  else ADALN_LAUNCH(4);
 #undef ADALN_LAUNCH
   B200_CHECK_LAUNCH("adaln");
   return B200_OK;

@@ -512,6 +512,32 @@ def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def vae_preprocess(pixels: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pixels NHWC fp32 [B,H,W,3] in [0,1] -> NHWC [B,H,W,8] in dtype: channels 0-2 = 2x-1, the rest zero."""
+    assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[3] == 3
+    n, h, w, _ = pixels.shape
+    if out is None:
+        out = torch.empty((n, h, w, 8), dtype=dtype, device=pixels.device)
+    _l.check(_l.load().b200_vae_preprocess(pixels.data_ptr(), out.data_ptr(), n * h * w, _dt(out), _stream()))
+    _count()
+    return out
+
+
+def vae_posterior(moments: torch.Tensor, channels: int, noise: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """moments NHWC [B,h,w,ld>=2C] -> latent NCHW fp32 [B,C,h,w] = (mean + std*noise)*scale (noise None: the mode)."""
+    assert moments.dim() == 4 and moments.is_contiguous()
+    n, h, w, ld = moments.shape
+    if out is None:
+        out = torch.empty((n, channels, h, w), dtype=torch.float32, device=moments.device)
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == out.shape
+    _l.check(_l.load().b200_vae_posterior(moments.data_ptr(), _p(noise), out.data_ptr(), n, channels, h * w, ld, scale,
+                                          _dt(moments), _stream()))
+    _count()
+    return out
+
+
 def sampler_update(x: torch.Tensor, denoised: torch.Tensor, *, kind: int, sigma: float, dt: float = 0.0,
                    noise: Optional[torch.Tensor] = None, noise_scale: float = 0.0,
                    old_denoised: Optional[torch.Tensor] = None, c_x: float = 0.0, c_d: float = 0.0,

@@ -235,6 +235,26 @@ class VAEDecodeWrapper:
         return img if self.output_device is None else img.to(self.output_device)
 
 
+class VAEEncodeWrapper:
+    """`model_options['model_vae_encode_wrapper']` (reference backend/patcher/vae.py:186-191):
+    wrapper(encode_inner_fn, pixel_samples [B,H,W,3] in [0,1]) -> latent [B,zc,h,w] fp32 on the output device, the
+    un-scaled posterior sample (the diffusion engine applies process_in afterwards, diffusion_engine/sdxl.py:128-132).
+    A `model_vae_regulation` hook or a size that is not a multiple of 8 goes back to Forge's own encode."""
+
+    def __init__(self, vae_engine, output_device=None, patcher=None):
+        self.engine = vae_engine
+        self.output_device = output_device
+        self.patcher = patcher
+
+    def __call__(self, encode_inner_fn: Callable, pixel_samples: torch.Tensor):
+        has_reg = self.patcher is not None and self.patcher.model_options.get("model_vae_regulation") is not None
+        if (has_reg or pixel_samples.dim() != 4 or pixel_samples.shape[-1] != 3 or pixel_samples.shape[1] % 8
+                or pixel_samples.shape[2] % 8 or not torch.cuda.is_available()):
+            return encode_inner_fn(pixel_samples)
+        z = self.engine.encode(pixel_samples.to(self.engine.device).float().contiguous())
+        return z if self.output_device is None else z.to(self.output_device)
+
+
 def install(modules: Optional[dict] = None, attention: bool = True, samplers: bool = True, operations: bool = False) -> None:
     """One call from inside Forge.  The per-checkpoint hooks (install_unet_wrapper, VAEDecodeWrapper) are attached when
     a model is loaded, e.g. from a `script_callbacks.on_model_loaded` callback."""

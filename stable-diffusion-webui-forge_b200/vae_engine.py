@@ -145,3 +145,120 @@ class VAEDecoderEngine:
         h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
         h = ops.conv3x3(h, w["conv_out.w"], w["conv_out.b"])
         return ops.vae_postprocess(h)
+
+
+class VAEEncoderEngine:
+    """Fused channels-last VAE encoder — `VAE.encode -> IntegratedAutoencoderKL.encode -> Encoder.forward ->
+    DiagonalGaussianDistribution.sample` (reference backend/patcher/vae.py:162-191, backend/nn/vae.py:16-32, 140-200,
+    293-303) on the same kernels as the decoder: GroupNorm stats/apply+SiLU, implicit-GEMM conv3x3 with the residual in
+    its epilogue, 1x1 convs as GEMMs, the stride-2 downsample (pad (0,1,0,1), 3x3, stride 2) as im2col + GEMM, the
+    single-head mid attention as GEMM -> row softmax -> GEMM.  img2img / hires-fix entry."""
+
+    def __init__(self, cfg: dict, state_dict: SD, dtype: torch.dtype = torch.bfloat16, device="cuda"):
+        self.cfg = dict(cfg)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        boc = list(cfg["block_out_channels"])
+        self.ch = boc[0]
+        self.ch_mult = [c // self.ch for c in boc]
+        self.nres = len(boc)
+        self.nrb = cfg["layers_per_block"]
+        self.zc = cfg["latent_channels"]
+        self.scaling = float(cfg["scaling_factor"])
+        self.shift = float(cfg.get("shift_factor", 0.0) or 0.0)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(state_dict)
+
+    _t = VAEDecoderEngine._t
+    _res = VAEDecoderEngine._res
+    _attn = VAEDecoderEngine._attn
+
+    def _pack(self, sd: SD) -> None:
+        w = self.w
+        g = lambda k: self._t(sd[k])  # noqa: E731
+        zc = self.zc
+        assert 2 * zc <= 8 and cfg_in(self.cfg) == 3
+        ci = g("encoder.conv_in.weight")  # [ch, 3, 3, 3] -> im2col on the 8-channel padded input: k = tap*8 + c
+        cip = torch.zeros((ci.shape[0], 3, 3, 8), dtype=self.dtype, device=self.device)
+        cip[..., :3] = ci.permute(0, 2, 3, 1)
+        w["conv_in.w"], w["conv_in.b"] = cip.reshape(ci.shape[0], 72).contiguous(), g("encoder.conv_in.bias")
+
+        def res(p):
+            for n in ("norm1", "norm2"):
+                w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight"), g(f"{p}.{n}.bias")
+            for n in ("conv1", "conv2"):
+                w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = ops.pack_conv3x3(g(f"{p}.{n}.weight")), g(f"{p}.{n}.bias")
+            if f"{p}.nin_shortcut.weight" in sd:
+                sw = g(f"{p}.nin_shortcut.weight")
+                w[f"{p}.skip.w"], w[f"{p}.skip.b"] = sw.reshape(sw.shape[0], sw.shape[1]).contiguous(), g(f"{p}.nin_shortcut.bias")
+
+        for lvl in range(self.nres):
+            for j in range(self.nrb):
+                res(f"encoder.down.{lvl}.block.{j}")
+            if lvl != self.nres - 1:
+                q = f"encoder.down.{lvl}.downsample.conv"
+                w[q + ".w"], w[q + ".b"] = ops.pack_conv3x3(g(q + ".weight")), g(q + ".bias")
+        res("encoder.mid.block_1")
+        res("encoder.mid.block_2")
+        p = "encoder.mid.attn_1"
+        w[p + ".norm.g"], w[p + ".norm.b"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+        for n in ("q", "k", "v", "proj_out"):
+            cw = g(f"{p}.{n}.weight")
+            w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = cw.reshape(cw.shape[0], cw.shape[1]).contiguous(), g(f"{p}.{n}.bias")
+        w["norm_out.g"], w["norm_out.b"] = g("encoder.norm_out.weight"), g("encoder.norm_out.bias")
+        co = ops.pack_conv3x3(g("encoder.conv_out.weight"))  # [2zc, 9*C]
+        cop = torch.zeros((8, co.shape[1]), dtype=self.dtype, device=self.device)
+        cop[: co.shape[0]] = co
+        cob = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        cob[: co.shape[0]] = g("encoder.conv_out.bias")
+        w["conv_out.w"], w["conv_out.b"] = cop, cob
+        qw = torch.zeros((8, 8), dtype=self.dtype, device=self.device)
+        qb = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        if "quant_conv.weight" in sd:
+            qw[: 2 * zc, : 2 * zc] = g("quant_conv.weight").reshape(2 * zc, 2 * zc)
+            qb[: 2 * zc] = g("quant_conv.bias")
+        else:
+            qw[: 2 * zc, : 2 * zc] = torch.eye(2 * zc, dtype=self.dtype, device=self.device)
+        w["quant.w"], w["quant.b"] = qw, qb
+
+    @torch.no_grad()
+    def moments(self, pixels: torch.Tensor) -> torch.Tensor:
+        """pixels fp32 NHWC [B, H, W, 3] in [0, 1] -> moments NHWC [B, H/8.., W/8.., 8] (mean | logvar) in the VAE dtype."""
+        w = self.w
+        n, H, W, _ = pixels.shape
+        x = ops.vae_preprocess(pixels.contiguous(), self.dtype)                      # 2x - 1, 8-channel padded
+        h = ops.gemm(ops.im2col3x3(x, ldo=72), w["conv_in.w"], w["conv_in.b"]).view(n, H, W, -1)
+        for lvl in range(self.nres):
+            for j in range(self.nrb):
+                h = self._res(f"encoder.down.{lvl}.block.{j}", h)
+            if lvl != self.nres - 1:
+                q = f"encoder.down.{lvl}.downsample.conv"
+                nn_, hh, ww, c = h.shape
+                cols = ops.im2col3x3(h, stride=2, pad_lo=0, pad_hi=1)              # F.pad(x, (0,1,0,1)) + stride-2 conv
+                h = ops.gemm(cols, w[q + ".w"], w[q + ".b"]).view(nn_, hh // 2, ww // 2, c)
+        h = self._res("encoder.mid.block_1", h)
+        h = self._attn("encoder.mid.attn_1", h)
+        h = self._res("encoder.mid.block_2", h)
+        h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
+        h = ops.conv3x3(h, w["conv_out.w"], w["conv_out.b"])                          # [B, h, w, 8]
+        n2, hh, ww, _ = h.shape
+        return ops.gemm(h.view(-1, 8), w["quant.w"], w["quant.b"]).view(n2, hh, ww, 8)
+
+    @torch.no_grad()
+    def encode(self, pixels: torch.Tensor, noise: torch.Tensor = None, *, mode: bool = False,
+               process_in: bool = False) -> torch.Tensor:
+        """VAE.encode: latent NCHW fp32 [B, zc, h, w] = mean + std * noise.  `noise` [B, zc, h, w] fp32; None draws it
+        the way the reference does (torch.randn on the CPU default generator, vae.py:28) unless `mode`.
+        process_in=True also applies (z - shift) * scaling_factor (backend/nn/vae.py:312-313)."""
+        mom = self.moments(pixels)
+        n, hh, ww, _ = mom.shape
+        if noise is None and not mode:
+            noise = torch.randn((n, self.zc, hh, ww)).to(self.device)
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        assert not process_in or self.shift == 0.0
+        return ops.vae_posterior(mom, self.zc, noise, scale=self.scaling if process_in else 1.0)
+
+
+def cfg_in(cfg: dict) -> int:
+    return int(cfg.get("in_channels", 3))

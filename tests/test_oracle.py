@@ -176,3 +176,19 @@ def test_flux_dev_parameter_count():
         m = IntegratedFluxTransformer2DModel(**OF.FLUX_DEV)
     n = sum(p.numel() for p in m.parameters())
     assert 11.89e9 < n < 11.91e9, n
+
+
+def test_vae_encode_oracle_matches_reference_golden():
+    from oracle import vae as OV
+    g = _gold("vae_enc_tiny.pt")
+    cfg = CF.VAE_CONFIGS[g["config"]]
+    sd = OV.random_encoder_state_dict(cfg, seed=g["weight_seed"])
+    assert abs(_sd_checksum(sd) - g["weight_checksum"]) <= 1e-6 * g["weight_checksum"]
+    with torch.no_grad():
+        mom = OV.encode_moments(sd, cfg, 2.0 * g["pixels"].movedim(-1, 1) - 1.0)
+        lat = OV.encode_first_stage(sd, cfg, g["pixels"], g["noise"])
+    zc = cfg["latent_channels"]
+    assert_close("oracle vae encode mean", mom[:, :zc], g["mean"], max_abs=5e-6)
+    assert_close("oracle vae encode logvar", mom[:, zc:].clamp(-30, 20), g["logvar"], max_abs=5e-6)
+    assert_close("oracle vae encode sample", OV.posterior(mom, g["noise"]), g["sample"], max_abs=5e-6)
+    assert_close("oracle vae encode latent", lat, g["latent"], max_abs=5e-6)

@@ -1,4 +1,4 @@
-"""GPU parity tests for the VAE decode path against the reference golden (tiny config,
+"""GPU parity tests for the VAE decode path and the VAE encode path (§8f rank 1) against the reference golden (tiny config,
 made on CPU fp32 by the imported reference) and the oracle in fp32 at SDXL width."""
 import os
 
@@ -44,3 +44,52 @@ def test_vae_decode_sdxl_width_vs_oracle_fp32():
     with torch.no_grad():
         ref = OV.decode_first_stage(sd32, cfg, z)
     assert_close("vae sdxl-width bf16 vs oracle fp32", img, ref, max_abs=1.5e-1, rel_rms=3e-2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, dict(max_abs=2e-2, rel_rms=5e-3)),
+                                       (torch.bfloat16, dict(max_abs=1.5e-1, rel_rms=3e-2))])
+def test_vae_encode_vs_reference_golden(dtype, tol):
+    """Encoder + quant_conv + DiagonalGaussianDistribution vs the imported reference (tests/golden/vae_enc_tiny.pt):
+    moments, the sample with the reference's own noise draw, and process_in."""
+    from b200forge.vae_engine import VAEEncoderEngine
+    g = torch.load(os.path.join(GOLD, "vae_enc_tiny.pt"), weights_only=False)
+    cfg = CF.VAE_CONFIGS[g["config"]]
+    sd = OV.random_encoder_state_dict(cfg, seed=g["weight_seed"])
+    eng = VAEEncoderEngine(cfg, sd, dtype=dtype, device=DEV)
+    px = g["pixels"].to(DEV)
+    mom = eng.moments(px)
+    torch.cuda.synchronize()
+    zc = cfg["latent_channels"]
+    assert_close(f"vae encode mean {dtype}", mom[..., :zc].movedim(-1, 1), g["mean"], **tol)
+    assert_close(f"vae encode logvar {dtype}", mom[..., zc:2 * zc].movedim(-1, 1).float().clamp(-30, 20), g["logvar"], **tol)
+    z = eng.encode(px, g["noise"])
+    zmode = eng.encode(px, mode=True)
+    lat = eng.encode(px, g["noise"], process_in=True)
+    torch.cuda.synchronize()
+    assert z.dtype == torch.float32 and z.shape == g["sample"].shape
+    assert_close(f"vae encode sample {dtype}", z, g["sample"], **tol)
+    assert_close(f"vae encode mode {dtype}", zmode, g["mean"], **tol)
+    assert_close(f"vae encode latent (process_in) {dtype}", lat, g["latent"], max_abs=tol["max_abs"], rel_rms=tol["rel_rms"])
+    # the default draw is the reference's: torch.randn on the CPU default generator
+    torch.manual_seed(1234)
+    z2 = eng.encode(px)
+    torch.cuda.synchronize()
+    assert torch.equal(z2, z)
+
+
+def test_vae_encode_sdxl_width_vs_oracle_fp32():
+    from b200forge.vae_engine import VAEEncoderEngine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = CF.VAE_CONFIGS["sdxl"]
+    sd = {k: v.bfloat16() for k, v in OV.random_encoder_state_dict(cfg, seed=23).items()}
+    eng = VAEEncoderEngine(cfg, sd, dtype=torch.bfloat16, device=DEV)
+    g = torch.Generator().manual_seed(24)
+    px = torch.rand(2, 256, 256, 3, generator=g).to(DEV)
+    noise = torch.randn(2, 4, 32, 32, generator=g).to(DEV)
+    lat = eng.encode(px, noise, process_in=True)
+    torch.cuda.synchronize()
+    sd32 = {k: v.float().to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        ref = OV.encode_first_stage(sd32, cfg, px, noise)
+    assert_close("vae encode sdxl-width bf16 vs oracle fp32", lat, ref, rel_rms=3e-2)
