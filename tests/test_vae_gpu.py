@@ -74,7 +74,8 @@ def test_vae_encode_vs_reference_golden(dtype, tol):
     torch.manual_seed(1234)
     z2 = eng.encode(px)
     torch.cuda.synchronize()
-    assert torch.equal(z2, z)
+    # same noise as the golden's; not bit-equal run to run because GroupNorm statistics are accumulated with float atomics
+    assert_close(f"vae encode default noise draw {dtype}", z2, z, rel_rms=2e-3)
 
 
 def test_vae_encode_sdxl_width_vs_oracle_fp32():
