@@ -50,6 +50,10 @@ static constexpr int kAtom = 128 * 128;       // bytes of one 128-row x 64-half 
 static constexpr int kTile128 = 2 * kAtom;    // 128 rows x 128 halfs
 static constexpr int kRing128 = 3;
 static constexpr float kRescale128 = 8.0f;    // log2(256)
+#ifndef B200_ATTN_POLY_MASK
+#define B200_ATTN_POLY_MASK 0x10
+#endif
+static constexpr unsigned kPolyMask = B200_ATTN_POLY_MASK;  // elements (i mod 8) whose exp2 runs on the FMA pipe
 
 template <bool BF16>
 __global__ void __launch_bounds__(384, 1)
@@ -213,7 +217,9 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+#ifndef B200_ATTN_NO_TURNS
     if (t == 1) named_bar_arrive(2, 256);  // warpgroup 0 takes the first turn on the MUFU
+#endif
 
     for (int j = 0; j < n_kv; ++j) {
       int nvalid = p.Lk - j * BKV;
@@ -264,7 +270,9 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           if (need) m_ref = m_blk;
         }
       }
+#ifndef B200_ATTN_NO_TURNS
       named_bar_sync(2 + t, 256);
+#endif
       float rs0 = 0.f, rs1 = 0.f;
       const float nm = -m_ref;
       if (full_blk) {
@@ -272,7 +280,10 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         for (int c = 0; c < 128; c += 8) {
           float pe[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm));
+          for (int i = 0; i < 8; ++i) {
+            const float xs = fmaf(__uint_as_float(v[c + i]), sl2, nm);
+            pe[i] = ((kPolyMask >> i) & 1) ? exp2_poly3(xs) : ex2a(xs);  // kPolyMask: which of every 8 exponentials run on the FMA pipe
+          }
           rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
           rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
           const uint32_t addr = p_row + (uint32_t)(c >> 6) * kAtom + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
@@ -294,7 +305,9 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           }
         }
       }
+#ifndef B200_ATTN_NO_TURNS
       if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
+#endif
       l_run += rs0 + rs1;
       fence_proxy_async_smem();
       tc_fence_before();

@@ -47,9 +47,23 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Phase profile of the softmax loop (compile with -DB200_ATTN_PROFILE): lane 0 of the first softmax warp of each tile in
+// CTA 0 accumulates clock64 deltas per phase and prints the per-key-block averages at the end.
+#ifdef B200_ATTN_PROFILE
+#define PROF_DECL long long pf_t = clock64(), pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(i) do { const long long pf_n = clock64(); pf_acc[i] += pf_n - pf_t; pf_t = pf_n; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
 static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
 static constexpr int kRingSlots = 4;
 static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
+#ifndef B200_ATTN_POLY_MASK
+#define B200_ATTN_POLY_MASK 0x10
+#endif
+static constexpr unsigned kPolyMask = B200_ATTN_POLY_MASK;  // elements (i mod 8) whose exp2 runs on the FMA pipe
 
 // ELECT: the MMA-issue warp runs converged with one elected lane (descriptors in uniform registers) instead of a
 // lane-0 branch.  The lane-0 build is kept for A/B measurements (B200_ATTN64_ISSUE=lane0).
@@ -258,13 +272,17 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+#ifndef B200_ATTN_NO_TURNS
     if (t == 1) named_bar_arrive(2, 256);  // warpgroup 0 takes the first turn on the MUFU
+#endif
+    PROF_DECL;
 
     for (int j = 0; j < n_kv; ++j) {
       int nvalid = p.Lk - j * BKV;
       if (nvalid > BKV) nvalid = BKV;
       mbar_wait(s_full(t), (uint32_t)j & 1u);
       tc_fence_after();
+      PROF_MARK(0);  // waiting for S_j
       // the whole S row -> registers in one TMEM round trip, then hand S back to the tensor core
       uint32_t v[128];
       tmem_ld_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -274,6 +292,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_cons(t));
+      PROF_MARK(1);  // TMEM -> registers
       const bool full_blk = nvalid == 128;
       float mx = -INFINITY;
       if (full_blk) {
@@ -285,11 +304,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       const float m_blk = mx * sl2;
+      PROF_MARK(2);  // row max
       // PV_{j-1} must have retired before O is rescaled and before P is overwritten
       if (j > 0) {
         mbar_wait(pv_done(t), (uint32_t)(j - 1) & 1u);
         tc_fence_after();
       }
+      PROF_MARK(3);  // waiting for PV_{j-1}
       if (j == 0) {
         m_ref = m_blk;
       } else {
@@ -313,7 +334,11 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       // p = exp2(s*scale - m_ref); row sum; stage P (128B-swizzled K-major A operand).
       // The two warpgroups take turns on this MUFU-bound phase (named-barrier hand-off) so that one group's
       // exponentials overlap the other group's TMEM loads / max / stores instead of both fighting for the MUFU.
+      PROF_MARK(4);  // rescale
+#ifndef B200_ATTN_NO_TURNS
       named_bar_sync(2 + t, 256);
+#endif
+      PROF_MARK(5);  // waiting for the turn
       float rs0 = 0.f, rs1 = 0.f;
       const float nm = -m_ref;
       if (full_blk) {
@@ -321,7 +346,10 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         for (int c = 0; c < 128; c += 8) {
           float pe[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pe[i] = ex2a(fmaf(__uint_as_float(v[c + i]), sl2, nm));
+          for (int i = 0; i < 8; ++i) {
+            const float xs = fmaf(__uint_as_float(v[c + i]), sl2, nm);
+            pe[i] = ((kPolyMask >> i) & 1) ? exp2_poly3(xs) : ex2a(xs);  // kPolyMask: which of every 8 exponentials run on the FMA pipe
+          }
           rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
           rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
           const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
@@ -343,12 +371,22 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           }
         }
       }
+      PROF_MARK(6);  // exp phase
+#ifndef B200_ATTN_NO_TURNS
       if (!(t == 1 && j == n_kv - 1)) named_bar_arrive(3 - t, 256);
+#endif
       l_run += rs0 + rs1;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(t));
+      PROF_MARK(7);  // hand-off
     }
+#ifdef B200_ATTN_PROFILE
+    if (blockIdx.x == 0 && quad == 0 && lane == 0)
+      printf("attn64 profile tile %d: per key block clk  waitS %lld  ldtm %lld  max %lld  waitPV %lld  rescale %lld  waitTurn %lld  exp %lld  handoff %lld  (n_kv %d)\n",
+             t, pf_acc[0] / n_kv, pf_acc[1] / n_kv, pf_acc[2] / n_kv, pf_acc[3] / n_kv, pf_acc[4] / n_kv, pf_acc[5] / n_kv,
+             pf_acc[6] / n_kv, pf_acc[7] / n_kv, n_kv);
+#endif
 
     // ---- output: O_t / l -> fp16 -> warp-private staging (the P tile is free now) -> coalesced stores
     mbar_wait(pv_done(t), (uint32_t)(n_kv - 1) & 1u);

@@ -296,6 +296,21 @@ __device__ __forceinline__ float silu_fast_f(float x) {
   return x * fmaf(0.5f, t, 0.5f);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 — a
+// fraction of an fp16 ulp).  Measured with the clock64 phase profile (scripts/attn_phase_profile.py): one warp's exp
+// phase of 128 exponentials takes 2040 clk = 16 clk per MUFU.EX2, twice the pipe's 8 clk/instruction peak, so the
+// attention kernels move a share of the exponentials here.  A/B on B200 (profiles/experiments/README.md): 1 of 8 is the
+// best split (+4.5 % at Dh = 64); larger shares lengthen the other tile's phases by as much as they shorten this one.
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;         // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);   // fractional part in [-0.5, 0.5]
+  float p = fmaf(0.0551716685f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // p * 2^n through the exponent field
+}
+
 // nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), MUFU.TANH (rel. error ~2^-11)
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);

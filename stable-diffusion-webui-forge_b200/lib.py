@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200forge.so")
+LIB_PATH = os.environ.get("B200FORGE_LIB") or os.path.join(_HERE, "libb200forge.so")  # override: instrumented builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 B200_F16, B200_BF16 = 0, 1
