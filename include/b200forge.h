@@ -205,7 +205,13 @@ int b200_unet_input_im2col(const float* x, const float* sigma, void* cols, int B
  *   euler / euler_a : x += (x - D)/sigma * dt  [+ noise * noise_scale]
  *   dpmpp_2m        : x = c_x * x + c_d * D + c_old * D_old
  */
-enum { B200_STEP_EULER = 0, B200_STEP_DPMPP_2M = 1 };
+enum {
+  B200_STEP_EULER = 0,
+  B200_STEP_DPMPP_2M = 1,
+  /* b200_sampler_update only: x = c_x*x + c_d*denoised + c_old*old_denoised + noise_scale*noise, all operands read-only
+   * (the second stage of Heun / DPM2 / DPM++ 2S steps, k_diffusion/sampling.py:188-290, 573-603) */
+  B200_STEP_LINEAR = 2
+};
 typedef struct {
   int kind;
   int B, C, H, W;

@@ -171,6 +171,37 @@ def gen_vae(name: str = "tiny", hw: int = 16):
     print("vae", name, "out std", out.std().item())
 
 
+def gen_samplers(steps: int = 7):
+    """The reference's own k-diffusion loops (k_diffusion/sampling.py) on CPU fp32 around oracle.sampling.toy_denoiser,
+    with the to_d override of modules/sd_schedulers.py:10-15 and a recorded noise stream."""
+    import k_diffusion.sampling as ks
+    from backend.modules.k_prediction import Prediction
+    from oracle import sampling as OS
+    ks.to_d = lambda x, sigma, denoised: (x - denoised) / sigma
+    pred = Prediction(prediction_type="epsilon")
+    sig = ks.get_sigmas_karras(steps, float(pred.sigma_min), float(pred.sigma_max))
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(2, 4, 16, 16, generator=g) * sig[0]
+    noise = torch.randn(4 * steps, 2, 4, 16, 16, generator=g)
+
+    class Model:
+        class _Inner:
+            predictor = pred
+        inner_model = _Inner()
+
+        def __call__(self, x, sigma, **kw):
+            return OS.toy_denoiser(x, sigma)
+
+    out = dict(sigmas=sig, x0=x0, noise=noise)
+    for name in ("sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral"):
+        k = iter(range(noise.shape[0]))
+        kw = dict(noise_sampler=lambda s, sn: noise[next(k)]) if "ancestral" in name else {}
+        with torch.no_grad():
+            out[name] = getattr(ks, name)(Model(), x0.clone(), sig, extra_args={}, disable=True, **kw)
+        print(name, float(out[name].std()))
+    torch.save(out, os.path.join(GOLD, "samplers_toy.pt"))
+
+
 def gen_vae_encode(name: str = "tiny", hw: int = 64):
     """Reference IntegratedAutoencoderKL.encode (backend/nn/vae.py:293-303): moments via a `regulation` hook, and the
     default .sample() with the global CPU generator seeded (the reference draws torch.randn(mean.shape) there)."""
@@ -221,7 +252,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "sched", "vae", "vae_enc", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "sched", "samplers", "vae", "vae_enc", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -232,6 +263,8 @@ if __name__ == "__main__":
         gen_schedules()
     if "vae" in which:
         gen_vae("tiny")
+    if "samplers" in which:
+        gen_samplers()
     if "vae_enc" in which:
         gen_vae_encode("tiny")
     if "flux" in which:

@@ -282,3 +282,89 @@ def const_noise_scaling(sigma, noise, latent):
 def const_denoised(x, model_output, sigma):
     """k_prediction.py:81-92 'const' branch: model_input - model_output * sigma (calculate_input is the identity, :74-76)."""
     return x - model_output * sigma
+
+
+# --------------------------------------------------------------------------------------------- two-evaluation samplers
+def _anc_t(sig_from: torch.Tensor, sig_to: torch.Tensor, eta: float):
+    """get_ancestral_step (k_diffusion/sampling.py:53-60) on 0-dim tensors."""
+    if not eta:
+        return sig_to, sig_to.new_zeros(())
+    up = torch.minimum(sig_to, eta * (sig_to ** 2 * (sig_from ** 2 - sig_to ** 2) / sig_from ** 2) ** 0.5)
+    return (sig_to ** 2 - up ** 2) ** 0.5, up
+
+
+def sample_heun(model, x, sigmas):
+    """k_diffusion/sampling.py:188-214 with s_churn = 0."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        d = to_d(x, sigmas[i], denoised)
+        dt = sigmas[i + 1] - sigmas[i]
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            d_2 = to_d(x_2, sigmas[i + 1], model(x_2, sigmas[i + 1] * s_in))
+            x = x + (d + d_2) / 2 * dt
+    return x
+
+
+def sample_dpm_2(model, x, sigmas):
+    """k_diffusion/sampling.py:217-246 with s_churn = 0."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        d = to_d(x, sigmas[i], denoised)
+        if sigmas[i + 1] == 0:
+            x = x + d * (sigmas[i + 1] - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigmas[i])
+            d_2 = to_d(x_2, sigma_mid, model(x_2, sigma_mid * s_in))
+            x = x + d_2 * (sigmas[i + 1] - sigmas[i])
+    return x
+
+
+def sample_dpm_2_ancestral(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0):
+    """k_diffusion/sampling.py:249-276; noise_sampler() -> N(0,1) like x, drawn only in the second-order branch."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = _anc_t(sigmas[i], sigmas[i + 1], eta)
+        d = to_d(x, sigmas[i], denoised)
+        if sigma_down == 0:
+            x = x + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigmas[i])
+            d_2 = to_d(x_2, sigma_mid, model(x_2, sigma_mid * s_in))
+            x = x + d_2 * (sigma_down - sigmas[i])
+            x = x + noise_sampler() * s_noise * sigma_up
+    return x
+
+
+def sample_dpmpp_2s_ancestral(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0):
+    """k_diffusion/sampling.py:573-603."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = _anc_t(sigmas[i], sigmas[i + 1], eta)
+        if sigma_down == 0:
+            x = x + to_d(x, sigmas[i], denoised) * (sigma_down - sigmas[i])
+        else:
+            t, t_next = sigmas[i].log().neg(), sigma_down.log().neg()
+            h = t_next - t
+            s = t + 0.5 * h
+            x_2 = (s.neg().exp() / t.neg().exp()) * x - (-h * 0.5).expm1() * denoised
+            denoised_2 = model(x_2, s.neg().exp() * s_in)
+            x = (t_next.neg().exp() / t.neg().exp()) * x - (-h).expm1() * denoised_2
+        if sigmas[i + 1] > 0:
+            x = x + noise_sampler() * s_noise * sigma_up
+    return x
+
+
+def toy_denoiser(x, sigma):
+    """A cheap deterministic stand-in for the CFG denoiser used to pin sampler arithmetic (fixtures: samplers_toy.pt):
+    smooth and non-linear in x, sigma-dependent, shape-preserving."""
+    s = sigma.view(-1, 1, 1, 1)
+    return x / (1.0 + s * s) + 0.3 * torch.tanh(x * 0.5) * s / (1.0 + s)

@@ -105,6 +105,11 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
       const float dd = (xv - D) / d.sigma;
       xn = xv + dd * d.dt;
       if (d.noise_scale != 0.f) xn = xn + noise[i] * d.noise_scale;
+    } else if (d.kind == B200_STEP_LINEAR) {
+      // generic linear step of the two-evaluation samplers (Heun, DPM2, DPM++ 2S): every operand is read-only
+      xn = d.c_x * xv + d.c_d * D;
+      if (d.c_old != 0.f) xn += d.c_old * old_denoised[i];
+      if (d.noise_scale != 0.f) xn += d.noise_scale * noise[i];
     } else {
       xn = d.c_x * xv + d.c_d * D;
       if (d.c_old != 0.f) xn += d.c_old * old_denoised[i];
@@ -137,7 +142,8 @@ extern "C" int b200_sampler_update(float* x, const float* denoised, const float*
                                    const b200_step_desc* d, b200_stream_t s) {
   B200_CHECK_ARG(x && denoised && d, "sampler_update: null argument");
   B200_CHECK_ARG(d->B > 0 && d->C > 0 && d->H > 0 && d->W > 0, "sampler_update: bad shape");
-  B200_CHECK_ARG(d->kind == B200_STEP_EULER || d->kind == B200_STEP_DPMPP_2M, "sampler_update: kind");
+  B200_CHECK_ARG(d->kind == B200_STEP_EULER || d->kind == B200_STEP_DPMPP_2M || d->kind == B200_STEP_LINEAR, "sampler_update: kind");
+  B200_CHECK_ARG(d->kind != B200_STEP_LINEAR || d->c_old == 0.f || old_denoised, "sampler_update: c_old without a third operand");
   B200_CHECK_ARG(d->kind != B200_STEP_DPMPP_2M || old_denoised, "sampler_update: dpm++ 2m needs old_denoised");
   B200_CHECK_ARG(d->noise_scale == 0.f || noise, "sampler_update: noise_scale without noise");
   B200_CHECK_ARG(d->kind != B200_STEP_EULER || d->sigma > 0.f, "sampler_update: sigma must be positive");

@@ -1,5 +1,7 @@
 """Plug point P4 — k-diffusion sampler functions with the reference's exact call contract
-(k_diffusion/sampling.py:119-137 sample_euler, :140-159 sample_euler_ancestral, :648-671 sample_dpmpp_2m):
+(k_diffusion/sampling.py:119-137 sample_euler, :140-159 sample_euler_ancestral, :648-671 sample_dpmpp_2m, and the
+two-evaluation samplers :188-214 sample_heun, :217-246 sample_dpm_2, :249-276 sample_dpm_2_ancestral,
+:573-603 sample_dpmpp_2s_ancestral):
 
     fn(model, x, sigmas, extra_args=None, callback=None, disable=None, ...) -> x
 
@@ -27,6 +29,10 @@ from . import ops, sampling
 reference_sample_euler = None
 reference_sample_euler_ancestral = None
 reference_sample_dpmpp_2m = None
+reference_sample_heun = None
+reference_sample_dpm_2 = None
+reference_sample_dpm_2_ancestral = None
+reference_sample_dpmpp_2s_ancestral = None
 
 
 def _randn_like(x):
@@ -120,4 +126,163 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
             callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
         ops.sampler_update(x, _prep(denoised.float()), kind=ops.STEP_DPMPP_2M, sigma=max(st.sigma, 1e-30), old_denoised=old,
                            c_x=st.c_x, c_d=st.c_d, c_old=st.c_old)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Two-evaluation samplers.  Scalars follow the reference's fp32 tensor arithmetic (computed here
+# on fp32 CPU scalars, once); each stage's tensor update is one launch: the first stage is the Euler kernel on a copy of
+# x, the second a 4-operand linear combination (B200_STEP_LINEAR).
+def _f32(v):
+    return torch.tensor(float(v), dtype=torch.float32)
+
+
+def _ancestral(sig_from, sig_to, eta):
+    """get_ancestral_step (k_diffusion/sampling.py:53-60) in fp32 like the reference's 0-dim tensors."""
+    if not eta:
+        return sig_to, _f32(0.0)
+    up = torch.minimum(sig_to, eta * (sig_to ** 2 * (sig_from ** 2 - sig_to ** 2) / sig_from ** 2) ** 0.5)
+    down = (sig_to ** 2 - up ** 2) ** 0.5
+    return down, up
+
+
+def _is_flux(model):
+    try:
+        from backend.modules.k_prediction import PredictionFlux  # type: ignore
+        return isinstance(model.inner_model.predictor, PredictionFlux)
+    except Exception:
+        return False
+
+
+def _defer(ref, name, *args):
+    if ref is None:
+        raise _l.B200Error(_l.E_UNSUPPORTED, f"{name}: this case needs the reference sampler")
+    return ref(*args)
+
+
+@torch.no_grad()
+def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0.,
+                s_tmax=float('inf'), s_noise=1.):
+    """k_diffusion/sampling.py:188-214 (Karras Algorithm 2) with s_churn = 0."""
+    if s_churn > 0 or not _fusable(x):
+        return _defer(reference_sample_heun, "sample_heun", model, x, sigmas, extra_args, callback, disable, s_churn, s_tmin, s_tmax, s_noise)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        _randn_like(x)  # eps is drawn every step (sampling.py:196) even when unused
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        dt = float(s1 - s0)
+        if float(s1) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=dt)
+        else:
+            x2 = x.clone()
+            ops.sampler_update(x2, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=dt)          # x_2 = x + d * dt
+            denoised2 = _prep(model(x2, sigmas[i + 1] * s_in, **extra_args).float())
+            # x + (d + d_2)/2 * dt,  d = (x - D)/s0,  d_2 = (x_2 - D_2)/s1
+            a, b = dt / (2.0 * float(s0)), dt / (2.0 * float(s1))
+            ops.sampler_update(x, denoised2, kind=ops.STEP_LINEAR, sigma=1.0, c_x=1.0 + a, c_d=-b, old_denoised=denoised,
+                               c_old=-a, noise=x2, noise_scale=b)
+    return x
+
+
+def _dpm2_stage(model, x, denoised, s0, s_target, sigmas_i_dev, s_in, extra_args):
+    """Shared DPM-Solver-2 stage (sampling.py:237-244 / 266-274): midpoint in log-sigma, second evaluation, full step."""
+    sigma_mid = s0.log().lerp(s_target.log(), 0.5).exp()
+    dt1, dt2 = float(sigma_mid - s0), float(s_target - s0)
+    x2 = x.clone()
+    ops.sampler_update(x2, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=dt1)                  # x_2 = x + d * dt_1
+    denoised2 = _prep(model(x2, float(sigma_mid) * s_in, **extra_args).float())
+    c = dt2 / float(sigma_mid)
+    ops.sampler_update(x, denoised2, kind=ops.STEP_LINEAR, sigma=1.0, c_x=1.0, c_d=-c, noise=x2, noise_scale=c)  # x + d_2 * dt_2
+
+
+@torch.no_grad()
+def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0.,
+                 s_tmax=float('inf'), s_noise=1.):
+    """k_diffusion/sampling.py:217-246 with s_churn = 0."""
+    if s_churn > 0 or not _fusable(x):
+        return _defer(reference_sample_dpm_2, "sample_dpm_2", model, x, sigmas, extra_args, callback, disable, s_churn, s_tmin, s_tmax, s_noise)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        _randn_like(x)
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(s1) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=float(s1 - s0))
+        else:
+            _dpm2_stage(model, x, denoised, s0, s1, sigmas[i], s_in, extra_args)
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
+                           noise_sampler=None):
+    """k_diffusion/sampling.py:249-276."""
+    if _is_flux(model) or not _fusable(x):
+        return _defer(reference_sample_dpm_2_ancestral, "sample_dpm_2_ancestral", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    extra_args = {} if extra_args is None else extra_args
+    if noise_sampler is None:
+        noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        down, up = _ancestral(s0, s1, eta)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(down) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=float(down - s0))
+        else:
+            _dpm2_stage(model, x, denoised, s0, down, sigmas[i], s_in, extra_args)
+            noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+            ops.sampler_update(x, noise, kind=ops.STEP_LINEAR, sigma=1.0, c_x=1.0, c_d=float(s_noise * up))
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
+                              noise_sampler=None):
+    """k_diffusion/sampling.py:573-603."""
+    if _is_flux(model) or not _fusable(x):
+        return _defer(reference_sample_dpmpp_2s_ancestral, "sample_dpmpp_2s_ancestral", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    extra_args = {} if extra_args is None else extra_args
+    if noise_sampler is None:
+        noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        down, up = _ancestral(s0, s1, eta)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(down) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=float(down - s0))
+        else:
+            t, t_next = s0.log().neg(), down.log().neg()
+            h = t_next - t
+            s = t + 0.5 * h
+            sig_s = s.neg().exp()
+            x2 = x.clone()
+            ops.sampler_update(x2, denoised, kind=ops.STEP_LINEAR, sigma=1.0, c_x=float(sig_s / t.neg().exp()),
+                               c_d=float(-(-h * 0.5).expm1()))
+            denoised2 = _prep(model(x2, float(sig_s) * s_in, **extra_args).float())
+            ops.sampler_update(x, denoised2, kind=ops.STEP_LINEAR, sigma=1.0, c_x=float(t_next.neg().exp() / t.neg().exp()),
+                               c_d=float(-(-h).expm1()))
+        if float(s1) > 0:
+            noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+            ops.sampler_update(x, noise, kind=ops.STEP_LINEAR, sigma=1.0, c_x=1.0, c_d=float(s_noise * up))
     return x

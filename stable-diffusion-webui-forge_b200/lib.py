@@ -17,7 +17,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 B200_F16, B200_BF16 = 0, 1
 EPI_NONE, EPI_SILU, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH = 0, 1, 2, 3, 4
-STEP_EULER, STEP_DPMPP_2M = 0, 1
+STEP_EULER, STEP_DPMPP_2M, STEP_LINEAR = 0, 1, 2
 E_UNSUPPORTED = -2
 
 

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _l
-from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER)  # noqa: F401
+from .lib import (B200Error, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH, EPI_NONE, EPI_SILU, STEP_DPMPP_2M, STEP_EULER, STEP_LINEAR)  # noqa: F401
 
 LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
 PROFILE = None  # set to a list to record (family, algorithmic flops, algorithmic bytes, start_evt, end_evt) per call

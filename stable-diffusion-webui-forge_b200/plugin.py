@@ -196,20 +196,23 @@ def install_flux_wrapper(unet_patcher, engine=None) -> FluxWrapper:
 
 
 # ------------------------------------------------------------------------------------------------- P4 samplers
+_SAMPLER_NAMES = ("sample_euler", "sample_euler_ancestral", "sample_dpmpp_2m", "sample_heun", "sample_dpm_2",
+                  "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral")
+
+
 def install_samplers(modules: Optional[dict] = None) -> None:
-    """Replace k_diffusion.sampling.sample_euler / sample_euler_ancestral / sample_dpmpp_2m: the sampler table
-    (modules/sd_samplers_kdiffusion.py:14-41) resolves them by getattr at sampler construction (:76)."""
+    """Replace the k_diffusion.sampling functions that have a fused version (Euler, Euler a, DPM++ 2M, Heun, DPM2, DPM2 a,
+    DPM++ 2S a): the sampler table (modules/sd_samplers_kdiffusion.py:14-41) resolves them by getattr at sampler
+    construction (:76).  The originals stay reachable as `k_samplers.reference_<name>` for the cases handed back."""
     mods = sys.modules if modules is None else modules
     ks = mods.get("k_diffusion.sampling")
     if ks is None:
         raise RuntimeError("k_diffusion.sampling is not imported")
     if "samplers" not in _installed:
-        _installed["samplers"] = (ks.sample_euler, ks.sample_euler_ancestral, ks.sample_dpmpp_2m)
-    (k_samplers.reference_sample_euler, k_samplers.reference_sample_euler_ancestral,
-     k_samplers.reference_sample_dpmpp_2m) = _installed["samplers"]
-    ks.sample_euler = k_samplers.sample_euler
-    ks.sample_euler_ancestral = k_samplers.sample_euler_ancestral
-    ks.sample_dpmpp_2m = k_samplers.sample_dpmpp_2m
+        _installed["samplers"] = {n: getattr(ks, n) for n in _SAMPLER_NAMES if hasattr(ks, n)}
+    for n, fn in _installed["samplers"].items():
+        setattr(k_samplers, "reference_" + n, fn)
+        setattr(ks, n, getattr(k_samplers, n))
 
 
 # ------------------------------------------------------------------------------------------------- P5 VAE

@@ -192,3 +192,14 @@ def test_vae_encode_oracle_matches_reference_golden():
     assert_close("oracle vae encode logvar", mom[:, zc:].clamp(-30, 20), g["logvar"], max_abs=5e-6)
     assert_close("oracle vae encode sample", OV.posterior(mom, g["noise"]), g["sample"], max_abs=5e-6)
     assert_close("oracle vae encode latent", lat, g["latent"], max_abs=5e-6)
+
+
+@pytest.mark.parametrize("name", ["sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral"])
+def test_two_evaluation_samplers_match_reference_golden(name):
+    """oracle/sampling.py restatements vs the reference's k-diffusion loops around the same toy denoiser (samplers_toy.pt)."""
+    g = _gold("samplers_toy.pt")
+    k = iter(range(g["noise"].shape[0]))
+    args = (lambda: g["noise"][next(k)],) if "ancestral" in name else ()
+    with torch.no_grad():
+        out = getattr(S, name)(S.toy_denoiser, g["x0"].clone(), g["sigmas"], *args)
+    assert_close(f"oracle {name} vs reference golden", out, g[name], max_abs=2e-5)

@@ -166,3 +166,84 @@ def test_p5_vae_decode_wrapper():
         ref = torch.clamp((OV.decode(sd, cfg, z.cpu()) + 1.0) / 2.0, 0.0, 1.0).movedim(1, -1)
     assert_close("P5 VAE decode wrapper", img, ref, max_abs=2e-2, rel_rms=4e-3)
     assert eng.scaling == cfg["scaling_factor"]
+
+
+def test_p3_flux_wrapper_vs_oracle():
+    """The same hook with a Flux KModel: `c` carries T5 states, pooled CLIP and the distilled guidance; the result is
+    PredictionFlux.calculate_denoised = x - sigma * v (k_prediction.py:81-92 'const')."""
+    from b200forge import plugin
+    from b200forge.flux_engine import FluxEngine
+    from oracle import flux as OF
+    cfg = OF.TINY_FLUX
+    sd = OF.random_state_dict(cfg, seed=5)
+    eng = FluxEngine(cfg, sd, dtype=torch.bfloat16, device=DEV)
+
+    class P:
+        prediction_type = "const"
+        timestep = staticmethod(lambda s: s)
+
+    w = plugin.FluxWrapper(eng, P())
+    g = torch.Generator().manual_seed(6)
+    n = 2
+    x = torch.randn(n, 16, 16, 16, generator=g).to(DEV)
+    sigma = torch.tensor([0.9, 0.2], device=DEV)
+    ctx = torch.randn(n, 128, cfg["context_in_dim"], generator=g).to(DEV)
+    y = torch.randn(n, cfg["vec_in_dim"], generator=g).to(DEV)
+    gd = torch.full((n,), 4.0)
+    c = {"c_crossattn": ctx, "y": y, "guidance": gd, "transformer_options": {}}
+    called = []
+    out = w(lambda *a, **k: called.append(1), {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]})
+    torch.cuda.synchronize()
+    assert not called and w.calls_fast == 1 and out.dtype == torch.float32 and out.shape == x.shape
+    with torch.no_grad():
+        v = OF.flux_forward(sd, cfg, x.cpu(), sigma.cpu(), ctx.cpu(), y.cpu(), gd)
+    ref = x.cpu() - v * sigma.cpu().view(-1, 1, 1, 1)
+    assert_close("P3 Flux wrapper denoised vs oracle", out, ref, rel_rms=3e-2)
+    # odd latent size (circular-pad branch) or a patch hook -> Forge's own apply_model
+    sentinel = torch.zeros(1)
+    xo = torch.randn(n, 16, 15, 16, generator=g).to(DEV)
+    assert w(lambda xx, ss, **kw: sentinel, {"input": xo, "timestep": sigma, "c": c, "cond_or_uncond": [0]}) is sentinel
+    c2 = dict(c, transformer_options={"patches_replace": {"dit": {}}})
+    assert w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c2, "cond_or_uncond": [0]}) is sentinel
+    assert w.calls_reference == 2
+
+
+def test_p5_vae_encode_wrapper():
+    """`model_vae_encode_wrapper` (backend/patcher/vae.py:186-191): NHWC pixels in [0,1] -> un-scaled posterior sample."""
+    from b200forge import plugin
+    from b200forge.vae_engine import VAEEncoderEngine
+    from oracle import vae as OV
+    cfg = CF.VAE_CONFIGS["tiny"]
+    sd = OV.random_encoder_state_dict(cfg, seed=8)
+    eng = VAEEncoderEngine(cfg, sd, dtype=torch.float16, device=DEV)
+    w = plugin.VAEEncodeWrapper(eng, output_device="cpu")
+    g = torch.Generator().manual_seed(9)
+    px = torch.rand(2, 64, 64, 3, generator=g)
+    torch.manual_seed(77)
+    out = w(lambda p: None, px)
+    torch.manual_seed(77)
+    noise = torch.randn(2, cfg["latent_channels"], 8, 8)
+    with torch.no_grad():
+        ref = OV.posterior(OV.encode_moments(sd, cfg, 2.0 * px.movedim(-1, 1) - 1.0), noise)
+    assert out.device.type == "cpu" and out.dtype == torch.float32
+    assert_close("P5 encode wrapper vs oracle", out, ref, max_abs=2e-2, rel_rms=5e-3)
+    sentinel = torch.zeros(1)
+    assert w(lambda p: sentinel, torch.rand(1, 60, 64, 3)) is sentinel  # not a multiple of 8 -> Forge's own encode
+
+
+@pytest.mark.parametrize("name", ["sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral"])
+def test_p4_two_evaluation_samplers_vs_reference_golden(name):
+    """Fused Heun / DPM2 / DPM2 a / DPM++ 2S a (k_samplers.py) against the reference's own loops on CPU fp32 around the
+    same toy denoiser (tests/golden/samplers_toy.pt): same call contract, callback per step, noise order."""
+    import os
+    from b200forge import k_samplers
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers_toy.pt"), weights_only=False)
+    steps = len(g["sigmas"]) - 1
+    k = iter(range(g["noise"].shape[0]))
+    kw = dict(noise_sampler=lambda s, sn: g["noise"][next(k)].to(DEV)) if "ancestral" in name else {}
+    seen = []
+    out = getattr(k_samplers, name)(lambda x, sigma, **kwargs: S.toy_denoiser(x, sigma), g["x0"].to(DEV), g["sigmas"].to(DEV),
+                                    extra_args={}, callback=lambda d: seen.append(d["i"]), disable=True, **kw)
+    torch.cuda.synchronize()
+    assert seen == list(range(steps))
+    assert_close(f"P4 {name} vs reference golden", out, g[name], rel_rms=2e-5)
