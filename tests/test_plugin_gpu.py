@@ -222,7 +222,7 @@ def test_p5_vae_encode_wrapper():
     torch.manual_seed(77)
     out = w(lambda p: None, px)
     torch.manual_seed(77)
-    noise = torch.randn(2, cfg["latent_channels"], 8, 8)
+    noise = torch.randn(2, cfg["latent_channels"], 32, 32)  # the tiny VAE has one downsample: 64 -> 32
     with torch.no_grad():
         ref = OV.posterior(OV.encode_moments(sd, cfg, 2.0 * px.movedim(-1, 1) - 1.0), noise)
     assert out.device.type == "cpu" and out.dtype == torch.float32

@@ -75,7 +75,7 @@ def test_vae_encode_vs_reference_golden(dtype, tol):
     z2 = eng.encode(px)
     torch.cuda.synchronize()
     # same noise as the golden's; not bit-equal run to run because GroupNorm statistics are accumulated with float atomics
-    assert_close(f"vae encode default noise draw {dtype}", z2, z, rel_rms=2e-3)
+    assert_close(f"vae encode default noise draw {dtype}", z2, z, rel_rms=2e-3 if dtype == torch.float16 else 1.5e-2)
 
 
 def test_vae_encode_sdxl_width_vs_oracle_fp32():
