@@ -17,7 +17,7 @@
 //
 // The A operand is fetched in one of two ways:
 //   mode 0  plain row-major [M, K] (optionally the channel concatenation of two matrices)
-//   mode 1  3x3 stride-1 pad-1 convolution on NHWC: k-chunk = (filter tap, 64-channel slice); the tile of
+//   mode 1  3x3 stride-1 pad-1 convolution on NHWC: k-chunk = (64-channel slice, filter tap); the tile of
 //           128 output pixels is a (tile_n x tile_h x tile_w) box and the tap shifts the box by (ky-1, kx-1);
 //           TMA zero-fills the out-of-image part, which is exactly the convolution's zero padding.
 #include "common.cuh"
@@ -58,6 +58,10 @@ struct GemmKParams {
   int seg_period, seg_split;
   const void* bias2;
   const void* rowvec2;
+  // tile order: 0 = consecutive tiles walk M (the B tile is shared by the CTAs running at the same time, A is re-streamed
+  // once per N tile), 1 = consecutive tiles walk N (A rows shared, B re-streamed once per group of M tiles).  The host
+  // re-streams whichever operand is smaller, i.e. the one that stays in L2.
+  int n_fast;
   int rowvec_mul;  // rowvec multiplies (per-sample gate) instead of being added
   int act_col0;    // the activation applies to output columns >= act_col0 only
 };
@@ -188,10 +192,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint32_t phase = 0;
     const uint32_t tx_bytes = ((uint32_t)kATileBytes + b_tile_bytes) * CG;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
-      const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
-      const int n_blk = tile / tiles_mu;
+      const int m_unit = p.n_fast ? tile / p.tiles_n : tile % tiles_mu;
+      const int n_blk = p.n_fast ? tile % p.tiles_n : tile / tiles_mu;
+      const int m_blk = m_unit * CG + (int)cta_rank;
       // a pair's 256 rows never straddle a segment boundary (host-checked), so the weight set is per tile
-      const CUtensorMap* mb = (EXT && p.seg_period && ((tile % tiles_mu) * (CG * 128)) % p.seg_period >= p.seg_split) ? &mapB2 : &mapB;
+      const CUtensorMap* mb = (EXT && p.seg_period && (m_unit * (CG * 128)) % p.seg_period >= p.seg_split) ? &mapB2 : &mapB;
       int cn = 0, ch = 0, cw = 0;
       if (p.mode == 1) {
         const int tpi = p.tiles_w * p.tiles_h;
@@ -206,19 +211,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const uint32_t fb = full_bar(stage);
         const uint32_t a_dst = a_base + (uint32_t)stage * kATileBytes;
         const uint32_t b_dst = b_base + (uint32_t)stage * b_tile_bytes;
+        int bcol = kc * 64;
         if constexpr (CG == 1) {
           mbar_expect_tx(fb, tx_bytes);
           if (p.mode == 0) {
             if (kc < p.split_chunk) tma_load_2d(a_dst, &mapA, fb, kc * 64, m_blk * 128);
             else tma_load_2d(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
           } else {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
+            // k order = (64-channel slice, tap): the nine shifted boxes of one slice are fetched back to back, so
+            // they hit L2 whatever the channel count (tap-major order re-streamed the whole activation from HBM nine
+            // times once 74 pairs x 256 pixels x C channels outgrew L2).  The weight column follows the tap-major packing.
+            const int cc = kc / 9;
+            const int tap = kc - cc * 9;
             const int ky = tap / 3, kx = tap - ky * 3;
+            bcol = (tap * p.chunks_per_tap + cc) * 64;
             if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d(b_dst, mb, fb, kc * 64, n_blk * BN);
+          tma_load_2d(b_dst, mb, fb, bcol, n_blk * BN);
         } else {
           // both CTAs' loads complete on the leader's barrier; the leader arms it for the pair's bytes
           if (cta_rank == 0) mbar_expect_tx(fb, tx_bytes);
@@ -227,13 +237,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (kc < p.split_chunk) tma_load_2d_cg2(a_dst, &mapA, fb, kc * 64, m_blk * 128);
             else tma_load_2d_cg2(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
           } else {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
+            const int cc = kc / 9;  // (slice, tap) order, see the single-CTA branch
+            const int tap = kc - cc * 9;
             const int ky = tap / 3, kx = tap - ky * 3;
+            bcol = (tap * p.chunks_per_tap + cc) * 64;
             if (cc < p.split_chunk) tma_load_4d_cg2(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d_cg2(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d_cg2(b_dst, mb, fb, kc * 64, n_blk * BN + (int)cta_rank * (BN / 2));
+          tma_load_2d_cg2(b_dst, mb, fb, bcol, n_blk * BN + (int)cta_rank * (BN / 2));
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -295,8 +306,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int ncols_out = geglu ? (BN >> 1) : BN;
     int it = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
-      const int m_blk = (tile % tiles_mu) * CG + (int)cta_rank;
-      const int n_blk = tile / tiles_mu;
+      const int m_unit = p.n_fast ? tile / p.tiles_n : tile % tiles_mu;
+      const int n_blk = p.n_fast ? tile % p.tiles_n : tile / tiles_mu;
+      const int m_blk = m_unit * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -306,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const bool row_ok = m < p.M;
       const int n0 = n_blk * BN;            // first accumulator column of this tile (weight row index)
       const int out_n0 = n_blk * ncols_out; // first output column
-      const bool seg1 = EXT && p.seg_period && ((tile % tiles_mu) * (CG * 128)) % p.seg_period >= p.seg_split;
+      const bool seg1 = EXT && p.seg_period && (m_unit * (CG * 128)) % p.seg_period >= p.seg_split;
       const void* const bias_p = seg1 ? p.bias2 : p.bias;
       const void* const rowvec_p = seg1 ? p.rowvec2 : p.rowvec;
       const bool act_on = !EXT || n0 >= p.act_col0;
@@ -495,6 +507,17 @@ static int pick_block_n(int N, int epilogue) {
   return bn;
 }
 
+// Tile order (GemmKParams::n_fast): re-stream the smaller operand.  B200_GEMM_RASTER = m | n forces one order.
+static int raster_n_fast(size_t a_elems, size_t b_elems, int tiles_n) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("B200_GEMM_RASTER");
+    forced = !e ? 0 : (e[0] == 'n' ? 2 : 1);
+  }
+  if (forced) return forced == 2;
+  return (tiles_n > 1 && a_elems > b_elems) ? 1 : 0;
+}
+
 static bool use_pair_kernel() {
   static int v = -1;
   if (v < 0) {
@@ -639,6 +662,7 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2), "gemm: LayerNorm folding needs ln_c and ln_d (single A source)");
   p.rowvec_mul = d->rowvec_mul;
   p.act_col0 = d->act_col0;
+  p.n_fast = raster_n_fast((size_t)d->M * d->K, (size_t)d->N * d->K, p.tiles_n);
   B200_CHECK_ARG(d->act_col0 >= 0 && d->act_col0 % bn == 0, "gemm: act_col0 (%d) must be a multiple of block_n (%d)", d->act_col0, bn);
   if (d->B2) {
     // tiles of 256 rows (CTA pairs) must not straddle a segment boundary
@@ -739,6 +763,7 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   B200_CHECK_ARG(!d->temb || d->ld_temb % 8 == 0, "conv3x3: ld_temb");
   p.rows_per_vec = d->H * d->W;
   p.epilogue = d->epilogue;
+  p.n_fast = raster_n_fast((size_t)p.M * C, (size_t)d->Cout * 9 * C, p.tiles_n);  // activations vs weights (each tap re-reads the same activation rows)
 
   CUtensorMap mA, mA2, mB;
   auto make4 = [&](CUtensorMap* m, const void* base, int Csrc) {
