@@ -500,7 +500,7 @@ def main():
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 # dram__bytes_read+write of one representative launch from the committed `ncu --set full` capture
                 # (profiles/ncu_r1_summary.md): gemm M=16384 N=10240 K=1280, algorithmic bytes 403.7 MB
-                "traffic": 475.2e6, "traffic_launch": "gemm M=16384 N=10240 K=1280 fp16 (algorithmic 403.7e6 B, 429.5e9 FLOP)",
+                "traffic": 367.5e6, "traffic_launch": "gemm M=16384 N=10240 K=1280 fp16 (algorithmic 403.7e6 B, 429.5e9 FLOP; 70.8e6 read + 296.7e6 written)",
                 "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                 "launches": tens["launches"], "avg_launch_ms": tens["ms"] / max(1, tens["launches"]),
                 "flops_per_launch_avg": tens["flops"] / max(1, tens["launches"])}

@@ -2,7 +2,7 @@
 # Round-end measurement bundle (one gpurun call): GPU test suite, SDXL bench (+ reference arm), Flux bench, ncu launch
 # list of exactly the timed region of one bench step, ncu full captures of the top kernels.
 mkdir -p gpurun_out
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -3
+echo "== pytest -m gpu (${B200_BUNDLE_TESTS:-tests})"; timeout 900 python -m pytest ${B200_BUNDLE_TESTS:-tests} -q -m gpu -p no:cacheprovider 2>&1 | tail -3
 echo "== bench sdxl"; timeout 600 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo "exit $?"; tail -c 200 gpurun_out/bench_r1.err; cut -c1-400 gpurun_out/bench_r1.json
 echo "== bench --impl reference"; timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_r1.json 2>/dev/null; echo "exit $?"; cut -c1-300 gpurun_out/bench_ref_r1.json
 echo "== bench flux"; timeout 600 python bench.py --workload flux --steps 2 --warmup 1 > gpurun_out/bench_flux_r1.json 2> gpurun_out/bench_flux_r1.err; echo "exit $?"; tail -c 200 gpurun_out/bench_flux_r1.err; cut -c1-400 gpurun_out/bench_flux_r1.json
