@@ -340,8 +340,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--sampler_steps", type=int, default=30)
-    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux"],
-                    help="sdxl = BASELINE.json's headline config (default); flux = configs[4]: Flux.1-dev 1024x1024, 20 steps, batch 4, bf16")
+    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "sd15", "flux"],
+                    help="sdxl = BASELINE.json's headline config (default); sd15 = configs[1]: SD1.5 512x512, Euler-a 20 steps, "
+                         "batch 8; flux = configs[4]: Flux.1-dev 1024x1024, 20 steps, batch 4, bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
@@ -373,9 +374,19 @@ def main():
     lib.check(lib.load().b200_device_ok())
     peaks = load_peaks()
 
+    sd15 = args.workload == "sd15"
+    if sd15:  # BASELINE.json configs[1]
+        if args.size == 1024:
+            args.size = 512
+        if args.sampler_steps == 30:
+            args.sampler_steps = 20
     B, S = args.batch, args.sampler_steps
     hw = args.size // 8
-    ucfg, vcfg = synthetic.SDXL, synthetic.VAE_SDXL
+    ucfg, vcfg = (synthetic.SD15, synthetic.VAE_SD15) if sd15 else (synthetic.SDXL, synthetic.VAE_SDXL)
+    wl_name = "SD1.5" if sd15 else "SDXL-base"
+    gflop_key = "sd15@64" if sd15 else "sdxl@128"
+    unet_gflop = synthetic.UNET_GFLOP_PER_SAMPLE[gflop_key] * (hw * hw) / ((64 * 64) if sd15 else (128 * 128))
+    vae_gflop = synthetic.VAE_GFLOP_PER_IMAGE["sdxl@1024"] * (args.size * args.size) / (1024 * 1024)  # same decoder architecture
     usd = synthetic.random_unet_state_dict(ucfg, device=dev, dtype=torch.float16, seed=0)
     vsd = synthetic.random_vae_decoder_state_dict(vcfg, device=dev, dtype=torch.bfloat16, seed=1)
     pipe = Txt2ImgPipeline(ucfg, usd, vae_cfg=vcfg, vae_state_dict=vsd, dtype=torch.float16, device=dev)
@@ -393,9 +404,9 @@ def main():
         "noise": draw().pin_memory(),
         "step_noise": torch.stack([draw() for _ in range(S - 1)]).pin_memory(),
         "cond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
-                 "vector": torch.randn(B, ucfg["adm_in_channels"], generator=g0).half().pin_memory()},
+                 "vector": torch.randn(B, ucfg["adm_in_channels"] or 8, generator=g0).half().pin_memory()},
         "uncond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
-                   "vector": torch.randn(B, ucfg["adm_in_channels"], generator=g0).half().pin_memory()},
+                   "vector": torch.randn(B, ucfg["adm_in_channels"] or 8, generator=g0).half().pin_memory()},
     }
     devin = {"noise": host["noise"].to(dev), "step_noise": host["step_noise"].to(dev),
              "cond": {k: v.to(dev) for k, v in host["cond"].items()},
@@ -511,12 +522,12 @@ def main():
     cpu_base = None
     gpu_ref_ms = None
     if rank == 0 and world == 1:
-        if not args.no_gpu_reference:
+        if not args.no_gpu_reference and not sd15:
             try:
                 gpu_ref_ms = gpu_reference_unet_ms(2 * B, hw)
             except Exception as ex:  # context number only
                 gpu_ref_ms = f"failed: {type(ex).__name__}"
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not sd15:
             threads = usable_cores()
             fwd = cpu_baseline_sample(hw, threads)
             t = fwd()
@@ -525,19 +536,18 @@ def main():
                                    f"= {t:.2f} s; images/s = 1/(2*{S}*t), VAE decode excluded")}
 
     if rank == 0:
-        flops_per_image = 2 * S * synthetic.UNET_GFLOP_PER_SAMPLE["sdxl@128"] * 1e9 + \
-            synthetic.VAE_GFLOP_PER_IMAGE["sdxl@1024"] * 1e9
+        flops_per_image = 2 * S * unet_gflop * 1e9 + vae_gflop * 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": (f"images_per_sec_sd15_{args.size}_euler_a_{S}steps_batch{B}" if sd15 else METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 (UNet) / bf16 (VAE), fp32 accumulate and sampler state", "data": "synthetic",
-            "config": {"workload": f"SDXL-base {args.size}x{args.size} txt2img, Euler-a {S} steps, CFG 7, batch {B}/GPU "
+            "config": {"workload": f"{wl_name} {args.size}x{args.size} txt2img, Euler-a {S} steps, CFG 7, batch {B}/GPU "
                                    f"(UNet batch {2 * B}), VAE decode included; 1 bench step = 1 batch of {B} images/GPU",
                        "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of images only)",
                        "l2": "working set (5.1 GB weights + activations) >> 126 MB L2; no explicit flush",
                        "roofline_pass": "separate instrumented eager pass after the timed region (graph replays cannot be bracketed)"},
             "unet_ms_per_step": unet_ms,
-            "unet_roofline_ms_per_step": 2 * B * synthetic.UNET_GFLOP_PER_SAMPLE["sdxl@128"] * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
+            "unet_roofline_ms_per_step": 2 * B * unet_gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
             "flop_roofline_frac_whole_job": value / world * flops_per_image / (peaks["bf16_tflops_sustained"] * 1e12),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -83,7 +83,8 @@ class GraphedUNet:
 class Txt2ImgPipeline:
     def __init__(self, unet_cfg: dict, unet_state_dict: Dict[str, torch.Tensor], *, vae_cfg: Optional[dict] = None,
                  vae_state_dict: Optional[Dict[str, torch.Tensor]] = None, dtype: torch.dtype = torch.float16,
-                 vae_dtype: torch.dtype = torch.bfloat16, device="cuda", use_graph: bool = True):
+                 vae_dtype: torch.dtype = torch.bfloat16, device="cuda", use_graph: bool = True,
+                 vae_encoder_state_dict: Optional[Dict[str, torch.Tensor]] = None):
         self.device = torch.device(device)
         self.dtype = dtype
         self.unet = UNetEngine(unet_cfg, unet_state_dict, dtype=dtype, device=device)
@@ -94,6 +95,10 @@ class Txt2ImgPipeline:
         if vae_cfg is not None:
             from .vae_engine import VAEDecoderEngine
             self.vae = VAEDecoderEngine(vae_cfg, vae_state_dict, dtype=vae_dtype, device=device)
+        self.vae_encoder = None
+        if vae_cfg is not None and vae_encoder_state_dict is not None:
+            from .vae_engine import VAEEncoderEngine
+            self.vae_encoder = VAEEncoderEngine(vae_cfg, vae_encoder_state_dict, dtype=vae_dtype, device=device)
 
     def _graph_for(self, batch, reps, hh, ww, n_ctx) -> GraphedUNet:
         key = (batch, reps, hh, ww, n_ctx)
@@ -105,8 +110,10 @@ class Txt2ImgPipeline:
     def sample(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, *, steps: int = 30,
                sampler: str = "euler_a", cfg_scale: float = 7.0, sigmas: Optional[torch.Tensor] = None,
                step_noise: Optional[torch.Tensor] = None, eta: float = 1.0, s_noise: float = 1.0,
-               callback: Optional[Callable] = None) -> torch.Tensor:
+               callback: Optional[Callable] = None, init_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns the final latent [B,4,h,w] fp32 on the device.
+        init_latent (img2img): the start is noise * sigmas[0] + init_latent (noise_scaling with max_denoise=False,
+        k_prediction.py:94-104) instead of the txt2img start.
         noise: [B,4,h,w] N(0,1) (host or device).  step_noise: [steps-1 or more, B,4,h,w] for ancestral samplers
         (row i is added after step i, matching the order in which ImageRNG.next() is drawn by the reference)."""
         dev = self.device
@@ -134,7 +141,10 @@ class Txt2ImgPipeline:
         x = gu.x
         # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: max_denoise, zero latent)
         x.copy_(put(noise, torch.float32))
-        x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)))
+        if init_latent is None:
+            x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)))
+        else:
+            x.mul_(float(sigmas[0])).add_(put(init_latent, torch.float32))
         sn_dev = put(step_noise, torch.float32) if step_noise is not None else None
         # per-step scalar tables (sigma per image, UNet timestep = index of nearest log-sigma)
         sig_tab = sigmas[:-1].to(dev).view(-1, 1).expand(-1, b).contiguous()
@@ -151,6 +161,32 @@ class Txt2ImgPipeline:
         sampling.run_sampler(eps_fn, x, plan, cfg_scale=cfg_scale, has_uncond=has_uncond, noise_fn=noise_fn,
                              callback=callback)
         return x
+
+    @staticmethod
+    def img2img_schedule(sigmas: torch.Tensor, steps: int, denoising_strength: float) -> torch.Tensor:
+        """setup_img2img_steps (modules/sd_samplers_common.py:24-33, default options) + the slice of
+        sample_img2img (modules/sd_samplers_kdiffusion.py:140-143): the last t_enc + 1 sigmas of the full schedule."""
+        t_enc = int(min(denoising_strength, 0.999) * steps)
+        return sigmas[steps - t_enc - 1:]
+
+    @torch.no_grad()
+    def img2img(self, cond: dict, uncond: Optional[dict], init: torch.Tensor, noise: torch.Tensor, *, steps: int = 30,
+                denoising_strength: float = 0.75, sampler: str = "euler_a", cfg_scale: float = 7.0,
+                vae_noise: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        """img2img / hires-fix second pass (KDiffusionSampler.sample_img2img, modules/sd_samplers_kdiffusion.py:136-194):
+        `init` is either pixels NHWC [B,H,W,3] in [0,1] (encoded through the fused VAE encoder + process_in, as
+        StableDiffusionProcessingImg2Img.init does via images_tensor_to_samples) or a latent NCHW [B,4,h,w].
+        Returns the final latent."""
+        if init.dim() == 4 and init.shape[-1] == 3:
+            if self.vae_encoder is None:
+                raise RuntimeError("pipeline built without a VAE encoder")
+            latent = self.vae_encoder.encode(init.to(self.device).float().contiguous(), vae_noise, process_in=True)
+        else:
+            latent = init
+        full = sampling.make_sigmas(self.pred, sampler, steps)
+        sched = self.img2img_schedule(full, steps, denoising_strength)
+        return self.sample(cond, uncond, noise, steps=len(sched) - 1, sampler=sampler, cfg_scale=cfg_scale, sigmas=sched,
+                           init_latent=latent, **kw)
 
     @torch.no_grad()
     def decode(self, latent: torch.Tensor) -> torch.Tensor:

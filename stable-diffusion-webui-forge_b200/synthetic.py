@@ -25,6 +25,8 @@ SDXL = dict(
 VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
 
+VAE_SD15 = dict(VAE_SDXL, scaling_factor=0.18215)
+
 # algorithmic FLOPs (2*MACs of conv/linear/attention matmuls) per sample-forward, measured on the reference
 # modules with torch.utils.flop_counter
 UNET_GFLOP_PER_SAMPLE = {"sdxl@128": 6761.2, "sd15@64": 803.3}

@@ -208,3 +208,17 @@ def test_flux_schedule_matches_oracle_and_known_values():
         assert torch.equal(a, b) and float(a[0]) == 1.0 and float(a[-1]) == 0.0 and bool((a[:-1] > a[1:]).all())
     noise = torch.randn(2, 16, 4, 4)
     assert torch.equal(p.noise_scaling(1.0, noise), OS.const_noise_scaling(1.0, noise, torch.zeros_like(noise)))
+
+
+def test_img2img_schedule_matches_setup_img2img_steps():
+    """modules/sd_samplers_common.py:24-33 (default options) + the sigma slice of sample_img2img
+    (modules/sd_samplers_kdiffusion.py:140-143): t_enc = int(min(strength, 0.999) * steps), last t_enc + 2 sigmas."""
+    import torch
+
+    from b200forge.pipeline import Txt2ImgPipeline
+    sig = torch.linspace(14.6, 0.03, 30).tolist() + [0.0]
+    sig = torch.tensor(sig)
+    for steps, strength, t_enc in ((30, 0.75, 22), (30, 1.0, 29), (30, 0.05, 1), (30, 0.0, 0), (20, 0.5, 10)):
+        s = Txt2ImgPipeline.img2img_schedule(sig[: steps + 1] if steps == 30 else torch.cat([sig[:steps], sig[-1:]]), steps, strength)
+        assert len(s) == t_enc + 2, (steps, strength, len(s))
+        assert float(s[-1]) == 0.0

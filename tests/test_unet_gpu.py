@@ -156,3 +156,40 @@ def test_sampler_loop_equals_oracle_loop_given_same_eps():
                        noise_fn=(lambda i: nd[i]) if sampler == "euler_a" else None)
         torch.cuda.synchronize()
         assert_close(f"loop {sampler} fused vs oracle", xd, ref, rel_rms=2e-6)
+
+
+def test_img2img_vs_oracle():
+    """img2img (sample_img2img, modules/sd_samplers_kdiffusion.py:136-194): pixels -> fused VAE encode + process_in ->
+    noise * sigma_sched[0] + latent -> Euler over the last t_enc + 1 sigmas, vs the same steps through the oracle in fp32."""
+    from b200forge.pipeline import Txt2ImgPipeline
+    from oracle import vae as OV
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg, vcfg = CF.CONFIGS["tiny_xl"], CF.VAE_CONFIGS["tiny"]
+    sd = OU.random_state_dict(cfg, seed=1)
+    esd = OV.random_encoder_state_dict(vcfg, seed=8)
+    pipe = Txt2ImgPipeline(cfg, sd, vae_cfg=vcfg, vae_state_dict=OV.random_state_dict(vcfg, seed=3),
+                           vae_encoder_state_dict=esd, dtype=torch.float16, vae_dtype=torch.float16, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    B, steps, strength = 2, 10, 0.5
+    px = torch.rand(B, 64, 64, 3, generator=g)
+    vnoise = torch.randn(B, 4, 32, 32, generator=g)
+    noise = torch.randn(B, 4, 32, 32, generator=g)
+    cond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    uncond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    x = pipe.img2img(cond, uncond, px, noise, steps=steps, denoising_strength=strength, sampler="euler", cfg_scale=5.0, vae_noise=vnoise)
+    torch.cuda.synchronize()
+    pred = S.EpsPrediction()
+    full = S.get_sigmas_uniform(pred, steps)
+    t_enc = int(min(strength, 0.999) * steps)
+    sched = full[steps - t_enc - 1:]
+    assert len(sched) == t_enc + 2 and float(sched[-1]) == 0.0
+    with torch.no_grad():
+        latent = OV.encode_first_stage(esd, vcfg, px, vnoise)
+        den = S.Denoiser(lambda xc, t, cx, yy: OU.unet_forward(sd, cfg, xc, t, cx, yy), pred, cond, uncond, 5.0)  # CPU fp32
+        ref = S.sample_euler(den, noise * sched[0] + latent, sched)
+    mse = (x.cpu() - ref).pow(2).mean()
+    psnr = float(10 * torch.log10(ref.abs().max() ** 2 / mse))
+    m, r = err_stats(x, ref)
+    print(f"[parity] img2img euler: PSNR={psnr:.1f} dB max_abs={m:.3e} rel_rms={r:.3e}")
+    assert psnr >= 35.0, psnr
