@@ -178,6 +178,12 @@ int b200_silu(const void* x, void* y, size_t n, int dtype, b200_stream_t s);
 /* Row softmax in place on [rows, cols] with scale; columns >= valid_cols are treated as masked and written as 0
  * (VAE single-head attention, backend/nn/vae.py:118-137; generic head dims with padded key counts). */
 int b200_softmax_rows(void* x, int rows, int cols, int valid_cols, int ld, float scale, int dtype, b200_stream_t s);
+/* Block-diagonal variant: row r attends to columns (r / block_rows) * block_cols + [0, valid_in_block) only and every other
+ * column is written as 0.  S = Q_h K_h^T over a whole batch [B*Lq, B*Lk] followed by this softmax and P V_h is per-sample
+ * attention for one head in three launches — the path for head dims the flash kernels do not cover (SD1.5's 160,
+ * backend/nn/unet.py:133-155 with num_heads = 8 at 1280 channels). */
+int b200_softmax_rows_blockdiag(void* x, int rows, int cols, int ld, float scale, int block_rows, int block_cols,
+                                int valid_in_block, int dtype, b200_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * UNet entry: sinusoidal timestep embedding (backend/nn/unet.py:55-67) -> [B, dim] in dtype,

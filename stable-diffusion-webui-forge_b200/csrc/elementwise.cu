@@ -348,18 +348,24 @@ __global__ void unet_input_im2col_kernel(const float* __restrict__ x, const floa
 }
 
 template <bool BF16>
-__global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2, int valid) {
-  // one CTA per row; cols up to 64K
+__global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2, int valid,
+                                    int block_rows, int block_cols) {
+  // one CTA per row; cols up to 64K.  The row attends to the column window [lo, hi): the prefix [0, valid) when
+  // block_rows == 0, else the diagonal block of its row group — (row / block_rows) * block_cols + [0, valid) — which
+  // turns one big GEMM over a whole batch into per-sample attention (everything outside the window is written as 0).
   const int row = blockIdx.x;
+  const int lo = block_rows > 0 ? (row / block_rows) * block_cols : 0;
+  const int hi = lo + valid;
+  const int c_begin = lo & ~7, c_end = (hi + 7) & ~7;
   __shared__ float red[32];
   char* base = reinterpret_cast<char*>(x) + (size_t)row * ld * 2;
   float mx = -INFINITY;
-  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+  for (int c = c_begin + threadIdx.x * 8; c < c_end; c += blockDim.x * 8) {
     float v[8];
     load8<BF16>(base, (size_t)c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (c + i < valid) mx = fmaxf(mx, v[i]);
+      if (c + i >= lo && c + i < hi) mx = fmaxf(mx, v[i]);
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -368,12 +374,12 @@ __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, in
   for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float s = 0.f;
-  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+  for (int c = c_begin + threadIdx.x * 8; c < c_end; c += blockDim.x * 8) {
     float v[8];
     load8<BF16>(base, (size_t)c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (c + i < valid) s += exp2f((v[i] - mx) * scale_log2);
+      if (c + i >= lo && c + i < hi) s += exp2f((v[i] - mx) * scale_log2);
   }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -383,9 +389,14 @@ __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, in
   const float inv = 1.0f / s;
   for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
     float v[8];
-    load8<BF16>(base, (size_t)c, v);
+    if (c >= c_begin && c < c_end) {
+      load8<BF16>(base, (size_t)c, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (c + i < valid) ? exp2f((v[i] - mx) * scale_log2) * inv : 0.f;
+      for (int i = 0; i < 8; ++i) v[i] = (c + i >= lo && c + i < hi) ? exp2f((v[i] - mx) * scale_log2) * inv : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
     store8<BF16>(base, (size_t)c, v);
   }
 }
@@ -591,8 +602,20 @@ extern "C" int b200_softmax_rows(void* x, int rows, int cols, int valid_cols, in
   B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && valid_cols > 0 && valid_cols <= cols,
                  "softmax_rows: bad arguments");
   DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(x, rows, cols, ld,
-                                                                                  scale * 1.4426950408889634f, valid_cols));
+                                                                                  scale * 1.4426950408889634f, valid_cols, 0, 0));
   B200_CHECK_LAUNCH("softmax_rows");
+  return B200_OK;
+}
+
+extern "C" int b200_softmax_rows_blockdiag(void* x, int rows, int cols, int ld, float scale, int block_rows, int block_cols,
+                                           int valid_in_block, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && block_rows > 0 && block_cols > 0 &&
+                     valid_in_block > 0 && valid_in_block <= block_cols && rows % block_rows == 0 &&
+                     (rows / block_rows - 1) * block_cols + valid_in_block <= cols,
+                 "softmax_rows_blockdiag: bad arguments");
+  DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(
+                            x, rows, cols, ld, scale * 1.4426950408889634f, valid_in_block, block_rows, block_cols));
+  B200_CHECK_LAUNCH("softmax_rows_blockdiag");
   return B200_OK;
 }
 

@@ -101,6 +101,7 @@ SIGNATURES = {
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_silu": (_i, [_vp, _vp, _sz, _i, _vp]),
     "b200_softmax_rows": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "b200_softmax_rows_blockdiag": (_i, [_vp, _i, _i, _i, _f, _i, _i, _i, _i, _vp]),
     "b200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_unet_input_im2col": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(StepDesc), _vp]),

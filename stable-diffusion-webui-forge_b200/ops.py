@@ -256,6 +256,36 @@ def attention_generic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: 
     return out
 
 
+def attention_blockdiag(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, scale: float,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Any head dim (multiple of 8) and any key count, batched over the samples: per head ONE S = Q_h K_h^T over the
+    whole batch [B*Lq, B*Lk], a block-diagonal row softmax (each sample's rows keep only their own keys) and ONE
+    O_h = P V_h — 3 launches per head instead of 3 per (sample, head).  q [B, Lq, H*Dh]; k, v [B, Lk, H*Dh] whose batch
+    stride equals Lk rows (so [B*Lk, H*Dh] is one matrix); B*Lk must be a multiple of 8."""
+    b, lq, hd = q.shape
+    lk = k.shape[1]
+    dh = hd // heads
+    assert dh % 8 == 0 and (b * lk) % 8 == 0
+    for t, L in ((q, lq), (k, lk), (v, lk)):
+        assert t.stride(2) == 1 and t.stride(0) == L * t.stride(1), "batch must be contiguous in rows"
+    q2 = q.as_strided((b * lq, hd), (q.stride(1), 1))
+    k2 = k.as_strided((b * lk, hd), (k.stride(1), 1))
+    v2 = v.as_strided((b * lk, hd), (v.stride(1), 1))
+    if out is None:
+        out = torch.empty((b, lq, hd), dtype=q.dtype, device=q.device)
+    o2 = out.view(b * lq, hd)
+    vt = transpose_rows(v2)  # V^T [H*Dh, B*Lk]
+    s = torch.empty((b * lq, b * lk), dtype=q.dtype, device=q.device)
+    for h in range(heads):
+        sl = slice(h * dh, (h + 1) * dh)
+        gemm(q2[:, sl], k2[:, sl], out=s)
+        _l.check(_l.load().b200_softmax_rows_blockdiag(s.data_ptr(), b * lq, b * lk, s.stride(0), scale, lq, lk, lk,
+                                                       _dt(s), _stream()))
+        _count()
+        gemm(s, vt[sl], out=o2[:, sl])
+    return out
+
+
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
               silu: bool = False, x2: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:

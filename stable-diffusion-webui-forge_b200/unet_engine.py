@@ -16,8 +16,8 @@ libb200forge launches on NHWC activations:
   LayerNorm           never a kernel: gamma is folded into the consumer GEMM's weights, mean / rstd are applied in its
                       epilogue from row sums that the producer GEMM's epilogue accumulated (ops.fold_layernorm)
   cross-attention K|V projected once per job from the constant context (fill_kv_cache), not once per step
-  head dims           40 / 80 (SD1.5) zero-padded to 64 / 128 in the packed projections; 160 through
-                      GEMM -> softmax_rows -> GEMM (ops.attention_generic)
+  head dims           40 / 80 (SD1.5) zero-padded to 64 / 128 in the packed projections; 160 through one
+                      GEMM -> block-diagonal softmax -> GEMM per head over the whole batch (ops.attention_blockdiag)
   skip concat         never materialised: GN-apply, the 1x1 skip GEMM and the conv read both sources
 
 No torch operator runs on the data path; torch only provides buffers (`torch.empty`) and the stream.
@@ -281,7 +281,10 @@ class UNetEngine:
             if flash:
                 att = ops.attention(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
             else:
-                att = ops.attention_generic(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
+                if (n * L) % 8 == 0:  # one GEMM / block-diagonal softmax / GEMM per head over the whole batch
+                    att = ops.attention_blockdiag(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
+                else:
+                    att = ops.attention_generic(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
             ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t, row_stats_out=ops.zero_(st2))
             # cross attention
             qq = ops.gemm(t, w[q + ".attn2.q"], ln=(st2, w[q + ".attn2.q.c"], w[q + ".attn2.q.d"], 1e-5)).view(n, L, cw)
@@ -293,6 +296,9 @@ class UNetEngine:
             if flash:
                 kv = kvb[: n * n_ctx].view(n, n_ctx, 2 * cw)
                 att = ops.attention(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale)
+            elif (n * n_ctx) % 8 == 0:
+                kv = kvb[: n * n_ctx].view(n, n_ctx, 2 * cw)
+                att = ops.attention_blockdiag(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale)
             else:
                 # key count rounded up to 8: the extra rows belong to the next image (or the zeroed slack) and are
                 # masked by the softmax (valid_keys), so they contribute exactly 0

@@ -356,3 +356,18 @@ def test_gemm_layernorm_fold_and_row_stats():
     torch.cuda.synchronize()
     refg = O.geglu(O.layer_norm(tf, gamma.float(), beta.float(), 1e-5), w2.float(), b2.float())
     assert_close("LN folded into GEGLU GEMM", g, refg, rel_rms=4e-3)
+
+
+def test_attention_blockdiag_vs_oracle():
+    """Head dim 160 (SD1.5, 1280 channels / 8 heads): per head one S = Q_h K_h^T over the whole batch, block-diagonal
+    softmax, one P V_h — against the oracle's per-sample attention; self (Lk = L) and cross (77 keys) shapes."""
+    ops = _ops()
+    B, H, Dh = 16, 8, 160
+    for L, Lk, seed in ((256, 256, 70), (64, 77, 71)):
+        q = _rand(B, L, H * Dh, seed=seed)
+        k = _rand(B, Lk, H * Dh, seed=seed + 10)
+        v = _rand(B, Lk, H * Dh, seed=seed + 20)
+        out = ops.attention_blockdiag(q, k, v, H, scale=Dh ** -0.5)
+        torch.cuda.synchronize()
+        ref = O.attention(q.float(), k.float(), v.float(), H)
+        assert_close(f"attention_blockdiag L={L} Lk={Lk}", out, ref, rel_rms=3e-3)
