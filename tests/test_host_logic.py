@@ -222,3 +222,39 @@ def test_img2img_schedule_matches_setup_img2img_steps():
         s = Txt2ImgPipeline.img2img_schedule(sig[: steps + 1] if steps == 30 else torch.cat([sig[:steps], sig[-1:]]), steps, strength)
         assert len(s) == t_enc + 2, (steps, strength, len(s))
         assert float(s[-1]) == 0.0
+
+
+def test_ctypes_descriptors_match_the_c_header_layout(tmp_path):
+    """The ctypes Structures in lib.py must have exactly the size and field offsets of the structs in
+    include/b200forge.h: a tiny C program (gcc) prints sizeof / offsetof for every field."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    from b200forge import lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"b200_gemm_desc": lib.GemmDesc, "b200_conv3x3_desc": lib.Conv3x3Desc, "b200_attn_desc": lib.AttnDesc,
+             "b200_gn_desc": lib.GnDesc, "b200_step_desc": lib.StepDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200forge.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, val = ln.split()
+        cls = pairs[cname]
+        if field == "size":
+            assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
+        else:
+            assert getattr(cls, field).offset == int(val), (cname, field, getattr(cls, field).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
