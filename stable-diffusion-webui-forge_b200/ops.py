@@ -175,6 +175,20 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
 
 
+def conv3x3_supported(h: int, w: int) -> bool:
+    """Whether b200_conv3x3 can tile an [*, h, w, *] image: 128 output pixels per tile must form a box of whole rows
+    (w a power of two <= 128 with h a multiple of 128 // w, or the whole image when it has fewer than 128 pixels) or a
+    128-pixel row segment (w a multiple of 128).  Mirrors the host checks in csrc/gemm.cu."""
+    tile_w = w if w < 128 else 128
+    if 128 % tile_w or w % tile_w:
+        return False
+    tile_h = min(128 // tile_w, h)
+    if h % tile_h or 128 % (tile_w * tile_h):
+        return False
+    tile_n = 128 // (tile_w * tile_h)
+    return tile_n == 1 or (tile_w == w and tile_h == h)
+
+
 def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
             x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             temb: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None,

@@ -102,6 +102,9 @@ class Txt2ImgPipeline:
 
     def _graph_for(self, batch, reps, hh, ww, n_ctx) -> GraphedUNet:
         key = (batch, reps, hh, ww, n_ctx)
+        if not self.unet.supports_latent(hh, ww):
+            raise ops.B200Error(-2, f"latent size {hh}x{ww} does not tile on the TMA convolution path "
+                                    "(every UNet level needs a width that is a power of two <= 128 or a multiple of 128)")
         if key not in self._graphs:
             self._graphs[key] = GraphedUNet(self.unet, batch, reps, hh, ww, n_ctx, self.use_graph)
         return self._graphs[key]

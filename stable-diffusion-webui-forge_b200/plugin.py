@@ -114,7 +114,8 @@ class UNetWrapper:
         x, sigma, c = args["input"], args["timestep"], args["c"]
         ptype = getattr(self.predictor, "prediction_type", "epsilon")
         if (not fast_path_ok(c) or not x.is_cuda or x.dtype != torch.float32 or ptype not in ("epsilon", "v_prediction")
-                or (self.engine.has_label and c.get("y") is None)):
+                or (self.engine.has_label and c.get("y") is None) or x.dim() != 4
+                or not self.engine.supports_latent(x.shape[2], x.shape[3])):
             self.calls_reference += 1
             return apply_model_fn(x, sigma, **c)
         self.calls_fast += 1
@@ -227,7 +228,7 @@ class VAEDecodeWrapper:
         self.output_device = output_device
 
     def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
-        if not samples_in.is_cuda:
+        if not samples_in.is_cuda or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3]):
             return decode_inner_fn(samples_in)
         scaling = self.engine.scaling
         try:
@@ -242,7 +243,7 @@ class VAEEncodeWrapper:
     """`model_options['model_vae_encode_wrapper']` (reference backend/patcher/vae.py:186-191):
     wrapper(encode_inner_fn, pixel_samples [B,H,W,3] in [0,1]) -> latent [B,zc,h,w] fp32 on the output device, the
     un-scaled posterior sample (the diffusion engine applies process_in afterwards, diffusion_engine/sdxl.py:128-132).
-    A `model_vae_regulation` hook or a size that is not a multiple of 8 goes back to Forge's own encode."""
+    A `model_vae_regulation` hook or a size the TMA convolution path cannot tile goes back to Forge's own encode."""
 
     def __init__(self, vae_engine, output_device=None, patcher=None):
         self.engine = vae_engine
@@ -251,8 +252,8 @@ class VAEEncodeWrapper:
 
     def __call__(self, encode_inner_fn: Callable, pixel_samples: torch.Tensor):
         has_reg = self.patcher is not None and self.patcher.model_options.get("model_vae_regulation") is not None
-        if (has_reg or pixel_samples.dim() != 4 or pixel_samples.shape[-1] != 3 or pixel_samples.shape[1] % 8
-                or pixel_samples.shape[2] % 8 or not torch.cuda.is_available()):
+        if (has_reg or pixel_samples.dim() != 4 or pixel_samples.shape[-1] != 3 or not torch.cuda.is_available()
+                or not self.engine.supports_image(pixel_samples.shape[1], pixel_samples.shape[2])):
             return encode_inner_fn(pixel_samples)
         z = self.engine.encode(pixel_samples.to(self.engine.device).float().contiguous())
         return z if self.output_device is None else z.to(self.output_device)

@@ -373,6 +373,20 @@ class UNetEngine:
                                 None if y is None else y.to(self.dtype).contiguous())
         return ops.nhwc_to_nchw(eps, channels=self.out_channels, out_dtype=x.dtype)
 
+    def supports_latent(self, hh: int, ww: int) -> bool:
+        """True when every resolution level of the UNet tiles on the TMA convolution path (ops.conv3x3_supported) and the
+        stride-2 downsamples are exact.  1024x1024 / 512x512 and the other power-of-two sizes do; SDXL's non-square
+        buckets (e.g. 152x104 latents) do not yet — the plug-in hands those back to Forge's own forward."""
+        levels = len(self.cfg["channel_mult"])
+        for _ in range(levels):
+            if not ops.conv3x3_supported(hh, ww):
+                return False
+            if _ != levels - 1:
+                if hh % 2 or ww % 2:
+                    return False
+                hh, ww = hh // 2, ww // 2
+        return True
+
     def forward_sigma(self, x: torch.Tensor, sigma: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
                       y: Optional[torch.Tensor], reps: int, kv_cache=None) -> torch.Tensor:
         """KModel.apply_model's front half fused into the entry (k_model.py:27-36): x fp32 NCHW [B,4,h,w] is

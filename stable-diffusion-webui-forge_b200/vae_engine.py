@@ -121,6 +121,14 @@ class VAEDecoderEngine:
         out = ops.gemm(o.view(n * L, c), w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, c)
 
+    def supports_latent(self, hh: int, ww: int) -> bool:
+        """Every decoder resolution (latent size x 1, 2, 4, ...) must tile on the TMA convolution path."""
+        for _ in range(self.nres):
+            if not ops.conv3x3_supported(hh, ww):
+                return False
+            hh, ww = hh * 2, ww * 2
+        return True
+
     # ------------------------------------------------------------------------------------------ decode
     @torch.no_grad()
     def decode(self, latent: torch.Tensor) -> torch.Tensor:
@@ -220,6 +228,17 @@ class VAEEncoderEngine:
         else:
             qw[: 2 * zc, : 2 * zc] = torch.eye(2 * zc, dtype=self.dtype, device=self.device)
         w["quant.w"], w["quant.b"] = qw, qb
+
+    def supports_image(self, H: int, W: int) -> bool:
+        """Every encoder resolution (image size / 1, 2, 4, ...) must tile on the TMA convolution path."""
+        for lvl in range(self.nres):
+            if not ops.conv3x3_supported(H, W):
+                return False
+            if lvl != self.nres - 1:
+                if H % 2 or W % 2:
+                    return False
+                H, W = H // 2, W // 2
+        return True
 
     @torch.no_grad()
     def moments(self, pixels: torch.Tensor) -> torch.Tensor:

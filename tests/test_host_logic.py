@@ -258,3 +258,29 @@ def test_ctypes_descriptors_match_the_c_header_layout(tmp_path):
             assert getattr(cls, field).offset == int(val), (cname, field, getattr(cls, field).offset, val)
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
+
+
+def test_supported_latent_sizes_and_deferral():
+    """The TMA convolution path tiles power-of-two (<= 128) and multiple-of-128 widths; the engines report what they
+    support and the P3 / P5 wrappers hand everything else back to Forge's own callables."""
+    import torch
+
+    from b200forge import ops, plugin
+    assert all(ops.conv3x3_supported(s, s) for s in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024))
+    assert ops.conv3x3_supported(64, 128) and ops.conv3x3_supported(128, 256)
+    assert not any(ops.conv3x3_supported(h, w) for h, w in ((104, 152), (112, 144), (96, 168), (80, 192 + 8)))
+
+    class Eng:  # stands in for UNetEngine: the wrapper must not touch it for an unsupported size
+        has_label = False
+
+        def supports_latent(self, h, w):
+            return ops.conv3x3_supported(h, w)
+
+    class P:
+        prediction_type = "epsilon"
+
+    w = plugin.UNetWrapper(Eng(), P())
+    sentinel = torch.zeros(1)
+    x = torch.zeros(2, 4, 104, 152)
+    out = w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": torch.ones(2), "c": {"c_crossattn": torch.zeros(2, 77, 8)}})
+    assert out is sentinel and w.calls_reference == 1
