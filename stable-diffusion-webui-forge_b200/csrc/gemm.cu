@@ -64,6 +64,10 @@ struct GemmKParams {
   int n_fast;
   int rowvec_mul;  // rowvec multiplies (per-sample gate) instead of being added
   int act_col0;    // the activation applies to output columns >= act_col0 only
+  // mode 1, generic tiling (FEAT bit 2, experimental): tile_n = 1, tile_w / tile_h powers of two, tiles may overhang the
+  // image (loads zero-fill, stores are masked); the epilogue decodes (image, y, x) per row instead of assuming that a
+  // tile's 128 pixels are consecutive in NHWC order
+  int img_n, img_h, img_w, tile_w_log2;
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
@@ -119,7 +123,8 @@ __device__ __forceinline__ void ln_apply8(uint32_t c_smem, uint32_t d_smem, int 
 // FEAT selects the epilogue build so that each caller only carries the state it uses (the epilogue sits at the
 // 168-register cap):  bit 0 (LNS) LayerNorm folding + output row statistics (UNet transformer blocks),
 // bit 1 (EXT) the Flux-path features (row segments with two weight sets, multiplicative rowvec, partial activation,
-// tanh GELU).  Convolutions and plain linears run the FEAT = 0 build.
+// tanh GELU), bit 2 (GT) generic convolution tiling for image widths that are neither a power of two nor a multiple of
+// 128 (experimental, B200_CONV_GENERAL=1).  Convolutions and plain linears run the FEAT = 0 build.
 template <bool BF16, int CG, int FEAT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -128,6 +133,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   // CG == 2: launched with cluster dims (2,1,1); rank 0 of each pair is the MMA leader.
   constexpr bool LNS = (FEAT & 1) != 0;
   constexpr bool EXT = (FEAT & 2) != 0;
+  constexpr bool GT = (FEAT & 4) != 0;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair (or CTA) index
   const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -314,8 +320,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
-      const int m = m_blk * 128 + r;
-      const bool row_ok = m < p.M;
+      int m = m_blk * 128 + r;
+      bool row_ok = m < p.M;
+      int gt_img = 0, gt_y0 = 0, gt_x0 = 0;  // GT: image and origin of this tile
+      if constexpr (GT) {
+        const int tpi = p.tiles_w * p.tiles_h;
+        gt_img = m_blk / tpi;
+        const int rem = m_blk - gt_img * tpi;
+        const int ty = rem / p.tiles_w;
+        gt_y0 = ty * p.tile_h;
+        gt_x0 = (rem - ty * p.tiles_w) * p.tile_w;
+        const int y = gt_y0 + (r >> p.tile_w_log2), x = gt_x0 + (r & (p.tile_w - 1));
+        row_ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
+        m = (gt_img * p.img_h + y) * p.img_w + x;
+      }
       const int n0 = n_blk * BN;            // first accumulator column of this tile (weight row index)
       const int out_n0 = n_blk * ncols_out; // first output column
       const bool seg1 = EXT && p.seg_period && (m_unit * (CG * 128)) % p.seg_period >= p.seg_split;
@@ -469,8 +487,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const uint32_t addr = my_stg + (uint32_t)rl * 64u + ((((uint32_t)piece) ^ (((uint32_t)rl >> 1) & 3u)) << 4);
             uint32_t o0, o1, o2, o3;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
-            const int mm = m_blk * 128 + quad * 32 + rl;
-            if (mm < p.M && col < p.n_out) {
+            int mm = m_blk * 128 + quad * 32 + rl;
+            bool mm_ok = mm < p.M;
+            if constexpr (GT) {
+              const int rr = quad * 32 + rl;
+              const int y = gt_y0 + (rr >> p.tile_w_log2), x = gt_x0 + (rr & (p.tile_w - 1));
+              mm_ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
+              mm = (gt_img * p.img_h + y) * p.img_w + x;
+            }
+            if (mm_ok && col < p.n_out) {
               uint4 o = make_uint4(o0, o1, o2, o3);
               *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.C) + ((size_t)mm * p.ldc + col) * 2) = o;
             }
@@ -599,6 +624,7 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const 
                        const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
   const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH;
   const bool lns = p.ln_stats != nullptr || p.row_stats_out != nullptr;
+  if (p.tile_w_log2 >= 0 && p.mode == 1 && p.img_n > 0) return launch_gemm_e<4>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
   switch ((lns ? 1 : 0) | (ext ? 2 : 0)) {
     case 0: return launch_gemm_e<0>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
     case 1: return launch_gemm_e<1>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
@@ -724,12 +750,29 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   B200_CHECK_ARG(d->dtype == B200_F16 || d->dtype == B200_BF16, "conv3x3: dtype");
   // output tile = tile_n images x tile_h rows x tile_w columns = 128 consecutive NHWC pixels
   int tile_w = d->W < 128 ? d->W : 128;
-  B200_CHECK_ARG(128 % tile_w == 0 && d->W % tile_w == 0, "conv3x3: W=%d does not tile into 128-pixel rows", d->W);
-  int tile_h = 128 / tile_w;
+  int tile_h = tile_w > 0 && 128 % tile_w == 0 ? 128 / tile_w : 1;
   if (tile_h > d->H) tile_h = d->H;
-  B200_CHECK_ARG(d->H % tile_h == 0 && (128 % (tile_w * tile_h)) == 0, "conv3x3: H=%d does not tile", d->H);
-  int tile_n = 128 / (tile_w * tile_h);
-  B200_CHECK_ARG(tile_n == 1 || (tile_w == d->W && tile_h == d->H), "conv3x3: tiling");
+  int tile_n = (tile_w * tile_h) > 0 && 128 % (tile_w * tile_h) == 0 ? 128 / (tile_w * tile_h) : 0;
+  const bool exact = 128 % tile_w == 0 && d->W % tile_w == 0 && d->H % tile_h == 0 && tile_n > 0 &&
+                     (tile_n == 1 || (tile_w == d->W && tile_h == d->H));
+  int gt_log2 = -1;
+  if (!exact) {
+    static int general = -1;  // experimental until it has run on hardware: B200_CONV_GENERAL=1
+    if (general < 0) {
+      const char* e = getenv("B200_CONV_GENERAL");
+      general = (e && e[0] == '1') ? 1 : 0;
+    }
+    B200_CHECK_ARG(general, "conv3x3: %dx%d does not tile into 128-pixel boxes (width must be a power of two <= 128 or a multiple of 128)",
+                   d->H, d->W);
+    // generic tiling: the widest power-of-two column count that divides W (<= 128), rows to make 128 pixels; tiles
+    // overhang the bottom edge (masked stores, zero-filled loads)
+    tile_w = 1;
+    while (tile_w < 128 && d->W % (tile_w * 2) == 0) tile_w *= 2;
+    tile_h = 128 / tile_w;
+    tile_n = 1;
+    gt_log2 = 0;
+    while ((1 << gt_log2) < tile_w) ++gt_log2;
+  }
   const int C = d->C1 + d->C2;
   GemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -742,8 +785,14 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   p.tile_w = tile_w;
   p.tile_h = tile_h;
   p.tile_n = tile_n;
-  p.tiles_w = d->W / tile_w;
-  p.tiles_h = d->H / tile_h;
+  p.tiles_w = (d->W + tile_w - 1) / tile_w;
+  p.tiles_h = (d->H + tile_h - 1) / tile_h;
+  p.tile_w_log2 = gt_log2;
+  if (gt_log2 >= 0) {
+    p.img_n = d->N;
+    p.img_h = d->H;
+    p.img_w = d->W;
+  }
   int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, d->epilogue);
   B200_CHECK_ARG(bn % 32 == 0 && bn <= 256, "conv3x3: block_n %d invalid", bn);
   B200_CHECK_ARG(d->epilogue != B200_EPI_GEGLU, "conv3x3: GEGLU epilogue not supported");

@@ -371,3 +371,28 @@ def test_attention_blockdiag_vs_oracle():
         torch.cuda.synchronize()
         ref = O.attention(q.float(), k.float(), v.float(), H)
         assert_close(f"attention_blockdiag L={L} Lk={Lk}", out, ref, rel_rms=3e-3)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200_CONV_GENERAL") != "1",
+                    reason="generic convolution tiling is experimental: run with B200_CONV_GENERAL=1")
+@pytest.mark.parametrize("N,H,W,C1,C2,Cout", [(2, 104, 152, 320, 0, 320), (2, 52, 76, 640, 640, 640), (3, 26, 38, 1280, 0, 1280),
+                                              (2, 13, 19, 1280, 0, 1280), (1, 96, 168, 64, 64, 128)])
+def test_conv3x3_generic_tiling(N, H, W, C1, C2, Cout):
+    """Image widths that are neither a power of two nor a multiple of 128 (SDXL's non-square buckets: 1216x832 ->
+    152x104 latents and their /2, /4 levels; odd sizes): tiles overhang the image, loads zero-fill, stores are masked.
+    Includes the time-embedding row and the residual, which are addressed through the decoded pixel index."""
+    ops = _ops()
+    C = C1 + C2
+    x = _rand(N, C, H, W, seed=80)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=81)
+    b = _rand(Cout, seed=82)
+    temb = _rand(N, Cout, seed=83)
+    res = _rand(N, H, W, Cout, seed=84)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    x1 = xn[..., :C1].contiguous()
+    x2 = xn[..., C1:].contiguous() if C2 else None
+    guard = torch.full((N, H, W, Cout), 7.0, device=DEV, dtype=torch.float16)
+    y = ops.conv3x3(x1, ops.pack_conv3x3(w), b, x2=x2, temb=temb, residual=res, out=guard)
+    torch.cuda.synchronize()
+    ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    assert_close(f"conv3x3 generic {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3)
