@@ -193,12 +193,18 @@ def gen_samplers(steps: int = 7):
             return OS.toy_denoiser(x, sigma)
 
     out = dict(sigmas=sig, x0=x0, noise=noise)
-    for name in ("sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral"):
+    runs = [("sample_heun", {}), ("sample_dpm_2", {}), ("sample_dpm_2_ancestral", {}), ("sample_dpmpp_2s_ancestral", {}),
+            ("sample_lms", {}), ("sample_dpmpp_sde", {}), ("sample_dpmpp_2m_sde", {}),
+            ("sample_dpmpp_2m_sde", {"solver_type": "heun"}), ("sample_dpmpp_3m_sde", {})]
+    for name, extra in runs:
         k = iter(range(noise.shape[0]))
-        kw = dict(noise_sampler=lambda s, sn: noise[next(k)]) if "ancestral" in name else {}
+        kw = dict(extra)
+        if "ancestral" in name or "sde" in name:
+            kw["noise_sampler"] = lambda s, sn: noise[next(k)]
+        key = name + ("_heun" if extra.get("solver_type") == "heun" else "")
         with torch.no_grad():
-            out[name] = getattr(ks, name)(Model(), x0.clone(), sig, extra_args={}, disable=True, **kw)
-        print(name, float(out[name].std()))
+            out[key] = getattr(ks, name)(Model(), x0.clone(), sig, extra_args={}, disable=True, **kw)
+        print(key, float(out[key].std()))
     torch.save(out, os.path.join(GOLD, "samplers_toy.pt"))
 
 

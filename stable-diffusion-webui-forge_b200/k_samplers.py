@@ -1,7 +1,8 @@
 """Plug point P4 — k-diffusion sampler functions with the reference's exact call contract
 (k_diffusion/sampling.py:119-137 sample_euler, :140-159 sample_euler_ancestral, :648-671 sample_dpmpp_2m, and the
 two-evaluation samplers :188-214 sample_heun, :217-246 sample_dpm_2, :249-276 sample_dpm_2_ancestral,
-:573-603 sample_dpmpp_2s_ancestral):
+:573-603 sample_dpmpp_2s_ancestral; multistep / SDE: :310-345 sample_lms, :606-646 sample_dpmpp_sde,
+:675-724 sample_dpmpp_2m_sde, :727-778 sample_dpmpp_3m_sde):
 
     fn(model, x, sigmas, extra_args=None, callback=None, disable=None, ...) -> x
 
@@ -33,6 +34,10 @@ reference_sample_heun = None
 reference_sample_dpm_2 = None
 reference_sample_dpm_2_ancestral = None
 reference_sample_dpmpp_2s_ancestral = None
+reference_sample_lms = None
+reference_sample_dpmpp_sde = None
+reference_sample_dpmpp_2m_sde = None
+reference_sample_dpmpp_3m_sde = None
 
 
 def _randn_like(x):
@@ -285,4 +290,193 @@ def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, 
         if float(s1) > 0:
             noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
             ops.sampler_update(x, noise, kind=ops.STEP_LINEAR, sigma=1.0, c_x=1.0, c_d=float(s_noise * up))
+    return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multistep / SDE samplers.  Every update is a linear combination of x, up to two denoised tensors and one noise tensor
+# with host-computed coefficients (fp32 scalar arithmetic like the reference's 0-dim tensors), i.e. one or two
+# B200_STEP_LINEAR launches per model evaluation.  The noise sampler is whatever Forge passes (BrownianTreeNoiseSampler,
+# modules/sd_samplers_kdiffusion.py:196-213); without one the reference function builds its own tree, so that case is
+# handed back.
+def _lin(x, d, *, c_x, c_d, old=None, c_old=0.0, noise=None, c_noise=0.0):
+    ops.sampler_update(x, d, kind=ops.STEP_LINEAR, sigma=1.0, c_x=float(c_x), c_d=float(c_d), old_denoised=old,
+                       c_old=float(c_old) if old is not None else 0.0, noise=noise,
+                       noise_scale=float(c_noise) if noise is not None else 0.0)
+
+
+@torch.no_grad()
+def sample_lms(model, x, sigmas, extra_args=None, callback=None, disable=None, order=4):
+    """k_diffusion/sampling.py:310-345 (coefficients by the same scipy quadrature, :298-307)."""
+    if not _fusable(x):
+        return _defer(reference_sample_lms, "sample_lms", model, x, sigmas, extra_args, callback, disable, order)
+    from scipy import integrate
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    t = sigmas.detach().cpu().numpy()
+
+    def coeff(cur_order, i, j):
+        def fn(tau):
+            prod = 1.
+            for k in range(cur_order):
+                if j == k:
+                    continue
+                prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+            return prod
+        return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+    x = _prep(x).clone()
+    ds = []
+    for i in range(len(t) - 1):
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        d = x.clone()
+        inv = 1.0 / float(t[i])
+        _lin(d, denoised, c_x=inv, c_d=-inv)                      # d = (x - denoised) / sigma
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        cur_order = min(i + 1, order)
+        cs = [coeff(cur_order, i, j) for j in range(cur_order)]
+        hist = list(reversed(ds))[:cur_order]
+        _lin(x, hist[0], c_x=1.0, c_d=cs[0], old=hist[1] if cur_order > 1 else None, c_old=cs[1] if cur_order > 1 else 0.0,
+             noise=hist[2] if cur_order > 2 else None, c_noise=cs[2] if cur_order > 2 else 0.0)
+        if cur_order > 3:
+            _lin(x, hist[3], c_x=1.0, c_d=cs[3])
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None,
+                     r=1 / 2):
+    """k_diffusion/sampling.py:606-646."""
+    if noise_sampler is None or not _fusable(x):
+        return _defer(reference_sample_dpmpp_sde, "sample_dpmpp_sde", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler, r)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(s1) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=float(s1 - s0))
+            continue
+        t, t_next = s0.log().neg(), s1.log().neg()
+        h = t_next - t
+        s = t + h * r
+        fac = 1 / (2 * r)
+        sig_t, sig_s, sig_n = t.neg().exp(), s.neg().exp(), t_next.neg().exp()
+        # step 1
+        sd, su = _ancestral(sig_t, sig_s, eta)
+        s_ = sd.log().neg()
+        x2 = x.clone()
+        n1 = _prep(noise_sampler(float(sig_t) * s_in[0], float(sig_s) * s_in[0]).float())
+        _lin(x2, denoised, c_x=s_.neg().exp() / sig_t, c_d=-(t - s_).expm1(), noise=n1, c_noise=s_noise * su)
+        denoised2 = _prep(model(x2, float(sig_s) * s_in, **extra_args).float())
+        # step 2
+        sd, su = _ancestral(sig_t, sig_n, eta)
+        tn_ = sd.log().neg()
+        b = -(t - tn_).expm1()
+        n2 = _prep(noise_sampler(float(sig_t) * s_in[0], float(sig_n) * s_in[0]).float())
+        _lin(x, denoised2, c_x=tn_.neg().exp() / sig_t, c_d=b * fac, old=denoised, c_old=b * (1 - fac), noise=n2,
+             c_noise=s_noise * su)
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
+                        noise_sampler=None, solver_type='midpoint'):
+    """k_diffusion/sampling.py:675-724."""
+    if solver_type not in {'heun', 'midpoint'}:
+        raise ValueError('solver_type must be \'heun\' or \'midpoint\'')
+    if (noise_sampler is None and eta) or not _fusable(x):
+        return _defer(reference_sample_dpmpp_2m_sde, "sample_dpmpp_2m_sde", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler, solver_type)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    old, h_last = None, None
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(s1) == 0:
+            _lin(x, denoised, c_x=0.0, c_d=1.0)                   # x = denoised
+        else:
+            t, s = -s0.log(), -s1.log()
+            h = s - t
+            eta_h = eta * h
+            c_x = s1 / s0 * (-eta_h).exp()
+            c_d = (-h - eta_h).expm1().neg()
+            c2 = _f32(0.0)
+            if old is not None:
+                r = h_last / h
+                if solver_type == 'heun':
+                    c2 = ((-h - eta_h).expm1().neg() / (-h - eta_h) + 1) * (1 / r)
+                else:
+                    c2 = 0.5 * (-h - eta_h).expm1().neg() * (1 / r)
+            noise, c_n = None, 0.0
+            if eta:
+                noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+                c_n = s1 * (-2 * eta_h).expm1().neg().sqrt() * s_noise
+            _lin(x, denoised, c_x=c_x, c_d=c_d + c2, old=old, c_old=-c2, noise=noise, c_noise=c_n)
+            h_last = h
+        old = denoised
+    return x
+
+
+@torch.no_grad()
+def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
+                        noise_sampler=None):
+    """k_diffusion/sampling.py:727-778."""
+    if (noise_sampler is None and eta) or not _fusable(x):
+        return _defer(reference_sample_dpmpp_3m_sde, "sample_dpmpp_3m_sde", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    d_1, d_2, h_1, h_2 = None, None, None, None
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(s1) == 0:
+            _lin(x, denoised, c_x=0.0, c_d=1.0)
+        else:
+            t, s = -s0.log(), -s1.log()
+            h = s - t
+            h_eta = h * (eta + 1)
+            c_x = torch.exp(-h_eta)
+            c_d = (-h_eta).expm1().neg()
+            c_1, c_2 = _f32(0.0), _f32(0.0)                       # coefficients of denoised_1, denoised_2
+            if h_2 is not None:
+                r0, r1 = h_1 / h, h_2 / h
+                phi_2 = h_eta.neg().expm1() / h_eta + 1
+                phi_3 = phi_2 / h_eta - 0.5
+                # x += phi_2 * d1 - phi_3 * d2 with d1, d2 the divided differences of (denoised, denoised_1, denoised_2)
+                a = phi_2
+                bc = (phi_2 * r0 - phi_3) / (r0 + r1)
+                c_d = c_d + (a + bc) / r0
+                c_1 = -(a + bc) / r0 - bc / r1
+                c_2 = bc / r1
+            elif h_1 is not None:
+                r = h_1 / h
+                phi_2 = h_eta.neg().expm1() / h_eta + 1
+                c_d = c_d + phi_2 / r
+                c_1 = -phi_2 / r
+            noise, c_n = None, 0.0
+            if eta:
+                noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+                c_n = s1 * (-2 * h * eta).expm1().neg().sqrt() * s_noise
+            _lin(x, denoised, c_x=c_x, c_d=c_d, old=d_1, c_old=c_1, noise=noise, c_noise=c_n)
+            if d_2 is not None and float(c_2) != 0.0:
+                _lin(x, d_2, c_x=1.0, c_d=c_2)
+            h_1, h_2 = h, h_1
+        d_1, d_2 = denoised, d_1
     return x

@@ -198,7 +198,8 @@ def install_flux_wrapper(unet_patcher, engine=None) -> FluxWrapper:
 
 # ------------------------------------------------------------------------------------------------- P4 samplers
 _SAMPLER_NAMES = ("sample_euler", "sample_euler_ancestral", "sample_dpmpp_2m", "sample_heun", "sample_dpm_2",
-                  "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral")
+                  "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral", "sample_lms", "sample_dpmpp_sde",
+                  "sample_dpmpp_2m_sde", "sample_dpmpp_3m_sde")
 
 
 def install_samplers(modules: Optional[dict] = None) -> None:

@@ -284,3 +284,58 @@ def test_supported_latent_sizes_and_deferral():
     x = torch.zeros(2, 4, 104, 152)
     out = w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": torch.ones(2), "c": {"c_crossattn": torch.zeros(2, 77, 8)}})
     assert out is sentinel and w.calls_reference == 1
+
+
+def _emulated_sampler_update(x, denoised, *, kind, sigma, dt=0.0, noise=None, noise_scale=0.0, old_denoised=None,
+                             c_x=0.0, c_d=0.0, c_old=0.0):
+    """fp32 torch restatement of csrc/sampler.cu::sampler_update_kernel (the three step kinds), so that the host logic
+    of k_samplers.py can be pinned against the reference's loops without a GPU.  The kernel itself is compared with the
+    oracle in tests/test_kernels_gpu.py / test_plugin_gpu.py."""
+    import torch
+
+    from b200forge import ops
+    f = torch.float32
+    if kind == ops.STEP_EULER:
+        xn = x + ((x - denoised) / torch.tensor(sigma, dtype=f)) * torch.tensor(dt, dtype=f)
+        if noise_scale != 0.0:
+            xn = xn + noise * torch.tensor(noise_scale, dtype=f)
+    else:
+        xn = torch.tensor(c_x, dtype=f) * x + torch.tensor(c_d, dtype=f) * denoised
+        if c_old != 0.0:
+            xn = xn + torch.tensor(c_old, dtype=f) * old_denoised
+        if kind == ops.STEP_LINEAR:
+            if noise_scale != 0.0:
+                xn = xn + torch.tensor(noise_scale, dtype=f) * noise
+        else:
+            old_denoised.copy_(denoised)
+    x.copy_(xn)
+
+
+@pytest.mark.parametrize("key", ["sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral",
+                                 "sample_lms", "sample_dpmpp_sde", "sample_dpmpp_2m_sde", "sample_dpmpp_2m_sde_heun",
+                                 "sample_dpmpp_3m_sde"])
+def test_k_sampler_host_logic_vs_reference_golden(key, monkeypatch):
+    """The per-step coefficient plans of the fused samplers (k_samplers.py) drive an emulation of the update kernel on the
+    CPU and must land on the reference's k-diffusion result for the same toy denoiser and noise stream
+    (tests/golden/samplers_toy.pt, made by oracle/gen_golden.py from k_diffusion/sampling.py itself)."""
+    import os
+
+    import torch
+
+    from b200forge import k_samplers
+    from oracle import sampling as OS
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers_toy.pt"), weights_only=False)
+    monkeypatch.setattr(k_samplers.ops, "sampler_update", _emulated_sampler_update)
+    monkeypatch.setattr(k_samplers, "_fusable", lambda x: True)
+    name = key.replace("_heun", "") if key.endswith("sde_heun") else key
+    kw = {"solver_type": "heun"} if key.endswith("sde_heun") else {}
+    k = iter(range(g["noise"].shape[0]))
+    if "ancestral" in name or "sde" in name:
+        kw["noise_sampler"] = lambda s, sn: g["noise"][next(k)]
+    seen = []
+    out = getattr(k_samplers, name)(lambda x, sigma, **kwargs: OS.toy_denoiser(x, sigma), g["x0"].clone(), g["sigmas"],
+                                    extra_args={}, callback=lambda d: seen.append(d["i"]), disable=True, **kw)
+    assert seen == list(range(len(g["sigmas"]) - 1))
+    err = (out - g[key]).abs().max().item()
+    scale = g[key].abs().max().item()
+    assert err <= 2e-5 * max(1.0, scale), (key, err, scale)
