@@ -247,7 +247,7 @@ class UNetEngine:
     def _kv_buffer(self, n: int, n_ctx: int, width: int) -> torch.Tensor:
         # 8 zeroed slack rows: the GEMM-softmax-GEMM path reads the key count rounded up to a multiple of 8
         buf = torch.empty((n * n_ctx + 8, 2 * width), dtype=self.dtype, device=self.device)
-        ops._l.check(ops._l.load().b200_fill_zero(buf[n * n_ctx:].data_ptr(), 8 * 2 * width * 2, ops._stream()))
+        ops.zero_(buf[n * n_ctx:])
         return buf
 
     def alloc_kv_cache(self, n: int, n_ctx: int) -> Dict[str, torch.Tensor]:

@@ -1,0 +1,341 @@
+"""TEST INFRASTRUCTURE — a torch (CPU, fp32-friendly) emulation of every wrapper in `b200forge.ops`, with the same
+signatures, layouts, epilogue options and in-place / `out=` behaviour as the C-ABI calls they stand in for.
+
+Purpose: the engines (`unet_engine.py`, `flux_engine.py`, `vae_engine.py`), the pipelines and the plug-in wrappers are
+pure launch sequences over `ops.*`.  With this module patched in (`install(monkeypatch)`), those sequences run on the CPU
+in fp32 and can be compared *tightly* (1e-4, not an fp16 tolerance) with the reference goldens — which pins weight
+packing, LayerNorm folding, GEGLU interleaving, two-segment GEMMs, K/V hoisting, head-dim padding, schedules and plans
+without a GPU.  It says nothing about the CUDA kernels themselves: those are compared with the oracle through the C ABI
+in the `-m gpu` tests.  Nothing in the product imports this file.
+
+Each function documents the kernel it mirrors (csrc/*.cu) where the semantics are not obvious from the signature.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+EPI_NONE, EPI_SILU, EPI_GEGLU, EPI_GELU, EPI_GELU_TANH = 0, 1, 2, 3, 4
+STEP_EULER, STEP_DPMPP_2M, STEP_LINEAR = 0, 1, 2
+
+
+def _ret(val: torch.Tensor, out: Optional[torch.Tensor], dtype=None) -> torch.Tensor:
+    if out is None:
+        return val.to(dtype) if dtype is not None else val
+    out.copy_(val.to(out.dtype))
+    return out
+
+
+def _act(x: torch.Tensor, epilogue: int) -> torch.Tensor:
+    if epilogue == EPI_SILU:
+        return x * torch.sigmoid(x)
+    if epilogue == EPI_GELU:
+        return 0.5 * x * (1.0 + torch.erf(x * 0.7071067811865476))
+    if epilogue == EPI_GELU_TANH:
+        return 0.5 * x * (1.0 + torch.tanh(0.7978845608028654 * (x + 0.044715 * x * x * x)))
+    return x
+
+
+def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogue=EPI_NONE, a2=None, bias_along_m=False,
+         out=None, block_n=0, ln=None, row_stats_out=None, rowvec_mul=False, act_col0=0, seg=None):
+    """csrc/gemm.cu epilogue order: LayerNorm fold -> bias -> rowvec (add or multiply) -> activation -> residual ->
+    row statistics of the final fp32 values."""
+    A = a.float() if a2 is None else torch.cat([a.float(), a2.float()], 1)
+    M, K = A.shape
+    rows = torch.arange(M)
+
+    def one(wm, bm, rv):
+        acc = A @ wm.float().t()
+        if ln is not None:
+            st, lc, ld_, eps = ln
+            mean = st[:, 0] / K
+            rstd = torch.rsqrt(torch.clamp(st[:, 1] / K - mean * mean, min=0.0) + eps)
+            acc = rstd[:, None] * (acc - mean[:, None] * lc[None, :].float()) + ld_[None, :].float()
+        if bm is not None:
+            acc = acc + (bm.float()[:, None] if bias_along_m else bm.float()[None, :])
+        if rv is not None and epilogue != EPI_GEGLU:
+            v = rv.float()[rows // rows_per_vec]
+            acc = acc * v if rowvec_mul else acc + v
+        return acc
+
+    acc = one(w, bias, rowvec)
+    if seg is not None:
+        period, split, w2, bias2, rowvec2 = seg
+        acc2 = one(w2, bias2, rowvec2)
+        acc = torch.where(((rows % period) >= split)[:, None], acc2, acc)
+    if epilogue == EPI_GEGLU:
+        N = acc.shape[1]
+        bn = block_n if block_n > 0 else 256
+        t = acc.view(M, N // bn, bn)
+        half = bn // 2
+        val, gate = t[:, :, :half], t[:, :, half:]
+        acc = (val * _act(gate, EPI_GELU)).reshape(M, N // 2)
+    elif epilogue != EPI_NONE:
+        if act_col0 > 0:
+            acc = torch.cat([acc[:, :act_col0], _act(acc[:, act_col0:], epilogue)], 1)
+        else:
+            acc = _act(acc, epilogue)
+    if residual is not None:
+        acc = acc + residual.float()
+    if row_stats_out is not None:
+        row_stats_out[:, 0] += acc.sum(1)
+        row_stats_out[:, 1] += (acc * acc).sum(1)
+    return _ret(acc, out, a.dtype)
+
+
+def zero_(t):
+    return t.zero_()
+
+
+def conv3x3(x1, w_packed, bias=None, *, x2=None, residual=None, temb=None, epilogue=EPI_NONE, out=None, block_n=0):
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    n, h, w_, c = x.shape
+    cout = w_packed.shape[0]
+    wt = w_packed.float().view(cout, 3, 3, c).permute(0, 3, 1, 2)  # k = (ky*3 + kx)*C + c
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None if bias is None else bias.float(), padding=1)
+    if temb is not None:
+        y = y + temb.float()[:, :cout, None, None]
+    y = _act(y, epilogue).permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float().reshape(y.shape)
+    return _ret(y.contiguous(), out, x1.dtype)
+
+
+def attention(q, k, v, heads, *, scale=None, out=None):
+    b, lq, hd = q.shape
+    dh = hd // heads
+    sc = scale if scale is not None else dh ** -0.5
+
+    def split(t):
+        return t.float().reshape(b, t.shape[1], heads, dh).permute(0, 2, 1, 3)
+
+    s = torch.matmul(split(q), split(k).transpose(-1, -2)) * sc
+    o = torch.matmul(torch.softmax(s, -1), split(v)).permute(0, 2, 1, 3).reshape(b, lq, hd)
+    return _ret(o, out, q.dtype)
+
+
+def attention_generic(q, k, v, heads, *, scale, valid_keys=None, out=None):
+    lk = k.shape[1] if valid_keys is None else valid_keys
+    return attention(q, k[:, :lk], v[:, :lk], heads, scale=scale, out=out)
+
+
+def attention_blockdiag(q, k, v, heads, *, scale, out=None):
+    return attention(q, k, v, heads, scale=scale, out=out)
+
+
+def groupnorm(x1, gamma, beta, *, groups=32, eps=1e-5, silu=False, x2=None, sums=None, out=None):
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    shp = x.shape
+    n, c = shp[0], shp[-1]
+    xf = x.float().reshape(n, -1, groups, c // groups)
+    mean = xf.mean(dim=(1, 3), keepdim=True)
+    var = xf.var(dim=(1, 3), unbiased=False, keepdim=True)
+    y = ((xf - mean) * torch.rsqrt(var + eps)).reshape(n, -1, c) * gamma.float() + beta.float()
+    if silu:
+        y = y * torch.sigmoid(y)
+    return _ret(y.reshape(shp), out, x1.dtype)
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    y = F.layer_norm(x.float(), (x.shape[-1],), None if gamma is None else gamma.float(), None if beta is None else beta.float(), eps)
+    return _ret(y, out, x.dtype)
+
+
+def upsample2x(x, out=None):
+    return _ret(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2), out)
+
+
+def im2col3x3(x, *, stride=1, pad_lo=1, pad_hi=1, ldo=None, out=None):
+    n, h, w, c = x.shape
+    ho = (h + pad_lo + pad_hi - 3) // stride + 1
+    wo = (w + pad_lo + pad_hi - 3) // stride + 1
+    ldo = ldo or (9 * c + 7) // 8 * 8
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (pad_lo, pad_hi + 2, pad_lo, pad_hi + 2))
+    cols = torch.zeros((n, ho, wo, ldo), dtype=torch.float32)
+    for ky in range(3):
+        for kx in range(3):
+            tap = ky * 3 + kx
+            patch = xp[:, :, ky:ky + (ho - 1) * stride + 1:stride, kx:kx + (wo - 1) * stride + 1:stride]
+            cols[..., tap * c:(tap + 1) * c] = patch.permute(0, 2, 3, 1)
+    return _ret(cols.reshape(n * ho * wo, ldo), out, x.dtype)
+
+
+def nchw_to_nhwc(x, dtype, *, ldy=None, scale=1.0, out=None):
+    n, c, h, w = x.shape
+    ldy = ldy or c
+    y = torch.zeros((n, h, w, ldy), dtype=torch.float32)
+    y[..., :c] = x.float().permute(0, 2, 3, 1) * scale
+    return _ret(y, out, dtype)
+
+
+def nhwc_to_nchw(x, channels=None, out_dtype=None, out=None):
+    c = channels or x.shape[3]
+    return _ret(x[..., :c].permute(0, 3, 1, 2).contiguous(), out, out_dtype or x.dtype)
+
+
+def transpose_rows(x, out=None):
+    return _ret(x.t().contiguous(), out)
+
+
+def silu(x, out=None):
+    return _ret(x.float() * torch.sigmoid(x.float()), out, x.dtype)
+
+
+def softmax_rows_(x, scale, valid_cols=None):
+    v = valid_cols or x.shape[1]
+    p = torch.zeros_like(x, dtype=torch.float32)
+    p[:, :v] = torch.softmax(x[:, :v].float() * scale, -1)
+    x.copy_(p.to(x.dtype))
+    return x
+
+
+def timestep_embedding(t, dim, dtype, max_period=10000.0, out=None):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t.float()[:, None] * freqs[None]
+    return _ret(torch.cat([torch.cos(args), torch.sin(args)], -1), out, dtype)
+
+
+def unet_input_im2col(x, sigma, dtype, *, reps, ldo, out=None):
+    """csrc/elementwise.cu::unet_input_im2col_kernel: x / sqrt(sigma^2 + 1), 3x3 patches (k = tap*C + c), zero padded to
+    ldo columns, the whole block repeated `reps` times."""
+    b, c, h, w = x.shape
+    xs = x / torch.sqrt(sigma.view(-1, 1, 1, 1) ** 2 + 1.0)
+    cols = im2col3x3(xs.permute(0, 2, 3, 1).contiguous(), ldo=ldo)
+    return _ret(cols.repeat(reps, 1), out, dtype)
+
+
+def adaln(x, shift, scale, *, eps=1e-6, shift1=None, scale1=None, seg_period=0, seg_split=0, out=None):
+    rows, c = x.shape
+    if seg_period <= 0:
+        seg_period = rows // shift.shape[0]
+        seg_split = seg_period
+    if shift1 is None:
+        shift1, scale1 = shift, scale
+    r = torch.arange(rows)
+    b = r // seg_period
+    g1 = ((r % seg_period) >= seg_split)[:, None]
+    sh = torch.where(g1, shift1.float()[b], shift.float()[b])
+    sc = torch.where(g1, scale1.float()[b], scale.float()[b])
+    y = (1.0 + sc) * F.layer_norm(x.float(), (c,), None, None, eps) + sh
+    return _ret(y, out, x.dtype)
+
+
+def qk_norm_rope_(qkv, heads, q_scale, k_scale, cos, sin, *, q_scale1=None, k_scale1=None, seg_split=0, eps=1e-6):
+    rows = qkv.shape[0]
+    period = cos.shape[0]
+    pos = torch.arange(rows) % period
+    g1 = (pos >= (seg_split if q_scale1 is not None else period))[:, None, None]
+    for part, (s0, s1) in enumerate(((q_scale, q_scale1), (k_scale, k_scale1))):
+        t = qkv[:, part * heads * 128:(part + 1) * heads * 128].float().reshape(rows, heads, 128)
+        t = t * torch.rsqrt((t * t).mean(-1, keepdim=True) + eps)
+        sc = s0.float()[None, None, :] if s1 is None else torch.where(g1, s1.float()[None, None, :], s0.float()[None, None, :])
+        t = (t * sc).to(qkv.dtype).float()  # the kernel rounds to the activation dtype here, as the reference's rms_norm does
+        t2 = t.reshape(rows, heads, 64, 2)
+        c, s = cos[pos][:, None, :], sin[pos][:, None, :]
+        o = torch.stack([c * t2[..., 0] - s * t2[..., 1], s * t2[..., 0] + c * t2[..., 1]], -1).reshape(rows, heads * 128)
+        qkv[:, part * heads * 128:(part + 1) * heads * 128] = o.to(qkv.dtype)
+    return qkv
+
+
+def flux_patchify(x, dtype, out=None):
+    B, C, H, W = x.shape
+    t = x.float().view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B * (H // 2) * (W // 2), C * 4)
+    if out is not None:
+        out[:, :4 * C] = t.to(out.dtype)
+        return out
+    return t.to(dtype)
+
+
+def flux_unpatchify(tokens, B, Cc, H, W, *, nchw_f32, out=None):
+    img = tokens[:, :4 * Cc].float().view(B, H // 2, W // 2, Cc, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, H, W)
+    if nchw_f32:
+        return _ret(img, out, torch.float32)
+    return _ret(img.permute(0, 2, 3, 1).contiguous(), out, tokens.dtype)
+
+
+def _denoised(x, e, sigma, prediction):
+    if prediction == 1:
+        s2 = sigma * sigma + 1.0
+        return x / s2 - e * sigma / torch.sqrt(s2)
+    return x - e * sigma
+
+
+def sampler_step(x, eps, denoised, *, kind, sigma, cfg_scale, has_uncond, dt=0.0, noise=None, noise_scale=0.0,
+                 old_denoised=None, c_x=0.0, c_d=0.0, c_old=0.0, prediction=0):
+    """csrc/sampler.cu::sampler_step_kernel."""
+    b, c, h, w = x.shape
+    e = eps[..., :c].float().permute(0, 3, 1, 2)
+    sg = torch.tensor(sigma, dtype=torch.float32)
+    if has_uncond:
+        Du, Dc = _denoised(x, e[:b], sg, prediction), _denoised(x, e[b:], sg, prediction)
+        D = Du + (Dc - Du) * cfg_scale
+    else:
+        D = _denoised(x, e, sg, prediction)
+    denoised.copy_(D)
+    sampler_update(x, D, kind=kind, sigma=sigma, dt=dt, noise=noise, noise_scale=noise_scale, old_denoised=old_denoised,
+                   c_x=c_x, c_d=c_d, c_old=c_old)
+
+
+def sampler_update(x, denoised, *, kind, sigma, dt=0.0, noise=None, noise_scale=0.0, old_denoised=None, c_x=0.0, c_d=0.0,
+                   c_old=0.0):
+    """csrc/sampler.cu::sampler_update_kernel."""
+    f = torch.float32
+    if kind == STEP_EULER:
+        xn = x + ((x - denoised) / torch.tensor(sigma, dtype=f)) * torch.tensor(dt, dtype=f)
+        if noise_scale != 0.0:
+            xn = xn + noise * torch.tensor(noise_scale, dtype=f)
+    else:
+        xn = torch.tensor(c_x, dtype=f) * x + torch.tensor(c_d, dtype=f) * denoised
+        if c_old != 0.0:
+            xn = xn + torch.tensor(c_old, dtype=f) * old_denoised
+        if kind == STEP_LINEAR:
+            if noise_scale != 0.0:
+                xn = xn + torch.tensor(noise_scale, dtype=f) * noise
+        else:
+            old_denoised.copy_(denoised)
+    x.copy_(xn)
+
+
+def eps_to_denoised(x, eps, sigma, prediction=0, out=None):
+    c = x.shape[1]
+    e = eps[..., :c].float().permute(0, 3, 1, 2)
+    return _ret(_denoised(x, e, sigma.view(-1, 1, 1, 1), prediction), out, torch.float32)
+
+
+def vae_postprocess(x, out=None):
+    return _ret(torch.clamp((x[..., :3].float() + 1.0) / 2.0, 0.0, 1.0), out, torch.float32)
+
+
+def vae_preprocess(pixels, dtype, out=None):
+    n, h, w, _ = pixels.shape
+    y = torch.zeros((n, h, w, 8), dtype=torch.float32)
+    y[..., :3] = 2.0 * pixels - 1.0
+    return _ret(y, out, dtype)
+
+
+def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
+    m = moments.float()
+    mean = m[..., :channels].permute(0, 3, 1, 2)
+    if noise is not None:
+        logvar = torch.clamp(m[..., channels:2 * channels].permute(0, 3, 1, 2), -30.0, 20.0)
+        mean = mean + torch.exp(0.5 * logvar) * noise
+    return _ret((mean * scale).contiguous(), out, torch.float32)
+
+
+_NAMES = ["gemm", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
+          "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
+          "timestep_embedding", "unet_input_im2col", "adaln", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
+          "sampler_step", "sampler_update", "eps_to_denoised", "vae_postprocess", "vae_preprocess", "vae_posterior"]
+
+
+def install(monkeypatch) -> None:
+    """Patch every kernel wrapper of b200forge.ops with its emulation (pure-torch helpers such as pack_geglu,
+    fold_layernorm, pack_conv3x3 and conv3x3_supported stay the product's own)."""
+    from b200forge import ops
+    g = globals()
+    for n in _NAMES:
+        monkeypatch.setattr(ops, n, g[n])
