@@ -45,6 +45,11 @@ TINY_15 = dict(
 # head-dim padding of the fused path
 TINY_15H = dict(TINY_15, num_heads=8, num_head_channels=-1)
 
+# SD2.x topology (4 levels, linear proj, head dim 64, no label_emb; v-prediction for the 768 models):
+# huggingface_guess SD20 unet_config restated: context_dim 1024, num_head_channels 64, use_linear_in_transformer True
+SD21 = dict(SD15, num_heads=-1, num_head_channels=64, use_linear_in_transformer=True, context_dim=1024)
+TINY_21 = dict(TINY_15, use_linear_in_transformer=True)
+
 # SDXL VAE (backend/huggingface/stabilityai/stable-diffusion-xl-base-1.0/vae/config.json)
 VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
@@ -53,5 +58,5 @@ VAE_SD15 = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512
 TINY_VAE = dict(in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
 
-CONFIGS = {"sd15": SD15, "sdxl": SDXL, "tiny_xl": TINY_XL, "tiny_15": TINY_15, "tiny_15h": TINY_15H}
+CONFIGS = {"sd15": SD15, "sdxl": SDXL, "sd21": SD21, "tiny_xl": TINY_XL, "tiny_15": TINY_15, "tiny_15h": TINY_15H, "tiny_21": TINY_21}
 VAE_CONFIGS = {"sdxl": VAE_SDXL, "sd15": VAE_SD15, "tiny": TINY_VAE}

@@ -52,6 +52,55 @@ def gen_unet(name: str, hw: int = 16):
     print("unet", name, "out std", out.std().item())
 
 
+def gen_v_trajectory(name: str = "tiny_21", hw: int = 16, steps: int = 5):
+    """SD2.x-style run: 4-level linear-transformer UNet without label_emb, v-prediction, Euler, CFG 6 — the reference's
+    KModel.apply_model -> sampling_function_inner -> k_diffusion.sample_euler on CPU fp32."""
+    import k_diffusion.sampling as ks
+    from backend.modules.k_model import KModel
+    from backend.modules.k_prediction import Prediction
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    from backend.sampling.condition import compile_conditions
+    from backend.sampling.sampling_function import sampling_function_inner
+    from k_diffusion.external import ForgeScheduleLinker
+    ks.to_d = lambda x, sigma, denoised: (x - denoised) / sigma
+    cfg = CF.CONFIGS[name]
+    sd = OU.random_state_dict(cfg, seed=1)
+    unet = RefUNet(**cfg).eval()
+    unet.load_state_dict(sd, strict=True)
+    unet.storage_dtype = torch.float32
+    unet.computation_dtype = torch.float32
+    pred = Prediction(prediction_type="v_prediction")
+    kmodel = KModel(unet, diffusers_scheduler=None, k_predictor=pred)
+    B = 2
+    g = torch.Generator().manual_seed(17)
+    cond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g))
+    uncond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g))
+    # SD1.x / 2.x conditioning is a bare tensor (condition.py:95-103): no pooled vector
+    cond_c, uncond_c = compile_conditions(cond["crossattn"]), compile_conditions(uncond["crossattn"])
+    cfg_scale = 6.0
+
+    class Wrap:
+        class _Inner:
+            predictor = pred
+        inner_model = _Inner()
+
+        def __call__(self, x, sigma, **kw):
+            return sampling_function_inner(kmodel, x, sigma, uncond_c, cond_c, cfg_scale, {}, None)
+
+    sig = ForgeScheduleLinker(pred).get_sigmas(steps)
+    noise0 = torch.randn(B, 4, hw, hw, generator=g)
+    with torch.no_grad():
+        x0 = pred.noise_scaling(sig[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+        x = make_inputs(cfg, B, hw, seed=2)[0]
+        fwd = unet(x, torch.tensor([981.0, 23.0]), context=cond["crossattn"], y=None, transformer_options={})
+        dens = []
+        out = ks.sample_euler(Wrap(), x0.clone(), sig, extra_args={}, callback=lambda d: dens.append(d["denoised"].clone()), disable=True)
+    torch.save(dict(config=name, weight_seed=1, weight_checksum=sd_checksum(sd), cond=cond, uncond=uncond, cfg_scale=cfg_scale,
+                    sigmas=sig, noise0=noise0, x0=x0, euler=out, denoised0=dens[0], fwd_x=x, fwd_t=torch.tensor([981.0, 23.0]),
+                    fwd_out=fwd), os.path.join(GOLD, f"traj_{name}_v.pt"))
+    print("v-pred traj", name, float(out.std()), float(fwd.std()))
+
+
 def gen_trajectories(name: str = "tiny_xl", hw: int = 16, steps: int = 6):
     """Reference denoise loop: KModel.apply_model -> sampling_function_inner (CFG) -> k_diffusion sample_*."""
     import k_diffusion.sampling as ks
@@ -258,13 +307,15 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "sched", "samplers", "vae", "vae_enc", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
         gen_unet("tiny_15h")
     if "traj" in which:
         gen_trajectories("tiny_xl")
+    if "vtraj" in which:
+        gen_v_trajectory("tiny_21")
     if "sched" in which:
         gen_schedules()
     if "vae" in which:

@@ -162,6 +162,15 @@ def dpmpp_2m_step(x, denoised, old_denoised, sigma_prev, sigma: float, sigma_nex
 
 
 # ------------------------------------------------------------------------------------------- denoiser + loops
+class VPrediction(EpsPrediction):
+    """Prediction(prediction_type='v_prediction') — SD2.x 768-v (backend/modules/k_prediction.py:81-92, v branch, sigma_data 1)."""
+
+    def calculate_denoised(self, sigma, model_output, model_input):
+        sigma = sigma.view(sigma.shape[:1] + (1,) * (model_output.ndim - 1))
+        sd = self.sigma_data
+        return model_input * sd ** 2 / (sigma ** 2 + sd ** 2) - model_output * sigma * sd / (sigma ** 2 + sd ** 2) ** 0.5
+
+
 class Denoiser:
     """KModel.apply_model (backend/modules/k_model.py:25-46) + calc_cond_uncond_batch / CFG
     (backend/sampling/sampling_function.py:154-322) for the plain txt2img case: one cond and one uncond

@@ -84,11 +84,13 @@ class Txt2ImgPipeline:
     def __init__(self, unet_cfg: dict, unet_state_dict: Dict[str, torch.Tensor], *, vae_cfg: Optional[dict] = None,
                  vae_state_dict: Optional[Dict[str, torch.Tensor]] = None, dtype: torch.dtype = torch.float16,
                  vae_dtype: torch.dtype = torch.bfloat16, device="cuda", use_graph: bool = True,
-                 vae_encoder_state_dict: Optional[Dict[str, torch.Tensor]] = None):
+                 vae_encoder_state_dict: Optional[Dict[str, torch.Tensor]] = None, prediction_type: str = "epsilon"):
         self.device = torch.device(device)
         self.dtype = dtype
         self.unet = UNetEngine(unet_cfg, unet_state_dict, dtype=dtype, device=device)
-        self.pred = sampling.Prediction()
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError(f"prediction_type {prediction_type!r}: epsilon (SD1.x, SDXL) or v_prediction (SD2.x 768-v)")
+        self.pred = sampling.Prediction(prediction_type=prediction_type)  # k_prediction.py:113-167
         self.use_graph = use_graph
         self._graphs: Dict[tuple, GraphedUNet] = {}
         self.vae = None
@@ -162,7 +164,7 @@ class Txt2ImgPipeline:
         if sampling.SAMPLERS[sampler][2] and noise_fn is None:
             raise ValueError(f"sampler {sampler} needs step_noise")
         sampling.run_sampler(eps_fn, x, plan, cfg_scale=cfg_scale, has_uncond=has_uncond, noise_fn=noise_fn,
-                             callback=callback)
+                             callback=callback, prediction=1 if self.pred.prediction_type == "v_prediction" else 0)
         return x
 
     @staticmethod

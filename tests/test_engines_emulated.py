@@ -101,3 +101,18 @@ def test_flux_pipeline_host_logic_vs_oracle_loop():
 
     ref = S.sample_euler(model, S.const_noise_scaling(float(sig[0]), noise, torch.zeros_like(noise)), sig)
     assert_close("emulated Flux pipeline vs oracle Euler loop", x, ref, rel_rms=2e-4)
+
+
+def test_v_prediction_pipeline_host_logic_vs_reference_trajectory():
+    """SD2.x-style model through the public pipeline: 4-level linear-transformer UNet without label embedding,
+    prediction_type="v_prediction" (the fused step's prediction switch), Euler, CFG 6 — against the reference's own run."""
+    from b200forge.pipeline import Txt2ImgPipeline
+    g = _gold("traj_tiny_21_v.pt")
+    cfg = CF.CONFIGS[g["config"]]
+    pipe = Txt2ImgPipeline(cfg, OU.random_state_dict(cfg, seed=g["weight_seed"]), dtype=F32, device="cpu", use_graph=False,
+                           prediction_type="v_prediction")
+    dens = []
+    x = pipe.sample(g["cond"], g["uncond"], g["noise0"], sampler="euler", cfg_scale=g["cfg_scale"], sigmas=g["sigmas"],
+                    callback=lambda i, xb, d: dens.append(d.clone()))
+    assert_close("emulated v-pred first denoised vs reference", dens[0], g["denoised0"], rel_rms=2e-5)
+    assert_close("emulated v-pred pipeline vs reference trajectory", x, g["euler"], rel_rms=2e-4)

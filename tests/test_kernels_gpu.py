@@ -396,3 +396,33 @@ def test_conv3x3_generic_tiling(N, H, W, C1, C2, Cout):
     torch.cuda.synchronize()
     ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
     assert_close(f"conv3x3 generic {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3)
+
+
+def test_sampler_step_and_denoised_v_prediction():
+    """prediction = 1 (SD2.x 768-v): denoised = x / (sigma^2 + 1) - v * sigma / sqrt(sigma^2 + 1)
+    (backend/modules/k_prediction.py:81-92, sigma_data = 1), inside the fused CFG + Euler step and in b200_eps_to_denoised."""
+    ops = _ops()
+    from oracle import sampling as S
+    B, C, H, W = 2, 4, 16, 16
+    g = torch.Generator().manual_seed(90)
+    x = torch.randn(B, C, H, W, generator=g) * 3
+    v = torch.randn(2 * B, H, W, 8, generator=g).half()
+    sigma, sigma_next, cfg = 3.5, 2.0, 6.0
+    pred = S.VPrediction()
+    vn = v[..., :C].permute(0, 3, 1, 2).float()
+    sg = torch.full((B,), sigma)
+    du, dc = pred.calculate_denoised(sg, vn[:B], x), pred.calculate_denoised(sg, vn[B:], x)
+    den_ref = du + (dc - du) * cfg
+    x_ref = S.euler_step(x, den_ref, sigma, sigma_next)
+    xd = x.to(DEV).clone()
+    den = torch.empty_like(xd)
+    ops.sampler_step(xd, v.to(DEV), den, kind=ops.STEP_EULER, sigma=sigma, cfg_scale=cfg, has_uncond=True,
+                     dt=sigma_next - sigma, prediction=1)
+    torch.cuda.synchronize()
+    assert_close("v-pred sampler denoised", den, den_ref, max_abs=3e-5)
+    assert_close("v-pred sampler euler x", xd, x_ref, max_abs=3e-5)
+    sig4 = torch.tensor([3.5, 3.5, 0.7, 14.0])
+    x4 = torch.cat([x, x])
+    out = ops.eps_to_denoised(x4.to(DEV), v.to(DEV), sig4.to(DEV), prediction=1)
+    torch.cuda.synchronize()
+    assert_close("v-pred eps_to_denoised", out, pred.calculate_denoised(sig4, vn, x4), max_abs=3e-5)

@@ -203,3 +203,23 @@ def test_two_evaluation_samplers_match_reference_golden(name):
     with torch.no_grad():
         out = getattr(S, name)(S.toy_denoiser, g["x0"].clone(), g["sigmas"], *args)
     assert_close(f"oracle {name} vs reference golden", out, g[name], max_abs=2e-5)
+
+
+def test_v_prediction_oracle_matches_reference_golden():
+    """SD2.x-style topology + v-prediction: oracle UNet forward and the Denoiser/Euler loop with VPrediction against the
+    reference's KModel.apply_model -> sampling_function_inner -> sample_euler (tests/golden/traj_tiny_21_v.pt)."""
+    g = _gold("traj_tiny_21_v.pt")
+    cfg = CF.CONFIGS[g["config"]]
+    sd = OU.random_state_dict(cfg, seed=g["weight_seed"])
+    assert abs(_sd_checksum(sd) - g["weight_checksum"]) <= 1e-6 * g["weight_checksum"]
+    with torch.no_grad():
+        fwd = OU.unet_forward(sd, cfg, g["fwd_x"], g["fwd_t"], g["cond"]["crossattn"], None)
+        assert_close("oracle unet tiny_21 vs reference golden", fwd, g["fwd_out"], max_abs=5e-5)
+        pred = S.VPrediction()
+        den = S.Denoiser(lambda xc, t, c, y: OU.unet_forward(sd, cfg, xc, t, c, y), pred, g["cond"], g["uncond"], g["cfg_scale"])
+        x0 = g["noise0"] * torch.sqrt(1.0 + g["sigmas"][0] ** 2.0)
+        assert_close("v-pred x0", x0, g["x0"], max_abs=1e-6)
+        seen = []
+        out = S.sample_euler(den, x0, g["sigmas"], callback=lambda i, x, d: seen.append(d.clone()))
+    assert_close("oracle v-pred first denoised vs reference", seen[0], g["denoised0"], rel_rms=1e-5)
+    assert_close("oracle v-pred Euler trajectory vs reference", out, g["euler"], rel_rms=1e-5)
