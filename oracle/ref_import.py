@@ -36,8 +36,7 @@ def _install_stubs() -> None:
         cfg.register_to_config = register_to_config
 
         class FlowMatchEulerDiscreteScheduler:
-            @staticmethod
-            def time_shift(mu, sigma, t):
+            def time_shift(self, mu, sigma, t):  # called unbound with self=None (k_prediction.py:300)
                 import math
                 return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
 

@@ -28,6 +28,11 @@ _ATTENTION_IMPORTERS = ("backend.nn.unet", "backend.nn.flux", "backend.nn.chroma
 _installed: Dict[str, Any] = {}
 
 
+def _on_device(t: torch.Tensor) -> bool:
+    """The fused path serves CUDA tensors only (one seam, so the CPU wiring tests can stand an emulation in)."""
+    return t.is_cuda
+
+
 def fast_path_ok(c: dict) -> bool:
     """True when the conditioning dict of one apply_model call can be served by the fused forward."""
     to = c.get("transformer_options") or {}
@@ -113,7 +118,7 @@ class UNetWrapper:
     def __call__(self, apply_model_fn: Callable, args: dict):
         x, sigma, c = args["input"], args["timestep"], args["c"]
         ptype = getattr(self.predictor, "prediction_type", "epsilon")
-        if (not fast_path_ok(c) or not x.is_cuda or x.dtype != torch.float32 or ptype not in ("epsilon", "v_prediction")
+        if (not fast_path_ok(c) or not _on_device(x) or x.dtype != torch.float32 or ptype not in ("epsilon", "v_prediction")
                 or (self.engine.has_label and c.get("y") is None) or x.dim() != 4
                 or not self.engine.supports_latent(x.shape[2], x.shape[3])):
             self.calls_reference += 1
@@ -160,7 +165,7 @@ class FluxWrapper:
     def __call__(self, apply_model_fn: Callable, args: dict):
         x, sigma, c = args["input"], args["timestep"], args["c"]
         eng = self.engine
-        ok = (fast_path_ok(c) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        ok = (fast_path_ok(c) and _on_device(x) and x.dtype == torch.float32 and x.dim() == 4
               and getattr(self.predictor, "prediction_type", None) == "const" and c.get("c_concat") is None
               and c.get("y") is not None and (x.shape[2] | x.shape[3]) % 2 == 0
               and (c.get("guidance") is not None or not eng.guidance_embed))
@@ -229,7 +234,7 @@ class VAEDecodeWrapper:
         self.output_device = output_device
 
     def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
-        if not samples_in.is_cuda or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3]):
+        if not _on_device(samples_in) or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3]):
             return decode_inner_fn(samples_in)
         scaling = self.engine.scaling
         try:

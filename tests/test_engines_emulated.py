@@ -116,3 +116,76 @@ def test_v_prediction_pipeline_host_logic_vs_reference_trajectory():
                     callback=lambda i, xb, d: dens.append(d.clone()))
     assert_close("emulated v-pred first denoised vs reference", dens[0], g["denoised0"], rel_rms=2e-5)
     assert_close("emulated v-pred pipeline vs reference trajectory", x, g["euler"], rel_rms=2e-4)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Plug point P3 wired into the UNMODIFIED reference: backend.sampling.sampling_function.sampling_function_inner calls
+# model_options['model_function_wrapper'] (sampling_function.py:270-273) exactly as Forge does; with the wrapper installed
+# the result must equal the reference's own apply_model path.  (CPU: the engine runs on the emulated ops.)
+from oracle import ref_import  # noqa: E402
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p3_unet_wrapper_inside_the_reference_sampling_function(monkeypatch):
+    ref_import.load()
+    from backend.modules.k_model import KModel
+    from backend.modules.k_prediction import Prediction
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    from backend.sampling.condition import compile_conditions
+    from backend.sampling.sampling_function import sampling_function_inner
+
+    from b200forge import plugin
+    from b200forge.unet_engine import UNetEngine
+    monkeypatch.setattr(plugin, "_on_device", lambda t: True)
+    cfg = CF.CONFIGS["tiny_xl"]
+    sd = OU.random_state_dict(cfg, seed=1)
+    unet = RefUNet(**cfg).eval()
+    unet.load_state_dict(sd, strict=True)
+    unet.storage_dtype = unet.computation_dtype = torch.float32
+    kmodel = KModel(unet, diffusers_scheduler=None, k_predictor=Prediction(prediction_type="epsilon"))
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    cond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    uncond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    cc, uc = compile_conditions(cond), compile_conditions(uncond)
+    x = torch.randn(B, 4, 16, 16, generator=g) * 4
+    sigma = torch.tensor([6.0, 6.0])
+    with torch.no_grad():
+        base = sampling_function_inner(kmodel, x, sigma, uc, cc, 7.0, {}, None)
+        w = plugin.UNetWrapper(UNetEngine(cfg, sd, dtype=F32, device="cpu"), kmodel.predictor)
+        out = sampling_function_inner(kmodel, x, sigma, uc, cc, 7.0, {"model_function_wrapper": w}, None)
+    assert w.calls_fast == 1 and w.calls_reference == 0
+    assert_close("reference sampling_function with the fused UNet wrapper vs without", out, base, rel_rms=1e-5)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p3_flux_wrapper_inside_the_reference_sampling_function(monkeypatch):
+    ref_import.load()
+    from backend.modules.k_model import KModel
+    from backend.modules.k_prediction import PredictionFlux
+    from backend.nn.flux import IntegratedFluxTransformer2DModel
+    from backend.sampling.condition import compile_conditions
+    from backend.sampling.sampling_function import sampling_function_inner
+
+    from b200forge import plugin
+    from b200forge.flux_engine import FluxEngine
+    monkeypatch.setattr(plugin, "_on_device", lambda t: True)
+    cfg = OF.TINY_FLUX
+    sd = OF.random_state_dict(cfg, seed=5)
+    m = IntegratedFluxTransformer2DModel(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    m.storage_dtype = m.computation_dtype = torch.float32
+    kmodel = KModel(m, diffusers_scheduler=None, k_predictor=PredictionFlux())
+    g = torch.Generator().manual_seed(6)
+    B = 2
+    cond = dict(crossattn=torch.randn(B, 64, cfg["context_in_dim"], generator=g), vector=torch.randn(B, cfg["vec_in_dim"], generator=g),
+                guidance=torch.full((B,), 4.0))
+    cc = compile_conditions(cond)
+    x = torch.randn(B, 16, 16, 16, generator=g)
+    sigma = torch.tensor([0.8, 0.8])
+    with torch.no_grad():
+        base = sampling_function_inner(kmodel, x, sigma, None, cc, 1.0, {}, None)
+        w = plugin.FluxWrapper(FluxEngine(cfg, sd, dtype=F32, device="cpu"), kmodel.predictor)
+        out = sampling_function_inner(kmodel, x, sigma, None, cc, 1.0, {"model_function_wrapper": w}, None)
+    assert w.calls_fast == 1 and w.calls_reference == 0
+    assert_close("reference sampling_function with the fused Flux wrapper vs without", out, base, rel_rms=1e-5)
