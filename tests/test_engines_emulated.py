@@ -189,3 +189,53 @@ def test_p3_flux_wrapper_inside_the_reference_sampling_function(monkeypatch):
         out = sampling_function_inner(kmodel, x, sigma, None, cc, 1.0, {"model_function_wrapper": w}, None)
     assert w.calls_fast == 1 and w.calls_reference == 0
     assert_close("reference sampling_function with the fused Flux wrapper vs without", out, base, rel_rms=1e-5)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p1_attention_operator_inside_the_reference_models(monkeypatch):
+    """plugin.install_attention() rebinds the by-value imports of attention_function in the reference's model files
+    (backend/nn/unet.py:5, flux.py:11); the reference UNet (Dh = 64, [b, L, H*Dh] layout) and Flux transformer (Dh = 128,
+    skip_reshape layout) then call the B200 operator and must reproduce their goldens.  (CPU: the operator's kernels are the emulated ops; the device / dtype gate is opened for the test.)"""
+    ref_import.load()
+    from backend.nn.flux import IntegratedFluxTransformer2DModel
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+
+    from b200forge import attention as A
+    from b200forge import plugin
+    calls = {"n": 0}
+    real_attn, real_single = A.attention_function, A.attention_function_single_head_spatial
+
+    def supports(q, k, v, heads, mask, skip_reshape):
+        return mask is None and (q.shape[-1] if skip_reshape else q.shape[-1] // heads) in A.SUPPORTED_HEAD_DIMS
+
+    monkeypatch.setattr(A, "supports", supports)
+    orig_attention = ops_emulator.attention
+
+    def counting_attention(*a, **kw):
+        calls["n"] += 1
+        return orig_attention(*a, **kw)
+
+    from b200forge import ops
+    monkeypatch.setattr(ops, "attention", counting_attention)
+    plugin.install_attention()
+    try:
+        g = _gold("unet_tiny_xl.pt")
+        cfg = CF.CONFIGS["tiny_xl"]
+        m = RefUNet(**cfg).eval()
+        m.load_state_dict(OU.random_state_dict(cfg, seed=g["weight_seed"]), strict=True)
+        with torch.no_grad():
+            out = m(g["x"], g["t"], context=g["context"], y=g["y"], transformer_options={})
+        assert calls["n"] > 0
+        assert_close("reference UNet calling the B200 attention operator", out, g["out"], max_abs=5e-5)
+        n_unet = calls["n"]
+        gf = _gold("flux_tiny.pt")
+        fcfg = OF.CONFIGS[gf["config"]]
+        fm = IntegratedFluxTransformer2DModel(**fcfg).eval()
+        fm.load_state_dict(OF.random_state_dict(fcfg, seed=gf["weight_seed"]), strict=True)
+        with torch.no_grad():
+            fout = fm(gf["x"], gf["t"], gf["context"], gf["y"], gf["guidance"])
+        assert calls["n"] > n_unet
+        assert_close("reference Flux transformer calling the B200 attention operator", fout, gf["out"], max_abs=5e-5)
+    finally:
+        plugin.uninstall_attention()
+    assert A.attention_function is real_attn and A.attention_function_single_head_spatial is real_single
