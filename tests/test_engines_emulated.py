@@ -239,3 +239,38 @@ def test_p1_attention_operator_inside_the_reference_models(monkeypatch):
     finally:
         plugin.uninstall_attention()
     assert A.attention_function is real_attn and A.attention_function_single_head_spatial is real_single
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p2_operator_classes_inside_the_reference_unet(monkeypatch):
+    """backend.operations.using_forge_operations(operations=B200Operations) (backend/operations.py:441-467): the
+    reference constructs its UNet from our Linear / Conv2d / GroupNorm / LayerNorm modules.  Their NCHW / [.., C] boundary
+    conversions and routing (3x3 stride 1 -> implicit GEMM, stride 2 -> im2col + GEMM, 1x1 -> GEMM) must reproduce the
+    golden.  (CPU: emulated kernels, device / dtype gate opened for the test.)"""
+    ref_import.load()
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    from backend.operations import using_forge_operations
+
+    from b200forge import operations as P2
+    monkeypatch.setattr(P2, "_fast", lambda x, w: w.dtype == x.dtype)
+    monkeypatch.setattr(P2, "DEFERRED", 0)
+    g = _gold("unet_tiny_xl.pt")
+    cfg = CF.CONFIGS["tiny_xl"]
+    with using_forge_operations(operations=P2.B200Operations, device=torch.device("cpu"), dtype=torch.float32):
+        m = RefUNet(**cfg).eval()
+    kinds = {type(mod) for mod in m.modules()}
+    assert P2.Linear in kinds and P2.Conv2d in kinds and P2.GroupNorm in kinds and P2.LayerNorm in kinds
+    m.load_state_dict(OU.random_state_dict(cfg, seed=g["weight_seed"]), strict=True)
+    counted = {"gemm": 0, "conv": 0, "gn": 0}
+    from b200forge import ops
+    for name, key in (("gemm", "gemm"), ("conv3x3", "conv"), ("groupnorm", "gn")):
+        fn = getattr(ops, name)
+
+        def wrap(*a, _fn=fn, _k=key, **kw):
+            counted[_k] += 1
+            return _fn(*a, **kw)
+        monkeypatch.setattr(ops, name, wrap)
+    with torch.no_grad():
+        out = m(g["x"], g["t"], context=g["context"], y=g["y"], transformer_options={})
+    assert counted["gemm"] > 50 and counted["conv"] > 20 and counted["gn"] > 20, counted
+    assert_close("reference UNet built from B200Operations modules", out, g["out"], max_abs=5e-5)
