@@ -145,11 +145,15 @@ class Txt2ImgPipeline:
         gu.set_context(torch.cat([put(t, self.dtype) for t in ctx], 0), yv)
         x = gu.x
         # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: max_denoise, zero latent)
+        if init_latent is not None:
+            init_latent = put(init_latent, torch.float32)
+            if init_latent.data_ptr() == x.data_ptr():  # a latent returned by a previous sample() IS this buffer
+                init_latent = init_latent.clone()
         x.copy_(put(noise, torch.float32))
         if init_latent is None:
             x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)))
         else:
-            x.mul_(float(sigmas[0])).add_(put(init_latent, torch.float32))
+            x.mul_(float(sigmas[0])).add_(init_latent)
         sn_dev = put(step_noise, torch.float32) if step_noise is not None else None
         # per-step scalar tables (sigma per image, UNet timestep = index of nearest log-sigma)
         sig_tab = sigmas[:-1].to(dev).view(-1, 1).expand(-1, b).contiguous()
@@ -192,6 +196,22 @@ class Txt2ImgPipeline:
         sched = self.img2img_schedule(full, steps, denoising_strength)
         return self.sample(cond, uncond, noise, steps=len(sched) - 1, sampler=sampler, cfg_scale=cfg_scale, sigmas=sched,
                            init_latent=latent, **kw)
+
+    @torch.no_grad()
+    def hires_fix(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, noise_hr: torch.Tensor, *, steps: int = 30,
+                  hr_steps: Optional[int] = None, denoising_strength: float = 0.7, latent_mode: str = "bilinear",
+                  antialias: bool = False, sampler: str = "euler_a", cfg_scale: float = 7.0,
+                  step_noise: Optional[torch.Tensor] = None, step_noise_hr: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """txt2img with a latent hires-fix second pass (StableDiffusionProcessingTxt2Img.sample + sample_hr_pass,
+        modules/processing.py:1342-1428, 1430-1540, latent upscalers only): first pass at noise.shape, the latent is
+        resized to noise_hr.shape with torch.nn.functional.interpolate exactly as the reference does (:1458 — Forge calls
+        torch there too, it is not part of the hot path), then img2img over the last t_enc + 1 sigmas of an
+        `hr_steps or steps` schedule.  Both passes run the same fused denoise path."""
+        first = self.sample(cond, uncond, noise, steps=steps, sampler=sampler, cfg_scale=cfg_scale, step_noise=step_noise)
+        up = torch.nn.functional.interpolate(first, size=tuple(noise_hr.shape[2:]), mode=latent_mode,
+                                             **({} if latent_mode == "nearest" else {"antialias": antialias}))
+        return self.img2img(cond, uncond, up, noise_hr, steps=hr_steps or steps, denoising_strength=denoising_strength,
+                            sampler=sampler, cfg_scale=cfg_scale, step_noise=step_noise_hr)
 
     @torch.no_grad()
     def decode(self, latent: torch.Tensor) -> torch.Tensor:

@@ -274,3 +274,46 @@ def test_p2_operator_classes_inside_the_reference_unet(monkeypatch):
         out = m(g["x"], g["t"], context=g["context"], y=g["y"], transformer_options={})
     assert counted["gemm"] > 50 and counted["conv"] > 20 and counted["gn"] > 20, counted
     assert_close("reference UNet built from B200Operations modules", out, g["out"], max_abs=5e-5)
+
+
+def test_hires_fix_host_logic_vs_oracle_composition():
+    """Latent hires fix = first pass, torch interpolate (as the reference, modules/processing.py:1458), img2img second pass
+    over the sliced schedule (sd_samplers_kdiffusion.py:136-194) — against the same composition of oracle loops."""
+    from b200forge.pipeline import Txt2ImgPipeline
+    cfg = CF.CONFIGS["tiny_xl"]
+    sd = OU.random_state_dict(cfg, seed=1)
+    pipe = Txt2ImgPipeline(cfg, sd, dtype=F32, device="cpu", use_graph=False)
+    g = torch.Generator().manual_seed(21)
+    B, steps, hr_steps, strength = 1, 4, 6, 0.5
+    noise, noise_hr = torch.randn(B, 4, 16, 16, generator=g), torch.randn(B, 4, 32, 32, generator=g)
+    cond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    uncond = dict(crossattn=torch.randn(B, 77, cfg["context_dim"], generator=g), vector=torch.randn(B, cfg["adm_in_channels"], generator=g))
+    out = pipe.hires_fix(cond, uncond, noise, noise_hr, steps=steps, hr_steps=hr_steps, denoising_strength=strength,
+                         sampler="euler", cfg_scale=5.0)
+    pred = S.EpsPrediction()
+    den = S.Denoiser(lambda xc, t, c, y: OU.unet_forward(sd, cfg, xc, t, c, y), pred, cond, uncond, 5.0)
+    with torch.no_grad():
+        s1 = S.get_sigmas_uniform(pred, steps)
+        first = S.sample_euler(den, noise * torch.sqrt(1.0 + s1[0] ** 2.0), s1)
+        up = torch.nn.functional.interpolate(first, size=(32, 32), mode="bilinear", antialias=False)
+        s2 = S.get_sigmas_uniform(pred, hr_steps)
+        sched = s2[hr_steps - int(min(strength, 0.999) * hr_steps) - 1:]
+        ref = S.sample_euler(den, noise_hr * sched[0] + up, sched)
+    assert out.shape == (B, 4, 32, 32)
+    assert_close("emulated hires fix vs oracle composition", out, ref, rel_rms=2e-4)
+
+
+def test_img2img_accepts_the_buffer_returned_by_sample():
+    """sample() returns its graph's static latent buffer; feeding it straight back as img2img's init latent at the same
+    size must not read the buffer after it was overwritten with the new noise."""
+    from b200forge.pipeline import Txt2ImgPipeline
+    cfg = CF.CONFIGS["tiny_xl"]
+    pipe = Txt2ImgPipeline(cfg, OU.random_state_dict(cfg, seed=1), dtype=F32, device="cpu", use_graph=False)
+    g = torch.Generator().manual_seed(23)
+    noise, noise2 = torch.randn(1, 4, 16, 16, generator=g), torch.randn(1, 4, 16, 16, generator=g)
+    cond = dict(crossattn=torch.randn(1, 77, cfg["context_dim"], generator=g), vector=torch.randn(1, cfg["adm_in_channels"], generator=g))
+    lat = pipe.sample(cond, None, noise, steps=2, sampler="euler", cfg_scale=1.0)
+    keep = lat.clone()
+    a = pipe.img2img(cond, None, lat, noise2, steps=4, denoising_strength=0.5, sampler="euler", cfg_scale=1.0).clone()
+    b = pipe.img2img(cond, None, keep, noise2, steps=4, denoising_strength=0.5, sampler="euler", cfg_scale=1.0)
+    assert torch.equal(a, b)
