@@ -169,7 +169,7 @@ class Txt2ImgPipeline:
             raise ValueError(f"sampler {sampler} needs step_noise")
         sampling.run_sampler(eps_fn, x, plan, cfg_scale=cfg_scale, has_uncond=has_uncond, noise_fn=noise_fn,
                              callback=callback, prediction=1 if self.pred.prediction_type == "v_prediction" else 0)
-        return x
+        return x.clone()  # x is the graph's static input buffer: the caller gets its own copy
 
     @staticmethod
     def img2img_schedule(sigmas: torch.Tensor, steps: int, denoising_strength: float) -> torch.Tensor:
@@ -315,4 +315,4 @@ class FluxTxt2ImgPipeline:
             return gf()
 
         sampling.run_sampler(model_fn, x, plan, cfg_scale=1.0, has_uncond=False, callback=callback)
-        return x
+        return x.clone()  # x is the graph's static input buffer: the caller gets its own copy
