@@ -280,6 +280,11 @@ int b200_qk_norm_rope(void* qkv, int rows, int H, int Dh, int ld, const void* q_
                       const void* q_scale1, const void* k_scale1, const float* cos_t, const float* sin_t, int seg_period,
                       int seg_split, float eps, int dtype, b200_stream_t s);
 
+/* RMSNorm over the rows of [rows, C]: y = x * rsqrt(mean(x^2) + eps) * scale[C]  (backend/nn/flux.py:115-126 RMSNorm as the
+ * Chroma Approximator applies it to hidden-wide rows, backend/nn/chroma.py:14-28).  Added after the round's GPU budget was
+ * spent: compiled and reviewed, exercised so far only through the CPU emulation of the Chroma engine's launch sequence. */
+int b200_rmsnorm_rows(const void* x, const void* scale, void* y, int rows, int C, float eps, int dtype, b200_stream_t s);
+
 /* 2x2 patchify: x NCHW [B, C, H, W] (fp32 if in_is_f32 else dtype) -> tokens [B*(H/2)*(W/2), ld], feature c*4 + ph*2 + pw
  * (flux.py:398-399; even H, W only: the circular-pad branch returns B200_EUNSUPPORTED). */
 int b200_flux_patchify(const void* x, void* tokens, int B, int C, int H, int W, int ld, int in_is_f32, int dtype,

@@ -283,6 +283,25 @@ def gen_vae_encode(name: str = "tiny", hw: int = 64):
     print("vae encode", name, "mean std", mean.std().item(), "logvar mean", logvar.mean().item())
 
 
+def gen_chroma(name: str = "tiny_chroma", hw: int = 16, txt_len: int = 64):
+    """Reference Chroma transformer (backend/nn/chroma.py) on CPU fp32."""
+    from backend.nn.chroma import IntegratedChromaTransformer2DModel
+    from oracle import chroma as OC
+    cfg = OC.CONFIGS[name]
+    sd = OC.random_state_dict(cfg, seed=5)
+    m = IntegratedChromaTransformer2DModel(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, cfg["in_channels"], hw, hw, generator=g)
+    ctx = torch.randn(2, txt_len, cfg["context_in_dim"], generator=g)
+    t = torch.tensor([0.93, 0.12])
+    with torch.no_grad():
+        out = m(x, t, ctx)
+    torch.save(dict(config=name, weight_seed=5, weight_checksum=sd_checksum(sd), x=x, t=t, context=ctx, out=out),
+               os.path.join(GOLD, "chroma_tiny.pt"))
+    print("chroma", name, "out std", out.std().item())
+
+
 def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: str = "flux_tiny.pt"):
     """Reference Flux transformer (backend/nn/flux.py) on CPU fp32, distilled-guidance input included."""
     from backend.nn.flux import IntegratedFluxTransformer2DModel
@@ -307,7 +326,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "chroma", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -324,6 +343,8 @@ if __name__ == "__main__":
         gen_samplers()
     if "vae_enc" in which:
         gen_vae_encode("tiny")
+    if "chroma" in which:
+        gen_chroma()
     if "flux" in which:
         gen_flux()                                                  # 64 img + 128 txt tokens: per-stream GEMM launches
         gen_flux(hw=32, txt_len=256, fname="flux_tiny_seg.pt")      # 256 + 256 tokens: two-segment GEMM path

@@ -102,6 +102,40 @@ __global__ void __launch_bounds__(128) adaln_kernel(const void* __restrict__ x, 
   }
 }
 
+// ------------------------------------------------------------------------------------------ RMSNorm over rows
+// y = x * rsqrt(mean(x^2) + eps) * scale   (RMSNorm, flux.py:115-126, as used on [.., hidden] rows by Chroma's Approximator,
+// backend/nn/chroma.py:14-28).  Same organisation as adaln_kernel: one 128-thread block per row, row in registers.
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(128) rmsnorm_rows_kernel(const void* __restrict__ x, const void* __restrict__ scale,
+                                                           void* __restrict__ y, int C, float eps) {
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
+  const int nvec = C >> 3;
+  float v[NV][8];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int cv = threadIdx.x + 128 * i;
+    if (cv < nvec) {
+      ld8<BF16>(x, (size_t)row * C + (size_t)cv * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
+    }
+  }
+  const float rn = rsqrtf(block_sum_128(q, sh) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int cv = threadIdx.x + 128 * i;
+    if (cv < nvec) {
+      float w[8], o[8];
+      ld8<BF16>(scale, (size_t)cv * 8, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rn * w[j];
+      st8<BF16>(y, (size_t)row * C + (size_t)cv * 8, o);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ QK RMSNorm + RoPE
 // In place on the q and k thirds of a fused QKV row [3, H, 128] (flux.py:128-139 QKNorm, 15-18 + 45-51 rope):
 //   t = rms_norm(x) * scale   (rounded to the activation dtype, as the reference's torch.rms_norm output is)
@@ -304,5 +338,22 @@ extern "C" int b200_flux_unpatchify(const void* tokens, void* out, int B, int C,
   if (out_nchw_f32) DISPATCH_BF(dtype, (flux_unpatchify_kernel<BF, true><<<grid, 256, 0, (cudaStream_t)s>>>(tokens, out, B, C, H / 2, W / 2, ld)));
   else DISPATCH_BF(dtype, (flux_unpatchify_kernel<BF, false><<<grid, 256, 0, (cudaStream_t)s>>>(tokens, out, B, C, H / 2, W / 2, ld)));
   B200_CHECK_LAUNCH("flux_unpatchify");
+  return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_rows(const void* x, const void* scale, void* y, int rows, int C, float eps, int dtype,
+                                 b200_stream_t s) {
+  B200_CHECK_ARG(x && scale && y && rows > 0 && C > 0, "rmsnorm_rows: bad arguments");
+  B200_CHECK_ARG(C % 8 == 0 && C <= 8192, "rmsnorm_rows: C (%d) must be a multiple of 8 and <= 8192", C);
+  B200_CHECK_ARG(dtype == B200_F16 || dtype == B200_BF16, "rmsnorm_rows: dtype");
+  const int nv = (C / 8 + 127) / 128;
+#define RMS_LAUNCH(NV) DISPATCH_BF(dtype, (rmsnorm_rows_kernel<BF, NV><<<rows, 128, 0, (cudaStream_t)s>>>(x, scale, y, C, eps)))
+  if (nv <= 1) RMS_LAUNCH(1);
+  else if (nv <= 2) RMS_LAUNCH(2);
+  else if (nv <= 4) RMS_LAUNCH(4);
+  else if (nv <= 6) RMS_LAUNCH(6);
+  else RMS_LAUNCH(8);
+#undef RMS_LAUNCH
+  B200_CHECK_LAUNCH("rmsnorm_rows");
   return B200_OK;
 }

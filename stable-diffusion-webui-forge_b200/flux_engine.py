@@ -132,19 +132,10 @@ class FluxEngine:
         ops.attention(v3[:, :, 0:hs], v3[:, :, hs:2 * hs], v3[:, :, 2 * hs:3 * hs], self.heads, out=out.view(B, L, hs))
         return out
 
-    # ------------------------------------------------------------------ forward
-    def forward_tokens(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor, y: torch.Tensor,
-                       guidance: Optional[torch.Tensor]) -> tuple:
-        """Runs the transformer; returns (token output [B*Li, 4*C], plan).  x NCHW fp32 or dtype; timestep / guidance
-        fp32 [B] (sigma in [0, 1] and the distilled guidance scale, k_model.py:25-46); context [B, Lt, ctx]; y [B, vec]."""
-        w, hs, Hh = self.w, self.hidden, self.heads
-        B, C, H, W = x.shape
-        Lt = context.shape[1]
-        if (H | W) & 1:
-            raise ops.B200Error(-2, "odd latent size (circular padding branch, flux.py:396-397) is not on the fused path")
-        p = self._plan(B, H, W, Lt)
-        L, rows = p["L"], p["rows"]
-        ops.flux_patchify(x, self.dtype, out=p["patches"])
+    # ------------------------------------------------------------------ modulation vectors
+    def _compute_modulation(self, p, timestep, y, guidance) -> None:
+        """Fills p["mod"] [B, mod_total]: every block's shift / scale / gate vectors for this forward."""
+        w, hs = self.w, self.hidden
         # vec = time_in(temb(1000 t)) [+ guidance_in(temb(1000 g))] + vector_in(y)      (flux.py:355-361, 52-72)
         torch.mul(timestep, 1000.0, out=p["t1000"])
         ops.timestep_embedding(p["t1000"], 256, self.dtype, out=p["temb"])
@@ -163,6 +154,21 @@ class FluxEngine:
         ops.gemm(p["h1"], w["vector_in.out_layer.weight"], w["vector_in.out_layer.bias"], residual=p["vec"], out=p["vec"])
         ops.silu(p["vec"], out=p["svec"])
         ops.gemm(p["svec"], w["mod.weight"], w["mod.bias"], out=p["mod"])
+
+    # ------------------------------------------------------------------ forward
+    def forward_tokens(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor, y: torch.Tensor,
+                       guidance: Optional[torch.Tensor]) -> tuple:
+        """Runs the transformer; returns (token output [B*Li, 4*C], plan).  x NCHW fp32 or dtype; timestep / guidance
+        fp32 [B] (sigma in [0, 1] and the distilled guidance scale, k_model.py:25-46); context [B, Lt, ctx]; y [B, vec]."""
+        w, hs, Hh = self.w, self.hidden, self.heads
+        B, C, H, W = x.shape
+        Lt = context.shape[1]
+        if (H | W) & 1:
+            raise ops.B200Error(-2, "odd latent size (circular padding branch, flux.py:396-397) is not on the fused path")
+        p = self._plan(B, H, W, Lt)
+        L, rows = p["L"], p["rows"]
+        ops.flux_patchify(x, self.dtype, out=p["patches"])
+        self._compute_modulation(p, timestep, y, guidance)
         # token streams into the joint activation
         xj = p["xj"]
         ctx2d = context.reshape(B * Lt, context.shape[2])
@@ -220,3 +226,78 @@ class FluxEngine:
         B, C, H, W = x.shape
         tok, _ = self.forward_tokens(x, timestep, context, y, guidance)
         return ops.flux_unpatchify(tok, B, C, H, W, nchw_f32=False, out=out)
+
+
+class ChromaEngine(FluxEngine):
+    """Chroma (backend/nn/chroma.py:138-307): Flux's blocks with the modulation vectors of all blocks produced by one
+    Approximator MLP (chroma.py:14-28) from [timestep embedding | zero-guidance embedding | modulation-index embedding]
+    — no time / vector / guidance embedders, no per-block Modulation linears, no pooled-text input.  Only the source of
+    p["mod"] and the vector order (distribute_modulations, chroma.py:181-243) differ from FluxEngine; the block launch
+    sequence is inherited.
+
+    Status: the launch sequence is pinned on the CPU against the imported reference (tests/test_engines_emulated.py);
+    `b200_rmsnorm_rows`, the one kernel this engine adds, has not run on hardware yet."""
+
+    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], dtype=torch.bfloat16, device="cuda"):
+        self.g_layers = cfg["guidance_n_layers"]
+        self.g_hidden = cfg["guidance_hidden_dim"]
+        if cfg["guidance_out_dim"] != cfg["hidden_size"]:
+            raise ValueError("Chroma: guidance_out_dim must equal hidden_size (the vectors modulate hidden-wide rows)")
+        super().__init__(dict(cfg, guidance_embed=False), sd, dtype=dtype, device=device)
+
+    def _pack(self, sd):
+        dt, dev = self.dtype, self.device
+        w = {k: v.to(device=dev, dtype=dt).contiguous() for k, v in sd.items()}
+        # vector order of distribute_modulations: single blocks (3 each), img_mod of every double block (6 each), txt_mod
+        # of every double block (6 each), final layer (2: shift, scale)
+        self.mod_off, idx = {}, 0
+        for i in range(self.depth_single):
+            self.mod_off[f"single_blocks.{i}.modulation.lin"] = idx * self.hidden
+            idx += 3
+        for s in ("img", "txt"):
+            for i in range(self.depth):
+                self.mod_off[f"double_blocks.{i}.{s}_mod.lin"] = idx * self.hidden
+                idx += 6
+        self.mod_off["final_layer.adaLN_modulation.1"] = idx * self.hidden
+        self.n_vec = idx + 2
+        self.mod_total = self.n_vec * self.hidden
+        # modulation-index embedding: timestep_embedding(arange(n_vec), 32) (chroma.py:257), a constant of the model
+        half = 16
+        freqs = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(half, dtype=torch.float32) / half)
+        args = (1000.0 * torch.arange(self.n_vec, dtype=torch.float32))[:, None] * freqs[None]
+        self.idx_emb = torch.cat([torch.cos(args), torch.sin(args)], -1).to(device=dev, dtype=dt)
+        return w
+
+    def _plan(self, B, H, W, Lt):
+        p = super()._plan(B, H, W, Lt)
+        if "g_in" not in p:
+            dt, dev, rows = self.dtype, self.device, B * self.n_vec
+            p["g_in"] = torch.zeros((rows, 64), dtype=dt, device=dev)
+            p["g_in"].view(B, self.n_vec, 64)[:, :, 32:] = self.idx_emb                      # modulation index part
+            p["g_in"].view(B, self.n_vec, 64)[:, :, 16:24] = 1.0                             # timestep_embedding(0, 16) = [cos 0 | sin 0]
+            p["t16"] = torch.empty((B, 16), dtype=dt, device=dev)
+            p["g_x"] = torch.empty((rows, self.g_hidden), dtype=dt, device=dev)
+            p["g_n"] = torch.empty((rows, self.g_hidden), dtype=dt, device=dev)
+            p["g_h"] = torch.empty((rows, self.g_hidden), dtype=dt, device=dev)
+        return p
+
+    def _compute_modulation(self, p, timestep, y, guidance) -> None:
+        w = self.w
+        B = timestep.shape[0]
+        torch.mul(timestep, 1000.0, out=p["t1000"])
+        ops.timestep_embedding(p["t1000"], 16, self.dtype, out=p["t16"])                     # chroma.py:255
+        p["g_in"].view(B, self.n_vec, 64)[:, :, :16] = p["t16"][:, None, :]
+        q = "distilled_guidance_layer"
+        ops.gemm(p["g_in"], w[q + ".in_proj.weight"], w[q + ".in_proj.bias"], out=p["g_x"])
+        for i in range(self.g_layers):                                                       # x = x + MLP(RMSNorm(x))
+            ops.rmsnorm_rows(p["g_x"], w[f"{q}.norms.{i}.scale"], out=p["g_n"])
+            ops.gemm(p["g_n"], w[f"{q}.layers.{i}.in_layer.weight"], w[f"{q}.layers.{i}.in_layer.bias"], epilogue=EPI_SILU, out=p["g_h"])
+            ops.gemm(p["g_h"], w[f"{q}.layers.{i}.out_layer.weight"], w[f"{q}.layers.{i}.out_layer.bias"], residual=p["g_x"], out=p["g_x"])
+        ops.gemm(p["g_x"], w[q + ".out_proj.weight"], w[q + ".out_proj.bias"], out=p["mod"].view(B * self.n_vec, self.hidden))
+
+    def forward(self, x, timestep, context, y=None, guidance=None) -> torch.Tensor:
+        """Reference signature: forward(x, timestep, context, **kwargs) (chroma.py:285)."""
+        B, C, H, W = x.shape
+        yy = torch.zeros((B, 8), dtype=self.dtype, device=self.device)  # unused placeholder (no pooled-text path)
+        tok, _ = self.forward_tokens(x.contiguous(), timestep.float().contiguous(), context.to(self.dtype).contiguous(), yy, None)
+        return ops.flux_unpatchify(tok, B, C, H, W, nchw_f32=True)

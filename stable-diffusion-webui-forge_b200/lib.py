@@ -112,6 +112,7 @@ SIGNATURES = {
     "b200_vae_posterior": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "b200_adaln": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_qk_norm_rope": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "b200_rmsnorm_rows": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_flux_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_flux_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

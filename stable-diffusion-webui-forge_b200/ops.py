@@ -476,6 +476,18 @@ def adaln(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, *, eps: flo
     return out
 
 
+def rmsnorm_rows(x: torch.Tensor, scale: torch.Tensor, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x * rsqrt(mean(x^2) + eps) * scale over the rows of a contiguous [rows, C] matrix."""
+    assert x.dim() == 2 and x.is_contiguous() and scale.is_contiguous() and scale.numel() == x.shape[1]
+    if out is None:
+        out = torch.empty_like(x)
+    with _prof("rmsnorm_rows", 0.0, 4.0 * x.numel()):
+        _l.check(_l.load().b200_rmsnorm_rows(x.data_ptr(), scale.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], eps,
+                                             _dt(x), _stream()))
+    _count()
+    return out
+
+
 def qk_norm_rope_(qkv: torch.Tensor, heads: int, q_scale: torch.Tensor, k_scale: torch.Tensor, cos: torch.Tensor,
                   sin: torch.Tensor, *, q_scale1: Optional[torch.Tensor] = None, k_scale1: Optional[torch.Tensor] = None,
                   seg_split: int = 0, eps: float = 1e-6) -> torch.Tensor:

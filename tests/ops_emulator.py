@@ -224,6 +224,11 @@ def adaln(x, shift, scale, *, eps=1e-6, shift1=None, scale1=None, seg_period=0, 
     return _ret(y, out, x.dtype)
 
 
+def rmsnorm_rows(x, scale, eps=1e-6, out=None):
+    xf = x.float()
+    return _ret(xf * torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps) * scale.float(), out, x.dtype)
+
+
 def qk_norm_rope_(qkv, heads, q_scale, k_scale, cos, sin, *, q_scale1=None, k_scale1=None, seg_split=0, eps=1e-6):
     rows = qkv.shape[0]
     period = cos.shape[0]
@@ -328,7 +333,7 @@ def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
 
 _NAMES = ["gemm", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
           "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
-          "timestep_embedding", "unet_input_im2col", "adaln", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
+          "timestep_embedding", "unet_input_im2col", "adaln", "rmsnorm_rows", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
           "sampler_step", "sampler_update", "eps_to_denoised", "vae_postprocess", "vae_preprocess", "vae_posterior"]
 
 

@@ -317,3 +317,15 @@ def test_img2img_accepts_the_buffer_returned_by_sample():
     a = pipe.img2img(cond, None, lat, noise2, steps=4, denoising_strength=0.5, sampler="euler", cfg_scale=1.0).clone()
     b = pipe.img2img(cond, None, keep, noise2, steps=4, denoising_strength=0.5, sampler="euler", cfg_scale=1.0)
     assert torch.equal(a, b)
+
+
+def test_chroma_engine_host_logic_vs_reference_golden():
+    """Chroma = the Flux block sequence fed by the Approximator's modulation vectors (backend/nn/chroma.py): the vector
+    order of distribute_modulations, the [timestep | zero guidance | index] input, the residual RMSNorm-MLP stack."""
+    from b200forge.flux_engine import ChromaEngine
+    from oracle import chroma as OC
+    g = _gold("chroma_tiny.pt")
+    cfg = OC.CONFIGS[g["config"]]
+    eng = ChromaEngine(cfg, OC.random_state_dict(cfg, seed=g["weight_seed"]), dtype=F32, device="cpu")
+    out = eng.forward(g["x"], g["t"], g["context"])
+    assert_close("emulated ChromaEngine vs reference golden", out, g["out"], max_abs=3e-4)

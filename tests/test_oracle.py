@@ -223,3 +223,14 @@ def test_v_prediction_oracle_matches_reference_golden():
         out = S.sample_euler(den, x0, g["sigmas"], callback=lambda i, x, d: seen.append(d.clone()))
     assert_close("oracle v-pred first denoised vs reference", seen[0], g["denoised0"], rel_rms=1e-5)
     assert_close("oracle v-pred Euler trajectory vs reference", out, g["euler"], rel_rms=1e-5)
+
+
+def test_chroma_oracle_matches_reference_golden():
+    from oracle import chroma as OC
+    g = _gold("chroma_tiny.pt")
+    cfg = OC.CONFIGS[g["config"]]
+    sd = OC.random_state_dict(cfg, seed=g["weight_seed"])
+    assert abs(_sd_checksum(sd) - g["weight_checksum"]) <= 1e-6 * g["weight_checksum"]
+    with torch.no_grad():
+        out = OC.chroma_forward(sd, cfg, g["x"], g["t"], g["context"])
+    assert_close("oracle chroma tiny vs reference golden", out, g["out"], max_abs=5e-5)
