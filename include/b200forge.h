@@ -249,6 +249,11 @@ int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, fl
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
 
+/* ControlNet residual: h NHWC [N, H, W, C] (dtype) += ctrl NCHW [N, C, H, W] (dtype, or fp32 when ctrl_is_f32)
+ * (backend/nn/unet.py:44-52 apply_control on the input / middle / output-skip activations).  C multiple of 8.
+ * Added after the round's GPU budget was spent: exercised so far only through the CPU emulation of the engine. */
+int b200_add_nchw(void* h, const void* ctrl, int N, int C, int H, int W, int ctrl_is_f32, int dtype, b200_stream_t s);
+
 /* VAE encode entry: pixels NHWC fp32 [pixels, 3] in [0, 1] -> [pixels, 8] in dtype, channels 0-2 = 2x - 1, 3-7 = 0
  * (backend/patcher/vae.py:177: `(2. * pixel_samples - 1.).to(vae_dtype)`; padded to 8 channels for the conv_in im2col). */
 int b200_vae_preprocess(const float* x, void* out, size_t pixels, int dtype, b200_stream_t s);

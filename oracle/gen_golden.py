@@ -283,6 +283,36 @@ def gen_vae_encode(name: str = "tiny", hw: int = 64):
     print("vae encode", name, "mean std", mean.std().item(), "logvar mean", logvar.mean().item())
 
 
+def gen_unet_control(name: str = "tiny_xl", hw: int = 16):
+    """Reference UNet forward with ControlNet-style residuals (backend/nn/unet.py:44-52, 714, 733, 739): one tensor per input
+    block, one for the middle block, one per output skip, plus a None entry, consumed from the end of each list."""
+    from backend.nn.unet import IntegratedUNet2DConditionModel as RefUNet
+    cfg = CF.CONFIGS[name]
+    sd = OU.random_state_dict(cfg, seed=1)
+    m = RefUNet(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    x, ctx, y = make_inputs(cfg, 2, hw, seed=2)
+    t = torch.tensor([981.0, 23.0])
+    # shapes of the activations the residuals are added to: run once with hooks
+    shapes = {"input": [], "middle": [], "output": []}
+    hooks = [blk.register_forward_hook(lambda mod, i, o, k="input": shapes[k].append(tuple(o.shape))) for blk in m.input_blocks]
+    hooks.append(m.middle_block.register_forward_hook(lambda mod, i, o: shapes["middle"].append(tuple(o.shape))))
+    with torch.no_grad():
+        m(x, t, context=ctx, y=y, transformer_options={})
+    for h in hooks:
+        h.remove()
+    g = torch.Generator().manual_seed(19)
+    ins = [torch.randn(s, generator=g) * 0.3 for s in shapes["input"]]
+    control = {"input": list(reversed(ins)),                                   # popped from the end: block 0 first
+               "middle": [torch.randn(shapes["middle"][0], generator=g) * 0.3],
+               "output": [None if i == 2 else torch.randn(s, generator=g) * 0.3 for i, s in enumerate(shapes["input"])]}
+    with torch.no_grad():
+        out = m(x, t, context=ctx, y=y, control={k: list(v) for k, v in control.items()}, transformer_options={})
+    torch.save(dict(config=name, weight_seed=1, weight_checksum=sd_checksum(sd), x=x, t=t, context=ctx, y=y, control=control, out=out),
+               os.path.join(GOLD, f"unet_{name}_control.pt"))
+    print("unet control", name, "out std", out.std().item())
+
+
 def gen_chroma(name: str = "tiny_chroma", hw: int = 16, txt_len: int = 64):
     """Reference Chroma transformer (backend/nn/chroma.py) on CPU fp32."""
     from backend.nn.chroma import IntegratedChromaTransformer2DModel
@@ -326,7 +356,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "chroma", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "control", "chroma", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -343,6 +373,8 @@ if __name__ == "__main__":
         gen_samplers()
     if "vae_enc" in which:
         gen_vae_encode("tiny")
+    if "control" in which:
+        gen_unet_control("tiny_xl")
     if "chroma" in which:
         gen_chroma()
     if "flux" in which:

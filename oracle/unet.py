@@ -164,8 +164,20 @@ def _run_layers(sd: SD, cfg: dict, layers, h, emb, context):
     return h
 
 
-def unet_forward(sd: SD, cfg: dict, x, timesteps, context, y: Optional[torch.Tensor] = None):
-    """backend/nn/unet.py:696-763 (IntegratedUNet2DConditionModel.forward, plain path)."""
+def _apply_control(h, control, name):
+    """backend/nn/unet.py:44-52."""
+    if control is not None and name in control and len(control[name]) > 0:
+        ctrl = control[name].pop()
+        if ctrl is not None:
+            h = h + ctrl
+    return h
+
+
+def unet_forward(sd: SD, cfg: dict, x, timesteps, context, y: Optional[torch.Tensor] = None, control: Optional[dict] = None):
+    """backend/nn/unet.py:696-763 (IntegratedUNet2DConditionModel.forward, plain path; `control` = ControlNet residual
+    lists consumed from their ends, :714, 733, 739)."""
+    if control is not None:
+        control = {k: list(v) for k, v in control.items()}
     st = structure(cfg)
     t_emb = O.timestep_embedding(timesteps, cfg["model_channels"]).to(x.dtype)
     emb = _lin(sd, "time_embed.2", O.silu(_lin(sd, "time_embed.0", t_emb)))
@@ -175,11 +187,11 @@ def unet_forward(sd: SD, cfg: dict, x, timesteps, context, y: Optional[torch.Ten
     hs = []
     h = x
     for layers in st["input"]:
-        h = _run_layers(sd, cfg, layers, h, emb, context)
+        h = _apply_control(_run_layers(sd, cfg, layers, h, emb, context), control, "input")
         hs.append(h)
-    h = _run_layers(sd, cfg, st["middle"], h, emb, context)
+    h = _apply_control(_run_layers(sd, cfg, st["middle"], h, emb, context), control, "middle")
     for layers in st["output"]:
-        h = torch.cat([h, hs.pop()], dim=1)
+        h = torch.cat([h, _apply_control(hs.pop(), control, "output")], dim=1)
         h = _run_layers(sd, cfg, layers, h, emb, context)
     h = _conv(sd, "out.2", O.silu(_gn(sd, "out.0", h, 1e-5)))
     return h.type(x.dtype)

@@ -448,6 +448,30 @@ __global__ void vae_posterior_kernel(const void* __restrict__ mom, const float* 
   }
 }
 
+// ControlNet residual (backend/nn/unet.py:44-52 apply_control, `h += ctrl`): h NHWC [N, H, W, C] (dtype) accumulates a
+// control tensor that arrives in the reference's NCHW layout (dtype or fp32).  One thread per 8 channels of one pixel.
+template <bool BF16>
+__global__ void add_nchw_kernel(void* __restrict__ h, const void* __restrict__ ctrl, int N, int C, int H, int W,
+                                int ctrl_is_f32) {
+  const int CV = C >> 3;
+  const size_t HW = (size_t)H * W;
+  const size_t total = (size_t)N * HW * CV;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const size_t t = i / CV;
+    const size_t hw = t % HW;
+    const size_t n = t / HW;
+    float v[8];
+    load8<BF16>(h, i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t src = (n * C + (size_t)(cv * 8 + j)) * HW + hw;
+      v[j] += ctrl_is_f32 ? reinterpret_cast<const float*>(ctrl)[src] : ld1<BF16>(ctrl, src);
+    }
+    store8<BF16>(h, i * 8, v);
+  }
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = (size_t)num_sms() * 16;
@@ -660,5 +684,14 @@ extern "C" int b200_vae_posterior(const void* moments, const float* noise, float
   DISPATCH_DTYPE(dtype, vae_posterior_kernel<BF><<<grid_for((size_t)N * C * HW, 256), 256, 0, (cudaStream_t)s>>>(
                             moments, noise, out, N, C, HW, ld, scale));
   B200_CHECK_LAUNCH("vae_posterior");
+  return B200_OK;
+}
+
+extern "C" int b200_add_nchw(void* h, const void* ctrl, int N, int C, int H, int W, int ctrl_is_f32, int dtype,
+                             b200_stream_t s) {
+  B200_CHECK_ARG(h && ctrl && N > 0 && C > 0 && H > 0 && W > 0 && C % 8 == 0, "add_nchw: bad arguments (C must be a multiple of 8)");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  DISPATCH_DTYPE(dtype, add_nchw_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(h, ctrl, N, C, H, W, ctrl_is_f32));
+  B200_CHECK_LAUNCH("add_nchw");
   return B200_OK;
 }

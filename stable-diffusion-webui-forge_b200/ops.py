@@ -568,6 +568,17 @@ def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def add_nchw_(h: torch.Tensor, ctrl: torch.Tensor) -> torch.Tensor:
+    """h NHWC [N,H,W,C] += ctrl NCHW [N,C,H,W] (same dtype as h, or fp32), in place."""
+    assert h.dim() == 4 and h.is_contiguous() and ctrl.is_contiguous()
+    n, hh, ww, c = h.shape
+    assert tuple(ctrl.shape) == (n, c, hh, ww) and ctrl.dtype in (h.dtype, torch.float32)
+    _l.check(_l.load().b200_add_nchw(h.data_ptr(), ctrl.data_ptr(), n, c, hh, ww, 1 if ctrl.dtype == torch.float32 else 0,
+                                     _dt(h), _stream()))
+    _count()
+    return h
+
+
 def vae_preprocess(pixels: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pixels NHWC fp32 [B,H,W,3] in [0,1] -> NHWC [B,H,W,8] in dtype: channels 0-2 = 2x-1, the rest zero."""
     assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[3] == 3

@@ -40,9 +40,26 @@ def fast_path_ok(c: dict) -> bool:
         v = to.get(k)
         if v:
             return False
-    if c.get("control") is not None or c.get("c_concat") is not None:
+    if c.get("c_concat") is not None:
+        return False
+    if c.get("control") is not None and not _control_ok(c["control"]):
         return False
     return c.get("c_crossattn") is not None
+
+
+def _control_ok(control) -> bool:
+    """ControlNet / T2I-Adapter residuals the fused UNet can add itself (UNetEngine.forward_cols(control=...)): a dict of
+    lists of CUDA tensors / None under the reference's three names (backend/nn/unet.py:44-52).  Experimental until it has
+    run on hardware: enabled with B200_CONTROL=1, else such calls keep going to Forge's own forward."""
+    import os
+    if os.environ.get("B200_CONTROL") != "1" or not isinstance(control, dict):
+        return False
+    for k, lst in control.items():
+        if k not in ("input", "middle", "output") or not isinstance(lst, (list, tuple)):
+            return False
+        if any(t is not None and not (torch.is_tensor(t) and t.dim() == 4) for t in lst):
+            return False
+    return True
 
 
 # ------------------------------------------------------------------------------------------------- P1 attention
@@ -131,7 +148,7 @@ class UNetWrapper:
         ctx = c["c_crossattn"].to(eng.dtype).contiguous()                  # k_model.py:36
         y = c.get("y")
         y = None if y is None else y.to(eng.dtype).contiguous()
-        eps = eng.forward_sigma(x, sigma, t, ctx, y, reps=1)                # k_model.py:27,34 fused into the entry
+        eps = eng.forward_sigma(x, sigma, t, ctx, y, reps=1, control=c.get("control"))  # k_model.py:27,34 fused into the entry
         return ops.eps_to_denoised(x, eps, sigma, prediction=1 if ptype == "v_prediction" else 0)  # k_model.py:45-46
 
 
@@ -165,7 +182,7 @@ class FluxWrapper:
     def __call__(self, apply_model_fn: Callable, args: dict):
         x, sigma, c = args["input"], args["timestep"], args["c"]
         eng = self.engine
-        ok = (fast_path_ok(c) and _on_device(x) and x.dtype == torch.float32 and x.dim() == 4
+        ok = (fast_path_ok(c) and c.get("control") is None and _on_device(x) and x.dtype == torch.float32 and x.dim() == 4
               and getattr(self.predictor, "prediction_type", None) == "const" and c.get("c_concat") is None
               and c.get("y") is not None and (x.shape[2] | x.shape[3]) % 2 == 0
               and (c.get("guidance") is not None or not eng.guidance_embed))

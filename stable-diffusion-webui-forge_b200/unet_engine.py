@@ -342,35 +342,52 @@ class UNetEngine:
         # every ResBlock applies Linear(SiLU(emb)) (unet.py:412-415): one stacked GEMM for all of them
         return ops.gemm(ops.silu(emb), w["emb_all.w"], w["emb_all.b"])
 
+    @staticmethod
+    def _apply_control(h: torch.Tensor, control: Optional[dict], name: str) -> torch.Tensor:
+        """apply_control (backend/nn/unet.py:44-52): pop the LAST tensor of control[name] and add it in place; the
+        residual arrives NCHW, `h` is channels-last."""
+        if control is not None and name in control and len(control[name]) > 0:
+            ctrl = control[name].pop()
+            if ctrl is not None:
+                ops.add_nchw_(h, ctrl.contiguous())
+        return h
+
     def forward_cols(self, cols: torch.Tensor, n: int, hh: int, ww: int, timesteps: torch.Tensor,
-                     context: torch.Tensor, y: Optional[torch.Tensor], kv_cache=None) -> torch.Tensor:
-        """cols: conv_in im2col rows [n*hh*ww, 64]; returns eps NHWC [n, hh, ww, 8] (channels >= 4 are zero)."""
+                     context: torch.Tensor, y: Optional[torch.Tensor], kv_cache=None, control: Optional[dict] = None) -> torch.Tensor:
+        """cols: conv_in im2col rows [n*hh*ww, 64]; returns eps NHWC [n, hh, ww, 8] (channels >= 4 are zero).
+        control: ControlNet / T2I-Adapter residuals {"input": [...], "middle": [...], "output": [...]} of NCHW tensors, consumed
+        from the end of each list exactly as the reference does (unet.py:714, 733, 739)."""
         w = self.w
         assert context.dtype == self.dtype and context.is_contiguous() and context.shape[0] == n
         n_ctx = context.shape[1]
         ctx2d = context.view(n * n_ctx, context.shape[2])
         temb_all = self._embeddings(timesteps, y)
+        if control is not None:
+            control = {k: list(v) for k, v in control.items()}  # the lists are consumed; leave the caller's intact
         p0 = self.st["input"][0][0][1]
         h = ops.gemm(cols, w[p0 + ".w"], w[p0 + ".b"]).view(n, hh, ww, self.mc)
+        h = self._apply_control(h, control, "input")
         hs = [h]
         for layers in self.st["input"][1:]:
             h = self._run(layers, h, None, temb_all, ctx2d, n_ctx, kv_cache)
+            h = self._apply_control(h, control, "input")
             hs.append(h)
         h = self._run(self.st["middle"], h, None, temb_all, ctx2d, n_ctx, kv_cache)
+        h = self._apply_control(h, control, "middle")
         for layers in self.st["output"]:
-            h = self._run(layers, h, hs.pop(), temb_all, ctx2d, n_ctx, kv_cache)
+            h = self._run(layers, h, self._apply_control(hs.pop(), control, "output"), temb_all, ctx2d, n_ctx, kv_cache)
         h = ops.groupnorm(h, w["out.0.g"], w["out.0.b"], eps=1e-5, silu=True)
         return ops.conv3x3(h, w["out.2.w"], w["out.2.b"])
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
-                y: Optional[torch.Tensor] = None) -> torch.Tensor:
+                y: Optional[torch.Tensor] = None, control: Optional[dict] = None) -> torch.Tensor:
         """Same contract as IntegratedUNet2DConditionModel.forward (unet.py:696): x NCHW [N,4,h,w] in the
         computation dtype, timesteps [N], context [N,77,ctx], y [N,adm] -> NCHW [N,4,h,w]."""
         n, c, hh, ww = x.shape
         xn = ops.nchw_to_nhwc(x.to(self.dtype).contiguous(), self.dtype)
         cols = ops.im2col3x3(xn, ldo=64)
         eps = self.forward_cols(cols, n, hh, ww, timesteps.float().contiguous(), context.to(self.dtype).contiguous(),
-                                None if y is None else y.to(self.dtype).contiguous())
+                                None if y is None else y.to(self.dtype).contiguous(), control=control)
         return ops.nhwc_to_nchw(eps, channels=self.out_channels, out_dtype=x.dtype)
 
     def supports_latent(self, hh: int, ww: int) -> bool:
@@ -388,10 +405,10 @@ class UNetEngine:
         return True
 
     def forward_sigma(self, x: torch.Tensor, sigma: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
-                      y: Optional[torch.Tensor], reps: int, kv_cache=None) -> torch.Tensor:
+                      y: Optional[torch.Tensor], reps: int, kv_cache=None, control: Optional[dict] = None) -> torch.Tensor:
         """KModel.apply_model's front half fused into the entry (k_model.py:27-36): x fp32 NCHW [B,4,h,w] is
         scaled by 1/sqrt(sigma^2+1), cast, laid out channels-last and replicated `reps` times (cond/uncond
         batch) in one pass.  Returns eps NHWC [reps*B, h, w, 8]."""
         b, c, hh, ww = x.shape
         cols = ops.unet_input_im2col(x, sigma, self.dtype, reps=reps, ldo=64)
-        return self.forward_cols(cols, reps * b, hh, ww, timesteps, context, y, kv_cache)
+        return self.forward_cols(cols, reps * b, hh, ww, timesteps, context, y, kv_cache, control)

@@ -311,6 +311,11 @@ def eps_to_denoised(x, eps, sigma, prediction=0, out=None):
     return _ret(_denoised(x, e, sigma.view(-1, 1, 1, 1), prediction), out, torch.float32)
 
 
+def add_nchw_(h, ctrl):
+    h.copy_((h.float() + ctrl.float().permute(0, 2, 3, 1)).to(h.dtype))
+    return h
+
+
 def vae_postprocess(x, out=None):
     return _ret(torch.clamp((x[..., :3].float() + 1.0) / 2.0, 0.0, 1.0), out, torch.float32)
 
@@ -334,7 +339,7 @@ def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
 _NAMES = ["gemm", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
           "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
           "timestep_embedding", "unet_input_im2col", "adaln", "rmsnorm_rows", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
-          "sampler_step", "sampler_update", "eps_to_denoised", "vae_postprocess", "vae_preprocess", "vae_posterior"]
+          "sampler_step", "sampler_update", "eps_to_denoised", "add_nchw_", "vae_postprocess", "vae_preprocess", "vae_posterior"]
 
 
 def install(monkeypatch) -> None:

@@ -329,3 +329,40 @@ def test_chroma_engine_host_logic_vs_reference_golden():
     eng = ChromaEngine(cfg, OC.random_state_dict(cfg, seed=g["weight_seed"]), dtype=F32, device="cpu")
     out = eng.forward(g["x"], g["t"], g["context"])
     assert_close("emulated ChromaEngine vs reference golden", out, g["out"], max_abs=3e-4)
+
+
+def test_unet_engine_control_residuals_vs_reference_golden(monkeypatch):
+    """ControlNet / T2I-Adapter residuals added inside the fused forward (apply_control, backend/nn/unet.py:44-52): order
+    of consumption, a None entry, NCHW residuals onto channels-last activations, skips carrying the input residuals — and
+    the P3 wrapper passing `c["control"]` through when B200_CONTROL=1 (else it defers)."""
+    from b200forge import plugin
+    from b200forge.unet_engine import UNetEngine
+    g = _gold("unet_tiny_xl_control.pt")
+    cfg = CF.CONFIGS[g["config"]]
+    sd = OU.random_state_dict(cfg, seed=g["weight_seed"])
+    eng = UNetEngine(cfg, sd, dtype=F32, device="cpu")
+    out = eng.forward(g["x"], g["t"], g["context"], g["y"], control=g["control"])
+    assert_close("emulated UNetEngine + control vs reference golden", out, g["out"], max_abs=3e-4)
+    assert len(g["control"]["input"]) == 9
+    # plug point: with the switch off the call goes to Forge's own forward, with it on the fused path takes the residuals
+    monkeypatch.setattr(plugin, "_on_device", lambda t: True)
+    pred = S.EpsPrediction()
+
+    class P:
+        prediction_type = "epsilon"
+        timestep = staticmethod(lambda s: pred.timestep(s))
+
+    w = plugin.UNetWrapper(eng, P())
+    x = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(3)) * 3
+    sigma = torch.tensor([4.0, 0.5])
+    c = {"c_crossattn": g["context"], "y": g["y"], "control": g["control"], "transformer_options": {}}
+    sentinel = torch.zeros(1)
+    monkeypatch.delenv("B200_CONTROL", raising=False)
+    assert w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]}) is sentinel
+    monkeypatch.setenv("B200_CONTROL", "1")
+    den = w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]})
+    assert den is not sentinel and w.calls_fast == 1
+    xc = pred.calculate_input(sigma, x)
+    with torch.no_grad():
+        eps = OU.unet_forward(sd, cfg, xc, pred.timestep(sigma).float(), g["context"], g["y"], control=g["control"])
+    assert_close("P3 wrapper with control vs oracle", den, pred.calculate_denoised(sigma, eps, x), rel_rms=1e-5)

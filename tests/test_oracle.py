@@ -234,3 +234,13 @@ def test_chroma_oracle_matches_reference_golden():
     with torch.no_grad():
         out = OC.chroma_forward(sd, cfg, g["x"], g["t"], g["context"])
     assert_close("oracle chroma tiny vs reference golden", out, g["out"], max_abs=5e-5)
+
+
+def test_unet_oracle_with_control_matches_reference_golden():
+    g = _gold("unet_tiny_xl_control.pt")
+    cfg = CF.CONFIGS[g["config"]]
+    sd = OU.random_state_dict(cfg, seed=g["weight_seed"])
+    with torch.no_grad():
+        out = OU.unet_forward(sd, cfg, g["x"], g["t"], g["context"], g["y"], control=g["control"])
+    assert_close("oracle unet tiny_xl + control vs reference golden", out, g["out"], max_abs=5e-5)
+    assert len(g["control"]["input"]) == 9 and g["control"]["output"][2] is None  # the caller's lists are left intact
