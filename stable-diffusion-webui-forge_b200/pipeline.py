@@ -291,9 +291,11 @@ class FluxTxt2ImgPipeline:
 
     @torch.no_grad()
     def sample(self, cond: dict, noise: torch.Tensor, *, steps: int = 20, guidance: float = 3.5,
-               sigmas: Optional[torch.Tensor] = None, callback: Optional[Callable] = None) -> torch.Tensor:
+               sigmas: Optional[torch.Tensor] = None, callback: Optional[Callable] = None,
+               init_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
         """cond = {"crossattn": [B, Lt, ctx] (T5), "vector": [B, vec] (pooled CLIP)}; noise [B, 16, h, w] N(0,1).
-        Returns the final latent [B, 16, h, w] fp32 on the device."""
+        init_latent (img2img): the start is sigma_0 * noise + (1 - sigma_0) * init_latent ('const' noise_scaling,
+        k_prediction.py:94-96).  Returns the final latent [B, 16, h, w] fp32 on the device."""
         dev = self.device
         b, c, hh, ww = noise.shape
         gf = self._graph_for(b, hh, ww, cond["crossattn"].shape[1])
@@ -306,8 +308,12 @@ class FluxTxt2ImgPipeline:
         gf.y.copy_(cond["vector"].to(device=dev, dtype=self.dtype, non_blocking=True))
         gf.guidance.fill_(float(guidance))
         x = gf.x
+        if init_latent is not None:
+            init_latent = init_latent.to(device=dev, dtype=torch.float32).clone()
         x.copy_(noise.to(device=dev, dtype=torch.float32, non_blocking=True))
-        x.mul_(float(sigmas[0]))  # 'const' noise_scaling with a zero latent (k_prediction.py:94-96)
+        x.mul_(float(sigmas[0]))  # 'const' noise_scaling (k_prediction.py:94-96): sigma * noise + (1 - sigma) * latent
+        if init_latent is not None:
+            x.add_(init_latent.mul_(1.0 - float(sigmas[0])))
         sig_tab = sigmas[:-1].to(dev).view(-1, 1).expand(-1, b).contiguous()
 
         def model_fn(i):
@@ -316,3 +322,15 @@ class FluxTxt2ImgPipeline:
 
         sampling.run_sampler(model_fn, x, plan, cfg_scale=1.0, has_uncond=False, callback=callback)
         return x.clone()  # x is the graph's static input buffer: the caller gets its own copy
+
+
+    @torch.no_grad()
+    def img2img(self, cond: dict, init_latent: torch.Tensor, noise: torch.Tensor, *, steps: int = 20,
+                denoising_strength: float = 0.75, guidance: float = 3.5, **kw) -> torch.Tensor:
+        """img2img on a Flux latent: the last t_enc + 1 sigmas of the Simple schedule (setup_img2img_steps,
+        modules/sd_samplers_common.py:24-33; sample_img2img, modules/sd_samplers_kdiffusion.py:140-146)."""
+        b, c, hh, ww = noise.shape
+        pred = sampling.FluxPrediction(seq_len=(hh // 2) * (ww // 2))
+        full = sampling.get_sigmas_simple(pred.sigmas, steps)
+        sched = Txt2ImgPipeline.img2img_schedule(full, steps, denoising_strength)
+        return self.sample(cond, noise, steps=len(sched) - 1, guidance=guidance, sigmas=sched, init_latent=init_latent, **kw)

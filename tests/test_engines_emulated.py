@@ -366,3 +366,55 @@ def test_unet_engine_control_residuals_vs_reference_golden(monkeypatch):
     with torch.no_grad():
         eps = OU.unet_forward(sd, cfg, xc, pred.timestep(sigma).float(), g["context"], g["y"], control=g["control"])
     assert_close("P3 wrapper with control vs oracle", den, pred.calculate_denoised(sigma, eps, x), rel_rms=1e-5)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p2_operator_classes_inside_the_reference_vae_and_flux(monkeypatch):
+    """Same as above for the reference VAE decoder (Conv2d / GroupNorm at 3 and 4-channel edges, 1x1 attention convs) and
+    the Flux transformer (Linear everywhere, LayerNorm without affine) built from B200Operations."""
+    ref_import.load()
+    from backend.nn.flux import IntegratedFluxTransformer2DModel
+    from backend.nn.vae import IntegratedAutoencoderKL
+    from backend.operations import using_forge_operations
+
+    from b200forge import operations as P2
+    monkeypatch.setattr(P2, "_fast", lambda x, w: w.dtype == x.dtype)
+    monkeypatch.setattr(P2, "_FAST_DTYPES", (torch.float16, torch.bfloat16, torch.float32))
+    gv = _gold("vae_tiny.pt")
+    vcfg = CF.VAE_CONFIGS[gv["config"]]
+    with using_forge_operations(operations=P2.B200Operations, device=torch.device("cpu"), dtype=torch.float32):
+        vae = IntegratedAutoencoderKL(**vcfg).eval()
+        gf = _gold("flux_tiny.pt")
+        fcfg = OF.CONFIGS[gf["config"]]
+        flux = IntegratedFluxTransformer2DModel(**fcfg).eval()
+    assert any(isinstance(m, P2.Conv2d) for m in vae.modules()) and any(isinstance(m, P2.Linear) for m in flux.modules())
+    vae.load_state_dict(OV.random_state_dict(vcfg, seed=gv["weight_seed"]), strict=False)
+    flux.load_state_dict(OF.random_state_dict(fcfg, seed=gf["weight_seed"]), strict=True)
+    with torch.no_grad():
+        img = vae.decode(vae.process_out(gv["z"]))
+        out = flux(gf["x"], gf["t"], gf["context"], gf["y"], gf["guidance"])
+    assert_close("reference VAE decoder built from B200Operations modules", img, gv["out"], max_abs=5e-5)
+    assert_close("reference Flux transformer built from B200Operations modules", out, gf["out"], max_abs=5e-5)
+
+
+def test_flux_img2img_host_logic_vs_oracle_loop():
+    from b200forge.pipeline import FluxTxt2ImgPipeline
+    cfg = OF.TINY_FLUX
+    sd = OF.random_state_dict(cfg, seed=31)
+    pipe = FluxTxt2ImgPipeline(cfg, sd, dtype=F32, device="cpu", use_graph=False)
+    g = torch.Generator().manual_seed(33)
+    B, hw, Lt, steps, strength = 1, 16, 64, 6, 0.5
+    noise, latent = torch.randn(B, 16, hw, hw, generator=g), torch.randn(B, 16, hw, hw, generator=g) * 0.7
+    cond = dict(crossattn=torch.randn(B, Lt, cfg["context_in_dim"], generator=g), vector=torch.randn(B, cfg["vec_in_dim"], generator=g))
+    x = pipe.img2img(cond, latent, noise, steps=steps, denoising_strength=strength, guidance=4.0)
+    full = S.simple_scheduler(steps, S.flux_sigma_table(seq_len=(hw // 2) ** 2))
+    sched = full[steps - int(min(strength, 0.999) * steps) - 1:]
+    gd = torch.full((B,), 4.0)
+
+    def model(xx, sigma):
+        with torch.no_grad():
+            v = OF.flux_forward(sd, cfg, xx, sigma, cond["crossattn"], cond["vector"], gd)
+        return S.const_denoised(xx, v, sigma.view(-1, 1, 1, 1))
+
+    ref = S.sample_euler(model, S.const_noise_scaling(float(sched[0]), noise, latent), sched)
+    assert_close("emulated Flux img2img vs oracle loop", x, ref, rel_rms=2e-4)
