@@ -254,6 +254,25 @@ def gen_samplers(steps: int = 7):
         with torch.no_grad():
             out[key] = getattr(ks, name)(Model(), x0.clone(), sig, extra_args={}, disable=True, **kw)
         print(key, float(out[key].std()))
+    # rectified-flow variants: the reference dispatches on isinstance(model.inner_model.predictor, PredictionFlux)
+    from backend.modules.k_prediction import PredictionFlux
+    from oracle import sampling as OS2
+    fpred = PredictionFlux()
+    fsig = OS2.simple_scheduler(steps, OS2.flux_sigma_table())
+
+    class FluxModel(Model):
+        class _Inner:
+            predictor = fpred
+        inner_model = _Inner()
+
+    xf0 = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(12)) * fsig[0]
+    out["flux_sigmas"], out["flux_x0"] = fsig, xf0
+    for name in ("sample_euler_ancestral", "sample_dpm_2_ancestral"):
+        k = iter(range(noise.shape[0]))
+        with torch.no_grad():
+            out[name + "_rf"] = getattr(ks, name)(FluxModel(), xf0.clone(), fsig, extra_args={}, disable=True,
+                                                  noise_sampler=lambda s, sn: noise[next(k)])
+        print(name + "_rf", float(out[name + "_rf"].std()))
     torch.save(out, os.path.join(GOLD, "samplers_toy.pt"))
 
 

@@ -84,16 +84,12 @@ def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None,
 @torch.no_grad()
 def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
                            noise_sampler=None):
-    is_flux = False
-    try:
-        from backend.modules.k_prediction import PredictionFlux  # type: ignore
-        is_flux = isinstance(model.inner_model.predictor, PredictionFlux)
-    except Exception:
-        pass
-    if is_flux or not _fusable(x):
+    if not _fusable(x):
         if reference_sample_euler_ancestral is None:
-            raise _l.B200Error(_l.E_UNSUPPORTED, "sample_euler_ancestral: rectified-flow / non-CUDA-fp32 case needs the reference sampler")
+            raise _l.B200Error(_l.E_UNSUPPORTED, "sample_euler_ancestral: non-CUDA-fp32 latents need the reference sampler")
         return reference_sample_euler_ancestral(model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    if _is_flux(model):  # the reference dispatches on the predictor type (k_diffusion/sampling.py:143-144)
+        return _sample_euler_ancestral_rf(model, x, sigmas, extra_args, callback, eta, s_noise, noise_sampler)
     extra_args = {} if extra_args is None else extra_args
     if noise_sampler is None:
         noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731  (default_noise_sampler, sampling.py:63-64)
@@ -233,8 +229,10 @@ def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None,
 def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1.,
                            noise_sampler=None):
     """k_diffusion/sampling.py:249-276."""
-    if _is_flux(model) or not _fusable(x):
+    if not _fusable(x):
         return _defer(reference_sample_dpm_2_ancestral, "sample_dpm_2_ancestral", model, x, sigmas, extra_args, callback, disable, eta, s_noise, noise_sampler)
+    if _is_flux(model):  # k_diffusion/sampling.py:251-252
+        return _sample_dpm_2_ancestral_rf(model, x, sigmas, extra_args, callback, eta, s_noise, noise_sampler)
     extra_args = {} if extra_args is None else extra_args
     if noise_sampler is None:
         noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731
@@ -479,4 +477,62 @@ def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disabl
                 _lin(x, d_2, c_x=1.0, c_d=c_2)
             h_1, h_2 = h, h_1
         d_1, d_2 = denoised, d_1
+    return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Rectified-flow variants the reference switches to for Flux (k_diffusion/sampling.py:162-186, 278-309): the down-step and
+# the re-noising coefficient come from alpha = 1 - sigma instead of the variance-exploding ancestral step.
+def _rf_coeffs(s0, s1, eta):
+    downstep_ratio = 1 + (s1 / s0 - 1) * eta
+    sigma_down = s1 * downstep_ratio
+    alpha_ip1, alpha_down = 1 - s1, 1 - sigma_down
+    renoise = (s1 ** 2 - sigma_down ** 2 * alpha_ip1 ** 2 / alpha_down ** 2) ** 0.5
+    return sigma_down, alpha_ip1 / alpha_down, renoise
+
+
+def _sample_euler_ancestral_rf(model, x, sigmas, extra_args, callback, eta, s_noise, noise_sampler):
+    extra_args = {} if extra_args is None else extra_args
+    if noise_sampler is None:
+        noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(s1) == 0:
+            _lin(x, denoised, c_x=0.0, c_d=1.0)
+            continue
+        sigma_down, a, renoise = _rf_coeffs(s0, s1, eta)
+        r = sigma_down / s0
+        if eta > 0:   # x = a * (r x + (1 - r) D) + noise * s_noise * renoise
+            noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+            _lin(x, denoised, c_x=a * r, c_d=a * (1 - r), noise=noise, c_noise=s_noise * renoise)
+        else:
+            _lin(x, denoised, c_x=r, c_d=1 - r)
+    return x
+
+
+def _sample_dpm_2_ancestral_rf(model, x, sigmas, extra_args, callback, eta, s_noise, noise_sampler):
+    extra_args = {} if extra_args is None else extra_args
+    if noise_sampler is None:
+        noise_sampler = lambda sigma, sigma_next: _randn_like(x)  # noqa: E731
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        s0, s1 = sig[i], sig[i + 1]
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        sigma_down, a, renoise = _rf_coeffs(s0, s1, eta)
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        if float(sigma_down) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(s0), dt=float(sigma_down - s0))
+        else:
+            _dpm2_stage(model, x, denoised, s0, sigma_down, sigmas[i], s_in, extra_args)
+            noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
+            _lin(x, noise, c_x=a, c_d=s_noise * renoise)       # x = (alpha_ip1 / alpha_down) x + noise * s_noise * renoise
     return x

@@ -339,3 +339,36 @@ def test_k_sampler_host_logic_vs_reference_golden(key, monkeypatch):
     err = (out - g[key]).abs().max().item()
     scale = g[key].abs().max().item()
     assert err <= 2e-5 * max(1.0, scale), (key, err, scale)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted (the dispatch is on the reference's PredictionFlux type)")
+@pytest.mark.parametrize("name", ["sample_euler_ancestral", "sample_dpm_2_ancestral"])
+def test_rectified_flow_ancestral_samplers_vs_reference_golden(name, monkeypatch):
+    """For a Flux model the reference's Euler a / DPM2 a switch to their rectified-flow variants
+    (k_diffusion/sampling.py:143-144, 162-186, 251-252, 278-309); the fused versions dispatch the same way."""
+    import os
+
+    import torch
+
+    ref_import.load()
+    from backend.modules.k_prediction import PredictionFlux
+
+    from b200forge import k_samplers
+    from oracle import sampling as OS
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers_toy.pt"), weights_only=False)
+    monkeypatch.setattr(k_samplers.ops, "sampler_update", _emulated_sampler_update)
+    monkeypatch.setattr(k_samplers, "_fusable", lambda x: True)
+
+    class FluxModel:
+        class _Inner:
+            predictor = PredictionFlux()
+        inner_model = _Inner()
+
+        def __call__(self, x, sigma, **kw):
+            return OS.toy_denoiser(x, sigma)
+
+    k = iter(range(g["noise"].shape[0]))
+    out = getattr(k_samplers, name)(FluxModel(), g["flux_x0"].clone(), g["flux_sigmas"], extra_args={}, disable=True,
+                                    noise_sampler=lambda s, sn: g["noise"][next(k)])
+    err = (out - g[name + "_rf"]).abs().max().item()
+    assert err <= 2e-5 * max(1.0, g[name + "_rf"].abs().max().item()), (name, err)
