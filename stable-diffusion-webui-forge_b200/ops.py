@@ -223,6 +223,33 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
+def any_size_enabled() -> bool:
+    """B200_ANY_SIZE=1: image sizes the TMA convolution cannot tile run their 3x3 convolutions as b200_im2col3x3 +
+    b200_gemm (both kernels are the ones the stride-2 and small-channel convolutions already use) instead of being
+    handed back to Forge.  Off by default until that route and the ragged-length attention it implies have run on
+    hardware."""
+    import os
+    return os.environ.get("B200_ANY_SIZE") == "1"
+
+
+def conv3x3_any(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                residual: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 on one contiguous NHWC tensor for ANY image size: the implicit-GEMM TMA kernel when the size
+    tiles (conv3x3_supported), else patch matrix + GEMM with the same epilogue (bias, per-image time-embedding row,
+    activation, residual).  9x the activation traffic of the TMA path — a functional route, not the fast one."""
+    n, h, w_, c = x.shape
+    if conv3x3_supported(h, w_):
+        return conv3x3(x, w_packed, bias, residual=residual, temb=temb, epilogue=epilogue, out=out)
+    cout = w_packed.shape[0]
+    if out is None:
+        out = torch.empty((n, h, w_, cout), dtype=x.dtype, device=x.device)
+    cols = im2col3x3(x)
+    gemm(cols, w_packed, bias, rowvec=temb, rows_per_vec=h * w_, epilogue=epilogue,
+         residual=None if residual is None else residual.reshape(n * h * w_, cout), out=out.view(n * h * w_, cout))
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, scale: Optional[float] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B, Lq, H*Dh], k/v [B, Lk, H*Dh] (unit inner stride; may be column slices of a fused projection)."""

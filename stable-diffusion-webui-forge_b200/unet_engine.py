@@ -222,7 +222,7 @@ class UNetEngine:
         m = n * hh * ww
         h = ops.groupnorm(x1, w[p + ".in_layers.0.g"], w[p + ".in_layers.0.b"], eps=1e-5, silu=True, x2=x2)
         off, _ = self.emb_off[p]
-        h = ops.conv3x3(h, w[p + ".conv1.w"], w[p + ".conv1.b"], temb=temb_all[:, off:off + cout])
+        h = ops.conv3x3_any(h, w[p + ".conv1.w"], w[p + ".conv1.b"], temb=temb_all[:, off:off + cout])
         h = ops.groupnorm(h, w[p + ".out_layers.0.g"], w[p + ".out_layers.0.b"], eps=1e-5, silu=True)
         if cin != cout:
             skip = ops.gemm(x1.view(m, c1), w[p + ".skip.w"], w[p + ".skip.b"],
@@ -230,7 +230,7 @@ class UNetEngine:
         else:
             assert x2 is None
             skip = x1
-        return ops.conv3x3(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
+        return ops.conv3x3_any(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
 
     # ---- cross-attention K/V: the text context is constant over the sampler steps of a job, so its projections
     # (reference: to_k / to_v recomputed in every CrossAttention.forward, unet.py:148-152) are loop-invariant.
@@ -326,7 +326,7 @@ class UNetEngine:
                 cols = ops.im2col3x3(h, stride=2)
                 h = ops.gemm(cols, self.w[p + ".w"], self.w[p + ".b"]).view(n, hh // 2, ww // 2, c)
             elif kind == "up":
-                h = ops.conv3x3(ops.upsample2x(h), self.w[p + ".w"], self.w[p + ".b"])
+                h = ops.conv3x3_any(ops.upsample2x(h), self.w[p + ".w"], self.w[p + ".b"])
         return h
 
     # ------------------------------------------------------------------------------------------ forward
@@ -377,7 +377,7 @@ class UNetEngine:
         for layers in self.st["output"]:
             h = self._run(layers, h, self._apply_control(hs.pop(), control, "output"), temb_all, ctx2d, n_ctx, kv_cache)
         h = ops.groupnorm(h, w["out.0.g"], w["out.0.b"], eps=1e-5, silu=True)
-        return ops.conv3x3(h, w["out.2.w"], w["out.2.b"])
+        return ops.conv3x3_any(h, w["out.2.w"], w["out.2.b"])
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
                 y: Optional[torch.Tensor] = None, control: Optional[dict] = None) -> torch.Tensor:
@@ -396,7 +396,7 @@ class UNetEngine:
         buckets (e.g. 152x104 latents) do not yet — the plug-in hands those back to Forge's own forward."""
         levels = len(self.cfg["channel_mult"])
         for _ in range(levels):
-            if not ops.conv3x3_supported(hh, ww):
+            if not (ops.conv3x3_supported(hh, ww) or ops.any_size_enabled()):
                 return False
             if _ != levels - 1:
                 if hh % 2 or ww % 2:

@@ -93,14 +93,14 @@ class VAEDecoderEngine:
         w = self.w
         n, hh, ww, cin = x.shape
         h = ops.groupnorm(x, w[p + ".norm1.g"], w[p + ".norm1.b"], eps=1e-6, silu=True)
-        h = ops.conv3x3(h, w[p + ".conv1.w"], w[p + ".conv1.b"])
+        h = ops.conv3x3_any(h, w[p + ".conv1.w"], w[p + ".conv1.b"])
         h = ops.groupnorm(h, w[p + ".norm2.g"], w[p + ".norm2.b"], eps=1e-6, silu=True)
         if (p + ".skip.w") in w:
             cout = w[p + ".skip.w"].shape[0]
             skip = ops.gemm(x.view(-1, cin), w[p + ".skip.w"], w[p + ".skip.b"]).view(n, hh, ww, cout)
         else:
             skip = x
-        return ops.conv3x3(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
+        return ops.conv3x3_any(h, w[p + ".conv2.w"], w[p + ".conv2.b"], residual=skip)
 
     def _attn(self, p: str, x: torch.Tensor) -> torch.Tensor:
         w = self.w
@@ -124,7 +124,7 @@ class VAEDecoderEngine:
     def supports_latent(self, hh: int, ww: int) -> bool:
         """Every decoder resolution (latent size x 1, 2, 4, ...) must tile on the TMA convolution path."""
         for _ in range(self.nres):
-            if not ops.conv3x3_supported(hh, ww):
+            if not (ops.conv3x3_supported(hh, ww) or ops.any_size_enabled()):
                 return False
             hh, ww = hh * 2, ww * 2
         return True
@@ -149,9 +149,9 @@ class VAEDecoderEngine:
                 h = self._res(f"decoder.up.{lvl}.block.{j}", h)
             if lvl != 0:
                 q = f"decoder.up.{lvl}.upsample.conv"
-                h = ops.conv3x3(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
+                h = ops.conv3x3_any(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
         h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
-        h = ops.conv3x3(h, w["conv_out.w"], w["conv_out.b"])
+        h = ops.conv3x3_any(h, w["conv_out.w"], w["conv_out.b"])
         return ops.vae_postprocess(h)
 
 
@@ -232,7 +232,7 @@ class VAEEncoderEngine:
     def supports_image(self, H: int, W: int) -> bool:
         """Every encoder resolution (image size / 1, 2, 4, ...) must tile on the TMA convolution path."""
         for lvl in range(self.nres):
-            if not ops.conv3x3_supported(H, W):
+            if not (ops.conv3x3_supported(H, W) or ops.any_size_enabled()):
                 return False
             if lvl != self.nres - 1:
                 if H % 2 or W % 2:
@@ -259,7 +259,7 @@ class VAEEncoderEngine:
         h = self._attn("encoder.mid.attn_1", h)
         h = self._res("encoder.mid.block_2", h)
         h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
-        h = ops.conv3x3(h, w["conv_out.w"], w["conv_out.b"])                          # [B, h, w, 8]
+        h = ops.conv3x3_any(h, w["conv_out.w"], w["conv_out.b"])                          # [B, h, w, 8]
         n2, hh, ww, _ = h.shape
         return ops.gemm(h.view(-1, 8), w["quant.w"], w["quant.b"]).view(n2, hh, ww, 8)
 

@@ -418,3 +418,50 @@ def test_flux_img2img_host_logic_vs_oracle_loop():
 
     ref = S.sample_euler(model, S.const_noise_scaling(float(sched[0]), noise, latent), sched)
     assert_close("emulated Flux img2img vs oracle loop", x, ref, rel_rms=2e-4)
+
+
+def test_any_size_route_host_logic(monkeypatch):
+    """B200_ANY_SIZE=1: latent sizes the TMA convolution cannot tile (SDXL's non-square buckets, e.g. 152x104 and its /2, /4
+    levels) run their 3x3 convolutions as im2col + GEMM with the same epilogue (bias, time-embedding row, residual).  Here
+    a 12x20 latent (levels 12x20, 6x10, 3x5 — none of which tiles) through the UNet and VAE engines against the oracle."""
+    from b200forge import ops
+    from b200forge.unet_engine import UNetEngine
+    from b200forge.vae_engine import VAEDecoderEngine
+    cfg = CF.CONFIGS["tiny_xl"]
+    sd = OU.random_state_dict(cfg, seed=1)
+    eng = UNetEngine(cfg, sd, dtype=F32, device="cpu")
+    assert not ops.conv3x3_supported(12, 20) and not ops.conv3x3_supported(6, 10) and not ops.conv3x3_supported(3, 5)
+    monkeypatch.delenv("B200_ANY_SIZE", raising=False)
+    assert not eng.supports_latent(12, 20) and eng.supports_latent(16, 16)
+    monkeypatch.setenv("B200_ANY_SIZE", "1")
+    assert eng.supports_latent(12, 20) and not eng.supports_latent(13, 20)  # odd sizes still need the reference's resize path
+    calls = {"im2col": 0, "tma": 0}
+    real_im2col, real_conv = ops.im2col3x3, ops.conv3x3
+
+    def im2col(*a, **kw):
+        calls["im2col"] += 1
+        return real_im2col(*a, **kw)
+
+    def conv(*a, **kw):
+        calls["tma"] += 1
+        return real_conv(*a, **kw)
+
+    monkeypatch.setattr(ops, "im2col3x3", im2col)
+    monkeypatch.setattr(ops, "conv3x3", conv)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 4, 12, 20, generator=g)
+    ctx = torch.randn(2, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(2, cfg["adm_in_channels"], generator=g)
+    t = torch.tensor([700.0, 40.0])
+    out = eng.forward(x, t, ctx, y)
+    with torch.no_grad():
+        ref = OU.unet_forward(sd, cfg, x, t, ctx, y)
+    assert calls["tma"] == 0 and calls["im2col"] > 20, calls
+    assert_close("emulated UNetEngine at a non-tiling size vs oracle", out, ref, max_abs=3e-4)
+    vcfg = CF.VAE_CONFIGS["tiny"]
+    vsd = OV.random_state_dict(vcfg, seed=3)
+    dec = VAEDecoderEngine(vcfg, vsd, dtype=F32, device="cpu")
+    z = torch.randn(1, 4, 12, 20, generator=g) * vcfg["scaling_factor"]
+    with torch.no_grad():
+        vref = OV.decode_first_stage(vsd, vcfg, z)
+    assert_close("emulated VAE decoder at a non-tiling size vs oracle", dec.decode(z), vref, max_abs=1e-4)

@@ -426,3 +426,29 @@ def test_sampler_step_and_denoised_v_prediction():
     out = ops.eps_to_denoised(x4.to(DEV), v.to(DEV), sig4.to(DEV), prediction=1)
     torch.cuda.synchronize()
     assert_close("v-pred eps_to_denoised", out, pred.calculate_denoised(sig4, vn, x4), max_abs=3e-5)
+
+
+_ANY = __import__("os").environ.get("B200_ANY_SIZE") == "1"
+
+
+@pytest.mark.skipif(not _ANY, reason="any-size route is experimental: run with B200_ANY_SIZE=1")
+def test_any_size_convolution_route_and_ragged_attention():
+    """What B200_ANY_SIZE=1 adds on hardware: (1) 3x3 convolutions of non-tiling images as im2col + GEMM with the time-embedding
+    row and the residual in the GEMM epilogue, (2) self-attention over token counts that are not multiples of the 128-key /
+    256-query tiles (152x104 latents -> 15808 / 3952 / 988 tokens)."""
+    ops = _ops()
+    N, H, W, C, Cout = 2, 52, 76, 640, 640
+    x = _rand(N, C, H, W, seed=100)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=101)
+    b = _rand(Cout, seed=102)
+    temb = _rand(N, Cout, seed=103)
+    res = _rand(N, H, W, Cout, seed=104)
+    y = ops.conv3x3_any(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), b, temb=temb, residual=res)
+    torch.cuda.synchronize()
+    ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    assert_close("conv3x3_any 52x76", y, ref, rel_rms=2e-3)
+    for (B, Hh, L, Dh) in ((2, 10, 3952, 64), (2, 20, 988, 64), (1, 4, 1000, 128)):
+        q, k, v = (_rand(B, L, Hh * Dh, seed=110 + i) for i in range(3))
+        out = ops.attention(q, k, v, Hh)
+        torch.cuda.synchronize()
+        assert_close(f"attention ragged L={L} Dh={Dh}", out, O.attention(q.float(), k.float(), v.float(), Hh), rel_rms=2e-3)
