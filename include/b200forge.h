@@ -65,13 +65,18 @@ typedef struct {
   int K1;
   /* LayerNorm folded into the GEMM (replaces F.layer_norm + F.linear, backend/nn/unet.py:171-175 with operations.py:323-329):
    * A holds the un-normalised rows, B = W.diag(gamma); y = rstd_m*(acc - mean_m*ln_c[n]) + ln_d[n] with
-   * ln_c = rowsum(B) and ln_d = W.beta (+ bias), both fp32 [N]; ln_stats [M,2] = (sum, sum of squares) of each A row. */
+   * ln_c = rowsum(B) and ln_d = W.beta (+ bias), both fp32 [N]; ln_stats [M, ln_stats_parts, 4] fp32 = partial row
+   * statistics (count, mean, sum of squared deviations, 0) of each A row as a producer GEMM's row_stats_out wrote them;
+   * the epilogue merges the partials with the parallel-variance formula (no sumsq/K - mean^2 cancellation). */
   const float* ln_stats;
+  int ln_stats_parts;
   const float* ln_c;
   const float* ln_d;
   float ln_eps;
-  /* when set, the epilogue accumulates (sum, sum of squares) of every output row into row_stats_out [M,2]
-   * (zeroed by the caller) — the ln_stats of the next GEMM, so no separate LayerNorm pass touches HBM. */
+  /* when set, the epilogue writes partial statistics of every output row into row_stats_out
+   * [M, b200_gemm_row_stats_parts(N, epilogue, block_n), 4] fp32 — the ln_stats of the next GEMM, so no separate
+   * LayerNorm pass touches HBM.  Each partial is written exactly once (no atomics, nothing to zero, bit-reproducible).
+   * N must be a multiple of 8; not available with the GEGLU epilogue. */
   float* row_stats_out;
   /* Two row segments with their own weights — Flux DoubleStreamBlock (backend/nn/flux.py:206-264) keeps txt and img
    * tokens in one joint [B, L_txt + L_img, C] activation: rows with (m % seg_period) < seg_split use B / bias / rowvec,
@@ -87,6 +92,8 @@ typedef struct {
 } b200_gemm_desc;
 
 int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);
+/* number of float4 partials per row that a b200_gemm with this N / epilogue / block_n writes to row_stats_out */
+int b200_gemm_row_stats_parts(int N, int epilogue, int block_n);
 
 /* ---------------------------------------------------------------------------------------------
  * 3x3 stride-1 pad-1 convolution on NHWC as an implicit GEMM (A tiles fetched by 4-D TMA boxes per
@@ -136,7 +143,6 @@ int b200_attention(const void* q, const void* k, const void* v, void* o, const b
  * GroupNorm on NHWC, split in a statistics pass and a fused apply(+SiLU)(+concat) pass.
  * replaces: torch.nn.functional.group_norm via backend/operations.py:304-310 and the following
  *           nn.SiLU (backend/nn/unet.py:395-396,418-419,691; backend/nn/vae.py:12-13,85).
- * sums: [N, G, 2] fp32 (sum, sum of squares), must be zeroed by the caller (b200_fill_zero).
  */
 typedef struct {
   int N, HW;
@@ -147,8 +153,13 @@ typedef struct {
   int dtype;
 } b200_gn_desc;
 
-int b200_groupnorm_stats(const void* x1, const void* x2, float* sums, const b200_gn_desc* d, b200_stream_t s);
-int b200_groupnorm_apply(const void* x1, const void* x2, const float* sums, const void* gamma, const void* beta,
+/* Two launches share a caller-owned workspace `ws` of b200_groupnorm_ws_bytes(d) bytes (16-byte aligned): _stats reduces
+ * each (sample, group) deterministically (fixed-order tree, sums shifted by a per-group pivot so that a large mean does not
+ * cancel) and leaves (mean, rstd) in it, _apply normalises.  The first 4*N bytes of `ws` (ticket counters) must be zero
+ * before the FIRST use; the kernel resets them, so one zero-initialised workspace serves any number of stream-ordered calls. */
+size_t b200_groupnorm_ws_bytes(const b200_gn_desc* d);
+int b200_groupnorm_stats(const void* x1, const void* x2, void* ws, const b200_gn_desc* d, b200_stream_t s);
+int b200_groupnorm_apply(const void* x1, const void* x2, const void* ws, const void* gamma, const void* beta,
                          void* y, const b200_gn_desc* d, b200_stream_t s);
 
 /* LayerNorm over the last dimension of [rows, C]; gamma/beta may be NULL (Flux: no affine).

@@ -90,7 +90,8 @@ def gen_v_trajectory(name: str = "tiny_21", hw: int = 16, steps: int = 5):
     sig = ForgeScheduleLinker(pred).get_sigmas(steps)
     noise0 = torch.randn(B, 4, hw, hw, generator=g)
     with torch.no_grad():
-        x0 = pred.noise_scaling(sig[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+        # modules/sd_samplers_kdiffusion.py:207 with opts.sgm_noise_multiplier at its default False (shared_options.py:410)
+        x0 = pred.noise_scaling(sig[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=False)
         x = make_inputs(cfg, B, hw, seed=2)[0]
         fwd = unet(x, torch.tensor([981.0, 23.0]), context=cond["crossattn"], y=None, transformer_options={})
         dens = []
@@ -154,7 +155,8 @@ def gen_trajectories(name: str = "tiny_xl", hw: int = 16, steps: int = 6):
                cfg_scale=cfg_scale, seeds=seeds, hw=hw, steps=steps, sigmas_auto=sig_auto, sigmas_karras=sig_karras)
     with torch.no_grad():
         noise0 = draw()
-        x0 = pred.noise_scaling(sig_auto[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+        # modules/sd_samplers_kdiffusion.py:207: max_denoise = opts.sgm_noise_multiplier, default False (shared_options.py:410)
+        x0 = pred.noise_scaling(sig_auto[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=False)
         out["noise0"] = noise0
         out["x0"] = x0
         step_noise = []
@@ -179,9 +181,13 @@ def gen_trajectories(name: str = "tiny_xl", hw: int = 16, steps: int = 6):
             out["euler_a_denoised_last"] = dens[-1]
             step_noise.clear()
             out["euler"] = ks.sample_euler(Wrap(), x0.clone(), sig_auto, extra_args={}, disable=True)
-            x0k = pred.noise_scaling(sig_karras[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+            x0k = pred.noise_scaling(sig_karras[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=False)
             out["x0_karras"] = x0k
             out["dpmpp_2m"] = ks.sample_dpmpp_2m(Wrap(), x0k.clone(), sig_karras, extra_args={}, disable=True)
+            # one run with the "SGM noise multiplier" option on (max_denoise=True)
+            x0s = pred.noise_scaling(sig_auto[0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+            out["x0_sgm"] = x0s
+            out["euler_sgm"] = ks.sample_euler(Wrap(), x0s.clone(), sig_auto, extra_args={}, disable=True)
         finally:
             ks.torch = torch
     torch.save(out, os.path.join(GOLD, f"traj_{name}.pt"))

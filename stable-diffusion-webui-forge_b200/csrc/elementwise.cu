@@ -26,23 +26,46 @@ __device__ __forceinline__ void store8(void* p, size_t elem_off, const float (&x
 }
 
 // ------------------------------------------------------------------------------------------ GroupNorm
+// Statistics are deterministic and cancellation-free:
+//   * every block reduces its slab of pixels in a fixed order (per-thread sums -> smem table -> fixed-order tree), no atomics
+//     on data;
+//   * sums are taken of (x - pivot) with pivot = x[n, pixel 0, first channel of the group], the same for every block of a
+//     sample, so block partials simply add and a large group mean does not cancel in sumsq/cnt - mean^2;
+//   * the last block of a sample to finish (ticket counter, self-resetting) adds the slab partials in slab order and writes
+//     (mean, rstd) per group — one launch, nothing to zero-fill per call.
+// Workspace layout (b200_groupnorm_ws_bytes): int tickets[N] (padded to 256 B) | float final[N][G][2] | float part[N][slabs][G][2].
 // grid (slabs, N), 256 threads arranged as (ry, tx): tx walks channel vectors, ry walks pixels.
+__device__ __forceinline__ float gn_tree8(float v) {  // fixed-order sum over the 8 lanes of a group team
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
-                                                       float* __restrict__ sums, int HW, int C1, int C2, int groups,
-                                                       int pix_per_slab) {
-  extern __shared__ float sh[];  // [C] sums, [C] sums of squares
+                                                       int* __restrict__ tickets, float* __restrict__ final_stats,
+                                                       float* __restrict__ part, int HW, int C1, int C2, int groups,
+                                                       int pix_per_slab, float eps) {
+  extern __shared__ float sh[];  // piv[C] | tab_s[RY][C] | tab_q[RY][C]
+  __shared__ int is_last;
   const int C = C1 + C2;
   const int CV = C >> 3;
-  float* csum = sh;
-  float* csq = sh + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  const int cpg = C / groups;
   const int TX = CV < 256 ? CV : 256;
   const int RY = 256 / TX;
   const int tx = threadIdx.x % TX;
   const int ry = threadIdx.x / TX;
   const int n = blockIdx.y;
+  const int slabs = gridDim.x;
+  float* piv = sh;
+  float* tab_s = sh + C;
+  float* tab_q = tab_s + (size_t)RY * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int c0 = (c / cpg) * cpg;
+    piv[c] = c0 < C1 ? ld1<BF16>(x1, (size_t)n * HW * C1 + c0) : ld1<BF16>(x2, (size_t)n * HW * C2 + (c0 - C1));
+  }
+  __syncthreads();
   const int p0 = blockIdx.x * pix_per_slab;
   int p1 = p0 + pix_per_slab;
   if (p1 > HW) p1 = HW;
@@ -53,58 +76,97 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
       const void* src = first ? x1 : x2;
       const int Cs = first ? C1 : C2;
       const int cs = first ? c : c - C1;
-      float s[8], q[8];
+      float s[8], q[8], pv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        s[i] = q[i] = 0.f;
+        pv[i] = piv[c + i];
+      }
       for (int px = p0 + ry; px < p1; px += RY) {
         float v[8];
         load8<BF16>(src, ((size_t)n * HW + px) * Cs + cs, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          s[i] += v[i];
-          q[i] = fmaf(v[i], v[i], q[i]);
+          const float dv = v[i] - pv[i];
+          s[i] += dv;
+          q[i] = fmaf(dv, dv, q[i]);
         }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        atomicAdd(&csum[c + i], s[i]);
-        atomicAdd(&csq[c + i], q[i]);
+        tab_s[(size_t)ry * C + c + i] = s[i];
+        tab_q[(size_t)ry * C + c + i] = q[i];
       }
     }
   }
   __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  // teams of 8 lanes per group: lane j adds table entries j, j + 8, ... in index order, then a fixed shuffle tree
+  const int team = threadIdx.x >> 3, tj = threadIdx.x & 7;
+  const int per_group = RY * cpg;
+  for (int g0 = 0; g0 < groups; g0 += 32) {  // warp-uniform trip count: the shuffles below use the full mask
+    const int g = g0 + team;
+    const bool g_ok = g < groups;
     float s = 0.f, q = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s += csum[c];
-      q += csq[c];
+    for (int e = tj; g_ok && e < per_group; e += 8) {
+      const int r = e / cpg, c = g * cpg + (e - r * cpg);
+      s += tab_s[(size_t)r * C + c];
+      q += tab_q[(size_t)r * C + c];
     }
-    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 0], s);
-    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 1], q);
+    s = gn_tree8(s);
+    q = gn_tree8(q);
+    if (tj == 0 && g_ok) {
+      float* dst = part + (((size_t)n * slabs + blockIdx.x) * groups + g) * 2;
+      dst[0] = s;
+      dst[1] = q;
+    }
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tickets[n], 1);
+    is_last = (t == slabs - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+  for (int g0 = 0; g0 < groups; g0 += 32) {
+    const int g = g0 + team;
+    const bool g_ok = g < groups;
+    float s = 0.f, q = 0.f;
+    for (int sl = tj; g_ok && sl < slabs; sl += 8) {
+      const float* src = part + (((size_t)n * slabs + sl) * groups + g) * 2;
+      s += __ldcg(src);
+      q += __ldcg(src + 1);
+    }
+    s = gn_tree8(s);
+    q = gn_tree8(q);
+    if (tj == 0 && g_ok) {
+      const float dm = s * inv_cnt;
+      const float var = fmaxf(fmaf(-dm, dm, q * inv_cnt), 0.f);
+      final_stats[((size_t)n * groups + g) * 2 + 0] = piv[g * cpg] + dm;
+      final_stats[((size_t)n * groups + g) * 2 + 1] = rsqrtf(var + eps);
+    }
+  }
+  if (threadIdx.x == 0) tickets[n] = 0;  // ready for the next launch on this stream
 }
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x1, const void* __restrict__ x2,
-                                                       const float* __restrict__ sums, const void* __restrict__ gamma,
+                                                       const float* __restrict__ final_stats, const void* __restrict__ gamma,
                                                        const void* __restrict__ beta, void* __restrict__ y, int HW,
-                                                       int C1, int C2, int groups, float eps, int silu,
-                                                       int pix_per_slab) {
+                                                       int C1, int C2, int groups, int silu, int pix_per_slab) {
   extern __shared__ float sh[];  // [C] scale, [C] shift
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
   float* sc = sh;
   float* sf = sh + C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = sums[((size_t)n * groups + g) * 2 + 0] * inv_cnt;
-    float var = sums[((size_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean;
-    var = fmaxf(var, 0.f);
-    const float rstd = rsqrtf(var + eps);
+    const float mean = final_stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = final_stats[((size_t)n * groups + g) * 2 + 1];
     const float a = ld1<BF16>(gamma, c) * rstd;
     sc[c] = a;
     sf[c] = ld1<BF16>(beta, c) - mean * a;
@@ -516,36 +578,54 @@ static int gn_check(const b200_gn_desc* d, const void* x1, const void* x2) {
   return B200_OK;
 }
 
-extern "C" int b200_groupnorm_stats(const void* x1, const void* x2, float* sums, const b200_gn_desc* d,
-                                    b200_stream_t s) {
-  int rc = gn_check(d, x1, x2);
-  if (rc) return rc;
-  B200_CHECK_ARG(sums, "groupnorm_stats: null sums");
+static size_t gn_ws_tickets_bytes(int N) { return (((size_t)N * sizeof(int)) + 255) / 256 * 256; }
+
+extern "C" size_t b200_groupnorm_ws_bytes(const b200_gn_desc* d) {
+  if (!d || d->N <= 0 || d->groups <= 0 || d->HW <= 0) return 0;
   int pps;
   const int slabs = gn_slabs(d, &pps);
-  const size_t smem = (size_t)(d->C1 + d->C2) * 2 * sizeof(float);
+  return gn_ws_tickets_bytes(d->N) + (size_t)d->N * d->groups * 2 * sizeof(float) * (1 + (size_t)slabs);
+}
+
+extern "C" int b200_groupnorm_stats(const void* x1, const void* x2, void* ws, const b200_gn_desc* d, b200_stream_t s) {
+  int rc = gn_check(d, x1, x2);
+  if (rc) return rc;
+  B200_CHECK_ARG(ws && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "groupnorm_stats: null / unaligned workspace");
+  int pps;
+  const int slabs = gn_slabs(d, &pps);
+  const int C = d->C1 + d->C2;
+  const int CV = C / 8;
+  const int TX = CV < 256 ? CV : 256;
+  const int RY = 256 / TX;
+  const size_t smem = (size_t)C * (1 + 2 * RY) * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "groupnorm: too many channels (%d)", C);
+  int* tickets = reinterpret_cast<int*>(ws);
+  float* fin = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + gn_ws_tickets_bytes(d->N));
+  float* part = fin + (size_t)d->N * d->groups * 2;
   dim3 grid(slabs, d->N);
   DISPATCH_DTYPE(d->dtype, {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(gn_stats_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    gn_stats_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, sums, d->HW, d->C1, d->C2, d->groups, pps);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gn_stats_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    gn_stats_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, tickets, fin, part, d->HW, d->C1, d->C2, d->groups, pps,
+                                                               d->eps);
   });
   B200_CHECK_LAUNCH("groupnorm_stats");
   return B200_OK;
 }
 
-extern "C" int b200_groupnorm_apply(const void* x1, const void* x2, const float* sums, const void* gamma,
+extern "C" int b200_groupnorm_apply(const void* x1, const void* x2, const void* ws, const void* gamma,
                                     const void* beta, void* y, const b200_gn_desc* d, b200_stream_t s) {
   int rc = gn_check(d, x1, x2);
   if (rc) return rc;
-  B200_CHECK_ARG(sums && gamma && beta && y, "groupnorm_apply: null argument");
+  B200_CHECK_ARG(ws && gamma && beta && y, "groupnorm_apply: null argument");
   int pps;
   const int slabs = gn_slabs(d, &pps);
   const size_t smem = (size_t)(d->C1 + d->C2) * 2 * sizeof(float);
+  const float* fin = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + gn_ws_tickets_bytes(d->N));
   dim3 grid(slabs, d->N);
   DISPATCH_DTYPE(d->dtype, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(gn_apply_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    gn_apply_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, sums, gamma, beta, y, d->HW, d->C1, d->C2,
-                                                               d->groups, d->eps, d->silu, pps);
+    gn_apply_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, fin, gamma, beta, y, d->HW, d->C1, d->C2,
+                                                               d->groups, d->silu, pps);
   });
   B200_CHECK_LAUNCH("groupnorm_apply");
   return B200_OK;

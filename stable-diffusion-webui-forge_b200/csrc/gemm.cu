@@ -48,11 +48,15 @@ struct GemmKParams {
   int epilogue;
   // LayerNorm folded into the GEMM (A is the *un-normalised* activation, B is W.diag(gamma)):
   //   y = rstd[m] * (acc - mean[m] * ln_c[n]) + ln_d[n],  ln_c = rowsum(W.diag(gamma)),  ln_d = W.beta (+ bias)
-  const float* ln_stats;  // [M, 2] (sum, sum of squares) of each A row, produced by the previous GEMM's epilogue
+  // Row statistics travel as PARTIALS, one float4 (count, mean, M2 = sum of squared deviations, 0) per (row, N tile,
+  // epilogue-warp half) of the producer: written once each (no atomics, no zero-fill, bit-reproducible) and merged by the
+  // consumer with the parallel-variance formula, so a large row mean does not cancel (sumsq/K - mean^2 did).
+  const float4* ln_stats;  // [M, ln_parts] partials of each A row, produced by the previous GEMM's epilogue
+  int ln_parts;
   const float* ln_c;
   const float* ln_d;
-  float ln_inv_k, ln_eps;
-  float* row_stats_out;   // [M, 2]: this GEMM accumulates (sum, sumsq) of its own output rows (caller zeroes it)
+  float ln_eps;
+  float4* row_stats_out;  // [M, 2 * tiles_n]: partial statistics of this GEMM's own output rows
   // two row segments with their own weights (Flux double-stream blocks: txt rows and img rows of one joint
   // [B, L_txt + L_img, C] activation): rows with (m % seg_period) >= seg_split use mapB2 / bias2 / rowvec2.
   int seg_period, seg_split;
@@ -305,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t lnc_smem = bias_smem + 1024u;                        // 256 floats
     const uint32_t lnd_smem = lnc_smem + 1024u;                         // 256 floats
     const bool ln = LNS && p.ln_stats != nullptr;
-    float* const row_stats_out = LNS ? p.row_stats_out : nullptr;
+    float4* const row_stats_out = LNS ? p.row_stats_out : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
@@ -317,11 +321,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const int m_blk = m_unit * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      int m = m_blk * 128 + r;
+      bool row_ok = m < p.M;
+      // folded LayerNorm: merge the producer's partial statistics of this row (Chan et al.): fetched before the wait on
+      // the accumulator so that the loads fly under the tile's MMAs
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ln && row_ok) {
+        const float4* sp = p.ln_stats + (size_t)m * p.ln_parts;
+        float cnt = 0.f, wsum = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float4 q = __ldg(sp + i);
+          cnt += q.x;
+          wsum = fmaf(q.x, q.y, wsum);
+        }
+        ln_mean = wsum / cnt;
+        float m2 = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float4 q = __ldg(sp + i);  // second pass hits L1
+          const float dm = q.y - ln_mean;
+          m2 += fmaf(q.x * dm, dm, q.z);
+        }
+        ln_rstd = rsqrtf(m2 / cnt + p.ln_eps);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
-      int m = m_blk * 128 + r;
-      bool row_ok = m < p.M;
       int gt_img = 0, gt_y0 = 0, gt_x0 = 0;  // GT: image and origin of this tile
       if constexpr (GT) {
         const int tpi = p.tiles_w * p.tiles_h;
@@ -345,13 +369,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const size_t rv_off = (rowvec_p && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
       // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
       const bool col_bias = bias_p && !p.bias_along_m;
-      float ln_mean = 0.f, ln_rstd = 1.f;
-      if (ln && row_ok) {
-        const float s1 = p.ln_stats[2 * (size_t)m], s2 = p.ln_stats[2 * (size_t)m + 1];
-        ln_mean = s1 * p.ln_inv_k;
-        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
-      }
-      float st_sum = 0.f, st_sq = 0.f;
+      // output row statistics: sums of (x - pivot), (x - pivot)^2 with the thread's first value as the pivot
+      float st_piv = 0.f, st_sum = 0.f, st_sq = 0.f, st_cnt = 0.f;
       if (col_bias || ln) {
         named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias / LN rows
         const int e0 = (int)(threadIdx.x - 128) * 8;
@@ -467,10 +486,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
           const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
           if (row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm
+            if (st_cnt == 0.f) st_piv = x[g * 8];
+            st_cnt += 8.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              st_sum += x[g * 8 + i];
-              st_sq = fmaf(x[g * 8 + i], x[g * 8 + i], st_sq);
+              const float dv = x[g * 8 + i] - st_piv;
+              st_sum += dv;
+              st_sq = fmaf(dv, dv, st_sq);
             }
           }
           const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
@@ -502,9 +524,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         }
       }
-      if (row_stats_out && row_ok) {
-        atomicAdd(row_stats_out + 2 * (size_t)m, st_sum);
-        atomicAdd(row_stats_out + 2 * (size_t)m + 1, st_sq);
+      if (row_stats_out && row_ok) {  // one partial per (row, N tile, warp half), written exactly once
+        const float inv = st_cnt > 0.f ? 1.0f / st_cnt : 0.f;
+        const float ds = st_sum * inv;
+        row_stats_out[(size_t)m * (2 * p.tiles_n) + 2 * n_blk + chalf] =
+            make_float4(st_cnt, st_piv + ds, fmaxf(fmaf(-st_sum, ds, st_sq), 0.f), 0.f);
       }
       tc_fence_before();
       if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -637,6 +661,12 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const 
 
 using namespace b200;
 
+extern "C" int b200_gemm_row_stats_parts(int N, int epilogue, int block_n) {
+  if (N <= 0) return 0;
+  const int bn = block_n > 0 ? block_n : pick_block_n(N, epilogue);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s) {
   B200_CHECK_ARG(A && B && C && d, "gemm: null argument");
   B200_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape %d %d %d", d->M, d->N, d->K);
@@ -679,13 +709,15 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.ld_rowvec = d->ld_rowvec;
   p.rows_per_vec = d->rows_per_vec > 0 ? d->rows_per_vec : 1;
   p.epilogue = d->epilogue;
-  p.ln_stats = d->ln_stats;
+  p.ln_stats = reinterpret_cast<const float4*>(d->ln_stats);
+  p.ln_parts = d->ln_stats_parts;
   p.ln_c = d->ln_c;
   p.ln_d = d->ln_d;
-  p.ln_inv_k = 1.0f / (float)d->K;
   p.ln_eps = d->ln_eps;
-  p.row_stats_out = d->row_stats_out;
-  B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2), "gemm: LayerNorm folding needs ln_c and ln_d (single A source)");
+  p.row_stats_out = reinterpret_cast<float4*>(d->row_stats_out);
+  B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2 && d->ln_stats_parts > 0),
+                 "gemm: LayerNorm folding needs ln_c, ln_d and ln_stats_parts (single A source)");
+  B200_CHECK_ARG(!d->row_stats_out || d->epilogue != B200_EPI_GEGLU, "gemm: row_stats_out excludes the GEGLU epilogue");
   p.rowvec_mul = d->rowvec_mul;
   p.act_col0 = d->act_col0;
   p.n_fast = raster_n_fast((size_t)d->M * d->K, (size_t)d->N * d->K, p.tiles_n);

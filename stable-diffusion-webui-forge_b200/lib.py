@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int),
         ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int), ("rows_per_vec", C.c_int),
         ("A2", C.c_void_p), ("lda2", C.c_int), ("K1", C.c_int),
-        ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_d", C.c_void_p), ("ln_eps", C.c_float),
+        ("ln_stats", C.c_void_p), ("ln_stats_parts", C.c_int), ("ln_c", C.c_void_p), ("ln_d", C.c_void_p), ("ln_eps", C.c_float),
         ("row_stats_out", C.c_void_p),
         ("B2", C.c_void_p), ("bias2", C.c_void_p), ("rowvec2", C.c_void_p),
         ("seg_period", C.c_int), ("seg_split", C.c_int), ("rowvec_mul", C.c_int), ("act_col0", C.c_int),
@@ -89,8 +89,10 @@ SIGNATURES = {
     "b200_device_ok": (_i, []),
     "b200_num_sms": (_i, []),
     "b200_gemm": (_i, [_vp, _vp, _vp, C.POINTER(GemmDesc), _vp]),
+    "b200_gemm_row_stats_parts": (_i, [_i, _i, _i]),
     "b200_conv3x3": (_i, [_vp, _vp, _vp, _vp, C.POINTER(Conv3x3Desc), _vp]),
     "b200_attention": (_i, [_vp, _vp, _vp, _vp, C.POINTER(AttnDesc), _vp]),
+    "b200_groupnorm_ws_bytes": (_sz, [C.POINTER(GnDesc)]),
     "b200_groupnorm_stats": (_i, [_vp, _vp, _vp, C.POINTER(GnDesc), _vp]),
     "b200_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(GnDesc), _vp]),
     "b200_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),

@@ -75,8 +75,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
     a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
     GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
-    ln = (stats [M,2] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
-    see `fold_layernorm`).  row_stats_out [M,2] fp32 (zeroed): receives (sum, sumsq) of the output rows.
+    ln = (stats [M,P,4] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
+    see `fold_layernorm`); stats = the partial row statistics a producer GEMM wrote.  row_stats_out [M,P,4] fp32
+    (`row_stats_buffer`; nothing to zero): receives partial (count, mean, M2) statistics of the output rows.
     rowvec_mul: out = residual + rowvec * (acc + bias) (modulation gate).  act_col0: the activation applies to output
     columns >= act_col0.  seg = (period, split, w2, bias2, rowvec2): rows with (m % period) >= split use the second
     weight set (Flux double-stream blocks on the joint [txt | img] activation).
@@ -113,11 +114,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), K1
     if ln is not None:
         st, lc, ld_, eps = ln
-        assert st.dtype == torch.float32 and st.shape == (M, 2) and st.is_contiguous()
+        assert st.dtype == torch.float32 and st.dim() == 3 and st.shape[0] == M and st.shape[2] == 4 and st.is_contiguous()
         assert lc.dtype == torch.float32 and ld_.dtype == torch.float32 and lc.numel() == N and ld_.numel() == N
-        d.ln_stats, d.ln_c, d.ln_d, d.ln_eps = st.data_ptr(), lc.data_ptr(), ld_.data_ptr(), eps
+        d.ln_stats, d.ln_stats_parts, d.ln_c, d.ln_d, d.ln_eps = st.data_ptr(), st.shape[1], lc.data_ptr(), ld_.data_ptr(), eps
     if row_stats_out is not None:
-        assert row_stats_out.dtype == torch.float32 and row_stats_out.shape == (M, 2) and row_stats_out.is_contiguous()
+        assert row_stats_out.dtype == torch.float32 and row_stats_out.is_contiguous()
+        assert tuple(row_stats_out.shape) == (M, row_stats_parts(N, epilogue, block_n), 4), (row_stats_out.shape, N)
         d.row_stats_out = row_stats_out.data_ptr()
     d.rowvec_mul = 1 if rowvec_mul else 0
     d.act_col0 = act_col0
@@ -132,6 +134,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
+
+
+def row_stats_parts(N: int, epilogue: int = EPI_NONE, block_n: int = 0) -> int:
+    """Partials per row that a GEMM with N output columns writes to `row_stats_out` (2 per N tile)."""
+    return int(_l.load().b200_gemm_row_stats_parts(N, epilogue, block_n))
+
+
+def row_stats_buffer(M: int, N: int, device, epilogue: int = EPI_NONE, block_n: int = 0) -> torch.Tensor:
+    """[M, P, 4] fp32 buffer for `gemm(..., row_stats_out=)`; every partial is overwritten by the GEMM (no zero-fill)."""
+    return torch.empty((M, row_stats_parts(N, epilogue, block_n), 4), dtype=torch.float32, device=device)
 
 
 def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor], block_n: int = 256):
@@ -327,10 +339,29 @@ def attention_blockdiag(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads
     return out
 
 
+_GN_WS: dict = {}  # device index -> zero-initialised workspace shared by all stream-ordered GroupNorm calls
+_GN_WS_BYTES = 4 << 20
+
+
+def gn_workspace(device) -> torch.Tensor:
+    """The GroupNorm workspace of `device` (ticket counters + statistics, b200_groupnorm_ws_bytes).  Created zeroed on
+    first use — engines call this at construction so that it never happens inside a CUDA-graph capture; the kernel resets
+    its counters, so the buffer is never zeroed again."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _GN_WS.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("groupnorm workspace must be created before CUDA-graph capture (ops.gn_workspace(device))")
+        ws = torch.zeros((_GN_WS_BYTES,), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _GN_WS[idx] = ws
+    return ws
+
+
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
-              silu: bool = False, x2: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU) over the channel concat of NHWC tensors x1, x2 -> NHWC [.., C1+C2]."""
+              silu: bool = False, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over the channel concat of NHWC tensors x1, x2 -> NHWC [.., C1+C2].  Two launches (deterministic
+    statistics, apply); bit-reproducible run to run."""
     assert x1.is_contiguous()
     n = x1.shape[0]
     c1 = x1.shape[-1]
@@ -339,20 +370,20 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     if x2 is not None:
         assert x2.is_contiguous() and x2.shape[:-1] == x1.shape[:-1]
         c2 = x2.shape[-1]
-    if sums is None:
-        sums = torch.empty((n, groups, 2), dtype=torch.float32, device=x1.device)
     if out is None:
         out = torch.empty(tuple(x1.shape[:-1]) + (c1 + c2,), dtype=x1.dtype, device=x1.device)
     d = _l.GnDesc()
     d.N, d.HW, d.C1, d.C2, d.groups, d.eps, d.silu, d.dtype = n, hw, c1, c2, groups, eps, 1 if silu else 0, _dt(x1)
     L = _l.load()
     st = _stream()
+    ws = gn_workspace(x1.device)
+    if L.b200_groupnorm_ws_bytes(C.byref(d)) > ws.numel():
+        raise B200Error(_l.E_UNSUPPORTED, f"groupnorm: batch {n} x {groups} groups exceeds the {ws.numel()}-byte workspace")
     with _prof("groupnorm", 0.0, 2.0 * 3 * n * hw * (c1 + c2)):
-        _l.check(L.b200_fill_zero(sums.data_ptr(), n * groups * 2 * 4, st))
-        _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), sums.data_ptr(), C.byref(d), st))
-        _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+        _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), ws.data_ptr(), C.byref(d), st))
+        _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), ws.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                         out.data_ptr(), C.byref(d), st))
-    _count(3)
+    _count(2)
     return out
 
 

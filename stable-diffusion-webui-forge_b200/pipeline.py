@@ -115,8 +115,11 @@ class Txt2ImgPipeline:
     def sample(self, cond: dict, uncond: Optional[dict], noise: torch.Tensor, *, steps: int = 30,
                sampler: str = "euler_a", cfg_scale: float = 7.0, sigmas: Optional[torch.Tensor] = None,
                step_noise: Optional[torch.Tensor] = None, eta: float = 1.0, s_noise: float = 1.0,
-               callback: Optional[Callable] = None, init_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+               callback: Optional[Callable] = None, init_latent: Optional[torch.Tensor] = None,
+               sgm_noise_multiplier: bool = False) -> torch.Tensor:
         """Returns the final latent [B,4,h,w] fp32 on the device.
+        sgm_noise_multiplier: Forge's option of that name (modules/shared_options.py:410, default False) — the txt2img start
+        is noise * sigmas[0] by default and noise * sqrt(1 + sigmas[0]^2) with it (max_denoise, k_prediction.py:94-104).
         init_latent (img2img): the start is noise * sigmas[0] + init_latent (noise_scaling with max_denoise=False,
         k_prediction.py:94-104) instead of the txt2img start.
         noise: [B,4,h,w] N(0,1) (host or device).  step_noise: [steps-1 or more, B,4,h,w] for ancestral samplers
@@ -144,14 +147,14 @@ class Txt2ImgPipeline:
             yv = torch.cat([put(t, self.dtype) for t in ys], 0)
         gu.set_context(torch.cat([put(t, self.dtype) for t in ctx], 0), yv)
         x = gu.x
-        # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: max_denoise, zero latent)
+        # modules/sd_samplers_kdiffusion.py:207 -> k_prediction.py:94-104 (txt2img: zero latent, max_denoise = the option)
         if init_latent is not None:
             init_latent = put(init_latent, torch.float32)
             if init_latent.data_ptr() == x.data_ptr():  # a latent returned by a previous sample() IS this buffer
                 init_latent = init_latent.clone()
         x.copy_(put(noise, torch.float32))
         if init_latent is None:
-            x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)))
+            x.mul_(float(torch.sqrt(1.0 + sigmas[0] ** 2.0)) if sgm_noise_multiplier else float(sigmas[0]))
         else:
             x.mul_(float(sigmas[0])).add_(init_latent)
         sn_dev = put(step_noise, torch.float32) if step_noise is not None else None

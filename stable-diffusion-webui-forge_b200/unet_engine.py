@@ -106,6 +106,8 @@ class UNetEngine:
         self.has_label = cfg.get("num_classes") is not None
         self.w: Dict[str, torch.Tensor] = {}
         self.head_pad: Dict[str, tuple] = {}
+        if self.device.type == "cuda":
+            ops.gn_workspace(self.device)  # created (zeroed) here so that it never happens inside a graph capture
         self._pack(state_dict)
 
     # ------------------------------------------------------------------------------------------ packing
@@ -267,8 +269,9 @@ class UNetEngine:
         m = n * L
         x2d = x.view(m, ch)
         t = ops.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], eps=1e-6, silu=False).view(m, ch)
-        st1, st2, st3 = (torch.empty((m, 2), dtype=torch.float32, device=self.device) for _ in range(3))
-        t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"], row_stats_out=ops.zero_(st1))
+        # partial row statistics (count, mean, M2) of the residual stream, written by each producer GEMM's epilogue
+        st1, st2, st3 = (ops.row_stats_buffer(m, ch, self.device) for _ in range(3))
+        t = ops.gemm(t, w[p + ".proj_in.w"], w[p + ".proj_in.b"], row_stats_out=st1)
         dh, dp = self.head_pad[p]
         cw = heads * dp          # width of the (head-padded) q / k / v / attention-output tensors
         scale = dh ** -0.5
@@ -285,7 +288,7 @@ class UNetEngine:
                     att = ops.attention_blockdiag(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
                 else:
                     att = ops.attention_generic(qkv[:, :, :cw], qkv[:, :, cw:2 * cw], qkv[:, :, 2 * cw:], heads, scale=scale)
-            ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t, row_stats_out=ops.zero_(st2))
+            ops.gemm(att.view(m, cw), w[q + ".attn1.o.w"], w[q + ".attn1.o.b"], residual=t, out=t, row_stats_out=st2)
             # cross attention
             qq = ops.gemm(t, w[q + ".attn2.q"], ln=(st2, w[q + ".attn2.q.c"], w[q + ".attn2.q.d"], 1e-5)).view(n, L, cw)
             if kv_cache is not None:
@@ -304,12 +307,12 @@ class UNetEngine:
                 # masked by the softmax (valid_keys), so they contribute exactly 0
                 kv = kvb.as_strided((n, nk8, 2 * cw), (n_ctx * 2 * cw, 2 * cw, 1))
                 att = ops.attention_generic(qq, kv[:, :, :cw], kv[:, :, cw:], heads, scale=scale, valid_keys=n_ctx)
-            ops.gemm(att.view(m, cw), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t, row_stats_out=ops.zero_(st3))
+            ops.gemm(att.view(m, cw), w[q + ".attn2.o.w"], w[q + ".attn2.o.b"], residual=t, out=t, row_stats_out=st3)
             # feed-forward (GEGLU)
             gg = ops.gemm(t, w[q + ".ff1.w"], None, epilogue=EPI_GEGLU, block_n=w[q + ".ff1.bn"],
                           ln=(st3, w[q + ".ff1.c"], w[q + ".ff1.d"], 1e-5))
             ops.gemm(gg, w[q + ".ff2.w"], w[q + ".ff2.b"], residual=t, out=t,
-                     row_stats_out=ops.zero_(st1) if d + 1 < depth else None)
+                     row_stats_out=st1 if d + 1 < depth else None)
         out = ops.gemm(t, w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, ch)
 

@@ -32,6 +32,8 @@ class VAEDecoderEngine:
         self.scaling = float(cfg["scaling_factor"])
         self.shift = float(cfg.get("shift_factor", 0.0) or 0.0)
         self.w: Dict[str, torch.Tensor] = {}
+        if self.device.type == "cuda":
+            ops.gn_workspace(self.device)  # created (zeroed) outside any graph capture
         self._pack(state_dict)
 
     def _t(self, t):
@@ -175,6 +177,8 @@ class VAEEncoderEngine:
         self.scaling = float(cfg["scaling_factor"])
         self.shift = float(cfg.get("shift_factor", 0.0) or 0.0)
         self.w: Dict[str, torch.Tensor] = {}
+        if self.device.type == "cuda":
+            ops.gn_workspace(self.device)  # created (zeroed) outside any graph capture
         self._pack(state_dict)
 
     _t = VAEDecoderEngine._t

@@ -51,8 +51,10 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
         acc = A @ wm.float().t()
         if ln is not None:
             st, lc, ld_, eps = ln
-            mean = st[:, 0] / K
-            rstd = torch.rsqrt(torch.clamp(st[:, 1] / K - mean * mean, min=0.0) + eps)
+            cnt = st[:, :, 0].sum(1)  # merge the producer's partials (count, mean, M2): parallel-variance formula
+            mean = (st[:, :, 0] * st[:, :, 1]).sum(1) / cnt
+            m2 = (st[:, :, 2] + st[:, :, 0] * (st[:, :, 1] - mean[:, None]) ** 2).sum(1)
+            rstd = torch.rsqrt(m2 / cnt + eps)
             acc = rstd[:, None] * (acc - mean[:, None] * lc[None, :].float()) + ld_[None, :].float()
         if bm is not None:
             acc = acc + (bm.float()[:, None] if bias_along_m else bm.float()[None, :])
@@ -81,9 +83,39 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
     if residual is not None:
         acc = acc + residual.float()
     if row_stats_out is not None:
-        row_stats_out[:, 0] += acc.sum(1)
-        row_stats_out[:, 1] += (acc * acc).sum(1)
+        # one partial per (N tile, epilogue-warp half): the half takes alternate 32-column chunks of the tile
+        N = acc.shape[1]
+        bn = block_n if block_n > 0 else _pick_block_n(N)
+        assert tuple(row_stats_out.shape) == (M, 2 * ((N + bn - 1) // bn), 4)
+        cols = torch.arange(N)
+        for tile in range((N + bn - 1) // bn):
+            for half in range(2):
+                sel = (cols // bn == tile) & (((cols % bn) // 32) % 2 == half)
+                part = acc[:, sel]
+                cnt = float(part.shape[1])
+                mean = part.mean(1) if cnt else torch.zeros(M)
+                m2 = ((part - mean[:, None]) ** 2).sum(1) if cnt else torch.zeros(M)
+                row_stats_out[:, 2 * tile + half] = torch.stack([torch.full((M,), cnt), mean, m2, torch.zeros(M)], 1)
     return _ret(acc, out, a.dtype)
+
+
+def _pick_block_n(N: int, step: int = 32) -> int:
+    """csrc/gemm.cu pick_block_n (non-GEGLU)."""
+    if N >= 256:
+        for bn in range(256, 127, -step):
+            if N % bn == 0:
+                return bn
+        return 256
+    return (N + step - 1) // step * step
+
+
+def row_stats_parts(N, epilogue=EPI_NONE, block_n=0):
+    bn = block_n if block_n > 0 else _pick_block_n(N)
+    return 2 * ((N + bn - 1) // bn)
+
+
+def row_stats_buffer(M, N, device, epilogue=EPI_NONE, block_n=0):
+    return torch.full((M, row_stats_parts(N, epilogue, block_n), 4), float("nan"), dtype=torch.float32, device=device)
 
 
 def zero_(t):
@@ -126,7 +158,7 @@ def attention_blockdiag(q, k, v, heads, *, scale, out=None):
     return attention(q, k, v, heads, scale=scale, out=out)
 
 
-def groupnorm(x1, gamma, beta, *, groups=32, eps=1e-5, silu=False, x2=None, sums=None, out=None):
+def groupnorm(x1, gamma, beta, *, groups=32, eps=1e-5, silu=False, x2=None, out=None):
     x = x1 if x2 is None else torch.cat([x1, x2], -1)
     shp = x.shape
     n, c = shp[0], shp[-1]
@@ -336,7 +368,7 @@ def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
     return _ret((mean * scale).contiguous(), out, torch.float32)
 
 
-_NAMES = ["gemm", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
+_NAMES = ["gemm", "row_stats_parts", "row_stats_buffer", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
           "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
           "timestep_embedding", "unet_input_im2col", "adaln", "rmsnorm_rows", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
           "sampler_step", "sampler_update", "eps_to_denoised", "add_nchw_", "vae_postprocess", "vae_preprocess", "vae_posterior"]

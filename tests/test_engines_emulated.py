@@ -54,6 +54,10 @@ def test_pipeline_host_logic_vs_reference_trajectory(sampler, key, sig):
     x = pipe.sample(g["cond"], g["uncond"], g["noise0"], sampler=sampler, cfg_scale=g["cfg_scale"], sigmas=g[sig],
                     step_noise=g["euler_a_step_noise"] if sampler == "euler_a" else None)
     assert_close(f"emulated pipeline {sampler} vs reference trajectory", x, g[key], rel_rms=2e-4)
+    if sampler == "euler":  # Forge's "SGM noise multiplier" option: start = noise * sqrt(1 + sigma_0^2)
+        xs = pipe.sample(g["cond"], g["uncond"], g["noise0"], sampler="euler", cfg_scale=g["cfg_scale"], sigmas=g[sig],
+                         sgm_noise_multiplier=True)
+        assert_close("emulated pipeline euler, sgm_noise_multiplier, vs reference trajectory", xs, g["euler_sgm"], rel_rms=2e-4)
 
 
 def test_vae_engines_host_logic_vs_reference_golden():
@@ -294,7 +298,7 @@ def test_hires_fix_host_logic_vs_oracle_composition():
     den = S.Denoiser(lambda xc, t, c, y: OU.unet_forward(sd, cfg, xc, t, c, y), pred, cond, uncond, 5.0)
     with torch.no_grad():
         s1 = S.get_sigmas_uniform(pred, steps)
-        first = S.sample_euler(den, noise * torch.sqrt(1.0 + s1[0] ** 2.0), s1)
+        first = S.sample_euler(den, noise * s1[0], s1)  # txt2img start, sgm_noise_multiplier off (Forge default)
         up = torch.nn.functional.interpolate(first, size=(32, 32), mode="bilinear", antialias=False)
         s2 = S.get_sigmas_uniform(pred, hr_steps)
         sched = s2[hr_steps - int(min(strength, 0.999) * hr_steps) - 1:]

@@ -94,8 +94,9 @@ def test_trajectories_match_reference_golden():
     hw = g["hw"]
     noise0, draw = S.image_rng_noise((4, hw, hw), g["seeds"])
     assert torch.equal(noise0, g["noise0"])
-    x0 = pred.noise_scaling(g["sigmas_auto"][0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True)
+    x0 = pred.noise_scaling(g["sigmas_auto"][0], noise0.clone(), torch.zeros_like(noise0), max_denoise=False)
     assert torch.equal(x0, g["x0"])
+    assert torch.equal(pred.noise_scaling(g["sigmas_auto"][0], noise0.clone(), torch.zeros_like(noise0), max_denoise=True), g["x0_sgm"])
     with torch.no_grad():
         dens = []
         xa = S.sample_euler_ancestral(den, x0.clone(), g["sigmas_auto"], draw, callback=lambda i, x, d: dens.append(d))
@@ -217,7 +218,7 @@ def test_v_prediction_oracle_matches_reference_golden():
         assert_close("oracle unet tiny_21 vs reference golden", fwd, g["fwd_out"], max_abs=5e-5)
         pred = S.VPrediction()
         den = S.Denoiser(lambda xc, t, c, y: OU.unet_forward(sd, cfg, xc, t, c, y), pred, g["cond"], g["uncond"], g["cfg_scale"])
-        x0 = g["noise0"] * torch.sqrt(1.0 + g["sigmas"][0] ** 2.0)
+        x0 = g["noise0"] * g["sigmas"][0]
         assert_close("v-pred x0", x0, g["x0"], max_abs=1e-6)
         seen = []
         out = S.sample_euler(den, x0, g["sigmas"], callback=lambda i, x, d: seen.append(d.clone()))
