@@ -89,6 +89,9 @@ typedef struct {
   int rowvec_mul; /* rowvec multiplies instead of adds: y = residual + rowvec * (acc + bias)  (modulation gate, flux.py:252-258,300) */
   int act_col0;   /* the activation applies to output columns >= act_col0 (multiple of block_n); SingleStreamBlock.linear1
                      = [qkv | mlp] with GELU on the mlp part only (flux.py:289-298) */
+  float alpha;    /* 0 or 1: off; else the fp32 accumulators are multiplied by alpha first: C = epi(alpha * A B^T + ...).
+                     The GEMM-softmax-GEMM attention paths put Dh^-1/2 here so that the stored logits are the SCALED ones
+                     (unscaled fp16 logits can overflow; the reference scales q or the fp32 product, backend/attention.py:64-70) */
 } b200_gemm_desc;
 
 int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);

@@ -24,9 +24,12 @@ fallback: Optional[Callable] = None
 fallback_single_head: Optional[Callable] = None
 
 
-def supports(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask, skip_reshape: bool) -> bool:
+def supports(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask, skip_reshape: bool,
+             attn_precision=None) -> bool:
     if mask is not None or not q.is_cuda:
         return False
+    # The flash kernels keep logits, softmax and accumulators in fp32 (what attn_precision=fp32 asks of attention_basic,
+    # backend/attention.py:64-67), so an fp32 request on fp16/bf16 inputs is honoured by construction.
     if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
         return False
     dh = q.shape[-1] if skip_reshape else q.shape[-1] // heads
@@ -40,7 +43,7 @@ def _unsupported(name, q, heads, mask, skip_reshape):
 
 
 def attention_function(q, k, v, heads, mask=None, attn_precision=None, skip_reshape=False):
-    if not supports(q, k, v, heads, mask, skip_reshape):
+    if not supports(q, k, v, heads, mask, skip_reshape, attn_precision):
         if fallback is not None:
             return fallback(q, k, v, heads, mask, attn_precision, skip_reshape)
         _unsupported("attention_function", q, heads, mask, skip_reshape)
@@ -68,7 +71,7 @@ def attention_function_single_head_spatial(q, k, v):
     o = torch.empty((b, L, c), dtype=q.dtype, device=q.device)
     s = torch.empty((L, L), dtype=q.dtype, device=q.device)
     for i in range(b):
-        ops.gemm(qt[i], kt[i], out=s)
-        ops.softmax_rows_(s, c ** -0.5)
+        ops.gemm(qt[i], kt[i], out=s, alpha=c ** -0.5)  # scaled logits: unscaled ones can leave the fp16 range at C = 512
+        ops.softmax_rows_(s, 1.0)
         ops.gemm(s, vv[i], out=o[i])
     return ops.nhwc_to_nchw(o.view(b, hh, ww, c))

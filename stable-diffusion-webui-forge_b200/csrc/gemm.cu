@@ -66,6 +66,7 @@ struct GemmKParams {
   // once per N tile), 1 = consecutive tiles walk N (A rows shared, B re-streamed once per group of M tiles).  The host
   // re-streams whichever operand is smaller, i.e. the one that stays in L2.
   int n_fast;
+  float alpha;     // EXT: accumulators are multiplied by alpha before anything else (0 = off)
   int rowvec_mul;  // rowvec multiplies (per-sample gate) instead of being added
   int act_col0;    // the activation applies to output columns >= act_col0 only
   // mode 1, generic tiling (FEAT bit 2, experimental): tile_n = 1, tile_w / tile_h powers of two, tiles may overhang the
@@ -128,7 +129,7 @@ __device__ __forceinline__ void ln_apply8(uint32_t c_smem, uint32_t d_smem, int 
 // 168-register cap):  bit 0 (LNS) LayerNorm folding + output row statistics (UNet transformer blocks),
 // bit 1 (EXT) the Flux-path features (row segments with two weight sets, multiplicative rowvec, partial activation,
 // tanh GELU), bit 2 (GT) generic convolution tiling for image widths that are neither a power of two nor a multiple of
-// 128 (experimental, B200_CONV_GENERAL=1).  Convolutions and plain linears run the FEAT = 0 build.
+// 128 (B200_CONV_GENERAL=0 turns it off).  Convolutions and plain linears run the FEAT = 0 build.
 template <bool BF16, int CG, int FEAT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -442,6 +443,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
+            if (EXT && p.alpha != 0.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xv[i] *= p.alpha;
+            }
             if (ln) ln_apply8(lnc_smem, lnd_smem, c + g * 8, ln_mean, ln_rstd, xv);
             if (col_bias) add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
             else if (bias_p) {
@@ -646,7 +651,7 @@ static int launch_gemm_e(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
 
 static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                        const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
-  const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH;
+  const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH || p.alpha != 0.f;
   const bool lns = p.ln_stats != nullptr || p.row_stats_out != nullptr;
   if (p.tile_w_log2 >= 0 && p.mode == 1 && p.img_n > 0) return launch_gemm_e<4>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
   switch ((lns ? 1 : 0) | (ext ? 2 : 0)) {
@@ -720,6 +725,8 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   B200_CHECK_ARG(!d->row_stats_out || d->epilogue != B200_EPI_GEGLU, "gemm: row_stats_out excludes the GEGLU epilogue");
   p.rowvec_mul = d->rowvec_mul;
   p.act_col0 = d->act_col0;
+  p.alpha = (d->alpha == 1.0f) ? 0.f : d->alpha;
+  B200_CHECK_ARG(p.alpha == 0.f || d->epilogue != B200_EPI_GEGLU, "gemm: alpha excludes the GEGLU epilogue");
   p.n_fast = raster_n_fast((size_t)d->M * d->K, (size_t)d->N * d->K, p.tiles_n);
   B200_CHECK_ARG(d->act_col0 >= 0 && d->act_col0 % bn == 0, "gemm: act_col0 (%d) must be a multiple of block_n (%d)", d->act_col0, bn);
   if (d->B2) {
@@ -789,13 +796,15 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
                      (tile_n == 1 || (tile_w == d->W && tile_h == d->H));
   int gt_log2 = -1;
   if (!exact) {
-    static int general = -1;  // experimental until it has run on hardware: B200_CONV_GENERAL=1
+    static int general = -1;  // B200_CONV_GENERAL=0: only exactly tiling sizes (the caller falls back to im2col + GEMM)
     if (general < 0) {
       const char* e = getenv("B200_CONV_GENERAL");
-      general = (e && e[0] == '1') ? 1 : 0;
+      general = (e && e[0] == '0') ? 0 : 1;
     }
-    B200_CHECK_ARG(general, "conv3x3: %dx%d does not tile into 128-pixel boxes (width must be a power of two <= 128 or a multiple of 128)",
-                   d->H, d->W);
+    if (!general) {
+      set_error("conv3x3: %dx%d does not tile into 128-pixel boxes and generic tiling is disabled (B200_CONV_GENERAL=0)", d->H, d->W);
+      return B200_EUNSUPPORTED;
+    }
     // generic tiling: the widest power-of-two column count that divides W (<= 128), rows to make 128 pixels; tiles
     // overhang the bottom edge (masked stores, zero-filled loads)
     tile_w = 1;

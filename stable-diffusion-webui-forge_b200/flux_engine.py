@@ -57,6 +57,10 @@ class FluxEngine:
         self._plans: dict = {}
 
     # ------------------------------------------------------------------ weights
+    def repack(self, sd) -> None:
+        """Re-pack after the module's parameters changed (Forge merged or removed a LoRA): same buffers, new contents."""
+        self.w = ops.refresh_packed(self.w, self._pack(sd))
+
     def _pack(self, sd):
         dt, dev = self.dtype, self.device
 

@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("row_stats_out", C.c_void_p),
         ("B2", C.c_void_p), ("bias2", C.c_void_p), ("rowvec2", C.c_void_p),
         ("seg_period", C.c_int), ("seg_split", C.c_int), ("rowvec_mul", C.c_int), ("act_col0", C.c_int),
+        ("alpha", C.c_float),
     ]
 
 

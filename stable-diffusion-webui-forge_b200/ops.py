@@ -70,8 +70,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          epilogue: int = EPI_NONE, a2: Optional[torch.Tensor] = None, bias_along_m: bool = False,
          out: Optional[torch.Tensor] = None, block_n: int = 0, ln: Optional[tuple] = None,
          row_stats_out: Optional[torch.Tensor] = None, rowvec_mul: bool = False, act_col0: int = 0,
-         seg: Optional[tuple] = None) -> torch.Tensor:
-    """out[M, N] = epi(cat(a, a2) @ w.T + bias + rowvec[row // rows_per_vec]) + residual.
+         seg: Optional[tuple] = None, alpha: float = 1.0) -> torch.Tensor:
+    """out[M, N] = epi(alpha * cat(a, a2) @ w.T + bias + rowvec[row // rows_per_vec]) + residual.
 
     a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
     GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
@@ -123,6 +123,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.row_stats_out = row_stats_out.data_ptr()
     d.rowvec_mul = 1 if rowvec_mul else 0
     d.act_col0 = act_col0
+    d.alpha = float(alpha)
     if seg is not None:
         period, split, w2, bias2, rowvec2 = seg
         _rowmajor2d(w2, "w2")
@@ -172,6 +173,20 @@ def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tens
     if b is not None:
         d = d + b.float()
     return wf, c, d.contiguous()
+
+
+def refresh_packed(old: dict, new: dict) -> dict:
+    """Engine re-pack after the source module's weights changed (LoRA merge): copy the freshly packed tensors INTO the old
+    buffers wherever shape and dtype agree, so device addresses — which captured CUDA graphs hold — stay valid."""
+    out = {}
+    for k, v in new.items():
+        o = old.get(k)
+        if torch.is_tensor(v) and torch.is_tensor(o) and o.shape == v.shape and o.dtype == v.dtype and o.device == v.device:
+            o.copy_(v)
+            out[k] = o
+        else:
+            out[k] = v
+    return out
 
 
 def zero_(t: torch.Tensor) -> torch.Tensor:
@@ -235,24 +250,35 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def any_size_enabled() -> bool:
-    """B200_ANY_SIZE=1: image sizes the TMA convolution cannot tile run their 3x3 convolutions as b200_im2col3x3 +
-    b200_gemm (both kernels are the ones the stride-2 and small-channel convolutions already use) instead of being
-    handed back to Forge.  Off by default until that route and the ragged-length attention it implies have run on
-    hardware."""
+def conv_route() -> str:
+    """How 3x3 convolutions of images that do not tile into 128-pixel TMA boxes run (B200_CONV_ROUTE):
+      generic (default)  inside the implicit-GEMM kernel with overhanging tiles and masked stores (FEAT = 4 build);
+      im2col             patch matrix (b200_im2col3x3) + b200_gemm with the same epilogue — 9x the activation traffic;
+      exact              not at all: such sizes raise B200_EUNSUPPORTED / are handed back to Forge (the round-1 behaviour)."""
     import os
-    return os.environ.get("B200_ANY_SIZE") == "1"
+    r = os.environ.get("B200_CONV_ROUTE", "generic")
+    if r not in ("generic", "im2col", "exact"):
+        raise ValueError(f"B200_CONV_ROUTE={r!r}: generic | im2col | exact")
+    return r
+
+
+def any_size_enabled() -> bool:
+    """Whether image sizes outside `conv3x3_supported` are served by the fused engines (see `conv_route`)."""
+    return conv_route() != "exact"
 
 
 def conv3x3_any(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
                 residual: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, route: Optional[str] = None) -> torch.Tensor:
     """3x3 / stride 1 / pad 1 on one contiguous NHWC tensor for ANY image size: the implicit-GEMM TMA kernel when the size
-    tiles (conv3x3_supported), else patch matrix + GEMM with the same epilogue (bias, per-image time-embedding row,
-    activation, residual).  9x the activation traffic of the TMA path — a functional route, not the fast one."""
+    tiles exactly (conv3x3_supported) or through its generic tiling, else patch matrix + GEMM with the same epilogue (bias,
+    per-image time-embedding row, activation, residual)."""
     n, h, w_, c = x.shape
-    if conv3x3_supported(h, w_):
+    route = route or conv_route()
+    if conv3x3_supported(h, w_) or (route == "generic" and c % 64 == 0):
         return conv3x3(x, w_packed, bias, residual=residual, temb=temb, epilogue=epilogue, out=out)
+    if route == "exact":
+        raise B200Error(_l.E_UNSUPPORTED, f"conv3x3: {h}x{w_} does not tile into 128-pixel boxes (B200_CONV_ROUTE=exact)")
     cout = w_packed.shape[0]
     if out is None:
         out = torch.empty((n, h, w_, cout), dtype=x.dtype, device=x.device)
@@ -303,8 +329,8 @@ def attention_generic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: 
         vt = transpose_rows(v[i])  # V^T [H*dh, Lk]
         for h in range(heads):
             sl = slice(h * dh, (h + 1) * dh)
-            gemm(q[i, :, sl], k[i, :, sl], out=s)
-            softmax_rows_(s, scale, valid_keys)
+            gemm(q[i, :, sl], k[i, :, sl], out=s, alpha=scale)  # scaled logits: the unscaled ones can leave the fp16 range
+            softmax_rows_(s, 1.0, valid_keys)
             gemm(s, vt[sl], out=out[i, :, sl])
     return out
 
@@ -331,8 +357,8 @@ def attention_blockdiag(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads
     s = torch.empty((b * lq, b * lk), dtype=q.dtype, device=q.device)
     for h in range(heads):
         sl = slice(h * dh, (h + 1) * dh)
-        gemm(q2[:, sl], k2[:, sl], out=s)
-        _l.check(_l.load().b200_softmax_rows_blockdiag(s.data_ptr(), b * lq, b * lk, s.stride(0), scale, lq, lk, lk,
+        gemm(q2[:, sl], k2[:, sl], out=s, alpha=scale)  # scaled logits (see attention_generic)
+        _l.check(_l.load().b200_softmax_rows_blockdiag(s.data_ptr(), b * lq, b * lk, s.stride(0), 1.0, lq, lk, lk,
                                                        _dt(s), _stream()))
         _count()
         gemm(s, vt[sl], out=o2[:, sl])
@@ -667,15 +693,36 @@ def sampler_update(x: torch.Tensor, denoised: torch.Tensor, *, kind: int, sigma:
                    noise: Optional[torch.Tensor] = None, noise_scale: float = 0.0,
                    old_denoised: Optional[torch.Tensor] = None, c_x: float = 0.0, c_d: float = 0.0,
                    c_old: float = 0.0) -> None:
-    """In-place sampler update from an already CFG-combined `denoised` (fp32, same shape as x)."""
-    assert x.dtype == torch.float32 and x.is_contiguous() and denoised.dtype == torch.float32 and denoised.is_contiguous()
+    """In-place sampler update from an already CFG-combined `denoised` (fp32, same shape as x).
+    `noise` / `old_denoised` come from the caller's world (Forge's or a user's noise_sampler): anything that is not an fp32
+    contiguous tensor of x's shape on x's device is brought there first (broadcast shapes are expanded) — the kernel reads
+    raw pointers."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+
+    def like_x(t, name):
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            raise TypeError(f"sampler_update: {name} must be a tensor")
+        if t.device != x.device or t.dtype != torch.float32:
+            t = t.to(device=x.device, dtype=torch.float32)
+        if t.shape != x.shape:
+            t = t.expand_as(x)  # raises on shapes that do not broadcast
+        return t.contiguous()
+
+    denoised_c = like_x(denoised, "denoised")
+    noise = like_x(noise, "noise")
+    old_c = like_x(old_denoised, "old_denoised")
+    if kind == STEP_DPMPP_2M and old_denoised is not None and old_c.data_ptr() != old_denoised.data_ptr():
+        raise ValueError("sampler_update: DPM++ 2M updates old_denoised in place — it must be an fp32 contiguous tensor like x")
     b, c, h, w = x.shape
     d = _l.StepDesc()
     d.kind, d.B, d.C, d.H, d.W = kind, b, c, h, w
     d.sigma, d.dt, d.noise_scale = sigma, dt, noise_scale
     d.c_x, d.c_d, d.c_old = c_x, c_d, c_old
-    _l.check(_l.load().b200_sampler_update(x.data_ptr(), denoised.data_ptr(), _p(noise), _p(old_denoised), C.byref(d),
-                                           _stream()))
+    with torch.cuda.device(x.device):  # the launch goes to x's device whatever the caller's current device is
+        _l.check(_l.load().b200_sampler_update(x.data_ptr(), denoised_c.data_ptr(), _p(noise), _p(old_c), C.byref(d),
+                                               _stream()))
     _count()
 
 

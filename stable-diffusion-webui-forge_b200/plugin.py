@@ -49,10 +49,10 @@ def fast_path_ok(c: dict) -> bool:
 
 def _control_ok(control) -> bool:
     """ControlNet / T2I-Adapter residuals the fused UNet can add itself (UNetEngine.forward_cols(control=...)): a dict of
-    lists of CUDA tensors / None under the reference's three names (backend/nn/unet.py:44-52).  Experimental until it has
-    run on hardware: enabled with B200_CONTROL=1, else such calls keep going to Forge's own forward."""
+    lists of CUDA tensors / None under the reference's three names (backend/nn/unet.py:44-52).  B200_CONTROL=0 sends such
+    calls to Forge's own forward instead."""
     import os
-    if os.environ.get("B200_CONTROL") != "1" or not isinstance(control, dict):
+    if os.environ.get("B200_CONTROL") == "0" or not isinstance(control, dict):
         return False
     for k, lst in control.items():
         if k not in ("input", "middle", "output") or not isinstance(lst, (list, tuple)):
@@ -106,29 +106,67 @@ def uninstall_attention(modules: Optional[dict] = None) -> None:
 def install_operations(modules: Optional[dict] = None) -> None:
     """Make `using_forge_operations(operations=None)` (backend/loader.py:159) build models from B200Operations:
     the default operator set is looked up as `backend.operations.ForgeOperations` at call time (:447-453)."""
-    from .operations import B200Operations
+    from .operations import make_operations
     mods = sys.modules if modules is None else modules
     bo = mods.get("backend.operations")
     if bo is None:
         raise RuntimeError("backend.operations is not imported")
     if "operations" not in _installed:
         _installed["operations"] = bo.ForgeOperations
-    base = _installed["operations"]
-    # keep every Forge-specific attribute (lazy weights, manual cast...) of the ops we do not replace
-    merged = type("B200ForgeOperations", (base,), {k: getattr(B200Operations, k) for k in ("Linear", "Conv2d", "GroupNorm", "LayerNorm")})
-    bo.ForgeOperations = merged
+    # the four hot-path classes subclass Forge's own (lazy weights, manual cast, online LoRA keep working: whatever the
+    # fused kernels do not cover runs the parent's forward), every other attribute is inherited
+    bo.ForgeOperations = make_operations(_installed["operations"])
 
 
 # ------------------------------------------------------------------------------------------------- P3 whole model
+class _WeightTracker:
+    """Keeps an engine's packed weights in step with the torch module Forge patches.
+
+    Forge applies LoRA per generation, after the model (and this plug-in's engine) was built: `networks.load_networks`
+    clones the patcher (the clone keeps `model_options`, so the wrapper survives), `ModelPatcher.refresh_loras`
+    (backend/patcher/base.py:125-126) calls `LoraLoader.refresh` (backend/patcher/lora.py:352-446), which either MERGES the
+    deltas into fresh Parameters of the module or — `online_mode` — attaches `forge_online_loras` to the layers and leaves the
+    weights alone; `loaded_hash` names the set that is currently applied.  So before every fused forward:
+      * hash changed            -> re-pack the engine from the module's live state dict (in place: buffers keep their
+                                   addresses, so captured CUDA graphs stay valid);
+      * any online LoRA present -> not servable by the fused forward (low-rank terms inside every Linear): reference path.
+    A module without a `lora_loader` (standalone use, tests) is treated as never patched."""
+
+    def __init__(self, engine, owner, module):
+        self.engine, self.owner, self.module = engine, owner, module
+        self.packed_hash = self._hash()
+        self.online = self._has_online()
+        self.repacks = 0
+
+    def _hash(self):
+        loader = getattr(self.owner, "lora_loader", None)
+        return getattr(loader, "loaded_hash", None)
+
+    def _has_online(self) -> bool:
+        mods = getattr(self.module, "modules", None)
+        return bool(mods) and any(hasattr(m, "forge_online_loras") for m in self.module.modules())
+
+    def servable(self) -> bool:
+        h = self._hash()
+        if h != self.packed_hash:
+            self.online = self._has_online()          # refresh() attaches / removes them together with the hash change
+            self.engine.repack(self.module.state_dict())
+            self.packed_hash = h
+            self.repacks += 1
+        return not self.online
+
+
 class UNetWrapper:
     """`model_options['model_function_wrapper']` (reference backend/sampling/sampling_function.py:270-273):
     wrapper(apply_model_fn, {"input": x fp32 [N,4,h,w], "timestep": sigma [N], "c": {...}, "cond_or_uncond": [...]})
     -> denoised fp32 [N,4,h,w].  Serves the call from the fused channels-last forward when `fast_path_ok`, else
     calls `apply_model_fn(input, timestep, **c)` (the reference path) unchanged."""
 
-    def __init__(self, engine: UNetEngine, predictor):
+    def __init__(self, engine: UNetEngine, predictor, kmodel=None):
         self.engine = engine
         self.predictor = predictor  # backend.modules.k_prediction.Prediction (for .timestep and .prediction_type)
+        # kmodel: the KModel whose diffusion_model Forge patches (LoRA); None = weights never change (standalone use)
+        self.weights = None if kmodel is None else _WeightTracker(engine, kmodel, kmodel.diffusion_model)
         self.calls_fast = 0
         self.calls_reference = 0
 
@@ -137,7 +175,8 @@ class UNetWrapper:
         ptype = getattr(self.predictor, "prediction_type", "epsilon")
         if (not fast_path_ok(c) or not _on_device(x) or x.dtype != torch.float32 or ptype not in ("epsilon", "v_prediction")
                 or (self.engine.has_label and c.get("y") is None) or x.dim() != 4
-                or not self.engine.supports_latent(x.shape[2], x.shape[3])):
+                or not self.engine.supports_latent(x.shape[2], x.shape[3])
+                or (self.weights is not None and not self.weights.servable())):
             self.calls_reference += 1
             return apply_model_fn(x, sigma, **c)
         self.calls_fast += 1
@@ -162,7 +201,7 @@ def install_unet_wrapper(unet_patcher, engine: Optional[UNetEngine] = None) -> U
         if cfg is None:
             raise ValueError("pass engine=UNetEngine(cfg, state_dict) — the module carries no config")
         engine = UNetEngine(cfg, dm.state_dict(), dtype=kmodel.computation_dtype, device=unet_patcher.load_device)
-    w = UNetWrapper(engine, kmodel.predictor)
+    w = UNetWrapper(engine, kmodel.predictor, kmodel)
     unet_patcher.set_model_unet_function_wrapper(w)
     return w
 
@@ -173,9 +212,10 @@ class FluxWrapper:
     the fused DiT forward.  `c` carries c_crossattn (T5 states), y (pooled CLIP) and guidance
     (backend/diffusion_engine/flux.py:92)."""
 
-    def __init__(self, engine, predictor):
+    def __init__(self, engine, predictor, kmodel=None):
         self.engine = engine
         self.predictor = predictor
+        self.weights = None if kmodel is None else _WeightTracker(engine, kmodel, kmodel.diffusion_model)
         self.calls_fast = 0
         self.calls_reference = 0
 
@@ -185,7 +225,8 @@ class FluxWrapper:
         ok = (fast_path_ok(c) and c.get("control") is None and _on_device(x) and x.dtype == torch.float32 and x.dim() == 4
               and getattr(self.predictor, "prediction_type", None) == "const" and c.get("c_concat") is None
               and c.get("y") is not None and (x.shape[2] | x.shape[3]) % 2 == 0
-              and (c.get("guidance") is not None or not eng.guidance_embed))
+              and (c.get("guidance") is not None or not eng.guidance_embed)
+              and (self.weights is None or self.weights.servable()))
         if not ok:
             self.calls_reference += 1
             return apply_model_fn(x, sigma, **c)
@@ -213,7 +254,7 @@ def install_flux_wrapper(unet_patcher, engine=None) -> FluxWrapper:
                 "depth_single_blocks", "axes_dim", "theta", "qkv_bias", "guidance_embed")
         engine = FluxEngine({k: cfg[k] for k in keys}, dm.state_dict(), dtype=kmodel.computation_dtype,
                             device=unet_patcher.load_device)
-    w = FluxWrapper(engine, kmodel.predictor)
+    w = FluxWrapper(engine, kmodel.predictor, kmodel)
     unet_patcher.set_model_unet_function_wrapper(w)
     return w
 
@@ -246,12 +287,15 @@ class VAEDecodeWrapper:
     NB: Forge hands this wrapper the *processed-out* latent (engine.decode_first_stage divides by the scaling factor
     first, diffusion_engine/sdxl.py:134-138), so the engine is driven with scaling 1."""
 
-    def __init__(self, vae_engine, output_device=None):
+    def __init__(self, vae_engine, output_device=None, vae_module=None):
         self.engine = vae_engine
         self.output_device = output_device
+        # vae_module: the torch VAE Forge may patch (it wraps it in a ModelPatcher too, backend/patcher/vae.py:60-75)
+        self.weights = None if vae_module is None else _WeightTracker(vae_engine, vae_module, vae_module)
 
     def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
-        if not _on_device(samples_in) or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3]):
+        if (not _on_device(samples_in) or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3])
+                or (self.weights is not None and not self.weights.servable())):
             return decode_inner_fn(samples_in)
         scaling = self.engine.scaling
         try:
@@ -268,15 +312,17 @@ class VAEEncodeWrapper:
     un-scaled posterior sample (the diffusion engine applies process_in afterwards, diffusion_engine/sdxl.py:128-132).
     A `model_vae_regulation` hook or a size the TMA convolution path cannot tile goes back to Forge's own encode."""
 
-    def __init__(self, vae_engine, output_device=None, patcher=None):
+    def __init__(self, vae_engine, output_device=None, patcher=None, vae_module=None):
         self.engine = vae_engine
         self.output_device = output_device
         self.patcher = patcher
+        self.weights = None if vae_module is None else _WeightTracker(vae_engine, vae_module, vae_module)
 
     def __call__(self, encode_inner_fn: Callable, pixel_samples: torch.Tensor):
         has_reg = self.patcher is not None and self.patcher.model_options.get("model_vae_regulation") is not None
         if (has_reg or pixel_samples.dim() != 4 or pixel_samples.shape[-1] != 3 or not torch.cuda.is_available()
-                or not self.engine.supports_image(pixel_samples.shape[1], pixel_samples.shape[2])):
+                or not self.engine.supports_image(pixel_samples.shape[1], pixel_samples.shape[2])
+                or (self.weights is not None and not self.weights.servable())):
             return encode_inner_fn(pixel_samples)
         z = self.engine.encode(pixel_samples.to(self.engine.device).float().contiguous())
         return z if self.output_device is None else z.to(self.output_device)

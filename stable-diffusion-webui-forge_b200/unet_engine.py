@@ -111,6 +111,12 @@ class UNetEngine:
         self._pack(state_dict)
 
     # ------------------------------------------------------------------------------------------ packing
+    def repack(self, state_dict: SD) -> None:
+        """Re-pack after the module's parameters changed (Forge merged or removed a LoRA): same buffers, new contents."""
+        old, self.w = self.w, {}
+        self._pack(state_dict)
+        self.w = ops.refresh_packed(old, self.w)
+
     def _t(self, t: torch.Tensor) -> torch.Tensor:
         return t.detach().to(device=self.device, dtype=self.dtype).contiguous()
 

@@ -39,6 +39,12 @@ class VAEDecoderEngine:
     def _t(self, t):
         return t.detach().to(device=self.device, dtype=self.dtype).contiguous()
 
+    def repack(self, state_dict: SD) -> None:
+        """Re-pack after the module's parameters changed: same buffers, new contents."""
+        old, self.w = self.w, {}
+        self._pack(state_dict)
+        self.w = ops.refresh_packed(old, self.w)
+
     def _pack(self, sd: SD) -> None:
         w = self.w
         g = lambda k: self._t(sd[k])  # noqa: E731
@@ -117,8 +123,8 @@ class VAEDecoderEngine:
         vt = torch.empty((c, L), dtype=self.dtype, device=self.device)
         for b in range(n):
             ops.gemm(w[p + ".v.w"], hn[b], w[p + ".v.b"], bias_along_m=True, out=vt)  # V^T [C, L]
-            ops.gemm(q[b], k[b], out=s)                                               # S = Q K^T [L, L]
-            ops.softmax_rows_(s, c ** -0.5)
+            ops.gemm(q[b], k[b], out=s, alpha=c ** -0.5)                              # S = Q K^T / sqrt(C) [L, L]
+            ops.softmax_rows_(s, 1.0)
             ops.gemm(s, vt, out=o[b])                                                 # O = P V [L, C]
         out = ops.gemm(o.view(n * L, c), w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, c)
@@ -184,6 +190,12 @@ class VAEEncoderEngine:
     _t = VAEDecoderEngine._t
     _res = VAEDecoderEngine._res
     _attn = VAEDecoderEngine._attn
+
+    def repack(self, state_dict: SD) -> None:
+        """Re-pack after the module's parameters changed: same buffers, new contents."""
+        old, self.w = self.w, {}
+        self._pack(state_dict)
+        self.w = ops.refresh_packed(old, self.w)
 
     def _pack(self, sd: SD) -> None:
         w = self.w

@@ -40,7 +40,7 @@ def _act(x: torch.Tensor, epilogue: int) -> torch.Tensor:
 
 
 def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogue=EPI_NONE, a2=None, bias_along_m=False,
-         out=None, block_n=0, ln=None, row_stats_out=None, rowvec_mul=False, act_col0=0, seg=None):
+         out=None, block_n=0, ln=None, row_stats_out=None, rowvec_mul=False, act_col0=0, seg=None, alpha=1.0):
     """csrc/gemm.cu epilogue order: LayerNorm fold -> bias -> rowvec (add or multiply) -> activation -> residual ->
     row statistics of the final fp32 values."""
     A = a.float() if a2 is None else torch.cat([a.float(), a2.float()], 1)
@@ -48,7 +48,7 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
     rows = torch.arange(M)
 
     def one(wm, bm, rv):
-        acc = A @ wm.float().t()
+        acc = (A @ wm.float().t()) * alpha
         if ln is not None:
             st, lc, ld_, eps = ln
             cnt = st[:, :, 0].sum(1)  # merge the producer's partials (count, mean, M2): parallel-variance formula

@@ -338,7 +338,7 @@ def test_chroma_engine_host_logic_vs_reference_golden():
 def test_unet_engine_control_residuals_vs_reference_golden(monkeypatch):
     """ControlNet / T2I-Adapter residuals added inside the fused forward (apply_control, backend/nn/unet.py:44-52): order
     of consumption, a None entry, NCHW residuals onto channels-last activations, skips carrying the input residuals — and
-    the P3 wrapper passing `c["control"]` through when B200_CONTROL=1 (else it defers)."""
+    the P3 wrapper passing `c["control"]` through (B200_CONTROL=0: it defers)."""
     from b200forge import plugin
     from b200forge.unet_engine import UNetEngine
     g = _gold("unet_tiny_xl_control.pt")
@@ -361,9 +361,9 @@ def test_unet_engine_control_residuals_vs_reference_golden(monkeypatch):
     sigma = torch.tensor([4.0, 0.5])
     c = {"c_crossattn": g["context"], "y": g["y"], "control": g["control"], "transformer_options": {}}
     sentinel = torch.zeros(1)
-    monkeypatch.delenv("B200_CONTROL", raising=False)
+    monkeypatch.setenv("B200_CONTROL", "0")
     assert w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]}) is sentinel
-    monkeypatch.setenv("B200_CONTROL", "1")
+    monkeypatch.delenv("B200_CONTROL", raising=False)
     den = w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]})
     assert den is not sentinel and w.calls_fast == 1
     xc = pred.calculate_input(sigma, x)
@@ -425,7 +425,7 @@ def test_flux_img2img_host_logic_vs_oracle_loop():
 
 
 def test_any_size_route_host_logic(monkeypatch):
-    """B200_ANY_SIZE=1: latent sizes the TMA convolution cannot tile (SDXL's non-square buckets, e.g. 152x104 and its /2, /4
+    """B200_CONV_ROUTE=im2col: latent sizes the TMA convolution cannot tile (SDXL's non-square buckets, e.g. 152x104 and its /2, /4
     levels) run their 3x3 convolutions as im2col + GEMM with the same epilogue (bias, time-embedding row, residual).  Here
     a 12x20 latent (levels 12x20, 6x10, 3x5 — none of which tiles) through the UNet and VAE engines against the oracle."""
     from b200forge import ops
@@ -435,9 +435,11 @@ def test_any_size_route_host_logic(monkeypatch):
     sd = OU.random_state_dict(cfg, seed=1)
     eng = UNetEngine(cfg, sd, dtype=F32, device="cpu")
     assert not ops.conv3x3_supported(12, 20) and not ops.conv3x3_supported(6, 10) and not ops.conv3x3_supported(3, 5)
-    monkeypatch.delenv("B200_ANY_SIZE", raising=False)
+    monkeypatch.setenv("B200_CONV_ROUTE", "exact")
     assert not eng.supports_latent(12, 20) and eng.supports_latent(16, 16)
-    monkeypatch.setenv("B200_ANY_SIZE", "1")
+    monkeypatch.delenv("B200_CONV_ROUTE", raising=False)
+    assert eng.supports_latent(12, 20)  # default route: generic tiling inside the implicit-GEMM kernel
+    monkeypatch.setenv("B200_CONV_ROUTE", "im2col")
     assert eng.supports_latent(12, 20) and not eng.supports_latent(13, 20)  # odd sizes still need the reference's resize path
     calls = {"im2col": 0, "tma": 0}
     real_im2col, real_conv = ops.im2col3x3, ops.conv3x3
@@ -469,3 +471,110 @@ def test_any_size_route_host_logic(monkeypatch):
     with torch.no_grad():
         vref = OV.decode_first_stage(vsd, vcfg, z)
     assert_close("emulated VAE decoder at a non-tiling size vs oracle", dec.decode(z), vref, max_abs=1e-4)
+
+
+def test_p3_wrapper_follows_lora_refresh(monkeypatch):
+    """Forge merges LoRA deltas into the torch module AFTER the engine was packed (backend/patcher/lora.py:352-446, hash in
+    `loaded_hash`): the wrapper must re-pack (in place) when the hash changes, and hand calls back to the reference while an
+    on-the-fly LoRA (`forge_online_loras`) is attached."""
+    from b200forge import plugin
+    from b200forge.unet_engine import UNetEngine
+    monkeypatch.setattr(plugin, "_on_device", lambda t: True)
+    cfg = CF.CONFIGS["tiny_xl"]
+    sd = OU.random_state_dict(cfg, seed=1)
+
+    class Layer:
+        pass
+
+    class Module:  # stands for IntegratedUNet2DConditionModel: live parameters + sub-modules
+        def __init__(self):
+            self.sd = {k: v.clone() for k, v in sd.items()}
+            self.layers = [Layer(), Layer()]
+
+        def state_dict(self):
+            return self.sd
+
+        def modules(self):
+            return self.layers
+
+    class Loader:
+        loaded_hash = str([])
+
+    class KModel:
+        def __init__(self):
+            self.diffusion_model = Module()
+            self.lora_loader = Loader()
+
+    pred = S.EpsPrediction()
+
+    class P:
+        prediction_type = "epsilon"
+        timestep = staticmethod(lambda s: pred.timestep(s))
+
+    km = KModel()
+    eng = UNetEngine(cfg, km.diffusion_model.state_dict(), dtype=F32, device="cpu")
+    w = plugin.UNetWrapper(eng, P(), km)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 16, 16, generator=g) * 3
+    sigma = torch.tensor([4.0, 0.5])
+    c = {"c_crossattn": torch.randn(2, 77, cfg["context_dim"], generator=g), "y": torch.randn(2, cfg["adm_in_channels"], generator=g),
+         "transformer_options": {}}
+    sentinel = torch.zeros(1)
+    call = lambda: w(lambda xx, ss, **kw: sentinel, {"input": x, "timestep": sigma, "c": c, "cond_or_uncond": [0]})  # noqa: E731
+    base = call()
+    ptr = eng.w["input_blocks.1.0.conv1.w"].data_ptr()
+    # "merge a LoRA": new parameter values + a new hash, exactly what LoraLoader.refresh leaves behind
+    key = "input_blocks.1.0.in_layers.2.weight"
+    km.diffusion_model.sd[key] = km.diffusion_model.sd[key] + 0.05 * torch.randn(km.diffusion_model.sd[key].shape, generator=g)
+    km.lora_loader.loaded_hash = str([("style.safetensors", 1.0, 1.0, False)])
+    patched = call()
+    assert w.weights.repacks == 1 and eng.w["input_blocks.1.0.conv1.w"].data_ptr() == ptr  # re-packed in place
+    assert (patched - base).abs().max() > 1e-3, "the fused forward ignored the merged LoRA"
+    xc = pred.calculate_input(sigma, x)
+    with torch.no_grad():
+        eps = OU.unet_forward(km.diffusion_model.sd, cfg, xc, pred.timestep(sigma).float(), c["c_crossattn"], c["y"])
+    assert_close("P3 wrapper after a LoRA merge vs oracle on the patched weights", patched, pred.calculate_denoised(sigma, eps, x), rel_rms=1e-5)
+    assert call() is not sentinel and w.weights.repacks == 1   # same hash: no second re-pack
+    # on-the-fly LoRA: weights untouched, low-rank terms inside the layers -> reference path
+    km.diffusion_model.layers[0].forge_online_loras = {"weight": []}
+    km.lora_loader.loaded_hash = str([("style.safetensors", 1.0, 1.0, True)])
+    assert call() is sentinel and w.calls_reference == 1
+    del km.diffusion_model.layers[0].forge_online_loras
+    km.lora_loader.loaded_hash = str([])
+    km.diffusion_model.sd[key] = sd[key].clone()
+    assert_close("P3 wrapper after the LoRA was removed", call(), base, rel_rms=1e-6)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_p2_installed_operations_subclass_forges_own_classes():
+    """plugin.install_operations(): the hot-path classes SUBCLASS ForgeOperations' classes, so lazy weights
+    (`dummy` / `_load_from_state_dict`), `parameters_manual_cast` (storage dtype != computation dtype: fp8 / bf16 storage) and
+    `forge_online_loras` keep the reference's behaviour — such calls run the parent's forward (backend/operations.py:126-156)."""
+    ref_import.load()
+    import backend.operations as bo
+
+    from b200forge import operations as B, plugin
+    forge = bo.ForgeOperations
+    plugin.install_operations()
+    try:
+        assert issubclass(bo.ForgeOperations, forge) and issubclass(bo.ForgeOperations.Linear, forge.Linear)
+        assert issubclass(bo.ForgeOperations.Conv2d, forge.Conv2d) and bo.ForgeOperations.Embedding is forge.Embedding
+        with bo.using_forge_operations(device="cpu", dtype=torch.bfloat16, manual_cast_enabled=True):
+            lin = torch.nn.Linear(16, 32)
+            conv = torch.nn.Conv2d(8, 16, 3, padding=1)
+        assert isinstance(lin, forge.Linear) and lin.parameters_manual_cast and lin.weight is None  # Forge's lazy init
+        g = torch.Generator().manual_seed(0)
+        wl, bl = torch.randn(32, 16, generator=g).bfloat16(), torch.randn(32, generator=g).bfloat16()
+        lin.load_state_dict({"weight": wl, "bias": bl})
+        conv.load_state_dict({"weight": torch.randn(16, 8, 3, 3, generator=g).bfloat16(), "bias": torch.zeros(16).bfloat16()})
+        x = torch.randn(4, 16, generator=g)  # fp32 activations on bf16 storage: manual cast in the parent's forward
+        n0 = B.DEFERRED
+        y = lin(x)
+        assert B.DEFERRED == n0 + 1 and y.dtype == torch.float32
+        assert_close("manual-cast Linear through the parent's forward", y, torch.nn.functional.linear(x, wl.float(), bl.float()), max_abs=1e-5)
+        assert conv(torch.randn(1, 8, 8, 8, generator=g)).dtype == torch.float32
+        lin.parameters_manual_cast = False
+        lin.forge_online_loras = {}
+        assert not B._plain(lin)
+    finally:
+        bo.ForgeOperations = plugin._installed.pop("operations")

@@ -440,8 +440,6 @@ def test_attention_blockdiag_vs_oracle():
         assert_close(f"attention_blockdiag L={L} Lk={Lk}", out, ref, rel_rms=3e-3)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_CONV_GENERAL") != "1",
-                    reason="generic convolution tiling is experimental: run with B200_CONV_GENERAL=1")
 @pytest.mark.parametrize("N,H,W,C1,C2,Cout", [(2, 104, 152, 320, 0, 320), (2, 52, 76, 640, 640, 640), (3, 26, 38, 1280, 0, 1280),
                                               (2, 13, 19, 1280, 0, 1280), (1, 96, 168, 64, 64, 128)])
 def test_conv3x3_generic_tiling(N, H, W, C1, C2, Cout):
@@ -462,7 +460,7 @@ def test_conv3x3_generic_tiling(N, H, W, C1, C2, Cout):
     y = ops.conv3x3(x1, ops.pack_conv3x3(w), b, x2=x2, temb=temb, residual=res, out=guard)
     torch.cuda.synchronize()
     ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
-    assert_close(f"conv3x3 generic {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3)
+    assert_close(f"conv3x3 generic {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, max_abs=2.5e-2, rel_rms=2e-3)
 
 
 def test_sampler_step_and_denoised_v_prediction():
@@ -495,12 +493,8 @@ def test_sampler_step_and_denoised_v_prediction():
     assert_close("v-pred eps_to_denoised", out, pred.calculate_denoised(sig4, vn, x4), max_abs=3e-5)
 
 
-_ANY = __import__("os").environ.get("B200_ANY_SIZE") == "1"
-
-
-@pytest.mark.skipif(not _ANY, reason="any-size route is experimental: run with B200_ANY_SIZE=1")
 def test_any_size_convolution_route_and_ragged_attention():
-    """What B200_ANY_SIZE=1 adds on hardware: (1) 3x3 convolutions of non-tiling images as im2col + GEMM with the time-embedding
+    """What the im2col route (B200_CONV_ROUTE=im2col) needs on hardware: (1) 3x3 convolutions of non-tiling images as im2col + GEMM with the time-embedding
     row and the residual in the GEMM epilogue, (2) self-attention over token counts that are not multiples of the 128-key /
     256-query tiles (152x104 latents -> 15808 / 3952 / 988 tokens)."""
     ops = _ops()
@@ -510,7 +504,7 @@ def test_any_size_convolution_route_and_ragged_attention():
     b = _rand(Cout, seed=102)
     temb = _rand(N, Cout, seed=103)
     res = _rand(N, H, W, Cout, seed=104)
-    y = ops.conv3x3_any(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), b, temb=temb, residual=res)
+    y = ops.conv3x3_any(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), b, temb=temb, residual=res, route="im2col")
     torch.cuda.synchronize()
     ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
     assert_close("conv3x3_any 52x76", y, ref, rel_rms=2e-3)
