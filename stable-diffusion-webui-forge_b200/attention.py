@@ -24,8 +24,7 @@ fallback: Optional[Callable] = None
 fallback_single_head: Optional[Callable] = None
 
 
-def supports(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask, skip_reshape: bool,
-             attn_precision=None) -> bool:
+def supports(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask, skip_reshape: bool) -> bool:
     if mask is not None or not q.is_cuda:
         return False
     # The flash kernels keep logits, softmax and accumulators in fp32 (what attn_precision=fp32 asks of attention_basic,
@@ -43,7 +42,7 @@ def _unsupported(name, q, heads, mask, skip_reshape):
 
 
 def attention_function(q, k, v, heads, mask=None, attn_precision=None, skip_reshape=False):
-    if not supports(q, k, v, heads, mask, skip_reshape, attn_precision):
+    if not supports(q, k, v, heads, mask, skip_reshape):
         if fallback is not None:
             return fallback(q, k, v, heads, mask, attn_precision, skip_reshape)
         _unsupported("attention_function", q, heads, mask, skip_reshape)
