@@ -26,7 +26,8 @@ def _rand(*shape, dtype=torch.float16, scale=1.0, seed=0):
 
 
 def _tol(dtype):
-    return dict(rel_rms=2e-3) if dtype == torch.float16 else dict(rel_rms=1.2e-2)
+    # max_rel (max-abs in units of the reference RMS) catches a single corrupted tile row that an RMS over the matrix hides
+    return dict(rel_rms=2e-3, max_rel=1.5e-2) if dtype == torch.float16 else dict(rel_rms=1.2e-2, max_rel=1e-1)
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
@@ -54,7 +55,7 @@ def test_gemm_no_bias_strided_output():
     buf = torch.zeros(M, 3 * N, dtype=torch.float16, device=DEV)
     ops.gemm(a, w, out=buf[:, N:2 * N])
     torch.cuda.synchronize()
-    assert_close("gemm strided out", buf[:, N:2 * N], O.linear(a.float(), w.float()), rel_rms=2e-3)
+    assert_close("gemm strided out", buf[:, N:2 * N], O.linear(a.float(), w.float()), rel_rms=2e-3, max_rel=1.6e-02)
     assert buf[:, :N].abs().max().item() == 0 and buf[:, 2 * N:].abs().max().item() == 0
 
 
@@ -70,7 +71,7 @@ def test_gemm_residual_rowvec_silu():
     torch.cuda.synchronize()
     pre = O.linear(a.float(), w.float(), b.float()) + rv.float().repeat_interleave(256, dim=0)
     ref = O.silu(pre) + res.float()
-    assert_close("gemm silu+rowvec+residual", y, ref, rel_rms=2e-3)
+    assert_close("gemm silu+rowvec+residual", y, ref, rel_rms=2e-3, max_rel=1.6e-02)
 
 
 def test_gemm_bias_along_m():
@@ -81,7 +82,7 @@ def test_gemm_bias_along_m():
     b = _rand(M, seed=13)
     y = ops.gemm(a, w, b, bias_along_m=True)
     torch.cuda.synchronize()
-    assert_close("gemm bias_m", y, O.linear(a.float(), w.float()) + b.float()[:, None], rel_rms=2e-3)
+    assert_close("gemm bias_m", y, O.linear(a.float(), w.float()) + b.float()[:, None], rel_rms=2e-3, max_rel=1.6e-02)
 
 
 @pytest.mark.parametrize("C", [640, 1280])
@@ -94,7 +95,7 @@ def test_gemm_geglu(C):
     wp, bp = ops.pack_geglu(w, b, 256)
     y = ops.gemm(a, wp, bp, epilogue=ops.EPI_GEGLU, block_n=256)
     torch.cuda.synchronize()
-    assert_close(f"geglu C={C}", y, O.geglu(a.float(), w.float(), b.float()), rel_rms=3e-3)
+    assert_close(f"geglu C={C}", y, O.geglu(a.float(), w.float(), b.float()), rel_rms=3e-3, max_rel=2.4e-02)
 
 
 def test_gemm_concat_sources():
@@ -105,7 +106,7 @@ def test_gemm_concat_sources():
     w = _rand(N, K1 + K2, scale=(K1 + K2) ** -0.5, seed=19)
     y = ops.gemm(a1, w, a2=a2)
     torch.cuda.synchronize()
-    assert_close("gemm concat", y, O.linear(torch.cat([a1, a2], 1).float(), w.float()), rel_rms=2e-3)
+    assert_close("gemm concat", y, O.linear(torch.cat([a1, a2], 1).float(), w.float()), rel_rms=2e-3, max_rel=1.6e-02)
 
 
 # ------------------------------------------------------------------------------------------------ conv
@@ -124,7 +125,7 @@ def test_conv3x3(N, H, W, C1, C2, Cout):
     y = ops.conv3x3(x1, ops.pack_conv3x3(w), b, x2=x2)
     torch.cuda.synchronize()
     ref = O.conv2d(x.float(), w.float(), b.float()).permute(0, 2, 3, 1)
-    assert_close(f"conv3x3 {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3)
+    assert_close(f"conv3x3 {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, rel_rms=2e-3, max_rel=1.6e-02)
 
 
 def test_conv3x3_temb_residual():
@@ -139,7 +140,7 @@ def test_conv3x3_temb_residual():
     torch.cuda.synchronize()
     ref = O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1) + res.float()
-    assert_close("conv3x3 temb+residual", y, ref, rel_rms=2e-3)
+    assert_close("conv3x3 temb+residual", y, ref, rel_rms=2e-3, max_rel=1.6e-02)
 
 
 def test_conv_via_im2col_stride2_and_small_c():
@@ -153,7 +154,7 @@ def test_conv_via_im2col_stride2_and_small_c():
     y = ops.gemm(cols, ops.pack_conv3x3(w), b).view(N, H // 2, W // 2, Cout)
     torch.cuda.synchronize()
     ref = O.conv2d(x.float(), w.float(), b.float(), stride=2).permute(0, 2, 3, 1)
-    assert_close("conv s2 via im2col", y, ref, rel_rms=2e-3)
+    assert_close("conv s2 via im2col", y, ref, rel_rms=2e-3, max_rel=1.6e-02)
     # 4-channel scalar path
     x4 = _rand(2, 4, 32, 32, seed=31)
     cols4 = ops.im2col3x3(x4.permute(0, 2, 3, 1).contiguous(), ldo=64)
@@ -177,7 +178,7 @@ def test_attention(B, H, Lq, Lk, Dh, dtype):
     o = ops.attention(q, k, v, H)
     torch.cuda.synchronize()
     ref = O.attention(q.float(), k.float(), v.float(), H)
-    tol = dict(rel_rms=3e-3) if dtype == torch.float16 else dict(rel_rms=1.5e-2)
+    tol = dict(rel_rms=3e-3, max_rel=2e-2) if dtype == torch.float16 else dict(rel_rms=1.5e-2, max_rel=1.2e-1)
     assert_close(f"attention B{B} H{H} {Lq}x{Lk} d{Dh} {dtype}", o, ref, **tol)
 
 
@@ -189,7 +190,7 @@ def test_attention_fused_qkv_views():
     o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
     torch.cuda.synchronize()
     ref = O.attention(qkv[:, :, :C].float(), qkv[:, :, C:2 * C].float(), qkv[:, :, 2 * C:].float(), H)
-    assert_close("attention fused qkv", o, ref, rel_rms=3e-3)
+    assert_close("attention fused qkv", o, ref, rel_rms=3e-3, max_rel=2.4e-02)
 
 
 def test_attention_peaked_logits():
@@ -201,7 +202,7 @@ def test_attention_peaked_logits():
     v = _rand(B, L, H * Dh, seed=38)
     o = ops.attention(q, k, v, H)
     torch.cuda.synchronize()
-    assert_close("attention peaked", o, O.attention(q.float(), k.float(), v.float(), H), rel_rms=5e-3)
+    assert_close("attention peaked", o, O.attention(q.float(), k.float(), v.float(), H), rel_rms=5e-3, max_rel=4.0e-02)
 
 
 # ------------------------------------------------------------------------------------------------ norms
@@ -234,8 +235,8 @@ def test_layernorm(rows, C):
     y = ops.layernorm(x, g, b, 1e-5)
     y2 = ops.layernorm(x, None, None, 1e-6)
     torch.cuda.synchronize()
-    assert_close(f"layernorm {rows}x{C}", y, O.layer_norm(x.float(), g.float(), b.float(), 1e-5), rel_rms=1.5e-3)
-    assert_close(f"layernorm noaffine {rows}x{C}", y2, O.layer_norm(x.float(), None, None, 1e-6), rel_rms=1.5e-3)
+    assert_close(f"layernorm {rows}x{C}", y, O.layer_norm(x.float(), g.float(), b.float(), 1e-5), rel_rms=1.5e-3, max_rel=1.5e-02)
+    assert_close(f"layernorm noaffine {rows}x{C}", y2, O.layer_norm(x.float(), None, None, 1e-6), rel_rms=1.5e-3, max_rel=1.5e-02)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -254,7 +255,7 @@ def test_layout_upsample_silu_temb():
     up = ops.upsample2x(xn)
     assert torch.equal(up, O.upsample_nearest2x(x).permute(0, 2, 3, 1).contiguous())
     s = ops.silu(x)
-    assert_close("silu", s, O.silu(x.float()), rel_rms=1e-3)
+    assert_close("silu", s, O.silu(x.float()), rel_rms=1e-3, max_rel=1.5e-02)
     t = torch.tensor([0.0, 1.0, 500.0, 999.0], device=DEV)
     e = ops.timestep_embedding(t, 320, torch.float32 if False else torch.float16)
     ref = O.timestep_embedding(t.cpu(), 320)
@@ -283,7 +284,7 @@ def test_softmax_rows():
     ref = torch.softmax(x.float() * 0.125, dim=-1)
     ops.softmax_rows_(x, 0.125)
     torch.cuda.synchronize()
-    assert_close("softmax_rows", x, ref, rel_rms=1e-2)
+    assert_close("softmax_rows", x, ref, rel_rms=1e-2, max_rel=8.0e-02)
 
 
 # ------------------------------------------------------------------------------------------------ sampler step
@@ -348,7 +349,7 @@ def test_gemm_layernorm_fold_and_row_stats():
     assert torch.all(cnt == C)
     # the statistics are taken from the fp32 values before they are rounded to fp16 for the store
     assert_close("row stats mean", mean.float(), tf.mean(1).cpu(), max_abs=2e-3, rel_rms=1e-3)
-    assert_close("row stats var", var.float(), tf.var(1, unbiased=False).cpu(), rel_rms=1e-3)
+    assert_close("row stats var", var.float(), tf.var(1, unbiased=False).cpu(), rel_rms=1e-3, max_rel=1.5e-02)
     gamma = (_rand(C, seed=53) * 0.2 + 1)
     beta = _rand(C, seed=54) * 0.2
     w1 = _rand(N, C, scale=C ** -0.5, seed=55)
@@ -395,7 +396,7 @@ def test_layernorm_fold_large_row_mean(C, mean, sigma):
     cnt, mu, var = _merge_partials(stats)
     tf = res.double().cpu()
     assert_close("large-mean row mean", mu.float(), tf.mean(1).float(), max_abs=abs(mean) * 2e-6)
-    assert_close("large-mean row var", var.float(), tf.var(1, unbiased=False).float(), rel_rms=1e-3)
+    assert_close("large-mean row var", var.float(), tf.var(1, unbiased=False).float(), rel_rms=1e-3, max_rel=1.5e-02)
     gamma = (_rand(C, seed=61) * 0.2 + 1)
     beta = _rand(C, seed=62) * 0.2
     w1 = _rand(N, C, scale=C ** -0.5, seed=63)
@@ -405,7 +406,7 @@ def test_layernorm_fold_large_row_mean(C, mean, sigma):
     torch.cuda.synchronize()
     ref = O.linear(O.layer_norm(res.float(), gamma.float(), beta.float(), 1e-5), w1.float(), b1.float())
     # acc - mean*c cancels |mean|/sigma digits of the fp32 accumulator: the bound scales with that ratio
-    assert_close(f"LN fold, row mean {mean} sigma {sigma}", y, ref, rel_rms=max(3e-3, 2e-6 * abs(mean) / sigma * C ** 0.5))
+    assert_close(f"LN fold, row mean {mean} sigma {sigma}", y, ref, rel_rms=max(3e-3, 5e-7 * abs(mean) / sigma * C ** 0.5))
 
 
 @pytest.mark.parametrize("N,H,W,C,mean,sigma", [(2, 32, 32, 320, 50.0, 0.1), (1, 64, 64, 128, -200.0, 0.5), (2, 16, 16, 1280, 8.0, 0.02)])
@@ -437,7 +438,7 @@ def test_attention_blockdiag_vs_oracle():
         out = ops.attention_blockdiag(q, k, v, H, scale=Dh ** -0.5)
         torch.cuda.synchronize()
         ref = O.attention(q.float(), k.float(), v.float(), H)
-        assert_close(f"attention_blockdiag L={L} Lk={Lk}", out, ref, rel_rms=3e-3)
+        assert_close(f"attention_blockdiag L={L} Lk={Lk}", out, ref, rel_rms=3e-3, max_rel=2.4e-02)
 
 
 @pytest.mark.parametrize("N,H,W,C1,C2,Cout", [(2, 104, 152, 320, 0, 320), (2, 52, 76, 640, 640, 640), (3, 26, 38, 1280, 0, 1280),
@@ -507,9 +508,9 @@ def test_any_size_convolution_route_and_ragged_attention():
     y = ops.conv3x3_any(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3(w), b, temb=temb, residual=res, route="im2col")
     torch.cuda.synchronize()
     ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
-    assert_close("conv3x3_any 52x76", y, ref, rel_rms=2e-3)
+    assert_close("conv3x3_any 52x76", y, ref, rel_rms=2e-3, max_rel=1.6e-02)
     for (B, Hh, L, Dh) in ((2, 10, 3952, 64), (2, 20, 988, 64), (1, 4, 1000, 128)):
         q, k, v = (_rand(B, L, Hh * Dh, seed=110 + i) for i in range(3))
         out = ops.attention(q, k, v, Hh)
         torch.cuda.synchronize()
-        assert_close(f"attention ragged L={L} Dh={Dh}", out, O.attention(q.float(), k.float(), v.float(), Hh), rel_rms=2e-3)
+        assert_close(f"attention ragged L={L} Dh={Dh}", out, O.attention(q.float(), k.float(), v.float(), Hh), rel_rms=2e-3, max_rel=1.6e-02)

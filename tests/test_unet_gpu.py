@@ -2,9 +2,9 @@
 (a) golden vectors made by the imported reference on CPU fp32 (tests/golden, oracle/gen_golden.py) and
 (b) the oracle evaluated in fp32 on the same device.
 
-Stated tolerances (fp16 compute, fp32 accumulate; BASELINE/SURVEY §8d): per-forward rel-RMS <= 1e-2 and
-max-abs <= 6e-2 against the fp32 reference with activations of O(1) — the same order as the reference's own
-fp16-vs-fp32 gap, which the test also measures with the oracle run in fp16 where the device supports it.
+Stated tolerances (fp16 compute, fp32 accumulate): per-forward rel-RMS <= 3e-3 and max-abs <= 2e-2 of
+the output RMS against the fp32 reference — the same order as the reference's own fp16-vs-fp32 gap, which the test
+also measures with the oracle run in fp16; Euler / DPM++ 2M trajectories PSNR >= 40 dB on the final latent.
 """
 import os
 
@@ -40,7 +40,7 @@ def test_unet_forward_vs_reference_golden(name):
     y = None if g["y"] is None else g["y"].to(DEV).half()
     out = eng.forward(x, g["t"].to(DEV), g["context"].to(DEV).half(), y)
     torch.cuda.synchronize()
-    assert_close(f"unet {name} fp16 engine vs reference fp32 golden", out, g["out"], max_abs=6e-2, rel_rms=1e-2)
+    assert_close(f"unet {name} fp16 engine vs reference fp32 golden", out, g["out"], max_rel=2e-2, rel_rms=3e-3)
     # how far the reference's own fp16 arithmetic is from fp32 on the same inputs (context for the tolerance)
     sd16 = {k: v.to(DEV).half() for k, v in sd.items()}
     ref16 = OU.unet_forward(sd16, cfg, x, g["t"].to(DEV), g["context"].to(DEV).half(), y)
@@ -53,7 +53,7 @@ def test_unet_forward_bf16():
     eng, cfg, sd = _engine("tiny_xl", g["weight_seed"], dtype=torch.bfloat16)
     out = eng.forward(g["x"].to(DEV).bfloat16(), g["t"].to(DEV), g["context"].to(DEV).bfloat16(), g["y"].to(DEV).bfloat16())
     torch.cuda.synchronize()
-    assert_close("unet tiny_xl bf16 engine vs reference fp32 golden", out, g["out"], max_abs=4e-1, rel_rms=6e-2)
+    assert_close("unet tiny_xl bf16 engine vs reference fp32 golden", out, g["out"], max_rel=1.6e-1, rel_rms=2.4e-2)  # 8x the fp16 bound (3 fewer mantissa bits)
 
 
 @pytest.mark.parametrize("name,hw,batch", [("sdxl", 32, 2), ("sd15", 32, 2)])
@@ -76,7 +76,7 @@ def test_unet_full_width_vs_oracle_fp32(name, hw, batch):
     sd32 = {k: v.float().to(DEV) for k, v in sd.items()}
     with torch.no_grad():
         ref = OU.unet_forward(sd32, cfg, x.float(), t, ctx.float(), None if y is None else y.float())
-    assert_close(f"unet {name} full width fp16 engine vs oracle fp32", out, ref, max_abs=8e-2, rel_rms=1e-2)
+    assert_close(f"unet {name} full width fp16 engine vs oracle fp32", out, ref, max_rel=2e-2, rel_rms=3e-3)
 
 
 def _pipeline(g, use_graph):
@@ -97,15 +97,15 @@ def test_first_step_denoised_vs_reference_golden(use_graph):
                 sigmas=g["sigmas_auto"][:2], step_noise=g["euler_a_step_noise"][:1],
                 callback=lambda i, x, d: dens.append(d.clone()))
     torch.cuda.synchronize()
-    assert_close("first-step denoised (CFG) vs reference golden", dens[0], g["euler_a_denoised0"], rel_rms=1.5e-2)
+    # denoised = x - sigma * eps with sigma_0 = 14.6 and CFG 7 amplify the UNet's relative error against x's scale
+    assert_close("first-step denoised (CFG) vs reference golden", dens[0], g["euler_a_denoised0"], rel_rms=6e-3)
 
 
 @pytest.mark.parametrize("sampler,key,sig", [("euler_a", "euler_a", "sigmas_auto"), ("euler", "euler", "sigmas_auto"),
                                              ("dpmpp_2m", "dpmpp_2m", "sigmas_karras")])
 def test_trajectory_vs_reference_golden(sampler, key, sig):
     """Whole loops (6 steps, CFG 7, identical injected noise) vs the reference's k-diffusion loops on CPU fp32.
-    The synthetic UNet is not a contraction, so fp16 differences are amplified step to step; the bound is on the
-    final latent's PSNR relative to its own dynamic range."""
+    The bound is on the final latent's PSNR relative to its own dynamic range (>= 40 dB)."""
     g = _gold("traj_tiny_xl.pt")
     pipe = _pipeline(g, True)
     x = pipe.sample(g["cond"], g["uncond"], g["noise0"], sampler=sampler, cfg_scale=g["cfg_scale"], sigmas=g[sig],
@@ -117,7 +117,7 @@ def test_trajectory_vs_reference_golden(sampler, key, sig):
     psnr = float(10 * torch.log10(peak ** 2 / mse))
     m, r = err_stats(x, ref)
     print(f"[parity] trajectory {sampler}: PSNR={psnr:.1f} dB max_abs={m:.3e} rel_rms={r:.3e}")
-    assert psnr >= 30.0, psnr
+    assert psnr >= 40.0, psnr
     # the oracle itself in fp16-rounded weights/activations lands at a comparable distance
     assert torch.isfinite(x).all()
 
@@ -192,4 +192,4 @@ def test_img2img_vs_oracle():
     psnr = float(10 * torch.log10(ref.abs().max() ** 2 / mse))
     m, r = err_stats(x, ref)
     print(f"[parity] img2img euler: PSNR={psnr:.1f} dB max_abs={m:.3e} rel_rms={r:.3e}")
-    assert psnr >= 35.0, psnr
+    assert psnr >= 40.0, psnr
