@@ -161,31 +161,116 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def gpu_reference_unet_ms(batch: int, hw: int, iters: int = 3):
-    """Context number (not the graded reference arm): the oracle port — the same ATen calls the reference makes
-    (F.conv2d / F.linear / F.group_norm / SDPA) — in fp16 on this GPU, UNet forward at the benchmark batch."""
-    from oracle import configs as CF
+def gpu_reference_job(ucfg, vcfg, B, S, hw, cond, uncond, noise, step_noise, sampler, cfg_scale, max_steps=None):
+    """Context numbers (not the graded reference arm): the reference's GPU path restated — the oracle port makes the same
+    ATen calls Forge makes (F.conv2d -> cuDNN, F.linear -> cuBLAS, F.group_norm, F.scaled_dot_product_attention; fp16 UNet,
+    bf16 VAE) and its Denoiser / sample_* loops follow KModel.apply_model + sampling_function_inner + k_diffusion's loop
+    with their per-step 0-dim-tensor arithmetic and host syncs.  One COMPLETE job (S sampler steps at UNet batch 2B + VAE
+    decode of B images) is timed after a 3-step warm-up; the final latent is returned for the parity check."""
+    from oracle import sampling as OS
     from oracle import unet as OU
+    from oracle import vae as OV
     from b200forge import synthetic
-    cfg = CF.SDXL
-    sd = synthetic.random_unet_state_dict(cfg, device="cuda", dtype=torch.float16, seed=0)
-    x = torch.randn(batch, 4, hw, hw, device="cuda", dtype=torch.float16)
-    ctx = torch.randn(batch, 77, cfg["context_dim"], device="cuda", dtype=torch.float16)
-    y = torch.randn(batch, cfg["adm_in_channels"], device="cuda", dtype=torch.float16)
-    t = torch.full((batch,), 500.0, device="cuda")
+    dev = noise.device
+    sd = synthetic.random_unet_state_dict(ucfg, device=dev, dtype=torch.float16, seed=0)   # same seeds as the timed pipeline
+    vsd = synthetic.random_vae_decoder_state_dict(vcfg, device=dev, dtype=torch.bfloat16, seed=1)
+    pred = OS.EpsPrediction()
+    sig = (OS.get_sigmas_karras(S, float(pred.sigma_min), float(pred.sigma_max)) if sampler == "dpmpp_2m"
+           else OS.get_sigmas_uniform(pred, S)).to(dev)
+    if max_steps is not None:
+        sig = sig[:max_steps + 1]
+    c16 = {k: v.to(dev).half() for k, v in cond.items()}
+    u16 = {k: v.to(dev).half() for k, v in uncond.items()}
+
+    def unet16(xc, t, c, yy):
+        return OU.unet_forward(sd, ucfg, xc, t, c, yy)
+
+    den = OS.Denoiser(unet16, pred, c16, u16, cfg_scale, compute_dtype=torch.float16)
+    x0 = noise.to(dev).float() * sig[0]
+    it = iter(range(step_noise.shape[0]))
     with torch.no_grad():
-        for _ in range(2):
-            OU.unet_forward(sd, cfg, x, t, ctx, y)
+        for _ in range(3):
+            den(x0, sig[0] * x0.new_ones([B]))
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         s.record()
-        for _ in range(iters):
-            OU.unet_forward(sd, cfg, x, t, ctx, y)
+        if sampler == "dpmpp_2m":
+            lat = OS.sample_dpmpp_2m(den, x0.clone(), sig)
+        else:
+            lat = OS.sample_euler_ancestral(den, x0.clone(), sig, lambda: step_noise[next(it)].to(dev))
+        m.record()
+        img = torch.cat([OV.decode_first_stage(vsd, vcfg, lat[i:i + 1].bfloat16()) for i in range(B)])
         e.record()
         torch.cuda.synchronize()
-    del sd
+    n_steps = sig.numel() - 1
+    out = {"unet_ms_per_step": s.elapsed_time(m) / n_steps, "steps_timed": n_steps, "vae_decode_ms": m.elapsed_time(e),
+           "job_ms": s.elapsed_time(e), "images_per_s": B / (s.elapsed_time(e) * 1e-3) if n_steps == S else None,
+           "what": "oracle port = the reference's ATen/cuDNN/cuBLAS/SDPA calls in fp16 (UNet) / bf16 (VAE), CFG + sampler loop "
+                   "with the reference's per-step tensor arithmetic; one complete job after 3 warm-up UNet steps"}
+    del sd, vsd, img
     torch.cuda.empty_cache()
-    return s.elapsed_time(e) / iters
+    return out, lat
+
+
+def unet_forward_parity(pipe, ucfg, hw, n, dev):
+    """One fused UNet forward at the benchmarked shape [n, 4, hw, hw] against the oracle in fp32 on the same device
+    (TF32 off, the engine's own fp16-rounded weights are regenerated from the same seed)."""
+    from oracle import unet as OU
+    from b200forge import synthetic
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(123)
+        x = torch.randn(n, 4, hw, hw, generator=g).half().to(dev)
+        ctx = torch.randn(n, 77, ucfg["context_dim"], generator=g).half().to(dev)
+        y = torch.randn(n, ucfg["adm_in_channels"], generator=g).half().to(dev) if ucfg["adm_in_channels"] else None
+        t = torch.linspace(999.0, 1.0, n).to(dev)
+        out = pipe.unet.forward(x, t, ctx, y).float()
+        sd32 = {k: v.float() for k, v in synthetic.random_unet_state_dict(ucfg, device=dev, dtype=torch.float16, seed=0).items()}
+        ref = torch.empty_like(out)
+        with torch.no_grad():
+            for i in range(0, n, 4):
+                ref[i:i + 4] = OU.unet_forward(sd32, ucfg, x[i:i + 4].float(), t[i:i + 4], ctx[i:i + 4].float(),
+                                               None if y is None else y[i:i + 4].float())
+        del sd32
+        torch.cuda.empty_cache()
+        diff = (out - ref)
+        rms = ref.pow(2).mean().sqrt()
+        return {"shape": [n, 4, hw, hw], "rel_rms": float(diff.pow(2).mean().sqrt() / rms), "max_abs": float(diff.abs().max()),
+                "max_abs_over_ref_rms": float(diff.abs().max() / rms), "finite": bool(torch.isfinite(out).all()),
+                "reference": "oracle fp32 on the GPU (TF32 off)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+
+
+def attention_vs_sdpa(dev, iters=20):
+    """The repo's Dh = 64 attention kernel beside the library the reference calls (F.scaled_dot_product_attention), at the two
+    SDXL self-attention shapes, same tensors, CUDA events, L2-sized inputs."""
+    from b200forge import ops
+    res = {}
+    for (b, h, L) in ((16, 10, 4096), (16, 20, 1024)):
+        q, k, v = (torch.randn(b, L, h * 64, device=dev, dtype=torch.float16) for _ in range(3))
+        qh, kh, vh = (t.view(b, L, h, 64).transpose(1, 2) for t in (q, k, v))
+        fl = 4.0 * b * h * L * L * 64
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) / iters
+
+        ours = timeit(lambda: ops.attention(q, k, v, h))
+        lib = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
+        res[f"B{b}_H{h}_L{L}_Dh64"] = {"b200_us": ours * 1e3, "b200_tflops": fl / ours / 1e9, "sdpa_us": lib * 1e3,
+                                       "sdpa_tflops": fl / lib / 1e9}
+    return res
 
 
 def run_flux(args):
@@ -343,8 +428,14 @@ def main():
     ap.add_argument("--workload", default="sdxl", choices=["sdxl", "sd15", "flux"],
                     help="sdxl = BASELINE.json's headline config (default); sd15 = configs[1]: SD1.5 512x512, Euler-a 20 steps, "
                          "batch 8; flux = configs[4]: Flux.1-dev 1024x1024, 20 steps, batch 4, bf16")
+    ap.add_argument("--sampler", default="euler_a", choices=["euler_a", "dpmpp_2m"],
+                    help="euler_a = the headline; dpmpp_2m = BASELINE.json configs[3] (DPM++ 2M, Karras schedule, run with --gpus 8)")
+    ap.add_argument("--path", default="plugin", choices=["plugin", "pipeline"],
+                    help="what `e2e` drives: plugin = the reference-facing plug points (P3 model_function_wrapper + P4 k-diffusion "
+                         "sampler function + P5 VAE decode wrapper, called as Forge calls them); pipeline = Txt2ImgPipeline.generate")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -369,7 +460,8 @@ def main():
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
 
-    from b200forge import lib, ops, synthetic
+    from b200forge import dist as bdist
+    from b200forge import k_samplers, lib, ops, plugin, synthetic
     from b200forge.pipeline import Txt2ImgPipeline
     lib.check(lib.load().b200_device_ok())
     peaks = load_peaks()
@@ -382,6 +474,8 @@ def main():
             args.sampler_steps = 20
     B, S = args.batch, args.sampler_steps
     hw = args.size // 8
+    sampler = args.sampler
+    cfg_scale = 7.0
     ucfg, vcfg = (synthetic.SD15, synthetic.VAE_SD15) if sd15 else (synthetic.SDXL, synthetic.VAE_SDXL)
     wl_name = "SD1.5" if sd15 else "SDXL-base"
     gflop_key = "sd15@64" if sd15 else "sdxl@128"
@@ -392,41 +486,83 @@ def main():
     pipe = Txt2ImgPipeline(ucfg, usd, vae_cfg=vcfg, vae_state_dict=vsd, dtype=torch.float16, device=dev)
     del usd, vsd
 
-    # ---- synthetic job inputs (pinned host copies for the e2e leg, device copies for the resident leg)
-    seeds = [1000 + rank * B + i for i in range(B)]  # contiguous-by-seed sharding: results independent of N
-    gens = [torch.Generator().manual_seed(s) for s in seeds]
+    # ---- synthetic job inputs (pinned host copies for the e2e legs, device copies for the resident leg)
+    seeds = bdist.shard_seeds(1000, B, rank, world)  # contiguous-by-seed sharding: results independent of N
+    gens = [torch.Generator().manual_seed(sd_) for sd_ in seeds]
 
     def draw():
         return torch.stack([torch.randn((4, hw, hw), generator=g) for g in gens])
 
     g0 = torch.Generator().manual_seed(7)
+    adm = ucfg["adm_in_channels"] or 8
     host = {
         "noise": draw().pin_memory(),
         "step_noise": torch.stack([draw() for _ in range(S - 1)]).pin_memory(),
         "cond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
-                 "vector": torch.randn(B, ucfg["adm_in_channels"] or 8, generator=g0).half().pin_memory()},
+                 "vector": torch.randn(B, adm, generator=g0).half().pin_memory()},
         "uncond": {"crossattn": torch.randn(B, 77, ucfg["context_dim"], generator=g0).half().pin_memory(),
-                   "vector": torch.randn(B, ucfg["adm_in_channels"] or 8, generator=g0).half().pin_memory()},
+                   "vector": torch.randn(B, adm, generator=g0).half().pin_memory()},
     }
     devin = {"noise": host["noise"].to(dev), "step_noise": host["step_noise"].to(dev),
              "cond": {k: v.to(dev) for k, v in host["cond"].items()},
              "uncond": {k: v.to(dev) for k, v in host["uncond"].items()}}
-    h2d = (host["noise"].numel() * 4 + host["step_noise"].numel() * 4 +
+    uses_noise = sampler == "euler_a"
+    h2d = (host["noise"].numel() * 4 + (host["step_noise"].numel() * 4 if uses_noise else 0) +
            sum(v.numel() * 2 for v in host["cond"].values()) + sum(v.numel() * 2 for v in host["uncond"].values()))
     out_host = torch.empty((B, args.size, args.size, 3), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
-    gathered = [torch.empty((B, args.size, args.size, 3), dtype=torch.float32, device=dev) for _ in range(world)] \
+    # multi-GPU: the only collective on the path — one gather of the finished images to rank 0, as uint8 (the conversion the
+    # reference does on the host after its D2H copy): a quarter of the fp32 bytes
+    gathered = [torch.empty((B, args.size, args.size, 3), dtype=torch.uint8, device=dev) for _ in range(world)] \
         if (dist is not None and rank == 0) else None
 
     def job(inp):
-        img = pipe.generate(inp["cond"], inp["uncond"], inp["noise"], steps=S, sampler="euler_a", cfg_scale=7.0,
-                            step_noise=inp["step_noise"])
-        return img
+        return pipe.generate(inp["cond"], inp["uncond"], inp["noise"], steps=S, sampler=sampler, cfg_scale=cfg_scale,
+                             step_noise=inp["step_noise"] if uses_noise else None)
 
     def finish(img):
-        # multi-GPU: the only collective on the path — gather of the finished images to rank 0
         if dist is not None:
-            dist.gather(img, gathered, dst=0)
+            bdist.gather_images_u8(img, bufs=gathered)
+
+    # ---- the plug-in path: the same job driven exactly as Forge drives its backend:
+    #   CFGDenoiser.forward -> sampling_function_inner batches [uncond | cond] and calls model_options['model_function_wrapper']
+    #   (P3, backend/sampling/sampling_function.py:270-273); the CFG combine stays in the caller's torch code (:292-322);
+    #   k_diffusion.sampling.sample_* (P4) owns the loop; VAE.decode calls model_options['model_vae_decode_wrapper'] (P5).
+    unet_w = plugin.UNetWrapper(pipe.unet, pipe.pred)
+    vae_w = plugin.VAEDecodeWrapper(pipe.vae)
+    has_y = pipe.unet.has_label
+    sig_sched = None
+
+    def plugin_job(inp):
+        nonlocal sig_sched
+        put = lambda t, dt: t.to(device=dev, dtype=dt, non_blocking=True)  # noqa: E731
+        ctx = torch.cat([put(inp["uncond"]["crossattn"], torch.float16), put(inp["cond"]["crossattn"], torch.float16)])
+        y = torch.cat([put(inp["uncond"]["vector"], torch.float16), put(inp["cond"]["vector"], torch.float16)]) if has_y else None
+        noise = put(inp["noise"], torch.float32)
+        sn = put(inp["step_noise"], torch.float32) if uses_noise else None
+        if sig_sched is None:
+            from b200forge import sampling as bs
+            sig_sched = bs.make_sigmas(pipe.pred, sampler, S).to(dev)
+        c = {"c_crossattn": ctx, "y": y, "transformer_options": {"cond_or_uncond": [1, 0]}}
+
+        def unreachable(*a, **k):
+            raise RuntimeError("the plug-in handed the call back to the reference path")
+
+        def denoiser(x, sigma, **kw):  # sampling_function_inner for one cond + one uncond entry, both in one batch
+            out = unet_w(unreachable, {"input": torch.cat([x, x]), "timestep": torch.cat([sigma, sigma]), "c": c,
+                                       "cond_or_uncond": [1, 0]})
+            un, co = out.chunk(2)
+            return un + (co - un) * cfg_scale
+
+        x0 = noise * sig_sched[0]  # predictor.noise_scaling(sigmas[0], noise, zeros, max_denoise=False)
+        if sampler == "euler_a":
+            it = iter(range(S))
+            lat = k_samplers.sample_euler_ancestral(denoiser, x0, sig_sched, extra_args={}, disable=True,
+                                                    noise_sampler=lambda s_, sn_: sn[next(it)])
+        else:
+            lat = k_samplers.sample_dpmpp_2m(denoiser, x0, sig_sched, extra_args={}, disable=True)
+        # Forge hands P5 the processed-out latent (diffusion_engine/sdxl.py:134-138)
+        return vae_w(unreachable, lat / pipe.vae.scaling), lat
 
     def barrier():
         torch.cuda.synchronize()
@@ -450,11 +586,19 @@ def main():
     def step_resident():
         finish(job(devin))
 
-    def step_e2e():
+    def step_e2e_pipeline():
         img = job(host)
         finish(img)
         out_host.copy_(img, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the device->host read of the step's result
+
+    def step_e2e_plugin():
+        img, _ = plugin_job(host)
+        finish(img)
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e = step_e2e_plugin if args.path == "plugin" else step_e2e_pipeline
 
     for _ in range(W):
         step_resident()
@@ -467,13 +611,19 @@ def main():
     if os.environ.get("B200_PROFILE_TIMED"):
         torch.cuda.profiler.stop()
     launches = ops.LAUNCHES - l0
-    step_e2e()
+    step_e2e()  # untimed: graph capture / first-call setup of this leg
+    l1 = ops.LAUNCHES
     sec_e2e = timed(step_e2e, K)
+    launches_e2e = ops.LAUNCHES - l1
+    other = step_e2e_pipeline if args.path == "plugin" else step_e2e_plugin
+    other()
+    sec_other = timed(other, K)
     clk = clocks.stop()
 
     total_images = B * world * K
     value = total_images / sec
     e2e_value = total_images / sec_e2e
+    other_value = total_images / sec_other
 
     # ---- UNet ms/step and the per-kernel-family roofline from one instrumented eager denoise step + VAE decode
     unet_ms = None
@@ -509,9 +659,9 @@ def main():
         peak = peaks["bf16_tflops_sustained"]
         roof = {"kernel": "b200::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3; 1 UNet forward @batch 16 + VAE decode)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # dram__bytes_read+write of one representative launch from the committed `ncu --set full` capture
-                # (profiles/ncu_r1_summary.md): gemm M=16384 N=10240 K=1280, algorithmic bytes 403.7 MB
-                "traffic": 367.5e6, "traffic_launch": "gemm M=16384 N=10240 K=1280 fp16 (algorithmic 403.7e6 B, 429.5e9 FLOP; 70.8e6 read + 296.7e6 written)",
+                # not measured in this run (ncu cannot wrap a timed run); per-kernel dram bytes from the committed
+                # `ncu --set full` captures are in profiles/ncu_r2_summary.md
+                "traffic": None,
                 "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                 "launches": tens["launches"], "avg_launch_ms": tens["ms"] / max(1, tens["launches"]),
                 "flops_per_launch_avg": tens["flops"] / max(1, tens["launches"])}
@@ -519,14 +669,51 @@ def main():
             d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
             d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
 
+    # ---- parity at the benchmarked shape, in the same process, after the timed region (rank 0, N = 1)
     cpu_base = None
-    gpu_ref_ms = None
+    gpu_ref = None
+    parity = None
+    attn_pair = None
     if rank == 0 and world == 1:
-        if not args.no_gpu_reference and not sd15:
+        img_chk, lat_plugin = plugin_job(devin)
+        lat_pipe = pipe.sample(devin["cond"], devin["uncond"], devin["noise"], steps=S, sampler=sampler, cfg_scale=cfg_scale,
+                               step_noise=devin["step_noise"] if uses_noise else None)
+        torch.cuda.synchronize()
+        finite = bool(torch.isfinite(lat_pipe).all() and torch.isfinite(lat_plugin).all() and torch.isfinite(img_chk).all())
+        if not finite:
+            print(json.dumps({"error": "non-finite output at the benchmarked shape", "metric": METRIC}), flush=True)
+            sys.exit(1)
+
+        def psnr(a, b):
+            mse = (a.float() - b.float()).pow(2).mean()
+            return float(10 * torch.log10(b.float().abs().max() ** 2 / mse.clamp_min(1e-30)))
+
+        parity = {"finite": True,
+                  "plugin_vs_pipeline_final_latent": {"psnr_db": psnr(lat_plugin, lat_pipe),
+                                                      "rel_rms": float((lat_plugin - lat_pipe).pow(2).mean().sqrt() / lat_pipe.pow(2).mean().sqrt())}}
+        if not args.no_parity:
+            parity["unet_forward_vs_oracle_fp32"] = unet_forward_parity(pipe, ucfg, hw, 2 * B, dev)
+        if not args.no_gpu_reference:
             try:
-                gpu_ref_ms = gpu_reference_unet_ms(2 * B, hw)
-            except Exception as ex:  # context number only
-                gpu_ref_ms = f"failed: {type(ex).__name__}"
+                attn_pair = attention_vs_sdpa(dev)
+                gpu_ref, lat_ref = gpu_reference_job(ucfg, vcfg, B, S, hw, devin["cond"], devin["uncond"], devin["noise"],
+                                                     devin["step_noise"], sampler, cfg_scale)
+                parity["final_latent_vs_reference_fp16_loop"] = {
+                    "psnr_db": psnr(lat_pipe, lat_ref), "steps": S, "sampler": sampler,
+                    "rel_rms": float((lat_pipe - lat_ref).pow(2).mean().sqrt() / lat_ref.pow(2).mean().sqrt()),
+                    "what": "same seeds / injected noise; ours = fused fp16 pipeline, reference = oracle-port loop in fp16 on this GPU"}
+                # short horizon: rounding differences have not yet been amplified by the (random-weight) UNet
+                _, lat_ref4 = gpu_reference_job(ucfg, vcfg, B, S, hw, devin["cond"], devin["uncond"], devin["noise"],
+                                                devin["step_noise"], sampler, cfg_scale, max_steps=4)
+                from b200forge import sampling as bs
+                sig4 = bs.make_sigmas(pipe.pred, sampler, S)[:5]
+                lat4 = pipe.sample(devin["cond"], devin["uncond"], devin["noise"], steps=4, sampler=sampler, cfg_scale=cfg_scale,
+                                   sigmas=sig4, step_noise=devin["step_noise"] if uses_noise else None)
+                parity["first_4_steps_vs_reference_fp16_loop"] = {
+                    "psnr_db": psnr(lat4, lat_ref4),
+                    "rel_rms": float((lat4 - lat_ref4).pow(2).mean().sqrt() / lat_ref4.pow(2).mean().sqrt())}
+            except Exception as ex:  # context numbers only
+                gpu_ref = {"failed": f"{type(ex).__name__}: {ex}"}
         if not args.no_cpu_baseline and not sd15:
             threads = usable_cores()
             fwd = cpu_baseline_sample(hw, threads)
@@ -537,25 +724,37 @@ def main():
 
     if rank == 0:
         flops_per_image = 2 * S * unet_gflop * 1e9 + vae_gflop * 1e9
+        samp_name = {"euler_a": "Euler-a", "dpmpp_2m": "DPM++ 2M (Karras)"}[sampler]
+        metric = METRIC if (not sd15 and sampler == "euler_a") else \
+            f"images_per_sec_{'sd15' if sd15 else 'sdxl'}_{args.size}_{sampler}_{S}steps_batch{B}"
+        e2e_name = {"plugin": "plug points P3 (model_function_wrapper) + P4 (k_diffusion sample_*) + P5 (VAE decode wrapper), CFG combine "
+                              "in the caller's torch code as in Forge",
+                    "pipeline": "Txt2ImgPipeline.generate (one-launch CFG + sampler step)"}
         line = {
-            "metric": (f"images_per_sec_sd15_{args.size}_euler_a_{S}steps_batch{B}" if sd15 else METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 (UNet) / bf16 (VAE), fp32 accumulate and sampler state", "data": "synthetic",
-            "config": {"workload": f"{wl_name} {args.size}x{args.size} txt2img, Euler-a {S} steps, CFG 7, batch {B}/GPU "
+            "config": {"workload": f"{wl_name} {args.size}x{args.size} txt2img, {samp_name} {S} steps, CFG 7, batch {B}/GPU "
                                    f"(UNet batch {2 * B}), VAE decode included; 1 bench step = 1 batch of {B} images/GPU",
-                       "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of images only)",
+                       "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of uint8 images only)",
                        "l2": "working set (5.1 GB weights + activations) >> 126 MB L2; no explicit flush",
-                       "roofline_pass": "separate instrumented eager pass after the timed region (graph replays cannot be bracketed)"},
+                       "roofline_pass": "separate instrumented eager pass after the timed region (graph replays cannot be bracketed)",
+                       "e2e_path": args.path + ": " + e2e_name[args.path]},
             "unet_ms_per_step": unet_ms,
             "unet_roofline_ms_per_step": 2 * B * unet_gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
             "flop_roofline_frac_whole_job": value / world * flops_per_image / (peaks["bf16_tflops_sustained"] * 1e12),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "path": args.path,
+                    "gpu_launches": launches_e2e},
+            "e2e_other_path": {"value": other_value, "unit": UNIT, "path": "pipeline" if args.path == "plugin" else "plugin"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": roof,
             "kernel_families": fam,
+            "parity": parity,
             "cpu_baseline": cpu_base,
-            "gpu_reference_unet_ms_per_step": gpu_ref_ms,
+            "gpu_reference": gpu_ref,
+            "gpu_reference_unet_ms_per_step": None if not isinstance(gpu_ref, dict) else gpu_ref.get("unet_ms_per_step"),
+            "attention_vs_sdpa": attn_pair,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

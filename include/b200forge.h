@@ -263,6 +263,10 @@ int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, fl
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
 
+/* fp32 images in [0, 1] -> uint8, the conversion modules/processing.py:1039-1040 does on the host after the D2H copy
+ * (255 * x, astype(uint8): truncation); doing it on the device quarters the bytes that leave the GPU.  n % 4 == 0. */
+int b200_images_to_u8(const float* x, unsigned char* out, size_t n, b200_stream_t s);
+
 /* ControlNet residual: h NHWC [N, H, W, C] (dtype) += ctrl NCHW [N, C, H, W] (dtype, or fp32 when ctrl_is_f32)
  * (backend/nn/unet.py:44-52 apply_control on the input / middle / output-skip activations).  C multiple of 8.
  * Added after the round's GPU budget was spent: exercised so far only through the CPU emulation of the engine. */

@@ -475,6 +475,19 @@ __global__ void vae_post_kernel(const void* __restrict__ x, float* __restrict__ 
   }
 }
 
+// fp32 images in [0, 1] -> uint8 exactly as modules/processing.py:1039-1040 does on the host (255 * x, astype(uint8) = truncation)
+__global__ void images_to_u8_kernel(const float4* __restrict__ x, uchar4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    uchar4 o;
+    o.x = (unsigned char)(255.f * v.x);
+    o.y = (unsigned char)(255.f * v.y);
+    o.z = (unsigned char)(255.f * v.z);
+    o.w = (unsigned char)(255.f * v.w);
+    out[i] = o;
+  }
+}
+
 // VAE encode entry: pixels NHWC fp32 [pixels, 3] in [0, 1] -> [pixels, 8] in dtype, channels 0-2 = 2x - 1, 3-7 = 0
 // (backend/patcher/vae.py:177 `2. * pixel_samples - 1.` then the cast to the VAE dtype)
 template <bool BF16>
@@ -748,6 +761,15 @@ extern "C" int b200_vae_postprocess(const void* x, float* out, size_t pixels, in
   B200_CHECK_ARG(x && out && pixels > 0 && ldx >= 3, "vae_postprocess: bad arguments");
   DISPATCH_DTYPE(dtype, vae_post_kernel<BF><<<grid_for(pixels * 3, 256), 256, 0, (cudaStream_t)s>>>(x, out, pixels, ldx));
   B200_CHECK_LAUNCH("vae_postprocess");
+  return B200_OK;
+}
+
+extern "C" int b200_images_to_u8(const float* x, unsigned char* out, size_t n, b200_stream_t s) {
+  B200_CHECK_ARG(x && out && n > 0 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                 "images_to_u8: element count must be a multiple of 4, pointers 16 / 4-byte aligned");
+  images_to_u8_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)s>>>(reinterpret_cast<const float4*>(x),
+                                                                           reinterpret_cast<uchar4*>(out), n / 4);
+  B200_CHECK_LAUNCH("images_to_u8");
   return B200_OK;
 }
 

@@ -17,12 +17,24 @@ def shard_seeds(base_seed: int, per_rank: int, rank: int, world: int) -> List[in
     return [base_seed + rank * per_rank + i for i in range(per_rank)]
 
 
-def gather_to_rank0(t: torch.Tensor, group=None) -> Optional[torch.Tensor]:
-    """Gather equally-shaped per-rank results; returns the concatenation [world*B, ...] on rank 0, None elsewhere."""
+def gather_to_rank0(t: torch.Tensor, group=None, bufs: Optional[List[torch.Tensor]] = None) -> Optional[torch.Tensor]:
+    """Gather equally-shaped per-rank results; returns the concatenation [world*B, ...] on rank 0, None elsewhere.
+    `bufs` (rank 0): preallocated receive buffers reused across jobs; then the list itself is returned un-concatenated."""
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return t
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-    dist.gather(t, bufs, dst=0, group=group)
-    return torch.cat(bufs, 0) if rank == 0 else None
+    own = bufs is None
+    if rank == 0 and own:
+        bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.gather(t, bufs if rank == 0 else None, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat(bufs, 0) if own else bufs
+
+
+def gather_images_u8(img: torch.Tensor, group=None, bufs: Optional[List[torch.Tensor]] = None):
+    """The result gather of the multi-GPU path: fp32 images in [0, 1] are converted to uint8 on the device (the conversion
+    the reference does on the host, modules/processing.py:1039-1040) and gathered to rank 0 — a quarter of the fp32 bytes."""
+    from . import ops
+    return gather_to_rank0(ops.images_to_u8(img), group, bufs)

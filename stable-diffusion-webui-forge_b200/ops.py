@@ -652,6 +652,16 @@ def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def images_to_u8(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 images in [0, 1] (any shape, contiguous) -> uint8 with the host conversion of modules/processing.py:1039-1040."""
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.numel() % 4 == 0
+    if out is None:
+        out = torch.empty(img.shape, dtype=torch.uint8, device=img.device)
+    _l.check(_l.load().b200_images_to_u8(img.data_ptr(), out.data_ptr(), img.numel(), _stream()))
+    _count()
+    return out
+
+
 def add_nchw_(h: torch.Tensor, ctrl: torch.Tensor) -> torch.Tensor:
     """h NHWC [N,H,W,C] += ctrl NCHW [N,C,H,W] (same dtype as h, or fp32), in place."""
     assert h.dim() == 4 and h.is_contiguous() and ctrl.is_contiguous()

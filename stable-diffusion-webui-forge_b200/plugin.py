@@ -156,6 +156,50 @@ class _WeightTracker:
         return not self.online
 
 
+class _GraphedApplyModel:
+    """KModel.apply_model for one (batch, latent size, context length) as ONE CUDA graph with static buffers: entry scaling +
+    UNet forward + eps -> denoised (backend/modules/k_model.py:25-46).  The eager forward is ~1000 ctypes launches per call;
+    replaying the captured graph is what makes the plug-in path as fast as the standalone pipeline.  The engine's packed
+    weights are refreshed in place on a LoRA change (`UNetEngine.repack`), so a captured graph stays valid."""
+
+    def __init__(self, engine: UNetEngine, n: int, hh: int, ww: int, n_ctx: int, prediction: int):
+        dev, dt, cfg = engine.device, engine.dtype, engine.cfg
+        self.engine, self.prediction = engine, prediction
+        self.x = torch.zeros((n, cfg["in_channels"], hh, ww), dtype=torch.float32, device=dev)
+        self.sigma = torch.ones((n,), dtype=torch.float32, device=dev)
+        self.t = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.ctx = torch.zeros((n, n_ctx, cfg["context_dim"]), dtype=dt, device=dev)
+        self.y = torch.zeros((n, cfg["adm_in_channels"]), dtype=dt, device=dev) if engine.has_label else None
+        self.out = torch.empty_like(self.x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: first-call attribute setup, allocator pools
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self.launches = ops.LAUNCHES - n0
+
+    def _eager(self):
+        eps = self.engine.forward_sigma(self.x, self.sigma, self.t, self.ctx, self.y, reps=1)
+        ops.eps_to_denoised(self.x, eps, self.sigma, prediction=self.prediction, out=self.out)
+
+    def __call__(self, x, sigma, t, ctx, y):
+        self.x.copy_(x)
+        self.sigma.copy_(sigma)
+        self.t.copy_(t)
+        self.ctx.copy_(ctx)
+        if self.y is not None:
+            self.y.copy_(y)
+        self.graph.replay()
+        ops.LAUNCHES += self.launches
+        return self.out.clone()  # the static output buffer is overwritten by the next call
+
+
 class UNetWrapper:
     """`model_options['model_function_wrapper']` (reference backend/sampling/sampling_function.py:270-273):
     wrapper(apply_model_fn, {"input": x fp32 [N,4,h,w], "timestep": sigma [N], "c": {...}, "cond_or_uncond": [...]})
@@ -169,6 +213,10 @@ class UNetWrapper:
         self.weights = None if kmodel is None else _WeightTracker(engine, kmodel, kmodel.diffusion_model)
         self.calls_fast = 0
         self.calls_reference = 0
+        # one CUDA graph per call shape (B200_PLUGIN_GRAPH=0: eager launches); calls with control residuals stay eager
+        import os
+        self.use_graph = os.environ.get("B200_PLUGIN_GRAPH", "1") != "0"
+        self._graphs: Dict[tuple, _GraphedApplyModel] = {}
 
     def __call__(self, apply_model_fn: Callable, args: dict):
         x, sigma, c = args["input"], args["timestep"], args["c"]
@@ -187,8 +235,17 @@ class UNetWrapper:
         ctx = c["c_crossattn"].to(eng.dtype).contiguous()                  # k_model.py:36
         y = c.get("y")
         y = None if y is None else y.to(eng.dtype).contiguous()
+        pred = 1 if ptype == "v_prediction" else 0
+        if self.use_graph and x.is_cuda and c.get("control") is None and not torch.cuda.is_current_stream_capturing():
+            key = (tuple(x.shape), ctx.shape[1], pred)
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 4:  # a handful of shapes per job (cond/uncond batched or not, hires pass)
+                    self._graphs.pop(next(iter(self._graphs)))
+                g = self._graphs[key] = _GraphedApplyModel(eng, x.shape[0], x.shape[2], x.shape[3], ctx.shape[1], pred)
+            return g(x, sigma, t, ctx, y)
         eps = eng.forward_sigma(x, sigma, t, ctx, y, reps=1, control=c.get("control"))  # k_model.py:27,34 fused into the entry
-        return ops.eps_to_denoised(x, eps, sigma, prediction=1 if ptype == "v_prediction" else 0)  # k_model.py:45-46
+        return ops.eps_to_denoised(x, eps, sigma, prediction=pred)  # k_model.py:45-46
 
 
 def install_unet_wrapper(unet_patcher, engine: Optional[UNetEngine] = None) -> UNetWrapper:

@@ -32,6 +32,7 @@ class Prediction:
         self.log_sigmas = sig.log().float()
         self.prediction_type = prediction_type
         self.sigma_data = 1.0
+        self._log_sigmas_dev: dict = {}
 
     @property
     def sigma_min(self) -> float:
@@ -42,8 +43,14 @@ class Prediction:
         return float(self.sigmas[-1])
 
     def timestep(self, sigma: torch.Tensor) -> torch.Tensor:
-        """index of the nearest log-sigma (k_prediction.py:148-151); evaluated on the host for the schedule."""
-        dists = sigma.float().log() - self.log_sigmas[:, None]
+        """index of the nearest log-sigma (k_prediction.py:148-151), evaluated on sigma's device like the reference (whose
+        table is a module buffer): the host for the schedule, the GPU when Forge's sampler calls the P3 wrapper per step."""
+        ls = self.log_sigmas
+        if sigma.device != ls.device:
+            ls = self._log_sigmas_dev.get(sigma.device)
+            if ls is None:
+                ls = self._log_sigmas_dev[sigma.device] = self.log_sigmas.to(sigma.device)
+        dists = sigma.float().log() - ls[:, None]
         return dists.abs().argmin(dim=0).view(sigma.shape)
 
     def sigma(self, timestep: torch.Tensor) -> torch.Tensor:
