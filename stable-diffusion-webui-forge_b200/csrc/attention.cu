@@ -71,6 +71,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CU
   const int BKV = p.BKV;
   const int n_kv = p.n_kv;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
@@ -95,6 +96,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -272,7 +274,13 @@ static int launch_attn(const CUtensorMap& mQ, const CUtensorMap& mK, const CUten
     attr_done = true;
   }
   const int grid = p.q_tiles * p.H * p.B;
-  attn_kernel<DH, BF16><<<grid, 192, smem, stream>>>(mQ, mK, mV, p);
+  {
+    cudaError_t e = launch_pdl(attn_kernel<DH, BF16>, dim3(grid), dim3(192), smem, stream, 1, mQ, mK, mV, p);
+    if (e != cudaSuccess) {
+      set_error("attention: launch failed: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
+  }
   B200_CHECK_LAUNCH("attention");
   return B200_OK;
 }

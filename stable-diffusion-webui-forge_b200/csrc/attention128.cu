@@ -83,6 +83,7 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   const int BKV = p.BKV;
   const int n_kv = p.n_kv;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
@@ -109,6 +110,7 @@ attn128_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");  // 4 x (168 - 72) released = 8 x (216 - 168) taken below
@@ -375,7 +377,13 @@ static int launch_attn128(const CUtensorMap& mQ, const CUtensorMap& mK, const CU
     attr_done = true;
   }
   const int grid = p.q_tiles * p.H * p.B;
-  attn128_kernel<BF16><<<grid, 384, smem, stream>>>(mQ, mK, mV, p);
+  {
+    cudaError_t e = launch_pdl(attn128_kernel<BF16>, dim3(grid), dim3(384), smem, stream, 1, mQ, mK, mV, p);
+    if (e != cudaSuccess) {
+      set_error("attention128: launch failed: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
+  }
   B200_CHECK_LAUNCH("attention128");
   return B200_OK;
 }

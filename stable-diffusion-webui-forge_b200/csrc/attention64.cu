@@ -57,17 +57,63 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 #define PROF_MARK(i)
 #endif
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 process two floats of an even/odd register pair per instruction).  The exp
+// phase is bound by the FP32 pipe as much as by the MUFU (clock64 profile: 16 clk per exponential with one scalar FFMA + one
+// scalar FADD per element; a 32-lane FP32 instruction occupies the pipe for 2 clk), so the scale-and-subtract and the row sum
+// run packed: half the FP32-pipe instructions per element.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two 2^x on the FP32 pipe: the packed form of exp2_poly3 (common.cuh)
+__device__ __forceinline__ void exp2_poly3_x2(f32x2_t x, float& ea, float& eb) {
+  float xa, xb;
+  upk2(x, xa, xb);
+  const f32x2_t xc = pk2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
+  const f32x2_t t = add2(xc, pk2(12582912.0f, 12582912.0f));
+  const f32x2_t f = add2(xc, fma2(t, pk2(-1.0f, -1.0f), pk2(12582912.0f, 12582912.0f)));  // x - (t - magic)
+  f32x2_t p = fma2(pk2(0.0551716685f, 0.0551716685f), f, pk2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, f, pk2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, f, pk2(0.9999280572f, 0.9999280572f));
+  float pa, pb, ta, tb;
+  upk2(p, pa, pb);
+  upk2(t, ta, tb);
+  ea = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  eb = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+}
+
 static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
 static constexpr int kRingSlots = 4;
 static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
 #ifndef B200_ATTN_POLY_MASK
 #define B200_ATTN_POLY_MASK 0x10
 #endif
-static constexpr unsigned kPolyMask = B200_ATTN_POLY_MASK;  // elements (i mod 8) whose exp2 runs on the FMA pipe
+static constexpr unsigned kPolyMask = B200_ATTN_POLY_MASK;  // VER 0: elements (i mod 8) whose exp2 runs on the FMA pipe
+#ifndef B200_ATTN_POLY_PAIRS
+#define B200_ATTN_POLY_PAIRS 0x4
+#endif
+static constexpr unsigned kPolyPairs = B200_ATTN_POLY_PAIRS;  // VER 1: element PAIRS (of the 4 per 8 elements) on the FMA pipe
 
-// ELECT: the MMA-issue warp runs converged with one elected lane (descriptors in uniform registers) instead of a
-// lane-0 branch.  The lane-0 build is kept for A/B measurements (B200_ATTN64_ISSUE=lane0).
-template <bool BF16, bool ELECT>
+// VER 0: the round-1 kernel — ONE MMA-issue warp walks [QK t0, QK t1, PV t0, PV t1] in order; scalar FFMA / FADD softmax.
+// VER 1: one MMA-issue warp PER TILE (warps 1 and 3): the two tiles' softmax warpgroups run half a period apart, and a single
+//        in-order issuer made each tile's QK wait for the other tile's S to be consumed (clock64 profile: 440 clk per key
+//        block waiting for S); K/V ring slots are released by both issuers (barrier count 2).  Softmax arithmetic packed
+//        (FFMA2 / FADD2), row max over four independent chains, polynomial exp2 on whole pairs.
+// Both issue from a converged warp with one elected lane (descriptors stay in uniform registers).
+template <bool BF16, int VER>
 __global__ void __launch_bounds__(384, 1)
 attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const Attn64Params p) {
@@ -95,6 +141,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   const int BKV = p.BKV;
   const int n_kv = p.n_kv;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
@@ -102,7 +149,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < kRingSlots; ++i) {
       mbar_init(ring_full(i), 1);
-      mbar_init(ring_empty(i), 1);
+      mbar_init(ring_empty(i), VER == 1 ? 2 : 1);  // VER 1: one release per issuing warp
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(s_full(t), 1);
@@ -121,6 +168,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");  // 4 x (168 - 72) released = 8 x (216 - 168) taken by the softmax warps
@@ -137,7 +185,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_expect_tx(ring_full(slot), kv_bytes);
       tma_load_3d(ring_smem + slot * kTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
     }
-  } else if (ELECT && warp == 1) {
+  } else if (VER == 0 && warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: the warp stays converged and one
     // elected lane issues, so every descriptor below lives in uniform registers (a lane-0 branch costs ~75 clk per
     // tcgen05.mma in register-to-uniform moves; at N = 64 an MMA is only 32 clk of tensor time)
@@ -208,54 +256,64 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       if (elect_one()) umma_commit(ring_empty(vidx % kRingSlots));
       __syncwarp();
     }
-  } else if (!ELECT && warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (VER == 1 && (warp == 1 || warp == 3)) {
+    // ------------------------------------------------------------------ MMA issuer of tile t (warp 1: t = 0, warp 3: t = 1)
+    const int t = warp >> 1;
+    const uint64_t qdesc = make_smem_desc_sw128(q_smem, 0, 1024) + (uint64_t)(t * (kTile >> 4));
+    const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
+    const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kTile, 1024);  // MN-major V
+    const uint64_t pdesc = make_smem_desc_sw128(p_smem, 0, 1024) + (uint64_t)(t * 2 * (kTile >> 4));
+    const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+    const uint32_t s_tmem = tmem_base + (uint32_t)t * 128u;
+    const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
     auto wait_full = [&](int idx) {
       mbar_wait(ring_full(idx % kRingSlots), (uint32_t)(idx / kRingSlots) & 1u);
       tc_fence_after();
     };
-    auto issue_qk = [&](int idx, int t) {  // S_t = Q_t K^T
-      const uint32_t k_smem = ring_smem + (idx % kRingSlots) * kTile;
-      const uint32_t qs = q_smem + t * kTile;
+    auto issue_qk = [&](int idx) {  // S_t = Q_t K^T, then this warp's release of the K slot
+      const uint64_t kd = kdesc0 + (uint64_t)((idx % kRingSlots) * (kTile >> 4));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + (uint32_t)t * 128u, make_smem_desc_sw128(qs + k * 32u, 0, 1024),
-                 make_smem_desc_sw128(k_smem + k * 32u, 0, 1024), p.idesc_qk, k != 0 ? 1u : 0u);
-      umma_commit(s_full(t));
+        for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qdesc + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(s_full(t));
+        umma_commit(ring_empty(idx % kRingSlots));
+      }
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     wait_full(0);
-    issue_qk(0, 0);
-    issue_qk(0, 1);
-    umma_commit(ring_empty(0));
+    issue_qk(0);
     const int ksteps = BKV >> 4;
+#pragma unroll 1
     for (int j = 0; j < n_kv; ++j) {
       const int vidx = 2 * j + 1, kidx = 2 * j + 2;
-      // QK_{j+1} as soon as the softmax threads have pulled S_j into registers (runs under their exps)
+      // QK_{j+1} as soon as this tile's softmax threads have pulled S_j into registers (runs under their exps)
       if (j + 1 < n_kv) {
         wait_full(kidx);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(s_cons(t), (uint32_t)j & 1u);
-          tc_fence_after();
-          issue_qk(kidx, t);
-        }
-        umma_commit(ring_empty(kidx % kRingSlots));
+        mbar_wait(s_cons(t), (uint32_t)j & 1u);
+        tc_fence_after();
+        issue_qk(kidx);
       }
       wait_full(vidx);
-      const uint32_t v_smem = ring_smem + (vidx % kRingSlots) * kTile;
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(p_full(t), (uint32_t)j & 1u);
-        tc_fence_after();
-        const uint32_t ps = p_smem + t * 2 * kTile;
-        const uint32_t o_tmem = tmem_base + 256u + (uint32_t)t * 64u;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(ps + (uint32_t)(kk >> 2) * kTile + (uint32_t)(kk & 3) * 32u, 0, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(v_smem + (uint32_t)kk * 2048u, kTile, 1024);  // MN-major V
-          umma_f16(o_tmem, adesc, bdesc, p.idesc_pv, (j | kk) != 0 ? 1u : 0u);
+      const uint64_t vd = vdesc0 + (uint64_t)((vidx % kRingSlots) * (kTile >> 4));
+      mbar_wait(p_full(t), (uint32_t)j & 1u);
+      tc_fence_after();
+      const uint32_t acc0 = j != 0 ? 1u : 0u;
+      if (elect_one()) {
+        if (ksteps == 8) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16(o_tmem, pdesc + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2), vd + (uint64_t)(kk * (2048 >> 4)),
+                     idesc_pv, kk ? 1u : acc0);
+        } else {
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_f16(o_tmem, pdesc + (uint64_t)((kk >> 2) * (kTile >> 4) + (kk & 3) * 2), vd + (uint64_t)(kk * (2048 >> 4)),
+                     idesc_pv, kk ? 1u : acc0);
         }
         umma_commit(pv_done(t));
+        umma_commit(ring_empty(vidx % kRingSlots));
       }
-      umma_commit(ring_empty(vidx % kRingSlots));
+      __syncwarp();
     }
   }
   } else {
@@ -296,8 +354,21 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       const bool full_blk = nvalid == 128;
       float mx = -INFINITY;
       if (full_blk) {
+        if constexpr (VER == 1) {
+          // four independent chains: one chain of 64 dependent 3-input maxima cost ~375 clk of pure latency per key block
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          for (int i = 0; i < 128; i += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -341,7 +412,39 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       PROF_MARK(5);  // waiting for the turn
       float rs0 = 0.f, rs1 = 0.f;
       const float nm = -m_ref;
-      if (full_blk) {
+      if (VER == 1 && full_blk) {
+        // packed arithmetic: x = s * scale_log2 - m_ref and the row sum handle two elements per FP32-pipe instruction
+        const f32x2_t sl2p = pk2(sl2, sl2), nmp = pk2(nm, nm);
+        f32x2_t acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) {
+          float pe[8];
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) {
+            const f32x2_t x = fma2(pk2(__uint_as_float(v[c + 2 * q2]), __uint_as_float(v[c + 2 * q2 + 1])), sl2p, nmp);
+            if ((kPolyPairs >> q2) & 1) {
+              exp2_poly3_x2(x, pe[2 * q2], pe[2 * q2 + 1]);
+            } else {
+              float xa, xb;
+              upk2(x, xa, xb);
+              pe[2 * q2] = ex2a(xa);
+              pe[2 * q2 + 1] = ex2a(xb);
+            }
+          }
+          acc0 = add2(acc0, pk2(pe[0], pe[1]));
+          acc1 = add2(acc1, pk2(pe[2], pe[3]));
+          acc0 = add2(acc0, pk2(pe[4], pe[5]));
+          acc1 = add2(acc1, pk2(pe[6], pe[7]));
+          const uint32_t addr = p_row + (uint32_t)(c >> 6) * kTile + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+        }
+        float a0, a1, b0, b1;
+        upk2(acc0, a0, a1);
+        upk2(acc1, b0, b1);
+        rs0 = a0 + b0;
+        rs1 = a1 + b1;
+      } else if (full_blk) {
 #pragma unroll
         for (int c = 0; c < 128; c += 8) {
           float pe[8];
@@ -435,13 +538,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   }
 }
 
-template <bool BF16, bool ELECT>
+template <bool BF16, int VER>
 static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64Params& p,
                          cudaStream_t stream) {
   const size_t smem = (size_t)kTile * (2 + kRingSlots + 4) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn64_kernel<BF16, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("attention64: smem attr: %s", cudaGetErrorString(e));
       return B200_ECUDA;
@@ -449,7 +552,13 @@ static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUt
     attr_done = true;
   }
   const int grid = p.q_tiles * p.H * p.B;
-  attn64_kernel<BF16, ELECT><<<grid, 384, smem, stream>>>(mQ, mK, mV, p);
+  {
+    cudaError_t e = launch_pdl(attn64_kernel<BF16, VER>, dim3(grid), dim3(384), smem, stream, 1, mQ, mK, mV, p);
+    if (e != cudaSuccess) {
+      set_error("attention64: launch failed: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
+  }
   B200_CHECK_LAUNCH("attention64");
   return B200_OK;
 }
@@ -486,14 +595,13 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   if (rc) return rc;
   rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
   if (rc) return rc;
-  static int mode = -1;  // B200_ATTN64_ISSUE = elect | lane0 forces one build (A/B measurements)
-  if (mode < 0) {
-    const char* e = getenv("B200_ATTN64_ISSUE");
-    mode = !e ? 0 : (e[0] == 'e' ? 1 : 2);
+  static int ver = -1;  // B200_ATTN64_VER = 0 | 1 forces one build (A/B measurements); default 1
+  if (ver < 0) {
+    const char* e = getenv("B200_ATTN64_VER");
+    ver = (e && e[0] == '0') ? 0 : 1;
   }
-  const bool elect = mode != 2;  // measured: 611 vs 601 TF/s at L = 4096, 498 vs 484 at L = 1024
-  if (elect) return bf ? launch_attn64<true, true>(mQ, mK, mV, p, st) : launch_attn64<false, true>(mQ, mK, mV, p, st);
-  return bf ? launch_attn64<true, false>(mQ, mK, mV, p, st) : launch_attn64<false, false>(mQ, mK, mV, p, st);
+  if (ver == 1) return bf ? launch_attn64<true, 1>(mQ, mK, mV, p, st) : launch_attn64<false, 1>(mQ, mK, mV, p, st);
+  return bf ? launch_attn64<true, 0>(mQ, mK, mV, p, st) : launch_attn64<false, 0>(mQ, mK, mV, p, st);
 }
 
 }  // namespace b200

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
                                                        int* __restrict__ tickets, float* __restrict__ final_stats,
                                                        float* __restrict__ part, int HW, int C1, int C2, int groups,
                                                        int pix_per_slab, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // piv[C] | tab_s[RY][C] | tab_q[RY][C]
   __shared__ int is_last;
   const int C = C1 + C2;
@@ -156,6 +158,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
                                                        const float* __restrict__ final_stats, const void* __restrict__ gamma,
                                                        const void* __restrict__ beta, void* __restrict__ y, int HW,
                                                        int C1, int C2, int groups, int silu, int pix_per_slab) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // [C] scale, [C] shift
   const int C = C1 + C2;
   const int CV = C >> 3;
@@ -266,6 +270,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 
 // ------------------------------------------------------------------------------------------ layout helpers
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)N * (2 * H) * (2 * W) * CV;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -281,6 +287,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 // vector path: C % 8 == 0.  out row = (n, ho, wo); column = tap*C + c; columns [9C, ldo) zero.
 __global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int H, int W, int CV,
                                      int stride, int pad_lo, int Ho, int Wo, int ldoV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)N * Ho * Wo * ldoV;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int kv = (int)(i % ldoV);
@@ -325,6 +333,8 @@ __global__ void im2col3x3_scalar_kernel(const uint16_t* __restrict__ x, uint16_t
 template <bool BF16>
 __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, int N, int C, int H, int W,
                                     int ldy, float scale, int in_is_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)N * H * W * ldy;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % ldy);
@@ -346,6 +356,8 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, void* __restrict
 template <bool BF16>
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, void* __restrict__ y, int N, int C, int H, int W,
                                     int ldx, int out_is_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)N * C * H * W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
@@ -362,6 +374,8 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, void* __restrict
 
 template <bool BF16>
 __global__ void silu_kernel(const void* __restrict__ x, void* __restrict__ y, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     st1<BF16>(y, i, silu_f(ld1<BF16>(x, i)));
 }
@@ -370,6 +384,8 @@ __global__ void silu_kernel(const void* __restrict__ x, void* __restrict__ y, si
 template <bool BF16>
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, void* __restrict__ out, int B, int dim,
                                           float neg_log_period) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int total = B * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -386,6 +402,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, void* __r
 template <bool BF16>
 __global__ void unet_input_im2col_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                          void* __restrict__ cols, int B, int C, int H, int W, int ldo, int reps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t per_rep = (size_t)B * H * W * ldo;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_rep; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % ldo);
@@ -412,6 +430,8 @@ __global__ void unet_input_im2col_kernel(const float* __restrict__ x, const floa
 template <bool BF16>
 __global__ void softmax_rows_kernel(void* __restrict__ x, int rows, int cols, int ld, float scale_log2, int valid,
                                     int block_rows, int block_cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one CTA per row; cols up to 64K.  The row attends to the column window [lo, hi): the prefix [0, valid) when
   // block_rows == 0, else the diagonal block of its row group — (row / block_rows) * block_cols + [0, valid) — which
   // turns one big GEMM over a whole batch into per-sample attention (everything outside the window is written as 0).
@@ -618,7 +638,7 @@ extern "C" int b200_groupnorm_stats(const void* x1, const void* x2, void* ws, co
   dim3 grid(slabs, d->N);
   DISPATCH_DTYPE(d->dtype, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(gn_stats_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    gn_stats_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, tickets, fin, part, d->HW, d->C1, d->C2, d->groups, pps,
+    launch_pdl(gn_stats_kernel<BF>, dim3(grid), dim3(256), smem, (cudaStream_t)s, 1, x1, x2, tickets, fin, part, d->HW, d->C1, d->C2, d->groups, pps,
                                                                d->eps);
   });
   B200_CHECK_LAUNCH("groupnorm_stats");
@@ -637,7 +657,7 @@ extern "C" int b200_groupnorm_apply(const void* x1, const void* x2, const void* 
   dim3 grid(slabs, d->N);
   DISPATCH_DTYPE(d->dtype, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(gn_apply_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    gn_apply_kernel<BF><<<grid, 256, smem, (cudaStream_t)s>>>(x1, x2, fin, gamma, beta, y, d->HW, d->C1, d->C2,
+    launch_pdl(gn_apply_kernel<BF>, dim3(grid), dim3(256), smem, (cudaStream_t)s, 1, x1, x2, fin, gamma, beta, y, d->HW, d->C1, d->C2,
                                                                d->groups, d->silu, pps);
   });
   B200_CHECK_LAUNCH("groupnorm_apply");
@@ -664,7 +684,7 @@ extern "C" int b200_upsample2x(const void* x, void* y, int N, int H, int W, int 
   (void)dtype;
   B200_CHECK_ARG(x && y && C % 8 == 0 && N > 0 && H > 0 && W > 0, "upsample2x: bad arguments");
   const size_t total = (size_t)N * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)s, 1, (const uint4*)x, (uint4*)y, N, H, W, C / 8);
   B200_CHECK_LAUNCH("upsample2x");
   return B200_OK;
 }
@@ -676,7 +696,7 @@ extern "C" int b200_im2col3x3(const void* x, void* out, int N, int H, int W, int
                  "im2col3x3: bad arguments");
   if (C % 8 == 0) {
     const size_t total = (size_t)N * Ho * Wo * (ldo / 8);
-    im2col3x3_vec_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)out, N, H, W,
+    launch_pdl(im2col3x3_vec_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)s, 1, (const uint4*)x, (uint4*)out, N, H, W,
                                                                              C / 8, stride, pad_lo, Ho, Wo, ldo / 8);
   } else {
     const size_t total = (size_t)N * Ho * Wo * ldo;
@@ -691,7 +711,7 @@ extern "C" int b200_nchw_to_nhwc(const void* x, void* y, int N, int C, int H, in
                                  int in_is_f32, int dtype, b200_stream_t s) {
   B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && ldy >= C, "nchw_to_nhwc: bad arguments");
   const size_t total = (size_t)N * ldy * H * W;
-  DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W, ldy,
+  DISPATCH_DTYPE(dtype, launch_pdl(nchw_to_nhwc_kernel<BF>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)s, 1, x, y, N, C, H, W, ldy,
                                                                                                   scale, in_is_f32));
   B200_CHECK_LAUNCH("nchw_to_nhwc");
   return B200_OK;
@@ -701,7 +721,7 @@ extern "C" int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, in
                                  int dtype, b200_stream_t s) {
   B200_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && ldx >= C, "nhwc_to_nchw: bad arguments");
   const size_t total = (size_t)N * C * H * W;
-  DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, N, C, H, W, ldx,
+  DISPATCH_DTYPE(dtype, launch_pdl(nhwc_to_nchw_kernel<BF>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)s, 1, x, y, N, C, H, W, ldx,
                                                                                                   out_is_f32));
   B200_CHECK_LAUNCH("nhwc_to_nchw");
   return B200_OK;
@@ -709,7 +729,7 @@ extern "C" int b200_nhwc_to_nchw(const void* x, void* y, int N, int C, int H, in
 
 extern "C" int b200_silu(const void* x, void* y, size_t n, int dtype, b200_stream_t s) {
   B200_CHECK_ARG(x && y && n > 0, "silu: bad arguments");
-  DISPATCH_DTYPE(dtype, silu_kernel<BF><<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(x, y, n));
+  DISPATCH_DTYPE(dtype, launch_pdl(silu_kernel<BF>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)s, 1, x, y, n));
   B200_CHECK_LAUNCH("silu");
   return B200_OK;
 }
@@ -718,7 +738,7 @@ extern "C" int b200_softmax_rows(void* x, int rows, int cols, int valid_cols, in
                                  b200_stream_t s) {
   B200_CHECK_ARG(x && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && valid_cols > 0 && valid_cols <= cols,
                  "softmax_rows: bad arguments");
-  DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(x, rows, cols, ld,
+  DISPATCH_DTYPE(dtype, launch_pdl(softmax_rows_kernel<BF>, dim3(rows), dim3(256), 0, (cudaStream_t)s, 1, x, rows, cols, ld,
                                                                                   scale * 1.4426950408889634f, valid_cols, 0, 0));
   B200_CHECK_LAUNCH("softmax_rows");
   return B200_OK;
@@ -730,7 +750,7 @@ extern "C" int b200_softmax_rows_blockdiag(void* x, int rows, int cols, int ld, 
                      valid_in_block > 0 && valid_in_block <= block_cols && rows % block_rows == 0 &&
                      (rows / block_rows - 1) * block_cols + valid_in_block <= cols,
                  "softmax_rows_blockdiag: bad arguments");
-  DISPATCH_DTYPE(dtype, softmax_rows_kernel<BF><<<rows, 256, 0, (cudaStream_t)s>>>(
+  DISPATCH_DTYPE(dtype, launch_pdl(softmax_rows_kernel<BF>, dim3(rows), dim3(256), 0, (cudaStream_t)s, 1, 
                             x, rows, cols, ld, scale * 1.4426950408889634f, valid_in_block, block_rows, block_cols));
   B200_CHECK_LAUNCH("softmax_rows_blockdiag");
   return B200_OK;
@@ -740,7 +760,7 @@ extern "C" int b200_timestep_embedding(const float* t, void* out, int B, int dim
                                        b200_stream_t s) {
   B200_CHECK_ARG(t && out && B > 0 && dim > 1, "timestep_embedding: bad arguments");
   const float neg_log = -logf(max_period);
-  DISPATCH_DTYPE(dtype, timestep_embedding_kernel<BF><<<grid_for((size_t)B * (dim / 2), 128), 128, 0, (cudaStream_t)s>>>(
+  DISPATCH_DTYPE(dtype, launch_pdl(timestep_embedding_kernel<BF>, dim3(grid_for((size_t)B * (dim / 2), 128)), dim3(128), 0, (cudaStream_t)s, 1, 
                             t, out, B, dim, neg_log));
   B200_CHECK_LAUNCH("timestep_embedding");
   return B200_OK;
@@ -751,7 +771,7 @@ extern "C" int b200_unet_input_im2col(const float* x, const float* sigma, void* 
   B200_CHECK_ARG(x && sigma && cols && B > 0 && C > 0 && H > 0 && W > 0 && ldo >= 9 * C && ldo % 8 == 0 && reps > 0,
                  "unet_input_im2col: bad arguments");
   const size_t total = (size_t)B * H * W * ldo;
-  DISPATCH_DTYPE(dtype, unet_input_im2col_kernel<BF><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+  DISPATCH_DTYPE(dtype, launch_pdl(unet_input_im2col_kernel<BF>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)s, 1, 
                             x, sigma, cols, B, C, H, W, ldo, reps));
   B200_CHECK_LAUNCH("unet_input_im2col");
   return B200_OK;

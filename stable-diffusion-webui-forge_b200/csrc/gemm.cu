@@ -161,6 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();  // the next kernel's CTAs may take this SM as soon as this CTA leaves it
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapA2);
@@ -192,6 +193,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // barriers, TMEM and descriptors are ready: from here on the predecessor's output is read
 
   const int tiles_mu = (p.tiles_m + CG - 1) / CG;  // M tiles per unit: a pair covers two adjacent 128-row tiles
   const int total_tiles = tiles_mu * p.tiles_n;
@@ -607,27 +609,13 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
     }
     attr_done = true;
   }
-  if constexpr (CG == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(units * 2);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BF16, CG, FEAT>, mapA, mapA2, mapB, mapB2, p);
+  {
+    cudaError_t e = launch_pdl(gemm_kernel<BF16, CG, FEAT>, dim3(units * CG), dim3(kThreads), smem, stream, CG, mapA, mapA2, mapB,
+                               mapB2, p);
     if (e != cudaSuccess) {
-      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      set_error("gemm: launch failed: %s", cudaGetErrorString(e));
       return B200_ECUDA;
     }
-  } else {
-    gemm_kernel<BF16, CG, FEAT><<<units, kThreads, smem, stream>>>(mapA, mapA2, mapB, mapB2, p);
   }
   B200_CHECK_LAUNCH("gemm");
   return B200_OK;

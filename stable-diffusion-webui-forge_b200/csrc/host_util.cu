@@ -1,5 +1,6 @@
 // b200forge — host-side helpers: error string, device queries, TMA descriptor encoding.
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -22,6 +23,15 @@ int num_sms() {
     sms = v;
   }
   return sms;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 PFN_tmapEncodeTiled tmap_encoder() {

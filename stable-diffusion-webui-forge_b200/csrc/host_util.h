@@ -28,6 +28,41 @@ int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uin
               const uint64_t* strides_bytes, const uint32_t* box,
               CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
+// Programmatic dependent launch (B200_PDL=0 turns it off): a kernel launched through launch_pdl() may start — CTA scheduling,
+// barrier init, TMEM allocation, tensor-map prefetch — while its predecessor on the stream is still draining, and blocks in
+// `griddepcontrol.wait` until the predecessor grid has completed and flushed.  Every kernel launched this way MUST execute
+// pdl_wait() (common.cuh) on every CTA before it touches global memory: the transitive ordering A -> B -> C relies on B not
+// completing before A.  Inside a stream capture the edge becomes a programmatic dependency of the CUDA graph.
+bool pdl_enabled();
+
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                     A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+
 #define B200_CHECK_ARG(cond, ...)  \
   do {                             \
     if (!(cond)) {                 \
