@@ -250,7 +250,8 @@ def gen_samplers(steps: int = 7):
     out = dict(sigmas=sig, x0=x0, noise=noise)
     runs = [("sample_heun", {}), ("sample_dpm_2", {}), ("sample_dpm_2_ancestral", {}), ("sample_dpmpp_2s_ancestral", {}),
             ("sample_lms", {}), ("sample_dpmpp_sde", {}), ("sample_dpmpp_2m_sde", {}),
-            ("sample_dpmpp_2m_sde", {"solver_type": "heun"}), ("sample_dpmpp_3m_sde", {})]
+            ("sample_dpmpp_2m_sde", {"solver_type": "heun"}), ("sample_dpmpp_3m_sde", {}),
+            ("sample_heunpp2", {}), ("sample_ipndm", {}), ("sample_ipndm_v", {}), ("sample_deis", {})]
     for name, extra in runs:
         k = iter(range(noise.shape[0]))
         kw = dict(extra)

@@ -536,3 +536,191 @@ def _sample_dpm_2_ancestral_rf(model, x, sigmas, extra_args, callback, eta, s_no
             noise = _prep(noise_sampler(sigmas[i], sigmas[i + 1]).float())
             _lin(x, noise, c_x=a, c_d=s_noise * renoise)       # x = (alpha_ip1 / alpha_down) x + noise * s_noise * renoise
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Linear multistep samplers over the derivative history d_i = (x_i - denoised_i) / sigma_i (k_diffusion/sampling.py:771-978).
+# Every update is x <- x + sum_k c_k d_{i-k}: the coefficients are host scalars, the history lives in device buffers, one
+# 4-operand launch covers orders up to 3 and a second one adds the fourth history term.
+reference_sample_heunpp2 = None
+reference_sample_ipndm = None
+reference_sample_ipndm_v = None
+reference_sample_deis = None
+
+
+def _to_d(x, denoised, sigma: float):
+    d = x.clone()
+    inv = 1.0 / float(sigma)
+    _lin(d, denoised, c_x=inv, c_d=-inv)  # (x - denoised) / sigma
+    return d
+
+
+def _multistep_update(x, hist, cs):
+    """x += sum_k cs[k] * hist[k]  (hist[0] = newest derivative); 1 launch for <= 3 terms, 2 for 4."""
+    n = len(cs)
+    _lin(x, hist[0], c_x=1.0, c_d=cs[0], old=hist[1] if n > 1 else None, c_old=cs[1] if n > 1 else 0.0,
+         noise=hist[2] if n > 2 else None, c_noise=cs[2] if n > 2 else 0.0)
+    if n > 3:
+        _lin(x, hist[3], c_x=1.0, c_d=cs[3])
+
+
+def _multistep(model, x, sigmas, extra_args, callback, max_order, coeffs_fn):
+    """Shared loop of iPNDM / iPNDM-v / DEIS: coeffs_fn(i, order, t) -> [c_cur, c_prev1, ...] multiplying the derivatives."""
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    t = _host_sigmas(sigmas)
+    x = _prep(x).clone()
+    hist = []
+    for i in range(len(t) - 1):
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        hist.insert(0, _to_d(x, denoised, t[i]))
+        del hist[max_order:]
+        order = min(max_order, i + 1)
+        _multistep_update(x, hist, coeffs_fn(i, order, t))
+    return x
+
+
+@torch.no_grad()
+def sample_ipndm(model, x, sigmas, extra_args=None, callback=None, disable=None, max_order=4):
+    """k_diffusion/sampling.py:829-865: Adams-Bashforth weights on a uniform-step assumption."""
+    if not _fusable(x):
+        return _defer(reference_sample_ipndm, "sample_ipndm", model, x, sigmas, extra_args, callback, disable, max_order)
+    ab = {1: [1.0], 2: [3 / 2, -1 / 2], 3: [23 / 12, -16 / 12, 5 / 12], 4: [55 / 24, -59 / 24, 37 / 24, -9 / 24]}
+
+    def coeffs(i, order, t):
+        h = _f32(t[i + 1]) - _f32(t[i])  # the reference forms (t_next - t_cur) in fp32
+        return [float(h) * c for c in ab[order]]
+
+    return _multistep(model, x, sigmas, extra_args, callback, max_order, coeffs)
+
+
+@torch.no_grad()
+def sample_ipndm_v(model, x, sigmas, extra_args=None, callback=None, disable=None, max_order=4):
+    """k_diffusion/sampling.py:869-926: the variable-step Adams-Bashforth weights."""
+    if not _fusable(x):
+        return _defer(reference_sample_ipndm_v, "sample_ipndm_v", model, x, sigmas, extra_args, callback, disable, max_order)
+
+    def coeffs(i, order, t):
+        f = torch.float32
+        tt = [torch.tensor(v, dtype=f) for v in t]
+        h_n = tt[i + 1] - tt[i]
+        if order == 1:
+            return [float(h_n)]
+        h_n_1 = tt[i] - tt[i - 1]
+        if order == 2:
+            c1 = (2 + (h_n / h_n_1)) / 2
+            c2 = -(h_n / h_n_1) / 2
+            cs = [c1, c2]
+        elif order == 3:
+            h_n_2 = tt[i - 1] - tt[i - 2]
+            temp = (1 - h_n / (3 * (h_n + h_n_1)) * (h_n * (h_n + h_n_1)) / (h_n_1 * (h_n_1 + h_n_2))) / 2
+            cs = [(2 + (h_n / h_n_1)) / 2 + temp, -(h_n / h_n_1) / 2 - (1 + h_n_1 / h_n_2) * temp, temp * h_n_1 / h_n_2]
+        else:
+            h_n_2 = tt[i - 1] - tt[i - 2]
+            h_n_3 = tt[i - 2] - tt[i - 3]
+            temp1 = (1 - h_n / (3 * (h_n + h_n_1)) * (h_n * (h_n + h_n_1)) / (h_n_1 * (h_n_1 + h_n_2))) / 2
+            temp2 = ((1 - h_n / (3 * (h_n + h_n_1))) / 2 + (1 - h_n / (2 * (h_n + h_n_1))) * h_n / (6 * (h_n + h_n_1 + h_n_2))) \
+                * (h_n * (h_n + h_n_1) * (h_n + h_n_1 + h_n_2)) / (h_n_1 * (h_n_1 + h_n_2) * (h_n_1 + h_n_2 + h_n_3))
+            r12 = h_n_1 * (h_n_1 + h_n_2) / (h_n_2 * (h_n_2 + h_n_3))
+            cs = [(2 + (h_n / h_n_1)) / 2 + temp1 + temp2,
+                  -(h_n / h_n_1) / 2 - (1 + h_n_1 / h_n_2) * temp1 - (1 + (h_n_1 / h_n_2) + r12) * temp2,
+                  temp1 * h_n_1 / h_n_2 + ((h_n_1 / h_n_2) + r12 * (1 + h_n_2 / h_n_3)) * temp2,
+                  -temp2 * r12 * h_n_1 / h_n_2]
+        return [float(h_n * c) for c in cs]
+
+    return _multistep(model, x, sigmas, extra_args, callback, max_order, coeffs)
+
+
+def deis_coeff_list(t_steps: torch.Tensor, max_order: int, N: int = 10000):
+    """k_diffusion/deis.py:56-83 ('tab' mode): per step, the integrals of (Lagrange basis) x (-1/2 dlog(alpha)/dtau /
+    sqrt(alpha (1 - alpha))) over [t_cur, t_next] in the VP time that edm2t maps the sigmas to (:13-20).  dlog(alpha)/dtau
+    is written out (-(tau (beta_1 - beta_0) + beta_0)) instead of being taken by autograd; same N-point rectangle sum."""
+    sig = t_steps.detach().float().cpu()
+    eps_s, smin, smax = 1e-3, 0.002, 80.0
+    beta_d = 2 * (torch.log(torch.tensor(smin) ** 2 + 1) / eps_s - torch.log(torch.tensor(smax) ** 2 + 1)) / (eps_s - 1)
+    beta_min = torch.log(torch.tensor(smax) ** 2 + 1) - 0.5 * beta_d
+    ts = ((beta_min ** 2 + 2 * beta_d * (sig ** 2 + 1).log()).sqrt() - beta_min) / beta_d
+    beta_0, beta_1 = beta_min, beta_d + beta_min
+    C = []
+    for i in range(len(ts) - 1):
+        order = min(i + 1, max_order)
+        if order == 1:
+            C.append([])
+            continue
+        t_cur, t_next = ts[i], ts[i + 1]
+        taus = torch.linspace(float(t_cur), float(t_next), N)
+        dtau = (t_next - t_cur) / N
+        prev_t = ts[[i - k for k in range(order)]]
+        alpha = torch.exp(-0.5 * taus ** 2 * (beta_1 - beta_0) - taus * beta_0)
+        integrand = -0.5 * (-(taus * (beta_1 - beta_0) + beta_0)) / torch.sqrt(alpha * (1 - alpha))
+        row = []
+        for j in range(order):
+            poly = 1
+            for k in range(order):
+                if k != j:
+                    poly = poly * (taus - prev_t[k]) / (prev_t[j] - prev_t[k])
+            row.append(float(torch.sum(integrand * poly) * dtau))
+        C.append(row)
+    return C
+
+
+@torch.no_grad()
+def sample_deis(model, x, sigmas, extra_args=None, callback=None, disable=None, max_order=3, deis_mode='tab'):
+    """k_diffusion/sampling.py:933-978."""
+    if deis_mode != 'tab' or not _fusable(x):
+        return _defer(reference_sample_deis, "sample_deis", model, x, sigmas, extra_args, callback, disable, max_order, deis_mode)
+    C = deis_coeff_list(sigmas, max_order)
+
+    def coeffs(i, order, t):
+        if t[i + 1] <= 0 or order == 1:
+            return [float(_f32(t[i + 1]) - _f32(t[i]))]
+        return C[i]
+
+    return _multistep(model, x, sigmas, extra_args, callback, max_order, coeffs)
+
+
+@torch.no_grad()
+def sample_heunpp2(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0.,
+                   s_tmax=float('inf'), s_noise=1.):
+    """k_diffusion/sampling.py:771-824 with s_churn = 0: Euler on the last step, weighted Heun on the one before, else a
+    three-evaluation step whose derivative is w1 d + w2 d_2 + w3 d_3 with w_k = sigma_k / (3 sigma_0)."""
+    if s_churn > 0 or not _fusable(x):
+        return _defer(reference_sample_heunpp2, "sample_heunpp2", model, x, sigmas, extra_args, callback, disable, s_churn, s_tmin, s_tmax, s_noise)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = [_f32(v) for v in _host_sigmas(sigmas)]
+    s_end = sig[-1]
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        _randn_like(x)  # the reference draws eps every step (unused when gamma == 0): keep the RNG stream aligned
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        dt = sig[i + 1] - sig[i]
+        if sig[i + 1] == s_end:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(sig[i]), dt=float(dt))
+            continue
+        d = _to_d(x, denoised, float(sig[i]))
+        x2 = x.clone()
+        _lin(x2, d, c_x=1.0, c_d=float(dt))
+        den2 = _prep(model(x2, sigmas[i + 1] * s_in, **extra_args).float())
+        d2 = _to_d(x2, den2, float(sig[i + 1]))
+        if sig[i + 2] == s_end:
+            w = 2 * sig[0]
+            w2 = sig[i + 1] / w
+            w1 = 1 - w2
+            _lin(x, d, c_x=1.0, c_d=float(w1 * dt), old=d2, c_old=float(w2 * dt))
+        else:
+            dt2 = sig[i + 2] - sig[i + 1]
+            x3 = x2  # x_3 = x_2 + d_2 dt_2 (x_2 is not needed afterwards)
+            _lin(x3, d2, c_x=1.0, c_d=float(dt2))
+            den3 = _prep(model(x3, sigmas[i + 2] * s_in, **extra_args).float())
+            d3 = _to_d(x3, den3, float(sig[i + 2]))
+            w = 3 * sig[0]
+            w2 = sig[i + 1] / w
+            w3 = sig[i + 2] / w
+            w1 = 1 - w2 - w3
+            _lin(x, d, c_x=1.0, c_d=float(w1 * dt), old=d2, c_old=float(w2 * dt), noise=d3, c_noise=float(w3 * dt))
+    return x

@@ -319,7 +319,7 @@ def install_flux_wrapper(unet_patcher, engine=None) -> FluxWrapper:
 # ------------------------------------------------------------------------------------------------- P4 samplers
 _SAMPLER_NAMES = ("sample_euler", "sample_euler_ancestral", "sample_dpmpp_2m", "sample_heun", "sample_dpm_2",
                   "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral", "sample_lms", "sample_dpmpp_sde",
-                  "sample_dpmpp_2m_sde", "sample_dpmpp_3m_sde")
+                  "sample_dpmpp_2m_sde", "sample_dpmpp_3m_sde", "sample_heunpp2", "sample_ipndm", "sample_ipndm_v", "sample_deis")
 
 
 def install_samplers(modules: Optional[dict] = None) -> None:

@@ -118,9 +118,10 @@ def test_chroma_engine_vs_reference_golden():
 
 
 # ------------------------------------------------------------------------------------------------ f2: LMS / SDE plans
-@pytest.mark.parametrize("key", ["sample_lms", "sample_dpmpp_sde", "sample_dpmpp_2m_sde", "sample_dpmpp_2m_sde_heun", "sample_dpmpp_3m_sde"])
+@pytest.mark.parametrize("key", ["sample_lms", "sample_dpmpp_sde", "sample_dpmpp_2m_sde", "sample_dpmpp_2m_sde_heun", "sample_dpmpp_3m_sde",
+                                 "sample_heunpp2", "sample_ipndm", "sample_ipndm_v", "sample_deis"])
 def test_p4_lms_and_sde_samplers_vs_reference_golden(key):
-    """Host plans of LMS (order 4) and the three DPM++ SDE variants driving the update kernel on the device, against the
+    """Host plans of LMS (order 4), the three DPM++ SDE variants, Heun++ and the iPNDM / iPNDM-v / DEIS multistep samplers driving the update kernel on the device, against the
     reference's own k-diffusion loops around the same toy denoiser and noise stream (tests/golden/samplers_toy.pt)."""
     from b200forge import k_samplers
     g = _gold("samplers_toy.pt")

@@ -313,7 +313,7 @@ def _emulated_sampler_update(x, denoised, *, kind, sigma, dt=0.0, noise=None, no
 
 @pytest.mark.parametrize("key", ["sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral",
                                  "sample_lms", "sample_dpmpp_sde", "sample_dpmpp_2m_sde", "sample_dpmpp_2m_sde_heun",
-                                 "sample_dpmpp_3m_sde"])
+                                 "sample_dpmpp_3m_sde", "sample_heunpp2", "sample_ipndm", "sample_ipndm_v", "sample_deis"])
 def test_k_sampler_host_logic_vs_reference_golden(key, monkeypatch):
     """The per-step coefficient plans of the fused samplers (k_samplers.py) drive an emulation of the update kernel on the
     CPU and must land on the reference's k-diffusion result for the same toy denoiser and noise stream
