@@ -261,6 +261,33 @@ def gen_samplers(steps: int = 7):
         with torch.no_grad():
             out[key] = getattr(ks, name)(Model(), x0.clone(), sig, extra_args={}, disable=True, **kw)
         print(key, float(out[key].std()))
+    # Restart (modules/sd_samplers_extra.py imports only torch / tqdm / k_diffusion, so the reference file itself is run):
+    # 24 steps so that the automatic restart list is non-empty (steps >= 20); noise through k_diffusion.sampling.torch
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_sd_samplers_extra", os.path.join(ref_import.REF_ROOT, "modules", "sd_samplers_extra.py"))
+    extra = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(extra)
+    sig24 = ks.get_sigmas_karras(24, float(pred.sigma_min), float(pred.sigma_max))
+    x24 = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(13)) * sig24[0]
+    rn = torch.randn(8, 2, 4, 16, 16, generator=torch.Generator().manual_seed(14))
+    kk = iter(range(8))
+
+    class Hijack:
+        @staticmethod
+        def randn_like(x):
+            return rn[next(kk)]
+
+        def __getattr__(self, item):
+            return getattr(torch, item)
+
+    ks.torch = Hijack()
+    try:
+        with torch.no_grad():
+            out["restart_sampler"] = extra.restart_sampler(Model(), x24.clone(), sig24, extra_args={}, disable=True)
+    finally:
+        ks.torch = torch
+    out["restart_sigmas"], out["restart_x0"], out["restart_noise"] = sig24, x24, rn
+    print("restart_sampler", float(out["restart_sampler"].std()), "noise draws used", next(kk))
     # rectified-flow variants: the reference dispatches on isinstance(model.inner_model.predictor, PredictionFlux)
     from backend.modules.k_prediction import PredictionFlux
     from oracle import sampling as OS2

@@ -724,3 +724,95 @@ def sample_heunpp2(model, x, sigmas, extra_args=None, callback=None, disable=Non
             w1 = 1 - w2 - w3
             _lin(x, d, c_x=1.0, c_d=float(w1 * dt), old=d2, c_old=float(w2 * dt), noise=d3, c_noise=float(w3 * dt))
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Forge's extra samplers (modules/sd_samplers_extra.py:7-74 Restart, modules/sd_samplers_lcm.py:68-82 LCM).  They live in
+# Forge's `modules/` package and are registered by it; the fused versions keep the same call contracts.
+reference_restart_sampler = None
+reference_sample_lcm = None
+
+
+@torch.no_grad()
+def restart_sampler(model, x, sigmas, extra_args=None, callback=None, disable=None, s_noise=1., restart_list=None):
+    """modules/sd_samplers_extra.py:7-74 — Restart sampling (Xu et al. 2023): Heun steps over a Karras schedule with
+    re-noising jumps back to a higher sigma.  The schedule surgery is the reference's own (host scalars); every Heun step is
+    two model evaluations + three launches, the re-noising one launch."""
+    if not _fusable(x):
+        return _defer(reference_restart_sampler, "restart_sampler", model, x, sigmas, extra_args, callback, disable, s_noise, restart_list)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    steps = sigmas.shape[0] - 1
+    sig = sigmas.detach().float().cpu()
+    if restart_list is None:
+        if steps >= 20:
+            restart_steps = 9
+            restart_times = 1
+            if steps >= 36:
+                restart_steps = steps // 4
+                restart_times = 2
+            sig = sampling.get_sigmas_karras(steps - restart_steps * restart_times, sig[-2].item(), sig[0].item())
+            restart_list = {0.1: [restart_steps + 1, restart_times, 2]}
+        else:
+            restart_list = {}
+    restart_list = {int(torch.argmin(abs(sig - key), dim=0)): value for key, value in restart_list.items()}
+    step_list = []
+    for i in range(len(sig) - 1):
+        step_list.append((sig[i], sig[i + 1]))
+        if i + 1 in restart_list:
+            restart_steps, restart_times, restart_max = restart_list[i + 1]
+            min_idx = i + 1
+            max_idx = int(torch.argmin(abs(sig - restart_max), dim=0))
+            if max_idx < min_idx:
+                sigma_restart = sampling.get_sigmas_karras(restart_steps, sig[min_idx].item(), sig[max_idx].item())[:-1]
+                while restart_times > 0:
+                    restart_times -= 1
+                    step_list.extend(zip(sigma_restart[:-1], sigma_restart[1:]))
+    x = _prep(x).clone()
+    dev_sigma = lambda s: s.to(x.device) * s_in  # noqa: E731
+    last_sigma = None
+    step_id = 0
+    for old_sigma, new_sigma in step_list:
+        if last_sigma is None:
+            last_sigma = old_sigma
+        elif last_sigma < old_sigma:
+            noise = _prep(_randn_like(x).float())
+            _lin(x, noise, c_x=1.0, c_d=float(s_noise * (old_sigma ** 2 - last_sigma ** 2) ** 0.5))
+        denoised = _prep(model(x, dev_sigma(old_sigma), **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': step_id, 'sigma': new_sigma, 'sigma_hat': old_sigma, 'denoised': denoised})
+        dt = new_sigma - old_sigma
+        if float(new_sigma) == 0:
+            ops.sampler_update(x, denoised, kind=ops.STEP_EULER, sigma=float(old_sigma), dt=float(dt))
+        else:
+            d = _to_d(x, denoised, float(old_sigma))
+            x2 = x.clone()
+            _lin(x2, d, c_x=1.0, c_d=float(dt))
+            den2 = _prep(model(x2, dev_sigma(new_sigma), **extra_args).float())
+            d2 = _to_d(x2, den2, float(new_sigma))
+            _lin(x, d, c_x=1.0, c_d=float(dt / 2), old=d2, c_old=float(dt / 2))   # x + (d + d_2) / 2 * dt
+        step_id += 1
+        last_sigma = new_sigma
+    return x
+
+
+@torch.no_grad()
+def sample_lcm(model, x, sigmas, extra_args=None, callback=None, disable=None, noise_sampler=None):
+    """modules/sd_samplers_lcm.py:68-82: x <- denoised (+ sigma_next * noise while sigma_next > 0)."""
+    if not _fusable(x):
+        return _defer(reference_sample_lcm, "sample_lcm", model, x, sigmas, extra_args, callback, disable, noise_sampler)
+    extra_args = {} if extra_args is None else extra_args
+    s_in = x.new_ones([x.shape[0]])
+    sig = _host_sigmas(sigmas)
+    x = _prep(x).clone()
+    for i in range(len(sig) - 1):
+        denoised = _prep(model(x, sigmas[i] * s_in, **extra_args).float())
+        if callback is not None:
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        noise = None
+        if sig[i + 1] > 0:
+            noise = noise_sampler(sigmas[i], sigmas[i + 1]) if noise_sampler is not None else _randn_like(x)
+        # x = denoised + sigma_next * noise as one launch: 0 * x + 1 * denoised (+ noise term)
+        ops.sampler_update(x, denoised, kind=ops.STEP_LINEAR, sigma=1.0, c_x=0.0, c_d=1.0, noise=noise,
+                           noise_scale=float(sig[i + 1]) if noise is not None else 0.0)
+    return x

@@ -322,6 +322,25 @@ _SAMPLER_NAMES = ("sample_euler", "sample_euler_ancestral", "sample_dpmpp_2m", "
                   "sample_dpmpp_2m_sde", "sample_dpmpp_3m_sde", "sample_heunpp2", "sample_ipndm", "sample_ipndm_v", "sample_deis")
 
 
+def install_extra_samplers(modules: Optional[dict] = None) -> None:
+    """Forge's own extra samplers are plain functions referenced from sampler tables: Restart
+    (modules/sd_samplers_extra.py:7, table entry modules/sd_samplers_kdiffusion.py:38) and LCM (modules/sd_samplers_lcm.py:68,
+    :100).  Rebinding the module attribute before the tables are built (or patching the table entry) swaps them."""
+    mods = sys.modules if modules is None else modules
+    ex = mods.get("modules.sd_samplers_extra")
+    if ex is not None and hasattr(ex, "restart_sampler"):
+        if "restart" not in _installed:
+            _installed["restart"] = ex.restart_sampler
+        k_samplers.reference_restart_sampler = _installed["restart"]
+        ex.restart_sampler = k_samplers.restart_sampler
+    lcm = mods.get("modules.sd_samplers_lcm")
+    if lcm is not None and hasattr(lcm, "sample_lcm"):
+        if "lcm" not in _installed:
+            _installed["lcm"] = lcm.sample_lcm
+        k_samplers.reference_sample_lcm = _installed["lcm"]
+        lcm.sample_lcm = k_samplers.sample_lcm
+
+
 def install_samplers(modules: Optional[dict] = None) -> None:
     """Replace the k_diffusion.sampling functions that have a fused version (Euler, Euler a, DPM++ 2M, Heun, DPM2, DPM2 a,
     DPM++ 2S a): the sampler table (modules/sd_samplers_kdiffusion.py:14-41) resolves them by getattr at sampler
@@ -394,5 +413,6 @@ def install(modules: Optional[dict] = None, attention: bool = True, samplers: bo
         install_attention(modules)
     if samplers:
         install_samplers(modules)
+        install_extra_samplers(modules)
     if operations:
         install_operations(modules)

@@ -372,3 +372,45 @@ def test_rectified_flow_ancestral_samplers_vs_reference_golden(name, monkeypatch
                                     noise_sampler=lambda s, sn: g["noise"][next(k)])
     err = (out - g[name + "_rf"]).abs().max().item()
     assert err <= 2e-5 * max(1.0, g[name + "_rf"].abs().max().item()), (name, err)
+
+
+def test_restart_and_lcm_sampler_host_logic(monkeypatch):
+    """Restart (modules/sd_samplers_extra.py:7-74) against the reference file's own output around the toy denoiser, with the
+    re-noising draws replayed through k-diffusion's torch handle; LCM (modules/sd_samplers_lcm.py:68-82 — that module needs
+    Forge's `modules.shared`, so its ten-line loop is pinned against its restatement here, not against an import)."""
+    import os
+    import sys
+    import types
+
+    import torch
+
+    from b200forge import k_samplers
+    from oracle import sampling as OS
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers_toy.pt"), weights_only=False)
+    monkeypatch.setattr(k_samplers.ops, "sampler_update", _emulated_sampler_update)
+    monkeypatch.setattr(k_samplers, "_fusable", lambda x: True)
+    draws = iter(range(g["restart_noise"].shape[0]))
+    fake_t = types.SimpleNamespace(randn_like=lambda x: g["restart_noise"][next(draws)])
+    monkeypatch.setitem(sys.modules, "k_diffusion", types.ModuleType("k_diffusion"))
+    ks = types.ModuleType("k_diffusion.sampling")
+    ks.torch = fake_t
+    monkeypatch.setitem(sys.modules, "k_diffusion.sampling", ks)
+    seen = []
+    out = k_samplers.restart_sampler(lambda x, sigma, **kw: OS.toy_denoiser(x, sigma), g["restart_x0"].clone(), g["restart_sigmas"],
+                                     extra_args={}, callback=lambda d: seen.append(d["i"]), disable=True)
+    err = (out - g["restart_sampler"]).abs().max().item()
+    assert err <= 3e-5 * max(1.0, g["restart_sampler"].abs().max().item()), err
+    assert seen == list(range(len(seen))) and len(seen) > 15 and next(draws) == 1  # one restart jump -> one noise draw
+    # LCM
+    sig = g["sigmas"]
+    noise = g["noise"]
+    k = iter(range(noise.shape[0]))
+    out = k_samplers.sample_lcm(lambda x, sigma, **kw: OS.toy_denoiser(x, sigma), g["x0"].clone(), sig, extra_args={}, disable=True,
+                                noise_sampler=lambda s, sn: noise[next(k)])
+    x = g["x0"].clone()
+    k = iter(range(noise.shape[0]))
+    for i in range(len(sig) - 1):
+        x = OS.toy_denoiser(x, sig[i] * x.new_ones([x.shape[0]]))
+        if sig[i + 1] > 0:
+            x = x + sig[i + 1] * noise[next(k)]
+    assert (out - x).abs().max().item() <= 1e-5
