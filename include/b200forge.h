@@ -263,6 +263,15 @@ int b200_eps_to_denoised(const float* x, const void* eps, const float* sigma, fl
  * (backend/patcher/vae.py:142,147).  ldx = channel stride of x (the padded conv_out width). */
 int b200_vae_postprocess(const void* x, float* out, size_t pixels, int ldx, int dtype, b200_stream_t s);
 
+/* Tiled VAE decode (backend/patcher/vae.py:11-49 tiled_scale_multidim, :104-115 decode_tiled_): a decoded tile NHWC
+ * [th, tw, ld >= 3] (dtype) is accumulated into acc [H, W, 4] fp32 = (sum of (tile + bias) * mask for r, g, b; sum of mask) at
+ * (y0, x0), mask = linear ramps over the first / last `feather` rows and columns.  _resolve writes (or adds, `accumulate`)
+ * acc.rgb / acc.mask into out [H, W, 3] fp32 and, on the last pass (`finalize`), scales and clamps to [0, 1]. */
+int b200_tile_blend(const void* tile, float* acc, int H, int W, int y0, int x0, int th, int tw, int ld, float bias,
+                    int feather, int dtype, b200_stream_t s);
+int b200_tile_resolve(const float* acc, float* out, size_t pixels, int accumulate, float final_scale, int finalize,
+                      b200_stream_t s);
+
 /* fp32 images in [0, 1] -> uint8, the conversion modules/processing.py:1039-1040 does on the host after the D2H copy
  * (255 * x, astype(uint8): truncation); doing it on the device quarters the bytes that leave the GPU.  n % 4 == 0. */
 int b200_images_to_u8(const float* x, unsigned char* out, size_t n, b200_stream_t s);

@@ -226,6 +226,33 @@ def gen_vae(name: str = "tiny", hw: int = 16):
     print("vae", name, "out std", out.std().item())
 
 
+def gen_vae_tiled(name: str = "tiny"):
+    """The reference's tiled decode: its own `tiled_scale` (backend/patcher/vae.py:11-57) around its own
+    IntegratedAutoencoderKL.decode, composed as VAE.decode_tiled_ composes them (:104-115; the VAE wrapper class itself needs
+    the memory manager and a loaded model, the three-line composition is restated here)."""
+    from backend.nn.vae import IntegratedAutoencoderKL
+    from backend.patcher.vae import tiled_scale
+    from oracle import vae as OV
+    cfg = CF.VAE_CONFIGS[name]
+    sd = OV.random_state_dict(cfg, seed=3)
+    m = IntegratedAutoencoderKL(**{k: v for k, v in cfg.items()}).eval()
+    m.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn(2, cfg["latent_channels"], 20, 28, generator=g)
+    tile_x = tile_y = 8
+    overlap = 2
+    up = 2 ** (len(cfg["block_out_channels"]) - 1)
+    fn = lambda a: (m.decode(a) + 1.0).float()  # noqa: E731
+    with torch.no_grad():
+        zz = m.process_out(z)
+        out = torch.clamp(((tiled_scale(zz, fn, tile_x // 2, tile_y * 2, overlap, upscale_amount=up) +
+                            tiled_scale(zz, fn, tile_x * 2, tile_y // 2, overlap, upscale_amount=up) +
+                            tiled_scale(zz, fn, tile_x, tile_y, overlap, upscale_amount=up)) / 3.0) / 2.0, min=0.0, max=1.0)
+    torch.save(dict(config=name, weight_seed=3, weight_checksum=sd_checksum(sd), z=z, tile_x=tile_x, tile_y=tile_y, overlap=overlap,
+                    out=out.movedim(1, -1)), os.path.join(GOLD, f"vae_tiled_{name}.pt"))
+    print("vae tiled", name, "out std", out.std().item(), tuple(out.shape))
+
+
 def gen_samplers(steps: int = 7):
     """The reference's own k-diffusion loops (k_diffusion/sampling.py) on CPU fp32 around oracle.sampling.toy_denoiser,
     with the to_d override of modules/sd_schedulers.py:10-15 and a recorded noise stream."""
@@ -409,7 +436,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_enc", "control", "chroma", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_tiled", "vae_enc", "control", "chroma", "flux"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -422,6 +449,8 @@ if __name__ == "__main__":
         gen_schedules()
     if "vae" in which:
         gen_vae("tiny")
+    if "vae_tiled" in which:
+        gen_vae_tiled("tiny")
     if "samplers" in which:
         gen_samplers()
     if "vae_enc" in which:

@@ -81,6 +81,46 @@ def decode_first_stage(sd: SD, cfg: dict, latent: torch.Tensor) -> torch.Tensor:
     return torch.clamp((x.float() + 1.0) / 2.0, min=0.0, max=1.0).movedim(1, -1)
 
 
+def tiled_scale(samples, function, tile_y, tile_x, overlap, upscale):
+    """backend/patcher/vae.py:11-49 (tiled_scale_multidim, 2-D): per sample, tiles at stride (tile - overlap) clamped to the
+    image, each tile's result multiplied by a mask whose first / last `overlap * upscale` rows and columns ramp linearly, the
+    masked results and the masks accumulated, output = quotient."""
+    out_all = []
+    for b in range(samples.shape[0]):
+        s = samples[b:b + 1]
+        H, W = round(s.shape[2] * upscale), round(s.shape[3] * upscale)
+        out = torch.zeros((1, 3, H, W))
+        div = torch.zeros((1, 3, H, W))
+        for y in range(0, s.shape[2], tile_y - overlap):
+            for x in range(0, s.shape[3], tile_x - overlap):
+                py = max(0, min(s.shape[2] - overlap, y))
+                px = max(0, min(s.shape[3] - overlap, x))
+                ly, lx = min(tile_y, s.shape[2] - py), min(tile_x, s.shape[3] - px)
+                ps = function(s[:, :, py:py + ly, px:px + lx])
+                mask = torch.ones_like(ps)
+                feather = round(overlap * upscale)
+                for t in range(feather):
+                    for d in (2, 3):
+                        mask.narrow(d, t, 1).mul_((1.0 / feather) * (t + 1))
+                        mask.narrow(d, mask.shape[d] - 1 - t, 1).mul_((1.0 / feather) * (t + 1))
+                uy, ux = round(py * upscale), round(px * upscale)
+                out[:, :, uy:uy + ps.shape[2], ux:ux + ps.shape[3]] += ps * mask
+                div[:, :, uy:uy + ps.shape[2], ux:ux + ps.shape[3]] += mask
+        out_all.append(out / div)
+    return torch.cat(out_all)
+
+
+def decode_tiled(sd: SD, cfg: dict, latent: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16) -> torch.Tensor:
+    """VAE.decode_tiled_ (backend/patcher/vae.py:104-115) after process_out: three tilings averaged, tiles of decode + 1,
+    clamp(sum / 3 / 2, 0, 1); returns NHWC [B, H, W, 3] like decode_first_stage."""
+    z = latent / cfg["scaling_factor"] + cfg.get("shift_factor", 0.0)
+    up = 2 ** (len(cfg["block_out_channels"]) - 1)
+    fn = lambda a: (decode(sd, cfg, a) + 1.0).float()  # noqa: E731
+    out = (tiled_scale(z, fn, tile_y * 2, tile_x // 2, overlap, up) + tiled_scale(z, fn, tile_y // 2, tile_x * 2, overlap, up) +
+           tiled_scale(z, fn, tile_y, tile_x, overlap, up))
+    return torch.clamp(out / 3.0 / 2.0, min=0.0, max=1.0).movedim(1, -1)
+
+
 def random_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> SD:
     """Synthetic decoder weights (+ post_quant_conv) with the reference's names; the encoder half is not on
     the txt2img path and is left out."""

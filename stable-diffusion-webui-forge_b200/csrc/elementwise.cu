@@ -495,6 +495,56 @@ __global__ void vae_post_kernel(const void* __restrict__ x, float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------ tiled VAE blending
+// tiled_scale_multidim (backend/patcher/vae.py:11-49): every decoded tile is multiplied by a feather mask — the first and last
+// `feather` rows / columns ramp linearly ((t + 1) / feather) — and accumulated together with the mask; the result is the
+// quotient.  acc is [H, W, 4] fp32 (r, g, b, mask).
+__device__ __forceinline__ float feather_w(int i, int size, int feather, float inv_f) {
+  float w = 1.f;
+  if (i < feather) w *= inv_f * (float)(i + 1);
+  if (size - 1 - i < feather) w *= inv_f * (float)(size - i);
+  return w;
+}
+
+template <bool BF16>
+__global__ void tile_blend_kernel(const void* __restrict__ tile, float4* __restrict__ acc, int W, int y0, int x0, int th,
+                                  int tw, int ld, float bias, int feather) {
+  const float inv_f = feather > 0 ? 1.0f / (float)feather : 0.f;
+  const size_t total = (size_t)th * tw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ty = (int)(i / tw), tx = (int)(i - (size_t)ty * tw);
+    const float m = feather_w(ty, th, feather, inv_f) * feather_w(tx, tw, feather, inv_f);
+    float4 a = acc[(size_t)(y0 + ty) * W + (x0 + tx)];
+    a.x += (ld1<BF16>(tile, i * ld + 0) + bias) * m;
+    a.y += (ld1<BF16>(tile, i * ld + 1) + bias) * m;
+    a.z += (ld1<BF16>(tile, i * ld + 2) + bias) * m;
+    a.w += m;
+    acc[(size_t)(y0 + ty) * W + (x0 + tx)] = a;
+  }
+}
+
+// out[H, W, 3] (+)= acc.rgb / acc.w; the last pass scales and clamps (vae.py:109-114: clamp((A + B + C) / 3 / 2, 0, 1))
+__global__ void tile_resolve_kernel(const float4* __restrict__ acc, float* __restrict__ out, size_t pixels, int accumulate,
+                                    float final_scale, int finalize) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = acc[i];
+    float r = a.x / a.w, g = a.y / a.w, b = a.z / a.w;
+    if (accumulate) {
+      r += out[i * 3 + 0];
+      g += out[i * 3 + 1];
+      b += out[i * 3 + 2];
+    }
+    if (finalize) {
+      r = fminf(fmaxf(r * final_scale, 0.f), 1.f);
+      g = fminf(fmaxf(g * final_scale, 0.f), 1.f);
+      b = fminf(fmaxf(b * final_scale, 0.f), 1.f);
+    }
+    out[i * 3 + 0] = r;
+    out[i * 3 + 1] = g;
+    out[i * 3 + 2] = b;
+  }
+}
+
 // fp32 images in [0, 1] -> uint8 exactly as modules/processing.py:1039-1040 does on the host (255 * x, astype(uint8) = truncation)
 __global__ void images_to_u8_kernel(const float4* __restrict__ x, uchar4* __restrict__ out, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -781,6 +831,26 @@ extern "C" int b200_vae_postprocess(const void* x, float* out, size_t pixels, in
   B200_CHECK_ARG(x && out && pixels > 0 && ldx >= 3, "vae_postprocess: bad arguments");
   DISPATCH_DTYPE(dtype, vae_post_kernel<BF><<<grid_for(pixels * 3, 256), 256, 0, (cudaStream_t)s>>>(x, out, pixels, ldx));
   B200_CHECK_LAUNCH("vae_postprocess");
+  return B200_OK;
+}
+
+extern "C" int b200_tile_blend(const void* tile, float* acc, int H, int W, int y0, int x0, int th, int tw, int ld, float bias,
+                               int feather, int dtype, b200_stream_t s) {
+  B200_CHECK_ARG(tile && acc && th > 0 && tw > 0 && ld >= 3 && y0 >= 0 && x0 >= 0 && y0 + th <= H && x0 + tw <= W && feather >= 0,
+                 "tile_blend: tile [%d,%d]+(%d,%d) outside the %dx%d image", th, tw, y0, x0, H, W);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(acc) & 15) == 0, "tile_blend: acc must be 16-byte aligned");
+  DISPATCH_DTYPE(dtype, tile_blend_kernel<BF><<<grid_for((size_t)th * tw, 256), 256, 0, (cudaStream_t)s>>>(
+                            tile, reinterpret_cast<float4*>(acc), W, y0, x0, th, tw, ld, bias, feather));
+  B200_CHECK_LAUNCH("tile_blend");
+  return B200_OK;
+}
+
+extern "C" int b200_tile_resolve(const float* acc, float* out, size_t pixels, int accumulate, float final_scale, int finalize,
+                                 b200_stream_t s) {
+  B200_CHECK_ARG(acc && out && pixels > 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0, "tile_resolve: bad arguments");
+  tile_resolve_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)s>>>(reinterpret_cast<const float4*>(acc), out, pixels,
+                                                                           accumulate, final_scale, finalize);
+  B200_CHECK_LAUNCH("tile_resolve");
   return B200_OK;
 }
 

@@ -110,6 +110,8 @@ SIGNATURES = {
     "b200_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(StepDesc), _vp]),
     "b200_vae_postprocess": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "b200_images_to_u8": (_i, [_vp, _vp, _sz, _vp]),
+    "b200_tile_blend": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "b200_tile_resolve": (_i, [_vp, _vp, _sz, _i, _f, _i, _vp]),
     "b200_sampler_update": (_i, [_vp, _vp, _vp, _vp, C.POINTER(StepDesc), _vp]),
     "b200_eps_to_denoised": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_add_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

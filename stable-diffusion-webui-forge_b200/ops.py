@@ -652,6 +652,27 @@ def vae_postprocess(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def tile_blend_(acc: torch.Tensor, tile: torch.Tensor, y0: int, x0: int, *, feather: int, bias: float = 0.0) -> torch.Tensor:
+    """acc [H, W, 4] fp32 += feather-masked tile NHWC [1, th, tw, ld] (+ bias) at (y0, x0); channel 3 of acc sums the mask."""
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and acc.dim() == 3 and acc.shape[2] == 4
+    assert tile.is_contiguous() and tile.dim() == 4 and tile.shape[0] == 1
+    _, th, tw, ld = tile.shape
+    _l.check(_l.load().b200_tile_blend(tile.data_ptr(), acc.data_ptr(), acc.shape[0], acc.shape[1], y0, x0, th, tw, ld, bias,
+                                       feather, _dt(tile), _stream()))
+    _count()
+    return acc
+
+
+def tile_resolve_(acc: torch.Tensor, out: torch.Tensor, *, accumulate: bool, finalize: bool, final_scale: float = 1.0) -> torch.Tensor:
+    """out [H, W, 3] fp32 (+)= acc.rgb / acc.mask; `finalize`: out = clamp(out * final_scale, 0, 1)."""
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    assert out.shape == (acc.shape[0], acc.shape[1], 3)
+    _l.check(_l.load().b200_tile_resolve(acc.data_ptr(), out.data_ptr(), acc.shape[0] * acc.shape[1], 1 if accumulate else 0,
+                                         final_scale, 1 if finalize else 0, _stream()))
+    _count()
+    return out
+
+
 def images_to_u8(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 images in [0, 1] (any shape, contiguous) -> uint8 with the host conversion of modules/processing.py:1039-1040."""
     assert img.dtype == torch.float32 and img.is_contiguous() and img.numel() % 4 == 0

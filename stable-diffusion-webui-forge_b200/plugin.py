@@ -369,7 +369,20 @@ class VAEDecodeWrapper:
         # vae_module: the torch VAE Forge may patch (it wraps it in a ModelPatcher too, backend/patcher/vae.py:60-75)
         self.weights = None if vae_module is None else _WeightTracker(vae_engine, vae_module, vae_module)
 
+    def decode_tiled(self, samples_in: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16) -> torch.Tensor:
+        """VAE.decode_tiled (backend/patcher/vae.py:157-160): same contract (processed-out latent in, NHWC images out)."""
+        scaling = self.engine.scaling
+        try:
+            self.engine.scaling = 1.0
+            img = self.engine.decode_tiled(samples_in.to(self.engine.device).float().contiguous(), tile_x, tile_y, overlap)
+        finally:
+            self.engine.scaling = scaling
+        return img if self.output_device is None else img.to(self.output_device)
+
     def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
+        import os
+        if os.environ.get("B200_VAE_ALWAYS_TILED") == "1" and _on_device(samples_in) and samples_in.dim() == 4:
+            return self.decode_tiled(samples_in)  # memory_management.VAE_ALWAYS_TILED (backend/patcher/vae.py:129-130)
         if (not _on_device(samples_in) or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3])
                 or (self.weights is not None and not self.weights.servable())):
             return decode_inner_fn(samples_in)

@@ -141,6 +141,37 @@ class VAEDecoderEngine:
     @torch.no_grad()
     def decode(self, latent: torch.Tensor) -> torch.Tensor:
         """latent fp32 NCHW [B, zc, h, w] (sampler output) -> fp32 NHWC [B, 8h, 8w, 3] in [0, 1]."""
+        return ops.vae_postprocess(self._decode_raw(latent))
+
+    @torch.no_grad()
+    def decode_tiled(self, latent: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16) -> torch.Tensor:
+        """VAE.decode_tiled_ (backend/patcher/vae.py:104-115 over tiled_scale_multidim, :11-49) — the reference's low-memory /
+        always-tiled decode: three passes with tiles (2*tile_y, tile_x/2), (tile_y/2, 2*tile_x), (tile_y, tile_x), each tile
+        decoded on its own (its own GroupNorm statistics, as in the reference), feather-blended over `overlap` latent pixels,
+        the three passes averaged: clamp((A + B + C) / 3 / 2, 0, 1) with tiles of (decode + 1).  Same input / output contract
+        as `decode`.  Every tile runs the fused decoder; the blending is two small kernels."""
+        assert latent.dtype == torch.float32 and latent.dim() == 4
+        n, zc, hh, ww = latent.shape
+        up = 2 ** (self.nres - 1)
+        out = torch.empty((n, hh * up, ww * up, 3), dtype=torch.float32, device=latent.device)
+        acc = torch.empty((hh * up, ww * up, 4), dtype=torch.float32, device=latent.device)
+        passes = ((tile_y * 2, tile_x // 2), (tile_y // 2, tile_x * 2), (tile_y, tile_x))
+        for b in range(n):
+            for pi, (ty, tx) in enumerate(passes):
+                ops.zero_(acc)
+                for y in range(0, hh, ty - overlap):
+                    py = max(0, min(hh - overlap, y))
+                    ly = min(ty, hh - py)
+                    for x in range(0, ww, tx - overlap):
+                        px = max(0, min(ww - overlap, x))
+                        lx = min(tx, ww - px)
+                        raw = self._decode_raw(latent[b:b + 1, :, py:py + ly, px:px + lx].contiguous())
+                        ops.tile_blend_(acc, raw, py * up, px * up, feather=overlap * up, bias=1.0)
+                ops.tile_resolve_(acc, out[b], accumulate=pi > 0, finalize=pi == len(passes) - 1, final_scale=1.0 / 6.0)
+        return out
+
+    def _decode_raw(self, latent: torch.Tensor) -> torch.Tensor:
+        """Decoder output NHWC [B, 8h, 8w, ld] in the VAE dtype, before the (x + 1) / 2 clamp."""
         w = self.w
         assert latent.dtype == torch.float32 and self.shift == 0.0
         latent = latent.contiguous()
@@ -159,8 +190,7 @@ class VAEDecoderEngine:
                 q = f"decoder.up.{lvl}.upsample.conv"
                 h = ops.conv3x3_any(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
         h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
-        h = ops.conv3x3_any(h, w["conv_out.w"], w["conv_out.b"])
-        return ops.vae_postprocess(h)
+        return ops.conv3x3_any(h, w["conv_out.w"], w["conv_out.b"])
 
 
 class VAEEncoderEngine:

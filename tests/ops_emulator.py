@@ -352,6 +352,34 @@ def vae_postprocess(x, out=None):
     return _ret(torch.clamp((x[..., :3].float() + 1.0) / 2.0, 0.0, 1.0), out, torch.float32)
 
 
+def tile_blend_(acc, tile, y0, x0, *, feather, bias=0.0):
+    _, th, tw, _ = tile.shape
+
+    def ramp(size):
+        w = torch.ones(size)
+        for i in range(size):
+            if i < feather:
+                w[i] *= (1.0 / feather) * (i + 1)
+            if size - 1 - i < feather:
+                w[i] *= (1.0 / feather) * (size - i)
+        return w
+
+    m = ramp(th)[:, None] * ramp(tw)[None, :]
+    acc[y0:y0 + th, x0:x0 + tw, :3] += (tile[0, :, :, :3].float() + bias) * m[:, :, None]
+    acc[y0:y0 + th, x0:x0 + tw, 3] += m
+    return acc
+
+
+def tile_resolve_(acc, out, *, accumulate, finalize, final_scale=1.0):
+    v = acc[:, :, :3] / acc[:, :, 3:4]
+    if accumulate:
+        v = v + out
+    if finalize:
+        v = torch.clamp(v * final_scale, 0.0, 1.0)
+    out.copy_(v)
+    return out
+
+
 def vae_preprocess(pixels, dtype, out=None):
     n, h, w, _ = pixels.shape
     y = torch.zeros((n, h, w, 8), dtype=torch.float32)
@@ -371,7 +399,8 @@ def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
 _NAMES = ["gemm", "row_stats_parts", "row_stats_buffer", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
           "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
           "timestep_embedding", "unet_input_im2col", "adaln", "rmsnorm_rows", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
-          "sampler_step", "sampler_update", "eps_to_denoised", "add_nchw_", "vae_postprocess", "vae_preprocess", "vae_posterior"]
+          "sampler_step", "sampler_update", "eps_to_denoised", "add_nchw_", "vae_postprocess", "vae_preprocess", "vae_posterior",
+          "tile_blend_", "tile_resolve_"]
 
 
 def install(monkeypatch) -> None:

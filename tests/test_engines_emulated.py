@@ -578,3 +578,21 @@ def test_p2_installed_operations_subclass_forges_own_classes():
         assert not B._plain(lin)
     finally:
         bo.ForgeOperations = plugin._installed.pop("operations")
+
+
+def test_vae_tiled_decode_host_logic_vs_reference_golden():
+    """VAEDecoderEngine.decode_tiled (tile walk, clamped positions, feather mask, three-pass average) and the oracle's
+    restatement against the reference's own tiled_scale around its own decoder (tests/golden/vae_tiled_tiny.pt)."""
+    from b200forge.vae_engine import VAEDecoderEngine
+    g = _gold("vae_tiled_tiny.pt")
+    cfg = CF.VAE_CONFIGS[g["config"]]
+    sd = OV.random_state_dict(cfg, seed=g["weight_seed"])
+    kw = dict(tile_x=g["tile_x"], tile_y=g["tile_y"], overlap=g["overlap"])
+    with torch.no_grad():
+        ref = OV.decode_tiled(sd, cfg, g["z"], **kw)
+    assert_close("oracle tiled decode vs reference golden", ref, g["out"], max_abs=2e-5)
+    dec = VAEDecoderEngine(cfg, sd, dtype=F32, device="cpu")
+    img = dec.decode_tiled(g["z"], **kw)
+    assert_close("emulated VAEDecoderEngine.decode_tiled vs reference golden", img, g["out"], max_abs=1e-4)
+    whole = dec.decode(g["z"])
+    assert (img - whole).abs().max() > 1e-3  # tiles see their own GroupNorm statistics: tiled != whole-image decode
