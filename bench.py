@@ -300,8 +300,9 @@ def run_flux(args):
     hw, Lt = args.size // 8, 256
     cfg = synthetic.FLUX_DEV
     sd = synthetic.random_flux_state_dict(cfg, device=dev)
-    pipe = FluxTxt2ImgPipeline(cfg, sd, device=dev)
-    del sd
+    vsd = synthetic.random_vae_decoder_state_dict(synthetic.VAE_FLUX, device=dev, dtype=torch.bfloat16, seed=3)
+    pipe = FluxTxt2ImgPipeline(cfg, sd, device=dev, vae_cfg=synthetic.VAE_FLUX, vae_state_dict=vsd)
+    del sd, vsd
     torch.cuda.empty_cache()
     gens = [torch.Generator().manual_seed(1000 + rank * B + i) for i in range(B)]
     g0 = torch.Generator().manual_seed(7)
@@ -310,17 +311,18 @@ def run_flux(args):
                      "vector": torch.randn(B, cfg["vec_in_dim"], generator=g0).bfloat16().pin_memory()}}
     devin = {"noise": host["noise"].to(dev), "cond": {k: v.to(dev) for k, v in host["cond"].items()}}
     h2d = host["noise"].numel() * 4 + sum(v.numel() * 2 for v in host["cond"].values())
-    out_host = torch.empty((B, 16, hw, hw), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((B, args.size, args.size, 3), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
-    gathered = [torch.empty((B, 16, hw, hw), dtype=torch.float32, device=dev) for _ in range(world)] \
+    gathered = [torch.empty((B, args.size, args.size, 3), dtype=torch.uint8, device=dev) for _ in range(world)] \
         if (dist is not None and rank == 0) else None
 
     def job(inp):
-        return pipe.sample(inp["cond"], inp["noise"], steps=S, guidance=3.5)
+        return pipe.generate(inp["cond"], inp["noise"], steps=S, guidance=3.5)  # transformer steps + 16-channel VAE decode
 
-    def finish(lat):
+    def finish(img):
         if dist is not None:
-            dist.gather(lat, gathered, dst=0)
+            from b200forge import dist as bdist
+            bdist.gather_images_u8(img, bufs=gathered)
 
     def barrier():
         torch.cuda.synchronize()
@@ -401,13 +403,13 @@ def run_flux(args):
         line = {"metric": "images_per_sec_flux_dev_1024_euler_20steps_batch4", "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16, fp32 accumulate and sampler state", "data": "synthetic",
-                "config": {"workload": f"Flux.1-dev {args.size}x{args.size} txt2img (transformer only: latent out), Euler {S} steps, "
+                "config": {"workload": f"Flux.1-dev {args.size}x{args.size} txt2img (transformer + 16-channel VAE decode), Euler {S} steps, "
                                        f"Simple schedule, distilled guidance 3.5, batch {B}/GPU, {Lt} T5 tokens; 1 bench step = 1 batch",
                            "parallelism": f"replicas x{world} (request sharding by seed; NCCL gather of latents only)",
                            "l2": "working set (23.8 GB weights) >> 126 MB L2; no explicit flush"},
                 "transformer_ms_per_step": fwd_ms,
                 "transformer_roofline_ms_per_step": B * gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3,
-                "flop_roofline_frac_whole_job": value / world * S * gflop * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12),
+                "flop_roofline_frac_whole_job": value / world * (S * gflop + synthetic.VAE_GFLOP_PER_IMAGE["sdxl@1024"] * (args.size / 1024) ** 2) * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernel_families": fam, "cpu_baseline": None}
         print(json.dumps(line), flush=True)

@@ -50,6 +50,16 @@ TINY_15H = dict(TINY_15, num_heads=8, num_head_channels=-1)
 SD21 = dict(SD15, num_heads=-1, num_head_channels=64, use_linear_in_transformer=True, context_dim=1024)
 TINY_21 = dict(TINY_15, use_linear_in_transformer=True)
 
+# SDXL refiner (backend/huggingface/stabilityai/stable-diffusion-xl-refiner-1.0/unet/config.json: block_out_channels
+# 384/768/1536/1536, cross-attention in levels 1 and 2 with 4 transformer layers, head dim 64, linear projections,
+# cross_attention_dim 1280, projection_class_embeddings_input_dim 2560) in the LDM form the reference's loader builds
+SDXL_REFINER = dict(
+    in_channels=4, out_channels=4, model_channels=384, num_res_blocks=[2, 2, 2, 2], channel_mult=[1, 2, 4, 4],
+    transformer_depth=[0, 0, 4, 4, 4, 4, 0, 0], transformer_depth_output=[0, 0, 0, 4, 4, 4, 4, 4, 4, 0, 0, 0],
+    transformer_depth_middle=4, num_heads=-1, num_head_channels=64, use_spatial_transformer=True,
+    use_linear_in_transformer=True, context_dim=1280, adm_in_channels=2560, num_classes="sequential",
+)
+
 # SDXL VAE (backend/huggingface/stabilityai/stable-diffusion-xl-base-1.0/vae/config.json)
 VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
@@ -58,5 +68,11 @@ VAE_SD15 = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512
 TINY_VAE = dict(in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
 
-CONFIGS = {"sd15": SD15, "sdxl": SDXL, "sd21": SD21, "tiny_xl": TINY_XL, "tiny_15": TINY_15, "tiny_15h": TINY_15H, "tiny_21": TINY_21}
-VAE_CONFIGS = {"sdxl": VAE_SDXL, "sd15": VAE_SD15, "tiny": TINY_VAE}
+# Flux / SD3 VAE (backend/huggingface/black-forest-labs/FLUX.1-dev/vae/config.json): 16 latent channels, a shift factor,
+# no quant / post-quant convolutions
+VAE_FLUX = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_post_quant_conv=False)
+TINY_VAE_FLUX = dict(TINY_VAE, latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_post_quant_conv=False)
+
+CONFIGS = {"sd15": SD15, "sdxl": SDXL, "sd21": SD21, "sdxl_refiner": SDXL_REFINER, "tiny_xl": TINY_XL, "tiny_15": TINY_15, "tiny_15h": TINY_15H, "tiny_21": TINY_21}
+VAE_CONFIGS = {"sdxl": VAE_SDXL, "sd15": VAE_SD15, "tiny": TINY_VAE, "flux": VAE_FLUX, "tiny_flux": TINY_VAE_FLUX}

@@ -145,7 +145,8 @@ def random_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> SD:
 
     ch, ch_mult, nres, nrb = decoder_structure(cfg)
     zc = cfg["latent_channels"]
-    conv("post_quant_conv", zc, zc, 1)
+    if cfg.get("use_post_quant_conv", True):  # backend/nn/vae.py:285
+        conv("post_quant_conv", zc, zc, 1)
     block_in = ch * ch_mult[-1]
     conv("decoder.conv_in", zc, block_in, 3)
     res("decoder.mid.block_1", block_in, block_in)

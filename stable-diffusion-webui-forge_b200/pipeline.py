@@ -279,12 +279,29 @@ class FluxTxt2ImgPipeline:
     embedding, backend/diffusion_engine/flux.py), Euler over the "Simple" schedule.  One fused launch per sampler step."""
 
     def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], *, dtype: torch.dtype = torch.bfloat16, device="cuda",
-                 use_graph: bool = True):
+                 use_graph: bool = True, vae_cfg: Optional[dict] = None, vae_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 vae_dtype: torch.dtype = torch.bfloat16):
         from .flux_engine import FluxEngine
         self.device, self.dtype = torch.device(device), dtype
         self.model = FluxEngine(cfg, state_dict, dtype=dtype, device=device)
         self.use_graph = use_graph
         self._graphs: Dict[tuple, GraphedFlux] = {}
+        self.vae = None
+        if vae_cfg is not None:  # the 16-channel Flux VAE (process_out = z / 0.3611 + 0.1159) on the same fused decoder
+            from .vae_engine import VAEDecoderEngine
+            self.vae = VAEDecoderEngine(vae_cfg, vae_state_dict, dtype=vae_dtype, device=device)
+
+    @torch.no_grad()
+    def decode(self, latent: torch.Tensor) -> torch.Tensor:
+        if self.vae is None:
+            raise RuntimeError("pipeline built without a VAE")
+        return self.vae.decode(latent)
+
+    @torch.no_grad()
+    def generate(self, cond: dict, noise: torch.Tensor, **kw) -> torch.Tensor:
+        """sample + VAE decode: images [B, H, W, 3] fp32 in [0, 1] (the latent when no VAE was given)."""
+        latent = self.sample(cond, noise, **kw)
+        return self.decode(latent) if self.vae is not None else latent
 
     def _graph_for(self, batch, hh, ww, n_txt) -> GraphedFlux:
         key = (batch, hh, ww, n_txt)

@@ -360,8 +360,8 @@ def install_samplers(modules: Optional[dict] = None) -> None:
 class VAEDecodeWrapper:
     """`model_options['model_vae_decode_wrapper']` (reference backend/patcher/vae.py:150-155):
     wrapper(decode_inner_fn, samples_in [B,4,h,w]) -> images [B,H,W,3] fp32 in [0,1] on the output device.
-    NB: Forge hands this wrapper the *processed-out* latent (engine.decode_first_stage divides by the scaling factor
-    first, diffusion_engine/sdxl.py:134-138), so the engine is driven with scaling 1."""
+    NB: Forge hands this wrapper the *processed-out* latent (engine.decode_first_stage applies z / scaling + shift first,
+    diffusion_engine/sdxl.py:134-138), so the engine is told not to apply process_out again."""
 
     def __init__(self, vae_engine, output_device=None, vae_module=None):
         self.engine = vae_engine
@@ -371,12 +371,8 @@ class VAEDecodeWrapper:
 
     def decode_tiled(self, samples_in: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16) -> torch.Tensor:
         """VAE.decode_tiled (backend/patcher/vae.py:157-160): same contract (processed-out latent in, NHWC images out)."""
-        scaling = self.engine.scaling
-        try:
-            self.engine.scaling = 1.0
-            img = self.engine.decode_tiled(samples_in.to(self.engine.device).float().contiguous(), tile_x, tile_y, overlap)
-        finally:
-            self.engine.scaling = scaling
+        img = self.engine.decode_tiled(samples_in.to(self.engine.device).float().contiguous(), tile_x, tile_y, overlap,
+                                       processed_out=True)
         return img if self.output_device is None else img.to(self.output_device)
 
     def __call__(self, decode_inner_fn: Callable, samples_in: torch.Tensor):
@@ -386,12 +382,7 @@ class VAEDecodeWrapper:
         if (not _on_device(samples_in) or samples_in.dim() != 4 or not self.engine.supports_latent(samples_in.shape[2], samples_in.shape[3])
                 or (self.weights is not None and not self.weights.servable())):
             return decode_inner_fn(samples_in)
-        scaling = self.engine.scaling
-        try:
-            self.engine.scaling = 1.0
-            img = self.engine.decode(samples_in.float().contiguous())
-        finally:
-            self.engine.scaling = scaling
+        img = self.engine.decode(samples_in.float().contiguous(), processed_out=True)
         return img if self.output_device is None else img.to(self.output_device)
 
 

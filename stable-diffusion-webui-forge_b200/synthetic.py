@@ -26,6 +26,8 @@ VAE_SDXL = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512
                 latent_channels=4, scaling_factor=0.13025, shift_factor=0.0)
 
 VAE_SD15 = dict(VAE_SDXL, scaling_factor=0.18215)
+# Flux / SD3 VAE (backend/huggingface/black-forest-labs/FLUX.1-dev/vae/config.json): 16 latent channels, shift, no post-quant conv
+VAE_FLUX = dict(VAE_SDXL, latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_post_quant_conv=False)
 
 # algorithmic FLOPs (2*MACs of conv/linear/attention matmuls) per sample-forward, measured on the reference
 # modules with torch.utils.flop_counter
@@ -127,7 +129,8 @@ def random_vae_decoder_state_dict(cfg: dict, device="cuda", dtype=torch.bfloat16
         if cin != cout:
             g.conv(p + ".nin_shortcut", cin, cout, 1)
 
-    g.conv("post_quant_conv", zc, zc, 1)
+    if cfg.get("use_post_quant_conv", True):
+        g.conv("post_quant_conv", zc, zc, 1)
     block_in = ch * ch_mult[-1]
     g.conv("decoder.conv_in", zc, block_in, 3)
     res("decoder.mid.block_1", block_in, block_in)

@@ -49,22 +49,28 @@ class VAEDecoderEngine:
         w = self.w
         g = lambda k: self._t(sd[k])  # noqa: E731
         zc = self.zc
-        assert zc <= 8
-        # post_quant_conv 1x1 on the latent padded to 8 channels
-        pq = torch.zeros((8, 8), dtype=self.dtype, device=self.device)
-        pqb = torch.zeros((8,), dtype=self.dtype, device=self.device)
+        assert zc <= 16, "latent channels: 4 (SD / SDXL) or 16 (Flux, SD3)"
+        zp = self.zp = 8 if zc <= 8 else 16  # latent channels padded to a 16-byte row
+        # post_quant_conv 1x1 on the padded latent (identity when the VAE has none: Flux / SD3).  process_out is
+        # z / scaling + shift (backend/nn/vae.py:315-316): the scale rides on the layout kernel, the shift is folded into this
+        # GEMM's bias (W (z/s + shift) + b = W z/s + (W shift + b)), in fp32 before the cast.
+        pq = torch.zeros((zp, zp), dtype=torch.float32, device=self.device)
+        pqb = torch.zeros((zp,), dtype=torch.float32, device=self.device)
         if "post_quant_conv.weight" in sd:
-            pq[:zc, :zc] = g("post_quant_conv.weight").reshape(zc, zc)
-            pqb[:zc] = g("post_quant_conv.bias")
+            pq[:zc, :zc] = sd["post_quant_conv.weight"].detach().to(self.device).float().reshape(zc, zc)
+            pqb[:zc] = sd["post_quant_conv.bias"].detach().to(self.device).float()
         else:
-            pq[:zc, :zc] = torch.eye(zc, dtype=self.dtype, device=self.device)
-        w["pq.w"], w["pq.b"] = pq, pqb
-        # conv_in on 8-channel (zero padded) input via im2col: k = tap*8 + c
+            pq[:zc, :zc] = torch.eye(zc, dtype=torch.float32, device=self.device)
+        w["pq.b0"] = pqb.to(self.dtype)                       # for latents that already went through process_out
+        pqb = pqb.clone()
+        pqb[:zc] += pq[:zc, :zc].sum(dim=1) * self.shift
+        w["pq.w"], w["pq.b"] = pq.to(self.dtype), pqb.to(self.dtype)
+        # conv_in on the padded input via im2col: k = tap*zp + c
         ci = g("decoder.conv_in.weight")  # [Cb, zc, 3, 3]
         cb = ci.shape[0]
-        cip = torch.zeros((cb, 3, 3, 8), dtype=self.dtype, device=self.device)
+        cip = torch.zeros((cb, 3, 3, zp), dtype=self.dtype, device=self.device)
         cip[..., :zc] = ci.permute(0, 2, 3, 1)
-        w["conv_in.w"], w["conv_in.b"] = cip.reshape(cb, 72).contiguous(), g("decoder.conv_in.bias")
+        w["conv_in.w"], w["conv_in.b"] = cip.reshape(cb, 9 * zp).contiguous(), g("decoder.conv_in.bias")
 
         def res(p):
             for n in ("norm1", "norm2"):
@@ -139,12 +145,14 @@ class VAEDecoderEngine:
 
     # ------------------------------------------------------------------------------------------ decode
     @torch.no_grad()
-    def decode(self, latent: torch.Tensor) -> torch.Tensor:
-        """latent fp32 NCHW [B, zc, h, w] (sampler output) -> fp32 NHWC [B, 8h, 8w, 3] in [0, 1]."""
-        return ops.vae_postprocess(self._decode_raw(latent))
+    def decode(self, latent: torch.Tensor, processed_out: bool = False) -> torch.Tensor:
+        """latent fp32 NCHW [B, zc, h, w] (sampler output) -> fp32 NHWC [B, 8h, 8w, 3] in [0, 1].
+        processed_out: the latent already is z / scaling + shift (what Forge hands VAE.decode, diffusion_engine/sdxl.py:134-138)."""
+        return ops.vae_postprocess(self._decode_raw(latent, processed_out))
 
     @torch.no_grad()
-    def decode_tiled(self, latent: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16) -> torch.Tensor:
+    def decode_tiled(self, latent: torch.Tensor, tile_x: int = 64, tile_y: int = 64, overlap: int = 16,
+                     processed_out: bool = False) -> torch.Tensor:
         """VAE.decode_tiled_ (backend/patcher/vae.py:104-115 over tiled_scale_multidim, :11-49) — the reference's low-memory /
         always-tiled decode: three passes with tiles (2*tile_y, tile_x/2), (tile_y/2, 2*tile_x), (tile_y, tile_x), each tile
         decoded on its own (its own GroupNorm statistics, as in the reference), feather-blended over `overlap` latent pixels,
@@ -165,20 +173,21 @@ class VAEDecoderEngine:
                     for x in range(0, ww, tx - overlap):
                         px = max(0, min(ww - overlap, x))
                         lx = min(tx, ww - px)
-                        raw = self._decode_raw(latent[b:b + 1, :, py:py + ly, px:px + lx].contiguous())
+                        raw = self._decode_raw(latent[b:b + 1, :, py:py + ly, px:px + lx].contiguous(), processed_out)
                         ops.tile_blend_(acc, raw, py * up, px * up, feather=overlap * up, bias=1.0)
                 ops.tile_resolve_(acc, out[b], accumulate=pi > 0, finalize=pi == len(passes) - 1, final_scale=1.0 / 6.0)
         return out
 
-    def _decode_raw(self, latent: torch.Tensor) -> torch.Tensor:
+    def _decode_raw(self, latent: torch.Tensor, processed_out: bool = False) -> torch.Tensor:
         """Decoder output NHWC [B, 8h, 8w, ld] in the VAE dtype, before the (x + 1) / 2 clamp."""
         w = self.w
-        assert latent.dtype == torch.float32 and self.shift == 0.0
+        assert latent.dtype == torch.float32
         latent = latent.contiguous()
         n, zc, hh, ww = latent.shape
-        z = ops.nchw_to_nhwc(latent, self.dtype, ldy=8, scale=1.0 / self.scaling)  # process_out (vae.py:315-316)
-        z = ops.gemm(z.view(-1, 8), w["pq.w"], w["pq.b"]).view(n, hh, ww, 8)
-        cols = ops.im2col3x3(z, ldo=72)
+        zp = self.zp
+        z = ops.nchw_to_nhwc(latent, self.dtype, ldy=zp, scale=1.0 if processed_out else 1.0 / self.scaling)  # process_out (vae.py:315-316)
+        z = ops.gemm(z.view(-1, zp), w["pq.w"], w["pq.b0" if processed_out else "pq.b"]).view(n, hh, ww, zp)
+        cols = ops.im2col3x3(z, ldo=9 * zp)
         h = ops.gemm(cols, w["conv_in.w"], w["conv_in.b"]).view(n, hh, ww, -1)
         h = self._res("decoder.mid.block_1", h)
         h = self._attn("decoder.mid.attn_1", h)

@@ -596,3 +596,19 @@ def test_vae_tiled_decode_host_logic_vs_reference_golden():
     assert_close("emulated VAEDecoderEngine.decode_tiled vs reference golden", img, g["out"], max_abs=1e-4)
     whole = dec.decode(g["z"])
     assert (img - whole).abs().max() > 1e-3  # tiles see their own GroupNorm statistics: tiled != whole-image decode
+
+
+def test_vae_decoder_16_channel_latent_with_shift_host_logic():
+    """The Flux / SD3 VAE: 16 latent channels, process_out = z / scaling + shift (backend/nn/vae.py:315-316), no post-quant
+    convolution — the shift is folded into the entry GEMM's bias; `processed_out=True` (the P5 contract) skips both."""
+    from b200forge.vae_engine import VAEDecoderEngine
+    cfg = CF.VAE_CONFIGS["tiny_flux"]
+    sd = OV.random_state_dict(cfg, seed=4)
+    assert "post_quant_conv.weight" not in sd
+    dec = VAEDecoderEngine(cfg, sd, dtype=F32, device="cpu")
+    z = torch.randn(2, 16, 12, 16, generator=torch.Generator().manual_seed(8)) * cfg["scaling_factor"]
+    with torch.no_grad():
+        ref = OV.decode_first_stage(sd, cfg, z)
+    assert_close("emulated 16-channel VAE decoder vs oracle", dec.decode(z), ref, max_abs=1e-4)
+    zz = z / cfg["scaling_factor"] + cfg["shift_factor"]
+    assert_close("emulated 16-channel VAE decoder, processed-out latent", dec.decode(zz, processed_out=True), ref, max_abs=1e-4)

@@ -272,3 +272,29 @@ def test_gemm_alpha_and_fp16_logit_range():
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()  # (logits this large are beyond fp16 resolution either way; the point is no inf / NaN)
     assert out.abs().max().item() <= v.abs().max().item() * 1.01  # a convex combination of the value rows
+
+
+# ------------------------------------------------------------------------------------------------ f4: other LDM-UNet families
+@pytest.mark.parametrize("name", ["sd21", "sdxl_refiner"])
+def test_other_unet_families_full_width_vs_oracle_fp32(name):
+    """SD2.x (4 levels, linear transformer, head dim 64, 1024-wide context, no label embedding) and the SDXL refiner (384 base
+    channels, 4 transformer layers at levels 1-2, 1280-wide context, 2560-wide label embedding) are the same LDM UNet under
+    other configurations: full width on a 32x32 latent against the oracle in fp32."""
+    from b200forge import synthetic
+    from b200forge.unet_engine import UNetEngine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = CF.CONFIGS[name]
+    sd = synthetic.random_unet_state_dict(cfg, device=DEV, dtype=torch.float16, seed=3)
+    eng = UNetEngine(cfg, sd, dtype=torch.float16, device=DEV)
+    g = torch.Generator().manual_seed(60)
+    n, hw = 2, 32
+    x = torch.randn(n, 4, hw, hw, generator=g).half().to(DEV)
+    ctx = torch.randn(n, 77, cfg["context_dim"], generator=g).half().to(DEV)
+    y = torch.randn(n, cfg["adm_in_channels"], generator=g).half().to(DEV) if cfg["adm_in_channels"] else None
+    t = torch.tensor([850.0, 120.0], device=DEV)
+    out = eng.forward(x, t, ctx, y)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = OU.unet_forward({k: v.float() for k, v in sd.items()}, cfg, x.float(), t, ctx.float(), None if y is None else y.float())
+    assert_close(f"unet {name} full width fp16 engine vs oracle fp32", out, ref, max_rel=2e-2, rel_rms=3e-3)

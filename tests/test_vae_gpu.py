@@ -129,3 +129,26 @@ def test_vae_decode_tiled_vs_reference_golden_and_oracle():
     psnr = 10 * torch.log10(torch.tensor(1.0 / max(mse, 1e-20))).item()
     print(f"[parity] tiled vae decode SDXL width 768x512: PSNR {psnr:.1f} dB")
     assert psnr >= 40.0, psnr
+
+
+def test_flux_vae_decode_16_channels_vs_oracle_fp32():
+    """The 16-channel Flux / SD3 VAE (scaling 0.3611, shift 0.1159, no post-quant conv) at full width on a 32x32 latent."""
+    from b200forge import synthetic
+    from b200forge.vae_engine import VAEDecoderEngine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = synthetic.VAE_FLUX
+    sd = synthetic.random_vae_decoder_state_dict(cfg, device=DEV, dtype=torch.bfloat16, seed=3)
+    assert "post_quant_conv.weight" not in sd
+    eng = VAEDecoderEngine(cfg, sd, dtype=torch.bfloat16, device=DEV)
+    z = ((torch.randn(2, 16, 32, 32, generator=torch.Generator().manual_seed(51)) - cfg["shift_factor"]) * cfg["scaling_factor"]).to(DEV)
+    img = eng.decode(z)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = OV.decode_first_stage({k: v.float() for k, v in sd.items()}, cfg, z)
+        ref_bf = OV.decode_first_stage(sd, cfg, z.bfloat16()).float()
+    from tests.util import err_stats
+    r_ref = err_stats(ref_bf, ref)[1]
+    m, r = err_stats(img, ref)
+    print(f"[parity] flux vae: ours rel_rms={r:.3e} max_abs={m:.3e}; oracle-in-bf16 rel_rms={r_ref:.3e}")
+    assert r <= max(1.5 * r_ref, 5e-3)
