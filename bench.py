@@ -382,7 +382,7 @@ def run_flux(args):
         ops.PROFILE = []
         gf._eager()
         torch.cuda.synchronize()
-        for name, fl, by, s2, e2 in ops.PROFILE:
+        for name, fl, by, s2, e2, *_ in ops.PROFILE:
             d = fam.setdefault(name, {"launches": 0, "flops": 0.0, "bytes": 0.0, "ms": 0.0})
             d["launches"] += 1
             d["flops"] += fl
@@ -645,7 +645,7 @@ def main():
         gu._eager()
         pipe.decode(torch.randn(B, 4, hw, hw, device=dev) * 0.13025)
         torch.cuda.synchronize()
-        for name, fl, by, s2, e2 in ops.PROFILE:
+        for name, fl, by, s2, e2, *_ in ops.PROFILE:
             d = fam.setdefault(name, {"launches": 0, "flops": 0.0, "bytes": 0.0, "ms": 0.0})
             d["launches"] += 1
             d["flops"] += fl

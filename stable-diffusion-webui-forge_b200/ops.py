@@ -22,8 +22,8 @@ PROFILE = None  # set to a list to record (family, algorithmic flops, algorithmi
 class _prof:
     """CUDA-event bracket around one library call on the launching stream (bench.py roofline accounting)."""
 
-    def __init__(self, family: str, flops: float = 0.0, nbytes: float = 0.0):
-        self.family, self.flops, self.nbytes = family, flops, nbytes
+    def __init__(self, family: str, flops: float = 0.0, nbytes: float = 0.0, label: str = ""):
+        self.family, self.flops, self.nbytes, self.label = family, flops, nbytes, label
 
     def __enter__(self):
         if PROFILE is not None:
@@ -35,7 +35,7 @@ class _prof:
         if PROFILE is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            PROFILE.append((self.family, self.flops, self.nbytes, self.s, e))
+            PROFILE.append((self.family, self.flops, self.nbytes, self.s, e, self.label))
         return False
 
 
@@ -131,7 +131,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         assert rowvec2 is None or rowvec2.stride(0) == rowvec.stride(0)
         d.B2, d.bias2, d.rowvec2 = w2.data_ptr(), _p(bias2), _p(rowvec2)
         d.seg_period, d.seg_split = period, split
-    with _prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
+    with _prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out),
+               f"gemm M={M} N={N} K={K}" + (" ln" if ln is not None else "") + (" stats" if row_stats_out is not None else "") +
+               (" geglu" if epilogue == EPI_GEGLU else "") + (" res" if residual is not None else "") + (" a2" if a2 is not None else "")
+               if PROFILE is not None else ""):
         _l.check(_l.load().b200_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
@@ -244,7 +247,8 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     if temb is not None:
         _rowmajor2d(temb, "temb")
         d.temb, d.ld_temb = temb.data_ptr(), temb.stride(0)
-    with _prof("conv3x3", 2.0 * n * h * w_ * cout * 9 * (c1 + c2), 2.0 * (n * h * w_ * (c1 + c2 + cout) + cout * 9 * (c1 + c2))):
+    with _prof("conv3x3", 2.0 * n * h * w_ * cout * 9 * (c1 + c2), 2.0 * (n * h * w_ * (c1 + c2 + cout) + cout * 9 * (c1 + c2)),
+               f"conv {n}x{h}x{w_} {c1}+{c2}->{cout}" + (" res" if residual is not None else "") + (" temb" if temb is not None else "")):
         _l.check(_l.load().b200_conv3x3(x1.data_ptr(), _p(x2), w_packed.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
@@ -275,9 +279,9 @@ def conv3x3_any(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
     per-image time-embedding row, activation, residual)."""
     n, h, w_, c = x.shape
     route = route or conv_route()
-    if conv3x3_supported(h, w_) or (route == "generic" and c % 64 == 0):
+    if c % 64 == 0 and (conv3x3_supported(h, w_) or route == "generic"):  # the TMA path slices channels in 64s
         return conv3x3(x, w_packed, bias, residual=residual, temb=temb, epilogue=epilogue, out=out)
-    if route == "exact":
+    if route == "exact" and c % 64 == 0:
         raise B200Error(_l.E_UNSUPPORTED, f"conv3x3: {h}x{w_} does not tile into 128-pixel boxes (B200_CONV_ROUTE=exact)")
     cout = w_packed.shape[0]
     if out is None:
@@ -307,7 +311,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, 
     d.o_stride_b, d.o_stride_l = out.stride(0), out.stride(1)
     d.scale = float(scale if scale is not None else dh ** -0.5)
     d.dtype = _dt(q)
-    with _prof("attention", 4.0 * b * heads * lq * lk * dh, 2.0 * b * hd * (2 * lq + 2 * lk)):
+    with _prof("attention", 4.0 * b * heads * lq * lk * dh, 2.0 * b * hd * (2 * lq + 2 * lk), f"attn B={b} H={heads} Lq={lq} Lk={lk} Dh={dh}"):
         _l.check(_l.load().b200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
     _count()
     return out
@@ -405,7 +409,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, grou
     ws = gn_workspace(x1.device)
     if L.b200_groupnorm_ws_bytes(C.byref(d)) > ws.numel():
         raise B200Error(_l.E_UNSUPPORTED, f"groupnorm: batch {n} x {groups} groups exceeds the {ws.numel()}-byte workspace")
-    with _prof("groupnorm", 0.0, 2.0 * 3 * n * hw * (c1 + c2)):
+    with _prof("groupnorm", 0.0, 2.0 * 3 * n * hw * (c1 + c2), f"gn {n}x{hw}x{c1}+{c2}"):
         _l.check(L.b200_groupnorm_stats(x1.data_ptr(), _p(x2), ws.data_ptr(), C.byref(d), st))
         _l.check(L.b200_groupnorm_apply(x1.data_ptr(), _p(x2), ws.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                         out.data_ptr(), C.byref(d), st))

@@ -163,7 +163,7 @@ def test_sdxl_euler_trajectory_psnr_at_benchmark_latent():
     def unet16(xc, t, c, yy):
         return OU.unet_forward(sd, cfg, xc.half(), t, c, yy).float()
 
-    den = S.Denoiser(unet16, pred, c16, u16, 7.0)
+    den = S.Denoiser(unet16, pred, c16, u16, 7.0, compute_dtype=torch.float16)
     with torch.no_grad():
         ref = S.sample_euler(den, noise.to(DEV) * float(sig[0]), sig.to(DEV))  # sgm_noise_multiplier off (Forge default)
     mse = (x - ref).pow(2).mean()
