@@ -65,7 +65,7 @@ typedef struct {
   int K1;
   /* LayerNorm folded into the GEMM (replaces F.layer_norm + F.linear, backend/nn/unet.py:171-175 with operations.py:323-329):
    * A holds the un-normalised rows, B = W.diag(gamma); y = rstd_m*(acc - mean_m*ln_c[n]) + ln_d[n] with
-   * ln_c = rowsum(B) and ln_d = W.beta (+ bias), both fp32 [N]; ln_stats [M, ln_stats_parts, 4] fp32 = partial row
+   * ln_c = rowsum(B) and ln_d = W.beta (+ bias), both fp32 [N]; ln_stats [ln_stats_parts, M, 4] fp32 = partial row
    * statistics (count, mean, sum of squared deviations, 0) of each A row as a producer GEMM's row_stats_out wrote them;
    * the epilogue merges the partials with the parallel-variance formula (no sumsq/K - mean^2 cancellation). */
   const float* ln_stats;
@@ -74,9 +74,9 @@ typedef struct {
   const float* ln_d;
   float ln_eps;
   /* when set, the epilogue writes partial statistics of every output row into row_stats_out
-   * [M, b200_gemm_row_stats_parts(N, epilogue, block_n), 4] fp32 — the ln_stats of the next GEMM, so no separate
+   * [b200_gemm_row_stats_parts(N, epilogue, block_n), M, 4] fp32 (part-major) — the ln_stats of the next GEMM, so no separate
    * LayerNorm pass touches HBM.  Each partial is written exactly once (no atomics, nothing to zero, bit-reproducible).
-   * N must be a multiple of 8; not available with the GEGLU epilogue. */
+   * N must be a multiple of 32; not available with the GEGLU epilogue. */
   float* row_stats_out;
   /* Two row segments with their own weights — Flux DoubleStreamBlock (backend/nn/flux.py:206-264) keeps txt and img
    * tokens in one joint [B, L_txt + L_img, C] activation: rows with (m % seg_period) < seg_split use B / bias / rowvec,

@@ -61,23 +61,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // phase is bound by the FP32 pipe as much as by the MUFU (clock64 profile: 16 clk per exponential with one scalar FFMA + one
 // scalar FADD per element; a 32-lane FP32 instruction occupies the pipe for 2 clk), so the scale-and-subtract and the row sum
 // run packed: half the FP32-pipe instructions per element.
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pk2(float a, float b) {
-  f32x2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
-  f32x2_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
-  f32x2_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 // two 2^x on the FP32 pipe: the packed form of exp2_poly3 (common.cuh)
 __device__ __forceinline__ void exp2_poly3_x2(f32x2_t x, float& ea, float& eb) {
   float xa, xb;

@@ -264,6 +264,32 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, bool b
   return d;
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs
+// sm_100 FFMA2 / FADD2 / FMUL2 process the two floats of an even/odd register pair per instruction: half the FP32-pipe
+// issue slots per element for the epilogue's and the softmax's elementwise arithmetic.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ---------------------------------------------------------------- small math / pack helpers
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {

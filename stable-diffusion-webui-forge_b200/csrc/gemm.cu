@@ -51,12 +51,12 @@ struct GemmKParams {
   // Row statistics travel as PARTIALS, one float4 (count, mean, M2 = sum of squared deviations, 0) per (row, N tile,
   // epilogue-warp half) of the producer: written once each (no atomics, no zero-fill, bit-reproducible) and merged by the
   // consumer with the parallel-variance formula, so a large row mean does not cancel (sumsq/K - mean^2 did).
-  const float4* ln_stats;  // [M, ln_parts] partials of each A row, produced by the previous GEMM's epilogue
+  const float4* ln_stats;  // [ln_parts, M] partials of each A row, produced by the previous GEMM's epilogue
   int ln_parts;
   const float* ln_c;
   const float* ln_d;
   float ln_eps;
-  float4* row_stats_out;  // [M, 2 * tiles_n]: partial statistics of this GEMM's own output rows
+  float4* row_stats_out;  // [2 * tiles_n, M]: partial statistics of this GEMM's own output rows
   // two row segments with their own weights (Flux double-stream blocks: txt rows and img rows of one joint
   // [B, L_txt + L_img, C] activation): rows with (m % seg_period) >= seg_split use mapB2 / bias2 / rowvec2.
   int seg_period, seg_split;
@@ -112,6 +112,20 @@ __device__ __forceinline__ void add_smem8(uint32_t addr, float (&x)[8]) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   add_u4<BF16>(r, x);
+}
+
+__device__ __forceinline__ void lds_f4(uint32_t addr, float (&f)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr));
+}
+__device__ __forceinline__ void add_smem8_f32(uint32_t addr, float (&x)[8]) {  // x += 8 fp32 values at addr
+  float a[4], b[4];
+  lds_f4(addr, a);
+  lds_f4(addr + 16u, b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] += a[i];
+    x[4 + i] += b[i];
+  }
 }
 
 // x[i] = rstd * (x[i] - mean * c[col+i]) + d[col+i]   (c, d: fp32 rows of the current tile in smem)
@@ -330,17 +344,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       // the accumulator so that the loads fly under the tile's MMAs
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (ln && row_ok) {
-        const float4* sp = p.ln_stats + (size_t)m * p.ln_parts;
+        const float4* sp = p.ln_stats + m;  // [part][row]: a warp's 32 rows are 512 contiguous bytes per part
         float cnt = 0.f, wsum = 0.f;
         for (int i = 0; i < p.ln_parts; ++i) {
-          const float4 q = __ldg(sp + i);
+          const float4 q = __ldg(sp + (size_t)i * p.M);
           cnt += q.x;
           wsum = fmaf(q.x, q.y, wsum);
         }
         ln_mean = wsum / cnt;
         float m2 = 0.f;
         for (int i = 0; i < p.ln_parts; ++i) {
-          const float4 q = __ldg(sp + i);  // second pass hits L1
+          const float4 q = __ldg(sp + (size_t)i * p.M);  // second pass hits L1
           const float dm = q.y - ln_mean;
           m2 += fmaf(q.x * dm, dm, q.z);
         }
@@ -372,8 +386,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const size_t rv_off = (rowvec_p && row_ok) ? (size_t)(m / p.rows_per_vec) * p.ld_rowvec : 0;
       // per-column bias of this tile -> smem once (the per-chunk global loads were the epilogue's critical path)
       const bool col_bias = bias_p && !p.bias_along_m;
-      // output row statistics: sums of (x - pivot), (x - pivot)^2 with the thread's first value as the pivot
-      float st_piv = 0.f, st_sum = 0.f, st_sq = 0.f, st_cnt = 0.f;
+      // output row statistics: packed sums of (x - pivot), (x - pivot)^2 with the thread's first value as the pivot
+      float st_piv = 0.f, st_cnt = 0.f;
+      f32x2_t st_s2 = pk2(0.f, 0.f), st_q2 = pk2(0.f, 0.f);
       if (col_bias || ln) {
         named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias / LN rows
         const int e0 = (int)(threadIdx.x - 128) * 8;
@@ -386,34 +401,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnd_smem + 4u * e), "f"(dv) : "memory");
           }
         }
-        if (col_bias && e0 < BN) {
+        if (col_bias && e0 < BN) {  // the bias row is kept in fp32: the chunks add it with packed adds, no conversions
           uint4 bv = make_uint4(0, 0, 0, 0);
           if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bias_p) + (size_t)(n0 + e0) * 2));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 2u), "r"(bv.x), "r"(bv.y),
-                       "r"(bv.z), "r"(bv.w)
+          const float2 b0 = unpack2<BF16>(bv.x), b1 = unpack2<BF16>(bv.y), b2 = unpack2<BF16>(bv.z), b3 = unpack2<BF16>(bv.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 4u), "f"(b0.x), "f"(b0.y),
+                       "f"(b1.x), "f"(b1.y)
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 4u + 16u), "f"(b2.x), "f"(b2.y),
+                       "f"(b3.x), "f"(b3.y)
                        : "memory");
         }
         named_bar_sync(1, kEpiThreads);
       }
+      // global row of local row rl of this warp's quadrant (the coalesced residual loads and the coalesced stores walk rows
+      // as rl = j*8 + lane/4 with 16-byte pieces lane%4)
+      auto row_of = [&](int rl, int& mm) -> bool {
+        mm = m_blk * 128 + quad * 32 + rl;
+        bool ok = mm < p.M;
+        if constexpr (GT) {
+          const int rr = quad * 32 + rl;
+          const int y = gt_y0 + (rr >> p.tile_w_log2), x = gt_x0 + (rr & (p.tile_w - 1));
+          ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
+          mm = (gt_img * p.img_h + y) * p.img_w + x;
+        }
+        return ok;
+      };
+      const bool any_rs = p.residual != nullptr;  // warp-uniform
+      const int piece = lane & 3;
 
       for (int c = chalf * 32; c < ncols_out; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
-        uint4 rv[4], rs[4];
+        uint4 rv[4], rsc[4];
         const bool has_rv = rowvec_p && row_ok && !geglu;
-        const bool has_rs = p.residual && row_ok;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           rv[g] = make_uint4(0, 0, 0, 0);
-          rs[g] = make_uint4(0, 0, 0, 0);
           const int n = n0 + c + g * 8;
-          const int no = out_n0 + c + g * 8;
           if (has_rv && n < p.N)
             rv[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(rowvec_p) + (rv_off + (size_t)n) * 2));
-          if (has_rs && no < p.n_out)
-            rs[g] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)m * p.ldr + no) * 2);
+        }
+        // residual: COALESCED — each load instruction covers 8 rows x 64 contiguous bytes (the thread-per-row pattern of the
+        // TMEM layout touched 32 rows per instruction: 32 L1 wavefronts each, which saturated the load pipe on the K <= 1280
+        // shapes); the tile is transposed to thread-per-row through the warp's staging buffer below
+        if (any_rs) {
+          const int col = out_n0 + c + piece * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int mm;
+            const bool ok = row_of(j * 8 + (lane >> 2), mm) && col < p.n_out;
+            rsc[j] = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)mm * p.ldr + col) * 2)
+                        : make_uint4(0, 0, 0, 0);
+          }
         }
         uint32_t v[32];
-        float x[32];
+        f32x2_t xp[16];
         tmem_ld_32x32(t_addr + (uint32_t)c, v);
         if (geglu) {
           uint32_t vg[32];
@@ -432,83 +474,133 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               ln_apply8(lnc_smem, lnd_smem, ncols_out + c + g * 8, ln_mean, ln_rstd, gt);
             }
             if (col_bias) {
-              add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
-              add_smem8<BF16>(bias_smem + (uint32_t)(ncols_out + c + g * 8) * 2u, gt);
+              add_smem8_f32(bias_smem + (uint32_t)(c + g * 8) * 4u, xv);
+              add_smem8_f32(bias_smem + (uint32_t)(ncols_out + c + g * 8) * 4u, gt);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i] * gelu_erf_f(gt[i]);
+            for (int i = 0; i < 8; i += 2)
+              xp[g * 4 + (i >> 1)] = pk2(xv[i] * gelu_erf_f(gt[i]), xv[i + 1] * gelu_erf_f(gt[i + 1]));
           }
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float xv[8];
+          for (int k = 0; k < 16; ++k) xp[k] = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+          if (EXT && p.alpha != 0.f) {
+            const f32x2_t a2 = pk2(p.alpha, p.alpha);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xv[i] = __uint_as_float(v[g * 8 + i]);
-            if (EXT && p.alpha != 0.f) {
+            for (int k = 0; k < 16; ++k) xp[k] = mul2(xp[k], a2);
+          }
+          if (ln) {  // x = rstd * (x - mean * c) + d on pairs
+            const f32x2_t nmean2 = pk2(-ln_mean, -ln_mean), rstd2 = pk2(ln_rstd, ln_rstd);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xv[i] *= p.alpha;
+            for (int h = 0; h < 8; ++h) {
+              float cv[4], dv[4];
+              lds_f4(lnc_smem + 4u * (uint32_t)(c + h * 4), cv);
+              lds_f4(lnd_smem + 4u * (uint32_t)(c + h * 4), dv);
+              xp[2 * h] = fma2(fma2(pk2(cv[0], cv[1]), nmean2, xp[2 * h]), rstd2, pk2(dv[0], dv[1]));
+              xp[2 * h + 1] = fma2(fma2(pk2(cv[2], cv[3]), nmean2, xp[2 * h + 1]), rstd2, pk2(dv[2], dv[3]));
             }
-            if (ln) ln_apply8(lnc_smem, lnd_smem, c + g * 8, ln_mean, ln_rstd, xv);
-            if (col_bias) add_smem8<BF16>(bias_smem + (uint32_t)(c + g * 8) * 2u, xv);
-            else if (bias_p) {
+          }
+          if (col_bias) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xv[i] += bias_m;
+            for (int h = 0; h < 8; ++h) {
+              float bv[4];
+              lds_f4(bias_smem + 4u * (uint32_t)(c + h * 4), bv);
+              xp[2 * h] = add2(xp[2 * h], pk2(bv[0], bv[1]));
+              xp[2 * h + 1] = add2(xp[2 * h + 1], pk2(bv[2], bv[3]));
             }
-            if (has_rv) {
-              if (EXT && p.rowvec_mul) mul_u4<BF16>(rv[g], xv);
-              else add_u4<BF16>(rv[g], xv);
-            }
-            if (act_on) {
-              if (p.epilogue == B200_EPI_SILU) {
+          } else if (bias_p) {
+            const f32x2_t b2 = pk2(bias_m, bias_m);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xv[i] = silu_f(xv[i]);
-              } else if (p.epilogue == B200_EPI_GELU) {
+            for (int k = 0; k < 16; ++k) xp[k] = add2(xp[k], b2);
+          }
+          if (has_rv) {
+            const bool mulv = EXT && p.rowvec_mul;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xv[i] = gelu_erf_f(xv[i]);
-              } else if (EXT && p.epilogue == B200_EPI_GELU_TANH) {
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t w4[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xv[i] = gelu_tanh_f(xv[i]);
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2<BF16>(w4[i]);
+                xp[g * 4 + i] = mulv ? mul2(xp[g * 4 + i], pk2(f.x, f.y)) : add2(xp[g * 4 + i], pk2(f.x, f.y));
               }
             }
+          }
+          if (act_on && p.epilogue != B200_EPI_NONE) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
+            for (int k = 0; k < 16; ++k) {
+              float xa, xb;
+              upk2(xp[k], xa, xb);
+              if (p.epilogue == B200_EPI_SILU) {
+                xa = silu_f(xa);
+                xb = silu_f(xb);
+              } else if (p.epilogue == B200_EPI_GELU) {
+                xa = gelu_erf_f(xa);
+                xb = gelu_erf_f(xb);
+              } else if (EXT && p.epilogue == B200_EPI_GELU_TANH) {
+                xa = gelu_tanh_f(xa);
+                xb = gelu_tanh_f(xb);
+              }
+              xp[k] = pk2(xa, xb);
+            }
+          }
+        }
+        __syncwarp();  // the previous chunk's coalesced stores have read the staging buffer
+        if (any_rs) {
+          // residual tile -> staging (rows as loaded) -> each thread reads its own row's 64 bytes
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rl = j * 8 + (lane >> 2);
+            const uint32_t addr = my_stg + (uint32_t)rl * 64u + ((((uint32_t)piece) ^ (((uint32_t)rl >> 1) & 3u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(rsc[j].x), "r"(rsc[j].y), "r"(rsc[j].z),
+                         "r"(rsc[j].w)
+                         : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
+            uint32_t w4[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3]) : "r"(addr));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = unpack2<BF16>(w4[i]);
+              xp[g * 4 + i] = add2(xp[g * 4 + i], pk2(f.x, f.y));
+            }
+          }
+          __syncwarp();  // every lane has its residual row before the buffer is reused for the output tile
+        }
+        if (row_stats_out && out_n0 + c < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm (n_out % 32 == 0)
+          if (st_cnt == 0.f) {
+            float dummy;
+            upk2(xp[0], st_piv, dummy);
+          }
+          st_cnt += 32.f;
+          const f32x2_t np2 = pk2(-st_piv, -st_piv);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const f32x2_t d2 = add2(xp[k], np2);
+            st_s2 = add2(st_s2, d2);
+            st_q2 = fma2(d2, d2, st_q2);
           }
         }
         // stage this warp's 32 rows x 64 B in its private (64B-swizzled) smem tile, then write them out as
         // full 32-byte sectors: each store instruction covers 8 rows x 64 contiguous bytes
-        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (has_rs) {
-            float xv[8];
+          uint32_t o[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xv[i] = x[g * 8 + i];
-            add_u4<BF16>(rs[g], xv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[g * 8 + i] = xv[i];
-          }
-          const uint32_t o0 = pack2<BF16>(x[g * 8 + 0], x[g * 8 + 1]);
-          const uint32_t o1 = pack2<BF16>(x[g * 8 + 2], x[g * 8 + 3]);
-          const uint32_t o2 = pack2<BF16>(x[g * 8 + 4], x[g * 8 + 5]);
-          const uint32_t o3 = pack2<BF16>(x[g * 8 + 6], x[g * 8 + 7]);
-          if (row_stats_out && out_n0 + c + g * 8 < p.n_out) {  // row statistics for the next GEMM's folded LayerNorm
-            if (st_cnt == 0.f) st_piv = x[g * 8];
-            st_cnt += 8.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float dv = x[g * 8 + i] - st_piv;
-              st_sum += dv;
-              st_sq = fmaf(dv, dv, st_sq);
-            }
+          for (int i = 0; i < 4; ++i) {
+            float xa, xb;
+            upk2(xp[g * 4 + i], xa, xb);
+            o[i] = pack2<BF16>(xa, xb);
           }
           const uint32_t addr = my_stg + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
                        : "memory");
         }
         __syncwarp();
         {
-          const int piece = lane & 3;
           const int col = out_n0 + c + piece * 8;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -516,14 +608,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const uint32_t addr = my_stg + (uint32_t)rl * 64u + ((((uint32_t)piece) ^ (((uint32_t)rl >> 1) & 3u)) << 4);
             uint32_t o0, o1, o2, o3;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
-            int mm = m_blk * 128 + quad * 32 + rl;
-            bool mm_ok = mm < p.M;
-            if constexpr (GT) {
-              const int rr = quad * 32 + rl;
-              const int y = gt_y0 + (rr >> p.tile_w_log2), x = gt_x0 + (rr & (p.tile_w - 1));
-              mm_ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
-              mm = (gt_img * p.img_h + y) * p.img_w + x;
-            }
+            int mm;
+            const bool mm_ok = row_of(rl, mm);
             if (mm_ok && col < p.n_out) {
               uint4 o = make_uint4(o0, o1, o2, o3);
               *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.C) + ((size_t)mm * p.ldc + col) * 2) = o;
@@ -531,10 +617,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         }
       }
-      if (row_stats_out && row_ok) {  // one partial per (row, N tile, warp half), written exactly once
+      if (row_stats_out && row_ok) {  // one partial per (row, N tile, warp half), written exactly once; [part][row] layout:
+        float s0, s1, q0, q1;         // consecutive lanes (rows) write consecutive 16-byte slots
+        upk2(st_s2, s0, s1);
+        upk2(st_q2, q0, q1);
+        const float st_sum = s0 + s1, st_sq = q0 + q1;
         const float inv = st_cnt > 0.f ? 1.0f / st_cnt : 0.f;
         const float ds = st_sum * inv;
-        row_stats_out[(size_t)m * (2 * p.tiles_n) + 2 * n_blk + chalf] =
+        row_stats_out[(size_t)(2 * n_blk + chalf) * p.M + m] =
             make_float4(st_cnt, st_piv + ds, fmaxf(fmaf(-st_sum, ds, st_sq), 0.f), 0.f);
       }
       tc_fence_before();
@@ -710,7 +800,8 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.row_stats_out = reinterpret_cast<float4*>(d->row_stats_out);
   B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2 && d->ln_stats_parts > 0),
                  "gemm: LayerNorm folding needs ln_c, ln_d and ln_stats_parts (single A source)");
-  B200_CHECK_ARG(!d->row_stats_out || d->epilogue != B200_EPI_GEGLU, "gemm: row_stats_out excludes the GEGLU epilogue");
+  B200_CHECK_ARG(!d->row_stats_out || (d->epilogue != B200_EPI_GEGLU && d->N % 32 == 0),
+                 "gemm: row_stats_out needs N (%d) to be a multiple of 32 and excludes the GEGLU epilogue", d->N);
   p.rowvec_mul = d->rowvec_mul;
   p.act_col0 = d->act_col0;
   p.alpha = (d->alpha == 1.0f) ? 0.f : d->alpha;

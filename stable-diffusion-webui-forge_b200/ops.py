@@ -75,8 +75,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
     a [M, K1], a2 [M, K2] (optional), w [N, K1+K2] — all with unit inner stride (row strides free).
     GEGLU: w/bias rows must be pre-interleaved with `pack_geglu`; out is [M, N/2].
-    ln = (stats [M,P,4] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
-    see `fold_layernorm`); stats = the partial row statistics a producer GEMM wrote.  row_stats_out [M,P,4] fp32
+    ln = (stats [P,M,4] fp32, c [N] fp32, d [N] fp32, eps): LayerNorm of `a` folded into the GEMM (w must be W*gamma,
+    see `fold_layernorm`); stats = the partial row statistics a producer GEMM wrote.  row_stats_out [P,M,4] fp32
     (`row_stats_buffer`; nothing to zero): receives partial (count, mean, M2) statistics of the output rows.
     rowvec_mul: out = residual + rowvec * (acc + bias) (modulation gate).  act_col0: the activation applies to output
     columns >= act_col0.  seg = (period, split, w2, bias2, rowvec2): rows with (m % period) >= split use the second
@@ -114,12 +114,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.A2, d.lda2, d.K1 = a2.data_ptr(), a2.stride(0), K1
     if ln is not None:
         st, lc, ld_, eps = ln
-        assert st.dtype == torch.float32 and st.dim() == 3 and st.shape[0] == M and st.shape[2] == 4 and st.is_contiguous()
+        assert st.dtype == torch.float32 and st.dim() == 3 and st.shape[1] == M and st.shape[2] == 4 and st.is_contiguous()
         assert lc.dtype == torch.float32 and ld_.dtype == torch.float32 and lc.numel() == N and ld_.numel() == N
-        d.ln_stats, d.ln_stats_parts, d.ln_c, d.ln_d, d.ln_eps = st.data_ptr(), st.shape[1], lc.data_ptr(), ld_.data_ptr(), eps
+        d.ln_stats, d.ln_stats_parts, d.ln_c, d.ln_d, d.ln_eps = st.data_ptr(), st.shape[0], lc.data_ptr(), ld_.data_ptr(), eps
     if row_stats_out is not None:
         assert row_stats_out.dtype == torch.float32 and row_stats_out.is_contiguous()
-        assert tuple(row_stats_out.shape) == (M, row_stats_parts(N, epilogue, block_n), 4), (row_stats_out.shape, N)
+        assert tuple(row_stats_out.shape) == (row_stats_parts(N, epilogue, block_n), M, 4), (row_stats_out.shape, N)
         d.row_stats_out = row_stats_out.data_ptr()
     d.rowvec_mul = 1 if rowvec_mul else 0
     d.act_col0 = act_col0
@@ -146,8 +146,9 @@ def row_stats_parts(N: int, epilogue: int = EPI_NONE, block_n: int = 0) -> int:
 
 
 def row_stats_buffer(M: int, N: int, device, epilogue: int = EPI_NONE, block_n: int = 0) -> torch.Tensor:
-    """[M, P, 4] fp32 buffer for `gemm(..., row_stats_out=)`; every partial is overwritten by the GEMM (no zero-fill)."""
-    return torch.empty((M, row_stats_parts(N, epilogue, block_n), 4), dtype=torch.float32, device=device)
+    """[P, M, 4] fp32 buffer for `gemm(..., row_stats_out=)` (part-major: a warp's 32 rows of one part are contiguous); every
+    partial is overwritten by the GEMM (no zero-fill)."""
+    return torch.empty((row_stats_parts(N, epilogue, block_n), M, 4), dtype=torch.float32, device=device)
 
 
 def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor], block_n: int = 256):

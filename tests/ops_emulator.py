@@ -51,9 +51,9 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
         acc = (A @ wm.float().t()) * alpha
         if ln is not None:
             st, lc, ld_, eps = ln
-            cnt = st[:, :, 0].sum(1)  # merge the producer's partials (count, mean, M2): parallel-variance formula
-            mean = (st[:, :, 0] * st[:, :, 1]).sum(1) / cnt
-            m2 = (st[:, :, 2] + st[:, :, 0] * (st[:, :, 1] - mean[:, None]) ** 2).sum(1)
+            cnt = st[:, :, 0].sum(0)  # merge the producer's partials [P, M, (count, mean, M2)]: parallel-variance formula
+            mean = (st[:, :, 0] * st[:, :, 1]).sum(0) / cnt
+            m2 = (st[:, :, 2] + st[:, :, 0] * (st[:, :, 1] - mean[None, :]) ** 2).sum(0)
             rstd = torch.rsqrt(m2 / cnt + eps)
             acc = rstd[:, None] * (acc - mean[:, None] * lc[None, :].float()) + ld_[None, :].float()
         if bm is not None:
@@ -86,7 +86,7 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
         # one partial per (N tile, epilogue-warp half): the half takes alternate 32-column chunks of the tile
         N = acc.shape[1]
         bn = block_n if block_n > 0 else _pick_block_n(N)
-        assert tuple(row_stats_out.shape) == (M, 2 * ((N + bn - 1) // bn), 4)
+        assert tuple(row_stats_out.shape) == (2 * ((N + bn - 1) // bn), M, 4)
         cols = torch.arange(N)
         for tile in range((N + bn - 1) // bn):
             for half in range(2):
@@ -95,7 +95,7 @@ def gemm(a, w, bias=None, *, residual=None, rowvec=None, rows_per_vec=1, epilogu
                 cnt = float(part.shape[1])
                 mean = part.mean(1) if cnt else torch.zeros(M)
                 m2 = ((part - mean[:, None]) ** 2).sum(1) if cnt else torch.zeros(M)
-                row_stats_out[:, 2 * tile + half] = torch.stack([torch.full((M,), cnt), mean, m2, torch.zeros(M)], 1)
+                row_stats_out[2 * tile + half] = torch.stack([torch.full((M,), cnt), mean, m2, torch.zeros(M)], 1)
     return _ret(acc, out, a.dtype)
 
 
@@ -115,7 +115,7 @@ def row_stats_parts(N, epilogue=EPI_NONE, block_n=0):
 
 
 def row_stats_buffer(M, N, device, epilogue=EPI_NONE, block_n=0):
-    return torch.full((M, row_stats_parts(N, epilogue, block_n), 4), float("nan"), dtype=torch.float32, device=device)
+    return torch.full((row_stats_parts(N, epilogue, block_n), M, 4), float("nan"), dtype=torch.float32, device=device)
 
 
 def zero_(t):

@@ -323,11 +323,11 @@ def test_sampler_step_euler_ancestral_and_dpmpp():
 
 
 def _merge_partials(st):
-    """(count, mean, M2) partials [M, P, 4] -> (mean, biased variance) per row, in fp64 on the host."""
+    """(count, mean, M2) partials [P, M, 4] -> (mean, biased variance) per row, in fp64 on the host."""
     st = st.double().cpu()
-    cnt = st[:, :, 0].sum(1)
-    mean = (st[:, :, 0] * st[:, :, 1]).sum(1) / cnt
-    m2 = (st[:, :, 2] + st[:, :, 0] * (st[:, :, 1] - mean[:, None]) ** 2).sum(1)
+    cnt = st[:, :, 0].sum(0)
+    mean = (st[:, :, 0] * st[:, :, 1]).sum(0) / cnt
+    m2 = (st[:, :, 2] + st[:, :, 0] * (st[:, :, 1] - mean[None, :]) ** 2).sum(0)
     return cnt, mean, m2 / cnt
 
 
