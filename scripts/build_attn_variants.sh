@@ -10,7 +10,7 @@ build() {  # name, extra flags
   local name=$1; shift
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c attention64.cu -o build/var/attention64.$name.o
   nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../variants/lib_$name.so build/host_util.o build/gemm.o build/attention.o \
-       build/var/attention64.$name.o build/attention128.o build/elementwise.o build/sampler.o build/flux.o -cudart static
+       build/var/attention64.$name.o build/attention64s.o build/attention128.o build/elementwise.o build/sampler.o build/flux.o -cudart static
 }
 build p0 -DB200_ATTN_POLY_PAIRS=0x0 &
 build p4 -DB200_ATTN_POLY_PAIRS=0x4 &

@@ -10,5 +10,5 @@ mkdir -p build/prof ../variants
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr \
      -DB200_ATTN_PROFILE "$@" -c attention64.cu -o build/prof/attention64.$name.o
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../variants/libprof_$name.so build/host_util.o build/gemm.o build/attention.o \
-     build/prof/attention64.$name.o build/attention128.o build/elementwise.o build/sampler.o build/flux.o -cudart static
+     build/prof/attention64.$name.o build/attention64s.o build/attention128.o build/elementwise.o build/sampler.o build/flux.o -cudart static
 echo built ../variants/libprof_$name.so

@@ -290,6 +290,7 @@ static int launch_attn(const CUtensorMap& mQ, const CUtensorMap& mK, const CUten
 namespace b200 {
 int attention64_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
 int attention128_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
+int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
 }
 using namespace b200;
 
@@ -317,6 +318,12 @@ extern "C" int b200_attention(const void* q, const void* k, const void* v, void*
     // a single key block (cross-attention, Lk = 77) is latency- not throughput-bound: the one-tile kernel below keeps
     // two CTAs resident per SM and measured faster there (97 vs 125 us at B=16, H=10, Lq=4096)
     if (!use_old && d->Lk > 128) return attention64_dispatch(q, k, v, o, d, static_cast<cudaStream_t>(s));
+    static int cross_small = -1;  // B200_ATTN64_CROSS=s: the small-CTA kernel (3 CTAs / SM) also for a single key block
+    if (cross_small < 0) {
+      const char* e = getenv("B200_ATTN64_CROSS");
+      cross_small = (e && e[0] == 's') ? 1 : 0;
+    }
+    if (!use_old && cross_small) return attention64s_dispatch(q, k, v, o, d, static_cast<cudaStream_t>(s));
   }
   AttnKParams p;
   memset(&p, 0, sizeof(p));

@@ -86,7 +86,7 @@ static constexpr float kRescaleThreshold = 8.0f;  // log2(256)
 #endif
 static constexpr unsigned kPolyMask = B200_ATTN_POLY_MASK;  // VER 0: elements (i mod 8) whose exp2 runs on the FMA pipe
 #ifndef B200_ATTN_POLY_PAIRS
-#define B200_ATTN_POLY_PAIRS 0x4
+#define B200_ATTN_POLY_PAIRS 0x0
 #endif
 static constexpr unsigned kPolyPairs = B200_ATTN_POLY_PAIRS;  // VER 1: element PAIRS (of the 4 per 8 elements) on the FMA pipe
 
@@ -546,6 +546,8 @@ static int launch_attn64(const CUtensorMap& mQ, const CUtensorMap& mK, const CUt
   return B200_OK;
 }
 
+int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
+
 // called from b200_attention (attention.cu) for Dh == 64
 int attention64_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
   Attn64Params p;
@@ -578,11 +580,12 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   if (rc) return rc;
   rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
   if (rc) return rc;
-  static int ver = -1;  // B200_ATTN64_VER = 0 | 1 forces one build (A/B measurements); default 1
+  static int ver = -1;  // B200_ATTN64_VER = 0 | 1 | 2 forces one build (A/B measurements): 2 = the small-CTA kernel (attention64s.cu)
   if (ver < 0) {
     const char* e = getenv("B200_ATTN64_VER");
-    ver = (e && e[0] == '0') ? 0 : 1;
+    ver = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }
+  if (ver == 2) return attention64s_dispatch(q, k, v, o, d, st);
   if (ver == 1) return bf ? launch_attn64<true, 1>(mQ, mK, mV, p, st) : launch_attn64<false, 1>(mQ, mK, mV, p, st);
   return bf ? launch_attn64<true, 0>(mQ, mK, mV, p, st) : launch_attn64<false, 0>(mQ, mK, mV, p, st);
 }

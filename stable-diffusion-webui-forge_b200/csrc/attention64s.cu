@@ -1,0 +1,414 @@
+// b200forge — head-dim-64 attention forward, "small CTA" build: ONE 128-query tile per CTA, key blocks of 64, THREE CTAs per SM.
+//
+// Why a second organisation (measured on B200, profiles/experiments/README.md):
+//   * the exponential pipe (MUFU, 16 / clk / SM) bounds Dh = 64 attention; one softmax warp alone reaches ~10 clk per
+//     exponential with packed FP32 arithmetic (8 is the pipe's limit), two warps on one scheduler together 96 % of the pipe
+//     (scripts/micro/exp_mix_bench.cu) — so the pipe is saturated only while (at least) two warps per scheduler are inside
+//     their exp phase;
+//   * in the two-tiles-per-CTA kernel (attention64.cu) each softmax warp spends ~1400 clk per key block OUTSIDE the exp phase
+//     (waiting for S, TMEM -> registers, row max, waiting for P.V, lazy-rescale check, hand-off) against ~1900 inside, and
+//     there are exactly two softmax warps per scheduler: the pipe idles ~45 % of the time; CTA start-up (barrier init, TMEM
+//     allocation, first Q / K loads: ~5000 clk) and the output tail are not overlapped with anything either (one CTA per SM):
+//     19 % of the run at L = 1024.
+// Three resident CTAs give every scheduler three softmax warps from independent pipelines — the non-exp phases, the
+// start-up and the tail of one CTA run under the exp phases of the other two — without any cross-tile hand-shaking.
+// Per CTA: 64 KB smem (Q 16 K | K/V ring 4 x 8 K | P 16 K), 128 TMEM columns (S [0,64) | O [64,128)), 192 threads:
+//   warp 0  TMA producer          warp 1  TMEM owner + MMA issuer (converged warp, elected lane)
+//   warps 2-5  softmax, thread = query row: S row (64 fp32) -> registers in one TMEM round trip, S released at once
+//              (QK_{j+1} runs under the exponentials of block j), packed FFMA2 / FADD2 arithmetic, O accumulates in TMEM with
+//              lazy rescale, P staged in smem as the 128B-swizzled K-major A operand of P.V.
+#include "common.cuh"
+#include "host_util.h"
+#include <stdlib.h>
+
+namespace b200 {
+
+struct Attn64sParams {
+  int B, H, Lq, Lk;
+  int BKV, n_kv, q_tiles;  // q_tiles: 128-query CTA tiles
+  float scale_log2;
+  void* O;
+  long long o_stride_b, o_stride_l;
+  uint32_t idesc_qk, idesc_pv;
+};
+
+namespace {
+
+__device__ __forceinline__ float ex2s(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_32x32s(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_waits() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kQTile = 128 * 128;  // bytes: 128 query rows x 64 halfs
+constexpr int kKVTile = 64 * 128;  // bytes: 64 key rows x 64 halfs
+constexpr int kSlots = 4;
+constexpr float kRescale = 8.0f;   // log2(256): O is rescaled only when a row's block maximum exceeds the reference by more
+constexpr uint32_t kTmemCols = 128;
+
+}  // namespace
+
+// __maxnreg__(112): 3 CTAs x 192 threads x 112 registers = 63 K of the SM's 64 K; with setmaxnreg in the kernel ptxas takes the
+// cap as the launch-time count, which the dec / inc below redistribute (2 x (112 - 40) released >= 4 x (144 - 112) taken).
+// (__launch_bounds__(192, 3) made ptxas launch with 96 registers, and `inc` can only take what the CTA's own `dec` released.)
+template <bool BF16>
+__global__ void __maxnreg__(112)
+attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+               const __grid_constant__ CUtensorMap mapV, const Attn64sParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base;
+  const uint32_t ring_smem = base + kQTile;
+  const uint32_t p_smem = ring_smem + kSlots * kKVTile;
+  const uint32_t bar_base = p_smem + kQTile;
+  const uint32_t q_full = bar_base;
+  auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
+  auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kSlots + i); };
+  const uint32_t s_full = bar_base + 8u * (1 + 2 * kSlots);
+  const uint32_t s_cons = s_full + 8u;
+  const uint32_t p_full = s_full + 16u;
+  const uint32_t pv_done = s_full + 24u;
+  const uint32_t tmem_slot = s_full + 32u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int h = (blockIdx.x / p.q_tiles) % p.H;
+  const int b = blockIdx.x / (p.q_tiles * p.H);
+  const int q0 = qt * 128;
+  const int BKV = p.BKV;
+  const int n_kv = p.n_kv;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(ring_full(i), 1);
+      mbar_init(ring_empty(i), 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_cons, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up done; q / k / v are the predecessor's output
+
+  if (warp < 2) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        mbar_expect_tx(q_full, (uint32_t)kQTile);
+        tma_load_3d(q_smem, &mapQ, q_full, h * 64, q0, b);
+        const uint32_t kv_bytes = (uint32_t)BKV * 128u;
+        for (int idx = 0; idx < 2 * n_kv; ++idx) {  // even: K_{idx/2}, odd: V_{idx/2}
+          const int slot = idx % kSlots;
+          const uint32_t phase = (uint32_t)(idx / kSlots) & 1u;
+          mbar_wait(ring_empty(slot), phase ^ 1u);
+          mbar_expect_tx(ring_full(slot), kv_bytes);
+          tma_load_3d(ring_smem + slot * kKVTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+      const uint64_t qdesc = make_smem_desc_sw128(q_smem, 0, 1024);
+      const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
+      const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kKVTile, 1024);  // MN-major V (one 64-wide atom)
+      const uint64_t pdesc = make_smem_desc_sw128(p_smem, 0, 1024);
+      const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+      const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64u;
+      const int ksteps = BKV >> 4;
+      auto wait_full = [&](int idx) {
+        mbar_wait(ring_full(idx % kSlots), (uint32_t)(idx / kSlots) & 1u);
+        tc_fence_after();
+      };
+      auto issue_qk = [&](int idx) {  // S = Q K^T (M 128, N BKV, K 64), then release the K slot
+        const uint64_t kd = kdesc0 + (uint64_t)((idx % kSlots) * (kKVTile >> 4));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qdesc + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+          umma_commit(ring_empty(idx % kSlots));
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      wait_full(0);
+      issue_qk(0);
+#pragma unroll 1
+      for (int j = 0; j < n_kv; ++j) {
+        const int vidx = 2 * j + 1, kidx = 2 * j + 2;
+        if (j + 1 < n_kv) {  // QK_{j+1} as soon as the softmax threads have pulled S_j into registers
+          wait_full(kidx);
+          mbar_wait(s_cons, (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_qk(kidx);
+        }
+        wait_full(vidx);
+        const uint64_t vd = vdesc0 + (uint64_t)((vidx % kSlots) * (kKVTile >> 4));
+        mbar_wait(p_full, (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t acc0 = j != 0 ? 1u : 0u;
+        if (elect_one()) {
+          if (ksteps == 4) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(o_tmem, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_f16(o_tmem, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+          }
+          umma_commit(pv_done);
+          umma_commit(ring_empty(vidx % kSlots));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");  // 4 x 144 + 2 x 40 <= 6 x 112 (the launch-bound allocation)
+    // ------------------------------------------------------------------ softmax warps
+    const int quad = warp & 3;       // TMEM lane quadrant of this warp (warps 2,3,4,5 -> 2,3,0,1)
+    const int r = quad * 32 + lane;  // row inside the tile
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr;
+    const uint32_t o_addr = tmem_base + 64u + lane_addr;
+    const uint32_t p_row = p_smem + (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const float sl2 = p.scale_log2;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      int nvalid = p.Lk - j * BKV;
+      if (nvalid > BKV) nvalid = BKV;
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld_32x32(s_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_cons);  // S is in registers: the tensor core may overwrite it with QK_{j+1}
+      const bool full_blk = nvalid == 64;
+      float mx;
+      if (full_blk) {
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+        mx = fmaxf(m0, m1);
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_blk = mx * sl2;
+      // PV_{j-1} must have retired before O is rescaled and before the P tile is overwritten
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
+      if (j == 0) {
+        m_ref = m_blk;
+      } else {
+        const bool need = m_blk > m_ref + kRescale;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2s(m_ref - m_blk) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t w[32];
+            tmem_ld_32x32(o_addr + (uint32_t)c, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+            tmem_st_32x32s(o_addr + (uint32_t)c, w);
+          }
+          tmem_st_waits();
+          l_run *= alpha;
+          if (need) m_ref = m_blk;
+        }
+      }
+      // p = exp2(s * scale - m_ref), row sum, P -> smem (128B-swizzled K-major A operand: one 64-key atom per row)
+      const float nm = -m_ref;
+      float rs;
+      if (full_blk) {
+        const f32x2_t sl2p = pk2(sl2, sl2), nmp = pk2(nm, nm);
+        f32x2_t acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          float pe[8];
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) {
+            float xa, xb;
+            upk2(fma2(pk2(__uint_as_float(v[c + 2 * q2]), __uint_as_float(v[c + 2 * q2 + 1])), sl2p, nmp), xa, xb);
+            pe[2 * q2] = ex2s(xa);
+            pe[2 * q2 + 1] = ex2s(xb);
+          }
+          acc0 = add2(acc0, pk2(pe[0], pe[1]));
+          acc1 = add2(acc1, pk2(pe[2], pe[3]));
+          acc0 = add2(acc0, pk2(pe[4], pe[5]));
+          acc1 = add2(acc1, pk2(pe[6], pe[7]));
+          const uint32_t addr = p_row + ((((uint32_t)c >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+        }
+        float a0, a1, b0, b1;
+        upk2(acc0, a0, a1);
+        upk2(acc1, b0, b1);
+        rs = (a0 + b0) + (a1 + b1);
+      } else {
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          if (c < BKV) {
+            float pe[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2s(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
+            rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
+            rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
+            const uint32_t addr = p_row + ((((uint32_t)c >> 3) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                         "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+          }
+        }
+        rs = rs0 + rs1;
+      }
+      l_run += rs;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- output: O / l -> fp16 / bf16 -> warp-private staging (the P tile is free now) -> coalesced stores
+    mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const uint32_t stg = p_smem + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(o_addr + (uint32_t)c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t o0 = pack2<BF16>(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+        const uint32_t o1 = pack2<BF16>(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+        const uint32_t o2 = pack2<BF16>(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+        const uint32_t o3 = pack2<BF16>(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;  // 16B chunk index inside the 128B row
+        const uint32_t addr = stg + (uint32_t)lane * 128u + ((chunk ^ (uint32_t)(lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      }
+    }
+    __syncwarp();
+    {
+      const int piece = lane & 7;
+      char* obase = reinterpret_cast<char*>(p.O) + ((size_t)b * p.o_stride_b + (size_t)h * 64) * 2;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int rl = jj * 4 + (lane >> 3);
+        const uint32_t addr = stg + (uint32_t)rl * 128u + ((((uint32_t)piece) ^ (uint32_t)(rl & 7)) << 4);
+        uint32_t o0, o1, o2, o3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
+        const int q = q0 + quad * 32 + rl;
+        if (q < p.Lq)
+          *reinterpret_cast<uint4*>(obase + ((size_t)q * p.o_stride_l + piece * 8) * 2) = make_uint4(o0, o1, o2, o3);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <bool BF16>
+static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64sParams& p,
+                          cudaStream_t stream) {
+  const size_t smem = (size_t)kQTile * 2 + (size_t)kSlots * kKVTile + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn64s_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("attention64s: smem attr: %s", cudaGetErrorString(e));
+      return B200_ECUDA;
+    }
+    attr_done = true;
+  }
+  const int grid = p.q_tiles * p.H * p.B;
+  cudaError_t e = launch_pdl(attn64s_kernel<BF16>, dim3(grid), dim3(192), smem, stream, 1, mQ, mK, mV, p);
+  if (e != cudaSuccess) {
+    set_error("attention64s: launch failed: %s", cudaGetErrorString(e));
+    return B200_ECUDA;
+  }
+  B200_CHECK_LAUNCH("attention64s");
+  return B200_OK;
+}
+
+// called from attention64_dispatch (attention64.cu) when B200_ATTN64_VER = 2
+int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+  Attn64sParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B;
+  p.H = d->H;
+  p.Lq = d->Lq;
+  p.Lk = d->Lk;
+  p.BKV = d->Lk >= 64 ? 64 : ((d->Lk + 15) / 16) * 16;
+  p.n_kv = (d->Lk + p.BKV - 1) / p.BKV;
+  p.q_tiles = (d->Lq + 127) / 128;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.O = o;
+  p.o_stride_b = d->o_stride_b;
+  p.o_stride_l = d->o_stride_l;
+  const bool bf = d->dtype == B200_BF16;
+  p.idesc_qk = make_idesc_f16(128, p.BKV, bf, false, false);
+  p.idesc_pv = make_idesc_f16(128, 64, bf, false, true);
+  const uint64_t cols = (uint64_t)d->H * 64;
+  CUtensorMap mQ, mK, mV;
+  auto make3 = [&](CUtensorMap* m, const void* base, int L, long long sl, long long sb, int rows) {
+    uint64_t dims[3] = {cols, (uint64_t)L, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)sl * 2, (uint64_t)sb * 2};
+    uint32_t box[3] = {64, (uint32_t)rows, 1};
+    return make_tmap(m, d->dtype, base, 3, dims, str, box);
+  };
+  int rc = make3(&mQ, q, d->Lq, d->q_stride_l, d->q_stride_b, 128);
+  if (rc) return rc;
+  rc = make3(&mK, k, d->Lk, d->k_stride_l, d->k_stride_b, p.BKV);
+  if (rc) return rc;
+  rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
+  if (rc) return rc;
+  return bf ? launch_attn64s<true>(mQ, mK, mV, p, st) : launch_attn64s<false>(mQ, mK, mV, p, st);
+}
+
+}  // namespace b200

@@ -328,6 +328,33 @@ __device__ __forceinline__ float silu_fast_f(float x) {
   return x * fmaf(0.5f, t, 0.5f);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// F.gelu (exact / erf form) on TWO values: 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26
+//   erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + 0.3275911 z),  z >= 0,  |error| <= 1.5e-7
+// (far below the fp16 / bf16 output rounding): per element one MUFU.RCP, one MUFU.EX2 and ~5 packed FMAs instead of erff's
+// ~25-instruction branchy evaluation — the GEGLU epilogue of the feed-forward GEMM (the largest GEMM of the UNet) ran 11-18 %
+// under the same GEMM without an epilogue because of it.
+__device__ __forceinline__ f32x2_t gelu_erf_x2(f32x2_t x2) {
+  float xa, xb;
+  upk2(x2, xa, xb);
+  const float za = fabsf(xa) * 0.70710678118654752f, zb = fabsf(xb) * 0.70710678118654752f;
+  float ta, tb, ea, eb;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(fmaf(0.3275911f, za, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(fmaf(0.3275911f, zb, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(za * za * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(zb * zb * -1.4426950408889634f));
+  const f32x2_t t = pk2(ta, tb);
+  f32x2_t p = fma2(pk2(1.061405429f, 1.061405429f), t, pk2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, pk2(0.254829592f, 0.254829592f));
+  p = mul2(mul2(p, t), pk2(ea, eb));                       // 1 - erf(z)
+  float qa, qb;
+  upk2(p, qa, qb);
+  const float erfa = copysignf(1.0f - qa, xa), erfb = copysignf(1.0f - qb, xb);
+  const f32x2_t h = mul2(x2, pk2(0.5f, 0.5f));
+  return fma2(h, pk2(erfa, erfb), h);
+}
+
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 — a
 // fraction of an fp16 ulp).  Measured with the clock64 phase profile (scripts/attn_phase_profile.py): one warp's exp
 // phase of 128 exponentials takes 2040 clk = 16 clk per MUFU.EX2, twice the pipe's 8 clk/instruction peak, so the

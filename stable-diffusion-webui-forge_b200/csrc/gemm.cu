@@ -479,7 +479,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             }
 #pragma unroll
             for (int i = 0; i < 8; i += 2)
-              xp[g * 4 + (i >> 1)] = pk2(xv[i] * gelu_erf_f(gt[i]), xv[i + 1] * gelu_erf_f(gt[i + 1]));
+              xp[g * 4 + (i >> 1)] = mul2(pk2(xv[i], xv[i + 1]), gelu_erf_x2(pk2(gt[i], gt[i + 1])));
           }
         } else {
           tmem_ld_wait();
@@ -535,8 +535,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 xa = silu_f(xa);
                 xb = silu_f(xb);
               } else if (p.epilogue == B200_EPI_GELU) {
-                xa = gelu_erf_f(xa);
-                xb = gelu_erf_f(xb);
+                upk2(gelu_erf_x2(pk2(xa, xb)), xa, xb);
               } else if (EXT && p.epilogue == B200_EPI_GELU_TANH) {
                 xa = gelu_tanh_f(xa);
                 xb = gelu_tanh_f(xb);
