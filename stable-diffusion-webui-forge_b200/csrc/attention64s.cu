@@ -12,9 +12,10 @@
 //     19 % of the run at L = 1024.
 // Three resident CTAs give every scheduler three softmax warps from independent pipelines — the non-exp phases, the
 // start-up and the tail of one CTA run under the exp phases of the other two — without any cross-tile hand-shaking.
-// Per CTA: 64 KB smem (Q 16 K | K/V ring 4 x 8 K | P 16 K), 128 TMEM columns (S [0,64) | O [64,128)), 192 threads:
-//   warp 0  TMA producer          warp 1  TMEM owner + MMA issuer (converged warp, elected lane)
-//   warps 2-5  softmax, thread = query row: S row (64 fp32) -> registers in one TMEM round trip, S released at once
+// Per CTA: 64 KB smem (Q 16 K | K/V ring 4 x 8 K | P 16 K), 128 TMEM columns (S [0,64) | O [64,128)), 256 threads in two
+// warpgroups (setmaxnreg is a warpgroup-wide instruction: the register-poor and the register-rich roles must not share one):
+//   warp 0  TMA producer          warp 1  TMEM owner + MMA issuer (converged warp, elected lane)      warps 2-3  idle
+//   warps 4-7  softmax, thread = query row: S row (64 fp32) -> registers in one TMEM round trip, S released at once
 //              (QK_{j+1} runs under the exponentials of block j), packed FFMA2 / FADD2 arithmetic, O accumulates in TMEM with
 //              lazy rescale, P staged in smem as the 128B-swizzled K-major A operand of P.V.
 #include "common.cuh"
@@ -60,11 +61,10 @@ constexpr uint32_t kTmemCols = 128;
 
 }  // namespace
 
-// __maxnreg__(112): 3 CTAs x 192 threads x 112 registers = 63 K of the SM's 64 K; with setmaxnreg in the kernel ptxas takes the
-// cap as the launch-time count, which the dec / inc below redistribute (2 x (112 - 40) released >= 4 x (144 - 112) taken).
-// (__launch_bounds__(192, 3) made ptxas launch with 96 registers, and `inc` can only take what the CTA's own `dec` released.)
+// __maxnreg__(80): 3 CTAs x 256 threads x 80 registers = 60 K of the SM's 64 K; with setmaxnreg in the kernel ptxas takes the
+// cap as the launch-time count, which the dec / inc below redistribute (4 x (80 - 24) released = 4 x (136 - 80) taken).
 template <bool BF16>
-__global__ void __maxnreg__(112)
+__global__ void __maxnreg__(80)
 attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const Attn64sParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,9 +118,11 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
-  if (warp < 2) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp >= 2) {
+      // idle warps of the control warpgroup
+    } else if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------------ TMA producer
         mbar_expect_tx(q_full, (uint32_t)kQTile);
@@ -129,7 +131,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         for (int idx = 0; idx < 2 * n_kv; ++idx) {  // even: K_{idx/2}, odd: V_{idx/2}
           const int slot = idx % kSlots;
           const uint32_t phase = (uint32_t)(idx / kSlots) & 1u;
-          mbar_wait(ring_empty(slot), phase ^ 1u);
+          mbar_wait_quiet(ring_empty(slot), phase ^ 1u);
           mbar_expect_tx(ring_full(slot), kv_bytes);
           tma_load_3d(ring_smem + slot * kKVTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
         }
@@ -144,7 +146,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64u;
       const int ksteps = BKV >> 4;
       auto wait_full = [&](int idx) {
-        mbar_wait(ring_full(idx % kSlots), (uint32_t)(idx / kSlots) & 1u);
+        mbar_wait_quiet(ring_full(idx % kSlots), (uint32_t)(idx / kSlots) & 1u);
         tc_fence_after();
       };
       auto issue_qk = [&](int idx) {  // S = Q K^T (M 128, N BKV, K 64), then release the K slot
@@ -157,7 +159,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
         __syncwarp();
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_quiet(q_full, 0);
       wait_full(0);
       issue_qk(0);
 #pragma unroll 1
@@ -165,13 +167,13 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const int vidx = 2 * j + 1, kidx = 2 * j + 2;
         if (j + 1 < n_kv) {  // QK_{j+1} as soon as the softmax threads have pulled S_j into registers
           wait_full(kidx);
-          mbar_wait(s_cons, (uint32_t)j & 1u);
+          mbar_wait_quiet(s_cons, (uint32_t)j & 1u);
           tc_fence_after();
           issue_qk(kidx);
         }
         wait_full(vidx);
         const uint64_t vd = vdesc0 + (uint64_t)((vidx % kSlots) * (kKVTile >> 4));
-        mbar_wait(p_full, (uint32_t)j & 1u);
+        mbar_wait_quiet(p_full, (uint32_t)j & 1u);
         tc_fence_after();
         const uint32_t acc0 = j != 0 ? 1u : 0u;
         if (elect_one()) {
@@ -190,9 +192,9 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");  // 4 x 144 + 2 x 40 <= 6 x 112 (the launch-bound allocation)
-    // ------------------------------------------------------------------ softmax warps
-    const int quad = warp & 3;       // TMEM lane quadrant of this warp (warps 2,3,4,5 -> 2,3,0,1)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");  // 4 x 136 + 4 x 24 = 8 x 80 (the launch-time allocation)
+    // ------------------------------------------------------------------ softmax warpgroup (warps 4-7)
+    const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;  // row inside the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr;
@@ -367,7 +369,7 @@ static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CU
     attr_done = true;
   }
   const int grid = p.q_tiles * p.H * p.B;
-  cudaError_t e = launch_pdl(attn64s_kernel<BF16>, dim3(grid), dim3(192), smem, stream, 1, mQ, mK, mV, p);
+  cudaError_t e = launch_pdl(attn64s_kernel<BF16>, dim3(grid), dim3(256), smem, stream, 1, mQ, mK, mV, p);
   if (e != cudaSuccess) {
     set_error("attention64s: launch failed: %s", cudaGetErrorString(e));
     return B200_ECUDA;

@@ -69,6 +69,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// same wait without the diagnostic printf (whose argument marshalling costs registers): for warps that run on a 24-register
+// budget after setmaxnreg.dec
+__device__ __forceinline__ void mbar_wait_quiet(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#if B200_WATCHDOG
+  const unsigned t0 = (unsigned)clock();
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+#if B200_WATCHDOG
+    if ((unsigned)clock() - t0 > 3000000000u) __trap();  // ~1.5 s: the pipeline is dead
+#endif
+  }
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
