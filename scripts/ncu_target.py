@@ -47,7 +47,38 @@ def gn(N, H, W, C):
     torch.cuda.synchronize()
 
 
-if which == "all":
+def unet_gemms():
+    """The transformer GEMM flavours of the SDXL UNet at the 1280 level: producer (bias + residual + row statistics), LayerNorm-
+    fold consumer (QKV) and LayerNorm-fold + GEGLU (feed-forward), each launched twice (the second is the one to read)."""
+    M, C = 16384, 1280
+    a = torch.randn(M, C, device=DEV, dtype=torch.float16)
+    w = torch.randn(C, C, device=DEV, dtype=torch.float16) * C ** -0.5
+    b = torch.randn(C, device=DEV, dtype=torch.float16)
+    res = torch.randn(M, C, device=DEV, dtype=torch.float16)
+    t = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    st = ops.row_stats_buffer(M, C, DEV)
+    for _ in range(2):
+        ops.gemm(a, w, b, residual=res, out=t, row_stats_out=st)
+    wq = torch.randn(3 * C, C, device=DEV, dtype=torch.float16) * C ** -0.5
+    c = torch.randn(3 * C, device=DEV)
+    d = torch.randn(3 * C, device=DEV)
+    for _ in range(2):
+        ops.gemm(t, wq, None, ln=(st, c, d, 1e-5))
+    wf = torch.randn(8 * C, C, device=DEV, dtype=torch.float16) * C ** -0.5
+    wp, cp = ops.pack_geglu(wf, torch.randn(8 * C, device=DEV), 256)
+    _, dp = ops.pack_geglu(wf, torch.randn(8 * C, device=DEV), 256)
+    for _ in range(2):
+        ops.gemm(t, wp, None, epilogue=ops.EPI_GEGLU, block_n=256, ln=(st, cp, dp, 1e-5))
+    wo = torch.randn(C, 4 * C, device=DEV, dtype=torch.float16) * (4 * C) ** -0.5
+    g = torch.randn(M, 4 * C, device=DEV, dtype=torch.float16)
+    for _ in range(2):
+        ops.gemm(g, wo, b, residual=res, out=t, row_stats_out=st)
+    torch.cuda.synchronize()
+
+
+if which == "unetgemm":
+    unet_gemms()
+elif which == "all":
     gemm(16384, 10240, 1280)
     conv(16, 128, 128, 320, 320)
     attn(16, 10, 4096, 4096, 64)

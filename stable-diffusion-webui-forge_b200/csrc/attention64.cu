@@ -61,23 +61,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // phase is bound by the FP32 pipe as much as by the MUFU (clock64 profile: 16 clk per exponential with one scalar FFMA + one
 // scalar FADD per element; a 32-lane FP32 instruction occupies the pipe for 2 clk), so the scale-and-subtract and the row sum
 // run packed: half the FP32-pipe instructions per element.
-// two 2^x on the FP32 pipe: the packed form of exp2_poly3 (common.cuh)
-__device__ __forceinline__ void exp2_poly3_x2(f32x2_t x, float& ea, float& eb) {
-  float xa, xb;
-  upk2(x, xa, xb);
-  const f32x2_t xc = pk2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
-  const f32x2_t t = add2(xc, pk2(12582912.0f, 12582912.0f));
-  const f32x2_t f = add2(xc, fma2(t, pk2(-1.0f, -1.0f), pk2(12582912.0f, 12582912.0f)));  // x - (t - magic)
-  f32x2_t p = fma2(pk2(0.0551716685f, 0.0551716685f), f, pk2(0.2426111251f, 0.2426111251f));
-  p = fma2(p, f, pk2(0.6932609677f, 0.6932609677f));
-  p = fma2(p, f, pk2(0.9999280572f, 0.9999280572f));
-  float pa, pb, ta, tb;
-  upk2(p, pa, pb);
-  upk2(t, ta, tb);
-  ea = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
-  eb = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
-}
-
 static constexpr int kTile = 128 * 128;  // bytes of one 128-row x 64-half tile
 static constexpr int kRingSlots = 4;
 static constexpr float kRescaleThreshold = 8.0f;  // log2(256)

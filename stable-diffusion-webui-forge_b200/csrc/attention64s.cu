@@ -58,6 +58,10 @@ constexpr int kKVTile = 64 * 128;  // bytes: 64 key rows x 64 halfs
 constexpr int kSlots = 4;
 constexpr float kRescale = 8.0f;   // log2(256): O is rescaled only when a row's block maximum exceeds the reference by more
 constexpr uint32_t kTmemCols = 128;
+#ifndef B200_ATTN64S_POLY_PAIRS
+#define B200_ATTN64S_POLY_PAIRS 0x0
+#endif
+constexpr unsigned kPolyPairsS = B200_ATTN64S_POLY_PAIRS;  // element PAIRS (of the 4 per 8 elements) whose exp2 runs on the FMA pipe
 
 }  // namespace
 
@@ -268,10 +272,15 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           float pe[8];
 #pragma unroll
           for (int q2 = 0; q2 < 4; ++q2) {
-            float xa, xb;
-            upk2(fma2(pk2(__uint_as_float(v[c + 2 * q2]), __uint_as_float(v[c + 2 * q2 + 1])), sl2p, nmp), xa, xb);
-            pe[2 * q2] = ex2s(xa);
-            pe[2 * q2 + 1] = ex2s(xb);
+            const f32x2_t x = fma2(pk2(__uint_as_float(v[c + 2 * q2]), __uint_as_float(v[c + 2 * q2 + 1])), sl2p, nmp);
+            if ((kPolyPairsS >> q2) & 1) {
+              exp2_poly3_x2(x, pe[2 * q2], pe[2 * q2 + 1]);
+            } else {
+              float xa, xb;
+              upk2(x, xa, xb);
+              pe[2 * q2] = ex2s(xa);
+              pe[2 * q2 + 1] = ex2s(xb);
+            }
           }
           acc0 = add2(acc0, pk2(pe[0], pe[1]));
           acc1 = add2(acc1, pk2(pe[2], pe[3]));

@@ -384,6 +384,23 @@ __device__ __forceinline__ float exp2_poly3(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // p * 2^n through the exponent field
 }
 
+// two 2^x on the FP32 pipe: the packed form of exp2_poly3
+__device__ __forceinline__ void exp2_poly3_x2(f32x2_t x, float& ea, float& eb) {
+  float xa, xb;
+  upk2(x, xa, xb);
+  const f32x2_t xc = pk2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
+  const f32x2_t t = add2(xc, pk2(12582912.0f, 12582912.0f));
+  const f32x2_t f = add2(xc, fma2(t, pk2(-1.0f, -1.0f), pk2(12582912.0f, 12582912.0f)));  // x - (t - magic)
+  f32x2_t p = fma2(pk2(0.0551716685f, 0.0551716685f), f, pk2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, f, pk2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, f, pk2(0.9999280572f, 0.9999280572f));
+  float pa, pb, ta, tb;
+  upk2(p, pa, pb);
+  upk2(t, ta, tb);
+  ea = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  eb = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+}
+
 // nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), MUFU.TANH (rel. error ~2^-11)
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
