@@ -563,10 +563,12 @@ int attention64_dispatch(const void* q, const void* k, const void* v, void* o, c
   if (rc) return rc;
   rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
   if (rc) return rc;
-  static int ver = -1;  // B200_ATTN64_VER = 0 | 1 | 2 forces one build (A/B measurements): 2 = the small-CTA kernel (attention64s.cu)
+  // B200_ATTN64_VER = 0 | 1 | 2 forces one build (A/B measurements).  Default 2, the small-CTA kernel (attention64s.cu):
+  // measured on B200 at B16 H10 L4096 / B16 H20 L1024: VER 0 640 / 510 TF/s, VER 1 692 / 544, VER 2 790 / 652 (cuDNN SDPA 945 / 830)
+  static int ver = -1;
   if (ver < 0) {
     const char* e = getenv("B200_ATTN64_VER");
-    ver = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+    ver = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
   }
   if (ver == 2) return attention64s_dispatch(q, k, v, o, d, st);
   if (ver == 1) return bf ? launch_attn64<true, 1>(mQ, mK, mV, p, st) : launch_attn64<false, 1>(mQ, mK, mV, p, st);
