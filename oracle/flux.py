@@ -154,9 +154,13 @@ def unpatchify(o: torch.Tensor, C: int, Hh: int, Ww: int) -> torch.Tensor:
 
 def flux_forward(sd: SD, cfg: dict, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor, y: torch.Tensor,
                  guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """IntegratedFluxTransformer2DModel.forward (flux.py:389-422) for even latent sizes."""
+    """IntegratedFluxTransformer2DModel.forward (flux.py:389-422); odd latent sizes are padded circularly to the patch size
+    (:394-397) and the output is cropped back (:412)."""
+    h0, w0 = x.shape[2], x.shape[3]
+    if (h0 | w0) & 1:
+        xp = torch.nn.functional.pad(x, (0, w0 & 1, 0, h0 & 1), mode="circular")
+        return flux_forward(sd, cfg, xp, timestep, context, y, guidance)[:, :, :h0, :w0]
     B, C, Hh, Ww = x.shape
-    assert Hh % 2 == 0 and Ww % 2 == 0
     H, hidden = cfg["num_heads"], cfg["hidden_size"]
     img = O.linear(patchify(x), sd["img_in.weight"], sd["img_in.bias"])
     vec = _mlp_embedder(sd, "time_in", timestep_embedding(timestep, 256).to(img.dtype))

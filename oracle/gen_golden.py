@@ -402,7 +402,7 @@ def gen_chroma(name: str = "tiny_chroma", hw: int = 16, txt_len: int = 64):
     m = IntegratedChromaTransformer2DModel(**cfg).eval()
     m.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(2, cfg["in_channels"], hw, hw, generator=g)
+    x = torch.randn(2, cfg["in_channels"], hw, hw_w or hw, generator=g)
     ctx = torch.randn(2, txt_len, cfg["context_in_dim"], generator=g)
     t = torch.tensor([0.93, 0.12])
     with torch.no_grad():
@@ -412,7 +412,7 @@ def gen_chroma(name: str = "tiny_chroma", hw: int = 16, txt_len: int = 64):
     print("chroma", name, "out std", out.std().item())
 
 
-def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: str = "flux_tiny.pt"):
+def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: str = "flux_tiny.pt", hw_w: int = None):
     """Reference Flux transformer (backend/nn/flux.py) on CPU fp32, distilled-guidance input included."""
     from backend.nn.flux import IntegratedFluxTransformer2DModel
     from oracle import flux as OF
@@ -421,7 +421,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
     m = IntegratedFluxTransformer2DModel(**cfg).eval()
     m.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(2, cfg["in_channels"], hw, hw, generator=g)
+    x = torch.randn(2, cfg["in_channels"], hw, hw_w or hw, generator=g)
     ctx = torch.randn(2, txt_len, cfg["context_in_dim"], generator=g)
     y = torch.randn(2, cfg["vec_in_dim"], generator=g)
     t = torch.tensor([0.93, 0.12])
@@ -436,7 +436,7 @@ def gen_flux(name: str = "tiny_flux", hw: int = 16, txt_len: int = 128, fname: s
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref_import.load()
-    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_tiled", "vae_enc", "control", "chroma", "flux"]
+    which = sys.argv[1:] or ["unet", "traj", "vtraj", "sched", "samplers", "vae", "vae_tiled", "vae_enc", "control", "chroma", "flux", "flux_odd"]
     if "unet" in which:
         gen_unet("tiny_xl")
         gen_unet("tiny_15")
@@ -462,3 +462,5 @@ if __name__ == "__main__":
     if "flux" in which:
         gen_flux()                                                  # 64 img + 128 txt tokens: per-stream GEMM launches
         gen_flux(hw=32, txt_len=256, fname="flux_tiny_seg.pt")      # 256 + 256 tokens: two-segment GEMM path
+    if "flux_odd" in which:
+        gen_flux(hw=15, hw_w=18, txt_len=64, fname="flux_tiny_odd.pt")  # odd height: circular pad to the patch size + crop

@@ -219,8 +219,13 @@ class FluxEngine:
         return p["tok_out"], p
 
     def forward(self, x, timestep, context, y, guidance=None) -> torch.Tensor:
-        """Reference signature and output: NCHW fp32 [B, C, H, W] (flux.py:389-422; KModel casts to float, k_model.py:44)."""
+        """Reference signature and output: NCHW fp32 [B, C, H, W] (flux.py:389-422; KModel casts to float, k_model.py:44).
+        Odd latent sizes take the reference's route: circular padding to the patch size on the way in (:394-397, a tensor copy
+        of the 16-channel latent), crop on the way out (:412)."""
         B, C, H, W = x.shape
+        if (H | W) & 1:
+            xp = torch.nn.functional.pad(x, (0, W & 1, 0, H & 1), mode="circular")
+            return self.forward(xp, timestep, context, y, guidance)[:, :, :H, :W].contiguous()
         tok, _ = self.forward_tokens(x.contiguous(), timestep.float().contiguous(), context.to(self.dtype).contiguous(),
                                      y.to(self.dtype).contiguous(), None if guidance is None else guidance.float().contiguous())
         return ops.flux_unpatchify(tok, B, C, H, W, nchw_f32=True)

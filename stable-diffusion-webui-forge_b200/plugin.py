@@ -281,7 +281,7 @@ class FluxWrapper:
         eng = self.engine
         ok = (fast_path_ok(c) and c.get("control") is None and _on_device(x) and x.dtype == torch.float32 and x.dim() == 4
               and getattr(self.predictor, "prediction_type", None) == "const" and c.get("c_concat") is None
-              and c.get("y") is not None and (x.shape[2] | x.shape[3]) % 2 == 0
+              and c.get("y") is not None
               and (c.get("guidance") is not None or not eng.guidance_embed)
               and (self.weights is None or self.weights.servable()))
         if not ok:
@@ -292,8 +292,12 @@ class FluxWrapper:
         sigma = sigma.float().contiguous()
         t = self.predictor.timestep(sigma).float().contiguous()
         g = c.get("guidance")
-        out = eng.forward_nhwc(x, t, c["c_crossattn"].to(eng.dtype).contiguous(), c["y"].to(eng.dtype).contiguous(),
-                               None if g is None else g.to(x.device).float().contiguous())
+        g = None if g is None else g.to(x.device).float().contiguous()
+        ctx, y = c["c_crossattn"].to(eng.dtype).contiguous(), c["y"].to(eng.dtype).contiguous()
+        if (x.shape[2] | x.shape[3]) & 1:  # odd latent: the engine pads circularly and crops (flux.py:394-397, 412)
+            out = ops.nchw_to_nhwc(eng.forward(x, t, ctx, y, g), eng.dtype)
+        else:
+            out = eng.forward_nhwc(x, t, ctx, y, g)
         return ops.eps_to_denoised(x, out, sigma, prediction=0)  # x - sigma * v
 
 

@@ -73,7 +73,7 @@ def test_vae_engines_host_logic_vs_reference_golden():
     assert_close("emulated VAE encoder latent vs reference golden", enc.encode(e["pixels"], e["noise"], process_in=True), e["latent"], max_abs=1e-4)
 
 
-@pytest.mark.parametrize("fname", ["flux_tiny.pt", "flux_tiny_seg.pt"])
+@pytest.mark.parametrize("fname", ["flux_tiny.pt", "flux_tiny_seg.pt", "flux_tiny_odd.pt"])
 def test_flux_engine_host_logic_vs_reference_golden(fname):
     """Stacked modulation GEMM and its offsets, joint [txt | img] activation, two-segment GEMMs vs per-stream launches,
     QK-norm / RoPE tables, gated in-place residuals, [qkv | mlp] split of the single-stream blocks, final layer."""

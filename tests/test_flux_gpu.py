@@ -144,7 +144,7 @@ def _engine(cfg, sd):
     return FluxEngine(cfg, sd, dtype=BF, device=DEV)
 
 
-@pytest.mark.parametrize("fname", ["flux_tiny.pt", "flux_tiny_seg.pt"])
+@pytest.mark.parametrize("fname", ["flux_tiny.pt", "flux_tiny_seg.pt", "flux_tiny_odd.pt"])
 def test_flux_forward_vs_reference_golden(fname):
     """flux_tiny: 64 img + 128 txt tokens (per-stream launches); flux_tiny_seg: 256 + 256 tokens (two-segment GEMMs)."""
     g = torch.load(os.path.join(GOLD, fname), weights_only=False)

@@ -165,6 +165,10 @@ def test_flux_oracle_matches_reference_golden():
     with torch.no_grad():
         out = OF.flux_forward(sd, cfg, g["x"], g["t"], g["context"], g["y"], g["guidance"])
     assert_close("oracle flux tiny vs reference golden", out, g["out"], max_abs=5e-5)
+    go = _gold("flux_tiny_odd.pt")  # 15 x 18 latent: circular pad to the patch size, crop
+    with torch.no_grad():
+        outo = OF.flux_forward(sd, cfg, go["x"], go["t"], go["context"], go["y"], go["guidance"])
+    assert_close("oracle flux tiny (odd latent) vs reference golden", outo, go["out"], max_abs=5e-5)
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
