@@ -125,23 +125,31 @@ class VAEDecoderEngine:
         q = ops.gemm(hn.view(n * L, c), w[p + ".q.w"], w[p + ".q.b"]).view(n, L, c)
         k = ops.gemm(hn.view(n * L, c), w[p + ".k.w"], w[p + ".k.b"]).view(n, L, c)
         o = torch.empty((n, L, c), dtype=self.dtype, device=self.device)
-        # key count rounded up to a multiple of 8 (GEMM N / K granularity): the padded key rows are zero and masked by the
-        # softmax (valid_cols), so token counts such as the 12 of a 4x3 edge tile of the tiled decode are served too
-        L8 = (L + 7) // 8 * 8
-        s = torch.empty((L, L8), dtype=self.dtype, device=self.device)
-        vt = torch.empty((c, L8), dtype=self.dtype, device=self.device)
-        kb = k
-        if L8 != L:
-            kb = torch.empty((n, L8, c), dtype=self.dtype, device=self.device)
-            ops.zero_(kb)
-            ops.zero_(vt)
-        for b in range(n):
-            if L8 != L:
-                kb[b, :L].copy_(k[b])
-            ops.gemm(w[p + ".v.w"], hn[b], w[p + ".v.b"], bias_along_m=True, out=vt[:, :L] if L8 != L else vt)  # V^T [C, L]
-            ops.gemm(q[b], kb[b], out=s, alpha=c ** -0.5)                             # S = Q K^T / sqrt(C) [L, L8]
-            ops.softmax_rows_(s, 1.0, L)
-            ops.gemm(s, vt, out=o[b])                                                 # O = P V [L, C]
+        if L % 8 == 0:
+            s = torch.empty((L, L), dtype=self.dtype, device=self.device)
+            vt = torch.empty((c, L), dtype=self.dtype, device=self.device)
+            for b in range(n):
+                ops.gemm(w[p + ".v.w"], hn[b], w[p + ".v.b"], bias_along_m=True, out=vt)  # V^T [C, L]
+                ops.gemm(q[b], k[b], out=s, alpha=c ** -0.5)                              # S = Q K^T / sqrt(C) [L, L]
+                ops.softmax_rows_(s, 1.0)
+                ops.gemm(s, vt, out=o[b])                                                 # O = P V [L, C]
+        else:
+            # token counts that are not a multiple of 8 (e.g. the 4x3 edge tiles of the tiled decode): keys padded to L8 rows —
+            # the GEMM N / K granularity — and masked by the softmax (valid_cols), so the padded rows contribute exactly 0
+            L8 = (L + 7) // 8 * 8
+            s = torch.empty((L, L8), dtype=self.dtype, device=self.device)
+            vt = torch.empty((c, L8), dtype=self.dtype, device=self.device)
+            hn8 = torch.empty((L8, c), dtype=self.dtype, device=self.device)
+            k8 = torch.empty((L8, c), dtype=self.dtype, device=self.device)
+            ops.zero_(hn8)
+            ops.zero_(k8)
+            for b in range(n):
+                hn8[:L].copy_(hn[b])
+                k8[:L].copy_(k[b])
+                ops.gemm(w[p + ".v.w"], hn8, w[p + ".v.b"], bias_along_m=True, out=vt)    # V^T [C, L8]
+                ops.gemm(q[b], k8, out=s, alpha=c ** -0.5)                                # [L, L8]
+                ops.softmax_rows_(s, 1.0, L)
+                ops.gemm(s, vt, out=o[b])
         out = ops.gemm(o.view(n * L, c), w[p + ".proj_out.w"], w[p + ".proj_out.b"], residual=x2d)
         return out.view(n, hh, ww, c)
 
