@@ -76,8 +76,24 @@ def unet_gemms():
     torch.cuda.synchronize()
 
 
+def producer_gemms():
+    """Producer flavour (bias + residual + row statistics) at the two transformer levels, each twice (read the second)."""
+    for M, C in ((16384, 1280), (65536, 640)):
+        a = torch.randn(M, C, device=DEV, dtype=torch.float16)
+        w = torch.randn(C, C, device=DEV, dtype=torch.float16) * C ** -0.5
+        b = torch.randn(C, device=DEV, dtype=torch.float16)
+        res = torch.randn(M, C, device=DEV, dtype=torch.float16)
+        t = torch.empty(M, C, device=DEV, dtype=torch.float16)
+        st = ops.row_stats_buffer(M, C, DEV)
+        for _ in range(2):
+            ops.gemm(a, w, b, residual=res, out=t, row_stats_out=st)
+    torch.cuda.synchronize()
+
+
 if which == "unetgemm":
     unet_gemms()
+elif which == "producer":
+    producer_gemms()
 elif which == "all":
     gemm(16384, 10240, 1280)
     conv(16, 128, 128, 320, 320)

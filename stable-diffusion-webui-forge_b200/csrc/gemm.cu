@@ -153,6 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr bool LNS = (FEAT & 1) != 0;
   constexpr bool EXT = (FEAT & 2) != 0;
   constexpr bool GT = (FEAT & 4) != 0;
+  constexpr bool RV = FEAT != 1;  // the UNet transformer build (LNS alone) carries no per-sample row vector (host-routed)
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // pair (or CTA) index
   const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -360,8 +361,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         ln_rstd = rsqrtf(m2 / cnt + p.ln_eps);
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
       int gt_img = 0, gt_y0 = 0, gt_x0 = 0;  // GT: image and origin of this tile
       if constexpr (GT) {
@@ -390,20 +389,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       float st_piv = 0.f, st_cnt = 0.f;
       f32x2_t st_s2 = pk2(0.f, 0.f), st_q2 = pk2(0.f, 0.f);
       if (col_bias || ln) {
-        named_bar_sync(1, kEpiThreads);  // every warp is done with the previous tile's bias / LN rows
+        // this tile's bias / LN rows -> smem, all of it BEFORE the wait on the accumulator: the global loads are issued first,
+        // the first barrier (every warp is done with the previous tile's rows) then only guards the st.shared
         const int e0 = (int)(threadIdx.x - 128) * 8;
-        if (ln) {
-          const int e = (int)threadIdx.x - 128;
-          if (e < BN) {
-            const bool ok = n0 + e < p.N;
-            const float cv = ok ? __ldg(p.ln_c + n0 + e) : 0.f, dv = ok ? __ldg(p.ln_d + n0 + e) : 0.f;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnc_smem + 4u * e), "f"(cv) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnd_smem + 4u * e), "f"(dv) : "memory");
-          }
+        const int e = (int)threadIdx.x - 128;
+        float cv = 0.f, dv = 0.f;
+        if (ln && e < BN && n0 + e < p.N) {
+          cv = __ldg(p.ln_c + n0 + e);
+          dv = __ldg(p.ln_d + n0 + e);
+        }
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (col_bias && e0 < BN && n0 + e0 < p.N)
+          bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bias_p) + (size_t)(n0 + e0) * 2));
+        named_bar_sync(1, kEpiThreads);
+        if (ln && e < BN) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnc_smem + 4u * e), "f"(cv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(lnd_smem + 4u * e), "f"(dv) : "memory");
         }
         if (col_bias && e0 < BN) {  // the bias row is kept in fp32: the chunks add it with packed adds, no conversions
-          uint4 bv = make_uint4(0, 0, 0, 0);
-          if (n0 + e0 < p.N) bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bias_p) + (size_t)(n0 + e0) * 2));
           const float2 b0 = unpack2<BF16>(bv.x), b1 = unpack2<BF16>(bv.y), b2 = unpack2<BF16>(bv.z), b3 = unpack2<BF16>(bv.w);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_smem + (uint32_t)e0 * 4u), "f"(b0.x), "f"(b0.y),
                        "f"(b1.x), "f"(b1.y)
@@ -429,11 +432,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       };
       const bool any_rs = p.residual != nullptr;  // warp-uniform
       const int piece = lane & 3;
+      // residual: COALESCED — each load instruction covers 8 rows x 64 contiguous bytes (the thread-per-row pattern of the
+      // TMEM layout touched 32 rows per instruction: 32 L1 wavefronts each, which saturated the load pipe on the K <= 1280
+      // shapes); the tile is transposed to thread-per-row through the warp's staging buffer below.  The loads run one chunk
+      // ahead of the arithmetic (the first chunk's before the wait on the accumulator): a DRAM round trip per chunk in the
+      // dependent chain made the K <= 1280 producer GEMMs epilogue-bound.
+      auto load_res = [&](int c, uint4 (&dst)[4]) {
+        const int col = out_n0 + c + piece * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int mm;
+          const bool ok = row_of(j * 8 + (lane >> 2), mm) && col < p.n_out;
+          dst[j] = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)mm * p.ldr + col) * 2)
+                      : make_uint4(0, 0, 0, 0);
+        }
+      };
+      uint4 rsc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rsc[j] = make_uint4(0, 0, 0, 0);
+      if (any_rs) {
+        // the residual usually comes from DRAM (written several kernels ago): pull the NEXT tile's lines into L2 now, a whole
+        // mainloop ahead of their loads (prefetch instructions hold no registers), and the first tile's at the start
+        auto prefetch_res = [&](int t) {
+          const int t_mu = p.n_fast ? t / p.tiles_n : t % tiles_mu;
+          const int t_nb = p.n_fast ? t % p.tiles_n : t / tiles_mu;
+          const int t_mb = t_mu * CG + (int)cta_rank;
+          const int e = (int)threadIdx.x - 128;  // 256 epilogue threads: two per tile row
+          const int rr = e >> 1;
+          int mm = t_mb * 128 + rr;
+          bool ok = mm < p.M;
+          if constexpr (GT) {
+            const int tpi = p.tiles_w * p.tiles_h;
+            const int img = t_mb / tpi;
+            const int rem = t_mb - img * tpi;
+            const int ty = rem / p.tiles_w;
+            const int y = ty * p.tile_h + (rr >> p.tile_w_log2), x = (rem - ty * p.tiles_w) * p.tile_w + (rr & (p.tile_w - 1));
+            ok = img < p.img_n && y < p.img_h && x < p.img_w;
+            mm = (img * p.img_h + y) * p.img_w + x;
+          }
+          if (!ok) return;
+          const char* row = reinterpret_cast<const char*>(p.residual) + ((size_t)mm * p.ldr + (size_t)t_nb * ncols_out) * 2;
+          const int row_bytes = min(ncols_out, p.n_out - t_nb * ncols_out) * 2;
+          for (int off = (e & 1) * 128; off < row_bytes; off += 256)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+        };
+        if (it == 0) prefetch_res(tile);
+        if (tile + num_units < total_tiles) prefetch_res(tile + num_units);
+        if (chalf * 32 < ncols_out) load_res(chalf * 32, rsc);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
 
       for (int c = chalf * 32; c < ncols_out; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
-        uint4 rv[4], rsc[4];
-        const bool has_rv = rowvec_p && row_ok && !geglu;
+        uint4 rv[4], rsn[4];
+        const bool has_rv = RV && rowvec_p && row_ok && !geglu;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           rv[g] = make_uint4(0, 0, 0, 0);
@@ -441,19 +494,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           if (has_rv && n < p.N)
             rv[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(rowvec_p) + (rv_off + (size_t)n) * 2));
         }
-        // residual: COALESCED — each load instruction covers 8 rows x 64 contiguous bytes (the thread-per-row pattern of the
-        // TMEM layout touched 32 rows per instruction: 32 L1 wavefronts each, which saturated the load pipe on the K <= 1280
-        // shapes); the tile is transposed to thread-per-row through the warp's staging buffer below
-        if (any_rs) {
-          const int col = out_n0 + c + piece * 8;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            int mm;
-            const bool ok = row_of(j * 8 + (lane >> 2), mm) && col < p.n_out;
-            rsc[j] = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.residual) + ((size_t)mm * p.ldr + col) * 2)
-                        : make_uint4(0, 0, 0, 0);
-          }
-        }
+        for (int j = 0; j < 4; ++j) rsn[j] = make_uint4(0, 0, 0, 0);
+        if (any_rs && c + 64 < ncols_out) load_res(c + 64, rsn);
         uint32_t v[32];
         f32x2_t xp[16];
         tmem_ld_32x32(t_addr + (uint32_t)c, v);
@@ -615,6 +658,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rsc[j] = rsn[j];
       }
       if (row_stats_out && row_ok) {  // one partial per (row, N tile, warp half), written exactly once; [part][row] layout:
         float s0, s1, q0, q1;         // consecutive lanes (rows) write consecutive 16-byte slots
@@ -643,6 +688,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------- host
 static int pick_block_n(int N, int epilogue) {
   const int step = (epilogue == B200_EPI_GEGLU) ? 64 : 32;
+  // N >= 512: always 256 wide, even with a partly empty last tile: measured on B200 (M = 65536, N = 640) a 256-wide tile with
+  // 17 % of its columns wasted still beats four exact 160-wide tiles by 17-26 % (the A tile is re-read once per N tile and
+  // the wider MMA amortises it), and N = 1920 gains 5-10 % over 192
+  if (N >= 512) return 256;
   if (N >= 256) {
     for (int bn = 256; bn >= 128; bn -= step)
       if (N % bn == 0) return bn;
@@ -728,8 +777,9 @@ static int launch_gemm_e(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
 
 static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                        const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
-  const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH || p.alpha != 0.f;
   const bool lns = p.ln_stats != nullptr || p.row_stats_out != nullptr;
+  const bool ext = p.seg_period != 0 || p.rowvec_mul != 0 || p.act_col0 != 0 || p.epilogue == B200_EPI_GELU_TANH || p.alpha != 0.f ||
+                   (lns && p.rowvec != nullptr);  // the LNS-only build has the row vector compiled out
   if (p.tile_w_log2 >= 0 && p.mode == 1 && p.img_n > 0) return launch_gemm_e<4>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
   switch ((lns ? 1 : 0) | (ext ? 2 : 0)) {
     case 0: return launch_gemm_e<0>(mapA, mapA2, mapB, mapB2, p, dtype, cg, stream);
