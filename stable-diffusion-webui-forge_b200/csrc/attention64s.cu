@@ -12,12 +12,14 @@
 //     19 % of the run at L = 1024.
 // Three resident CTAs give every scheduler three softmax warps from independent pipelines — the non-exp phases, the
 // start-up and the tail of one CTA run under the exp phases of the other two — without any cross-tile hand-shaking.
-// Per CTA: 64 KB smem (Q 16 K | K/V ring 4 x 8 K | P 16 K), 128 TMEM columns (S [0,64) | O [64,128)), 256 threads in two
-// warpgroups (setmaxnreg is a warpgroup-wide instruction: the register-poor and the register-rich roles must not share one):
+// Per CTA: 48 KB smem (Q 16 K | K/V ring 4 x 8 K), 128 + 32 TMEM columns (S [0,64) | O [64,128) | P: 64 keys as fp16 pairs),
+// 256 threads in two warpgroups (setmaxnreg is a warpgroup-wide instruction: the register-poor and the register-rich roles must not share one):
 //   warp 0  TMA producer          warp 1  TMEM owner + MMA issuer (converged warp, elected lane)      warps 2-3  idle
 //   warps 4-7  softmax, thread = query row: S row (64 fp32) -> registers in one TMEM round trip, S released at once
 //              (QK_{j+1} runs under the exponentials of block j), packed FFMA2 / FADD2 arithmetic, O accumulates in TMEM with
-//              lazy rescale, P staged in smem as the 128B-swizzled K-major A operand of P.V.
+//              lazy rescale, P written straight into TMEM (tcgen05.st) as the A operand of P.V (tcgen05.mma with A in TMEM):
+//              no shared-memory round trip for P (it was half of the MMA's operand reads and 8 STS.128 per thread and block
+//              on the MIO queue that MUFU shares).  B200_ATTN64S_P_TMEM=0 builds the round-2 first form (P through smem).
 #include "common.cuh"
 #include "host_util.h"
 #include <stdlib.h>
@@ -51,6 +53,23 @@ __device__ __forceinline__ void tmem_st_32x32s(uint32_t taddr, const uint32_t (&
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]: A is M x K with one row per TMEM lane and two 16-bit K elements per 32-bit column
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_waits() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr int kQTile = 128 * 128;  // bytes: 128 query rows x 64 halfs
@@ -58,6 +77,11 @@ constexpr int kKVTile = 64 * 128;  // bytes: 64 key rows x 64 halfs
 constexpr int kSlots = 4;
 constexpr float kRescale = 8.0f;   // log2(256): O is rescaled only when a row's block maximum exceeds the reference by more
 constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemColsP = 32;
+#ifndef B200_ATTN64S_P_TMEM
+#define B200_ATTN64S_P_TMEM 1
+#endif
+constexpr bool kPT = B200_ATTN64S_P_TMEM != 0;
 #ifndef B200_ATTN64S_POLY_PAIRS
 #define B200_ATTN64S_POLY_PAIRS 0x1
 #endif
@@ -76,8 +100,8 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;
   const uint32_t ring_smem = base + kQTile;
-  const uint32_t p_smem = ring_smem + kSlots * kKVTile;
-  const uint32_t bar_base = p_smem + kQTile;
+  const uint32_t p_smem = ring_smem + kSlots * kKVTile;        // P tile (only without kPT)
+  const uint32_t bar_base = p_smem + (kPT ? 0u : (uint32_t)kQTile);
   const uint32_t q_full = bar_base;
   auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
   auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kSlots + i); };
@@ -114,6 +138,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
+    if (kPT) tmem_alloc(tmem_slot + 4u, kTmemColsP);  // 3 CTAs x (128 + 32) columns fit the SM's 512
     tmem_relinquish();
   }
   tc_fence_before();
@@ -121,6 +146,8 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  uint32_t tmem_p = 0;
+  if (kPT) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_p) : "r"(tmem_slot + 4u));
   pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
   if (warp < 4) {
@@ -182,7 +209,16 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         tc_fence_after();
         const uint32_t acc0 = j != 0 ? 1u : 0u;
         if (elect_one()) {
-          if (ksteps == 4) {
+          if (kPT) {  // A = P from TMEM: 16 keys = 8 columns per k step
+            if (ksteps == 4) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ts(o_tmem, tmem_p + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_f16_ts(o_tmem, tmem_p + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+            }
+          } else if (ksteps == 4) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma_f16(o_tmem, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
@@ -204,6 +240,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr;
     const uint32_t o_addr = tmem_base + 64u + lane_addr;
+    const uint32_t p_addr = tmem_p + lane_addr;
     const uint32_t p_row = p_smem + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
@@ -237,7 +274,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       const float m_blk = mx * sl2;
-      // PV_{j-1} must have retired before O is rescaled and before the P tile is overwritten
+      // PV_{j-1} must have retired before O is rescaled and before P is overwritten
       if (j > 0) {
         mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
@@ -246,7 +283,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         m_ref = m_blk;
       } else {
         const bool need = m_blk > m_ref + kRescale;
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need)) {  // lazy rescale: rare after the first few key blocks
           const float alpha = need ? ex2s(m_ref - m_blk) : 1.0f;
 #pragma unroll
           for (int c = 0; c < 64; c += 32) {
@@ -262,9 +299,25 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           if (need) m_ref = m_blk;
         }
       }
-      // p = exp2(s * scale - m_ref), row sum, P -> smem (128B-swizzled K-major A operand: one 64-key atom per row)
+      // p = exp2(s * scale - m_ref), row sum, P -> TMEM (two 16-column stores, the first under the second half's
+      // exponentials) or -> smem (128B-swizzled K-major A operand: one 64-key atom per row)
       const float nm = -m_ref;
       float rs;
+      uint32_t pq[16];  // kPT: 32 keys of this row as fp16 / bf16 pairs
+      auto put8 = [&](int c, const float (&pe)[8]) {
+        if (kPT) {
+          const int o = (c >> 1) & 15;
+          pq[o + 0] = pack2<BF16>(pe[0], pe[1]);
+          pq[o + 1] = pack2<BF16>(pe[2], pe[3]);
+          pq[o + 2] = pack2<BF16>(pe[4], pe[5]);
+          pq[o + 3] = pack2<BF16>(pe[6], pe[7]);
+          if ((c & 31) == 24) tmem_st_32x32_x16(p_addr + (uint32_t)(c >> 5) * 16u, pq);
+        } else {
+          const uint32_t addr = p_row + ((((uint32_t)c >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
+                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+        }
+      };
       if (full_blk) {
         const f32x2_t sl2p = pk2(sl2, sl2), nmp = pk2(nm, nm);
         f32x2_t acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
@@ -287,9 +340,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           acc1 = add2(acc1, pk2(pe[2], pe[3]));
           acc0 = add2(acc0, pk2(pe[4], pe[5]));
           acc1 = add2(acc1, pk2(pe[6], pe[7]));
-          const uint32_t addr = p_row + ((((uint32_t)c >> 3) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
-                       "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+          put8(c, pe);
         }
         float a0, a1, b0, b1;
         upk2(acc0, a0, a1);
@@ -299,30 +350,29 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 64; c += 8) {
-          if (c < BKV) {
+          if (kPT || c < BKV) {  // kPT: the whole 32-column P region is written (zeros past the block), the MMA reads BKV / 2
             float pe[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2s(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
             rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
             rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
-            const uint32_t addr = p_row + ((((uint32_t)c >> 3) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<BF16>(pe[0], pe[1])),
-                         "r"(pack2<BF16>(pe[2], pe[3])), "r"(pack2<BF16>(pe[4], pe[5])), "r"(pack2<BF16>(pe[6], pe[7])));
+            put8(c, pe);
           }
         }
         rs = rs0 + rs1;
       }
       l_run += rs;
-      fence_proxy_async_smem();
+      if (kPT) tmem_st_waits();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
 
-    // ---- output: O / l -> fp16 / bf16 -> warp-private staging (the P tile is free now) -> coalesced stores
+    // ---- output: O / l -> fp16 / bf16 -> warp-private staging (the Q tile, or the smem P tile, is free now) -> coalesced stores
     mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l_run;
-    const uint32_t stg = p_smem + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    const uint32_t stg = (kPT ? q_smem : p_smem) + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
@@ -362,13 +412,14 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (kPT) tmem_dealloc(tmem_p, kTmemColsP);
   }
 }
 
 template <bool BF16>
 static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64sParams& p,
                           cudaStream_t stream) {
-  const size_t smem = (size_t)kQTile * 2 + (size_t)kSlots * kKVTile + 1024 + 256;
+  const size_t smem = (size_t)kQTile * (kPT ? 1 : 2) + (size_t)kSlots * kKVTile + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn64s_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
