@@ -76,6 +76,10 @@ struct GemmKParams {
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
+// Two epilogue warps per TMEM lane quadrant.  Three (512 threads, setmaxnreg 48 / 152) were measured and are SLOWER on every
+// flavour (UNet step 118.3 vs 114.5 ms, LayerNorm-fold N3840 1187 vs 1296 TF/s): the mainloop sits on the shared-memory port
+// (TMA fill + MMA operand reads = 128 B/clk) and the epilogue's staging traffic (residual transpose + output transpose,
+// ~4 KB each way per 32-column chunk and warp) competes for it — more concurrent epilogue warps take more of it.
 static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 static constexpr int kEpiThreads = 256;
 static constexpr uint32_t kStageBufs = 8;          // one private epilogue staging tile per epilogue warp
