@@ -107,3 +107,5 @@ elif which == "gemm":
 elif which == "attn":
     attn(16, 10, 4096, 4096, 64)
     attn(16, 20, 1024, 1024, 64)
+elif which == "attncross":
+    attn(16, 20, 1024, 77, 64)

@@ -12,7 +12,7 @@
 //     19 % of the run at L = 1024.
 // Three resident CTAs give every scheduler three softmax warps from independent pipelines — the non-exp phases, the
 // start-up and the tail of one CTA run under the exp phases of the other two — without any cross-tile hand-shaking.
-// Per CTA: 48 KB smem (Q 16 K | K/V ring 4 x 8 K), 128 + 32 TMEM columns (S [0,64) | O [64,128) | P: 64 keys as fp16 pairs),
+// Per CTA: 64 KB smem (Q 2 x 16 K | K/V ring 4 x 8 K), 128 + 32 TMEM columns (S [0,64) | O [64,128) | P: 64 keys as fp16 pairs),
 // 256 threads in two warpgroups (setmaxnreg is a warpgroup-wide instruction: the register-poor and the register-rich roles must not share one):
 //   warp 0  TMA producer          warp 1  TMEM owner + MMA issuer (converged warp, elected lane)      warps 2-3  idle
 //   warps 4-7  softmax, thread = query row: S row (64 fp32) -> registers in one TMEM round trip, S released at once
@@ -28,7 +28,8 @@ namespace b200 {
 
 struct Attn64sParams {
   int B, H, Lq, Lk;
-  int BKV, n_kv, q_tiles;  // q_tiles: 128-query CTA tiles
+  int BKV, n_kv, q_tiles;  // q_tiles: 128-query tiles
+  int tiles_per_cta;       // consecutive query tiles of one (batch, head) per CTA (> 1 for short key sequences)
   float scale_log2;
   void* O;
   long long o_stride_b, o_stride_l;
@@ -98,14 +99,15 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                const __grid_constant__ CUtensorMap mapV, const Attn64sParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = base;
-  const uint32_t ring_smem = base + kQTile;
+  const uint32_t q_smem0 = base;                     // two Q buffers: tile t lives in buffer t & 1
+  const uint32_t ring_smem = base + 2 * kQTile;
   const uint32_t p_smem = ring_smem + kSlots * kKVTile;        // P tile (only without kPT)
   const uint32_t bar_base = p_smem + (kPT ? 0u : (uint32_t)kQTile);
-  const uint32_t q_full = bar_base;
-  auto ring_full = [&](int i) { return bar_base + 8u * (1 + i); };
-  auto ring_empty = [&](int i) { return bar_base + 8u * (1 + kSlots + i); };
-  const uint32_t s_full = bar_base + 8u * (1 + 2 * kSlots);
+  auto q_full = [&](int i) { return bar_base + 8u * i; };
+  auto q_empty = [&](int i) { return bar_base + 8u * (2 + i); };
+  auto ring_full = [&](int i) { return bar_base + 8u * (4 + i); };
+  auto ring_empty = [&](int i) { return bar_base + 8u * (4 + kSlots + i); };
+  const uint32_t s_full = bar_base + 8u * (4 + 2 * kSlots);
   const uint32_t s_cons = s_full + 8u;
   const uint32_t p_full = s_full + 16u;
   const uint32_t pv_done = s_full + 24u;
@@ -113,19 +115,25 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.q_tiles;
-  const int h = (blockIdx.x / p.q_tiles) % p.H;
-  const int b = blockIdx.x / (p.q_tiles * p.H);
-  const int q0 = qt * 128;
+  const int groups = (p.q_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  const int grp = blockIdx.x % groups;
+  const int h = (blockIdx.x / groups) % p.H;
+  const int b = blockIdx.x / (groups * p.H);
+  const int qt0 = grp * p.tiles_per_cta;
+  const int nt = min(p.tiles_per_cta, p.q_tiles - qt0);  // query tiles of this CTA
   const int BKV = p.BKV;
   const int n_kv = p.n_kv;
+  const int n_blk = nt * n_kv;  // key blocks over all tiles: the pipeline below runs over this flat sequence
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full(i), 1);
+      mbar_init(q_empty(i), 1 + 128);  // the tile's last Q.K^T retired + the softmax threads are done staging O in the buffer
+    }
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(ring_full(i), 1);
       mbar_init(ring_empty(i), 1);
@@ -157,20 +165,25 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     } else if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------------ TMA producer
-        mbar_expect_tx(q_full, (uint32_t)kQTile);
-        tma_load_3d(q_smem, &mapQ, q_full, h * 64, q0, b);
         const uint32_t kv_bytes = (uint32_t)BKV * 128u;
-        for (int idx = 0; idx < 2 * n_kv; ++idx) {  // even: K_{idx/2}, odd: V_{idx/2}
-          const int slot = idx % kSlots;
-          const uint32_t phase = (uint32_t)(idx / kSlots) & 1u;
-          mbar_wait_quiet(ring_empty(slot), phase ^ 1u);
-          mbar_expect_tx(ring_full(slot), kv_bytes);
-          tma_load_3d(ring_smem + slot * kKVTile, (idx & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (idx >> 1) * BKV, b);
+        for (int t = 0; t < nt; ++t) {
+          const int buf = t & 1;
+          if (t >= 2) mbar_wait_quiet(q_empty(buf), (uint32_t)((t >> 1) - 1) & 1u);
+          mbar_expect_tx(q_full(buf), (uint32_t)kQTile);
+          tma_load_3d(q_smem0 + buf * kQTile, &mapQ, q_full(buf), h * 64, (qt0 + t) * 128, b);
+          for (int i = 0; i < 2 * n_kv; ++i) {  // even: K_{i/2}, odd: V_{i/2}; the ring index runs on across tiles
+            const int idx = t * 2 * n_kv + i;
+            const int slot = idx % kSlots;
+            const uint32_t phase = (uint32_t)(idx / kSlots) & 1u;
+            mbar_wait_quiet(ring_empty(slot), phase ^ 1u);
+            mbar_expect_tx(ring_full(slot), kv_bytes);
+            tma_load_3d(ring_smem + slot * kKVTile, (i & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (i >> 1) * BKV, b);
+          }
         }
       }
     } else {
       // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane)
-      const uint64_t qdesc = make_smem_desc_sw128(q_smem, 0, 1024);
+      const uint64_t qdesc0 = make_smem_desc_sw128(q_smem0, 0, 1024);
       const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
       const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kKVTile, 1024);  // MN-major V (one 64-wide atom)
       const uint64_t pdesc = make_smem_desc_sw128(p_smem, 0, 1024);
@@ -181,33 +194,42 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         mbar_wait_quiet(ring_full(idx % kSlots), (uint32_t)(idx / kSlots) & 1u);
         tc_fence_after();
       };
-      auto issue_qk = [&](int idx) {  // S = Q K^T (M 128, N BKV, K 64), then release the K slot
+      // S = Q_t K_j^T for flat block g = t * n_kv + j (M 128, N BKV, K 64); releases the K slot, and the Q buffer after a
+      // tile's last block
+      auto issue_qk = [&](int g, int t, int j) {
+        if (j == 0) {
+          mbar_wait_quiet(q_full(t & 1), (uint32_t)(t >> 1) & 1u);
+          tc_fence_after();
+        }
+        const int idx = 2 * g;
+        wait_full(idx);
+        const uint64_t qd = qdesc0 + (uint64_t)((t & 1) * (kQTile >> 4));
         const uint64_t kd = kdesc0 + (uint64_t)((idx % kSlots) * (kKVTile >> 4));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qdesc + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(s_full);
           umma_commit(ring_empty(idx % kSlots));
+          if (j == n_kv - 1) umma_commit(q_empty(t & 1));
         }
         __syncwarp();
       };
-      mbar_wait_quiet(q_full, 0);
-      wait_full(0);
-      issue_qk(0);
+      issue_qk(0, 0, 0);
+      int t = 0, j = 0;  // tile and block of g
 #pragma unroll 1
-      for (int j = 0; j < n_kv; ++j) {
-        const int vidx = 2 * j + 1, kidx = 2 * j + 2;
-        if (j + 1 < n_kv) {  // QK_{j+1} as soon as the softmax threads have pulled S_j into registers
-          wait_full(kidx);
-          mbar_wait_quiet(s_cons, (uint32_t)j & 1u);
+      for (int g = 0; g < n_blk; ++g) {
+        const int vidx = 2 * g + 1;
+        const int jn = (j + 1 == n_kv) ? 0 : j + 1, tn = (j + 1 == n_kv) ? t + 1 : t;
+        if (g + 1 < n_blk) {  // Q.K^T of the next block (or of the next tile's first) as soon as S_g sits in registers
+          mbar_wait_quiet(s_cons, (uint32_t)g & 1u);
           tc_fence_after();
-          issue_qk(kidx);
+          issue_qk(g + 1, tn, jn);
         }
         wait_full(vidx);
         const uint64_t vd = vdesc0 + (uint64_t)((vidx % kSlots) * (kKVTile >> 4));
-        mbar_wait_quiet(p_full, (uint32_t)j & 1u);
+        mbar_wait_quiet(p_full, (uint32_t)g & 1u);
         tc_fence_after();
-        const uint32_t acc0 = j != 0 ? 1u : 0u;
+        const uint32_t acc0 = j != 0 ? 1u : 0u;  // a tile's first P.V overwrites O (its predecessor's O was read before P_g was published)
         if (elect_one()) {
           if (kPT) {  // A = P from TMEM: 16 keys = 8 columns per k step
             if (ksteps == 4) {
@@ -230,6 +252,8 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           umma_commit(ring_empty(vidx % kSlots));
         }
         __syncwarp();
+        t = tn;
+        j = jn;
       }
     }
   } else {
@@ -244,12 +268,14 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const uint32_t p_row = p_smem + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
-    float m_ref = -INFINITY, l_run = 0.f;
 
+    for (int t = 0; t < nt; ++t) {
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
+      const int g = t * n_kv + j;  // flat block index: every barrier's phase runs on across the CTA's tiles
       int nvalid = p.Lk - j * BKV;
       if (nvalid > BKV) nvalid = BKV;
-      mbar_wait(s_full, (uint32_t)j & 1u);
+      mbar_wait(s_full, (uint32_t)g & 1u);
       tc_fence_after();
       uint32_t v[64];
       tmem_ld_32x32(s_addr + 0u, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -274,9 +300,11 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           if (i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       const float m_blk = mx * sl2;
-      // PV_{j-1} must have retired before O is rescaled and before P is overwritten
+      // PV_{g-1} must have retired before O is rescaled and before P is overwritten (a tile's first block: the previous
+      // tile's output phase has waited for it).  Moving this wait behind the first 32 exponentials was measured: slower
+      // (825 -> 785 TF/s at L4096) — the warps of a CTA then reach their MUFU phases together instead of staggered.
       if (j > 0) {
-        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        mbar_wait(pv_done, (uint32_t)(g - 1) & 1u);
         tc_fence_after();
       }
       if (j == 0) {
@@ -352,8 +380,13 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         for (int c = 0; c < 64; c += 8) {
           if (kPT || c < BKV) {  // kPT: the whole 32-column P region is written (zeros past the block), the MMA reads BKV / 2
             float pe[8];
+            if (c < nvalid) {  // warp-uniform: groups past the block's last key cost no MUFU slots (cross-attention: 13 of 64)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2s(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
+              for (int i = 0; i < 8; ++i) pe[i] = (c + i < nvalid) ? ex2s(fmaf(__uint_as_float(v[c + i]), sl2, nm)) : 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pe[i] = 0.f;
+            }
             rs0 += (pe[0] + pe[2]) + (pe[4] + pe[6]);
             rs1 += (pe[1] + pe[3]) + (pe[5] + pe[7]);
             put8(c, pe);
@@ -369,10 +402,11 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     }
 
     // ---- output: O / l -> fp16 / bf16 -> warp-private staging (the Q tile, or the smem P tile, is free now) -> coalesced stores
-    mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+    mbar_wait(pv_done, (uint32_t)(t * n_kv + n_kv - 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l_run;
-    const uint32_t stg = (kPT ? q_smem : p_smem) + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    const int q0 = (qt0 + t) * 128;
+    const uint32_t stg = (kPT ? q_smem0 + (uint32_t)(t & 1) * kQTile : p_smem) + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
@@ -405,6 +439,9 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           *reinterpret_cast<uint4*>(obase + ((size_t)q * p.o_stride_l + piece * 8) * 2) = make_uint4(o0, o1, o2, o3);
       }
     }
+    tc_fence_before();          // O has been read out of TMEM: the next tile's first P.V may overwrite it (ordered by p_full)
+    mbar_arrive(q_empty(t & 1));  // ... and this tile's Q buffer (the staging tile) may take the tile after next
+    }  // tiles
   }
 
   tc_fence_before();
@@ -419,7 +456,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 template <bool BF16>
 static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64sParams& p,
                           cudaStream_t stream) {
-  const size_t smem = (size_t)kQTile * (kPT ? 1 : 2) + (size_t)kSlots * kKVTile + 1024 + 256;
+  const size_t smem = (size_t)kQTile * (kPT ? 2 : 3) + (size_t)kSlots * kKVTile + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn64s_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -429,7 +466,7 @@ static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CU
     }
     attr_done = true;
   }
-  const int grid = p.q_tiles * p.H * p.B;
+  const int grid = ((p.q_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta) * p.H * p.B;
   cudaError_t e = launch_pdl(attn64s_kernel<BF16>, dim3(grid), dim3(256), smem, stream, 1, mQ, mK, mV, p);
   if (e != cudaSuccess) {
     set_error("attention64s: launch failed: %s", cudaGetErrorString(e));
@@ -450,6 +487,28 @@ int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, 
   p.BKV = d->Lk >= 64 ? 64 : ((d->Lk + 15) / 16) * 16;
   p.n_kv = (d->Lk + p.BKV - 1) / p.BKV;
   p.q_tiles = (d->Lq + 127) / 128;
+  // Short key sequences (cross-attention: 77 keys = 2 blocks): a CTA's life is a latency chain (set-up, Q from DRAM, two
+  // MMA -> softmax round trips, output) with ~1 us of work in it; several consecutive query tiles per CTA put the next
+  // tile's Q load and first Q.K^T under the current tile's softmax and output phases.  B200_ATTN64S_TP forces a count.
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("B200_ATTN64S_TP");
+      forced = e ? atoi(e) : 0;
+    }
+    int tp = 1;
+    if (forced > 0) {
+      tp = forced;
+    } else if (p.n_kv <= 2) {
+      const long long tiles = (long long)p.q_tiles * d->H * d->B;
+      const long long resident = 3LL * num_sms();
+      tp = (int)(tiles / (2 * resident));  // keep at least ~2 waves of CTAs
+      if (tp > 4) tp = 4;
+    }
+    if (tp < 1) tp = 1;
+    if (tp > p.q_tiles) tp = p.q_tiles;
+    p.tiles_per_cta = tp;
+  }
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.O = o;
   p.o_stride_b = d->o_stride_b;
