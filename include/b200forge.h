@@ -122,6 +122,20 @@ typedef struct {
 int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y, const b200_conv3x3_desc* d,
                  b200_stream_t s);
 
+/* Nearest-neighbour x2 upsample FOLDED into the following 3x3 convolution:
+ *   y[N,2H,2W,Cout] = epi(conv3x3(upsample2x(x[N,H,W,C])) + bias (+ temb + residual, indexed on the 2H x 2W grid))
+ * replaces: F.interpolate(scale_factor=2, mode="nearest") + self.conv in Upsample.forward (backend/nn/unet.py:330-355)
+ *           and the VAE decoder's Upsample (backend/nn/vae.py:38-58) — without materialising the 4x tensor.
+ * On the upsampled image every output pixel of parity (py, px) = (Y % 2, X % 2) sees only a 2x2 neighbourhood of the LOW-RES
+ * image (rows y + py - 1, y + py; columns x + px - 1, x + px), so the 3x3 filter collapses to four 2x2 filters whose taps are
+ * sums of the original ones (rows {0 | 1+2} for py = 0, {0+1 | 2} for py = 1; same for columns): 16 instead of 36
+ * multiply-adds per output pixel and channel pair.  w_packed4 is [4*Cout, 4*(C1+C2)]: row (py*2+px)*Cout + co,
+ * k = (ty*2+tx)*(C1+C2) + c, sums taken in fp32 and rounded once to the operand type (pack_conv3x3_up2x in ops.py).
+ * The descriptor carries the LOW-RES N, H, W; any H, W (generic tiling, masked stores).
+ */
+int b200_conv3x3_up2x(const void* x1, const void* x2, const void* w_packed4, void* y, const b200_conv3x3_desc* d,
+                      b200_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-head attention forward  O = softmax(Q K^T * scale) V   (FlashAttention-style, S and O tiles in
  * TMEM, K/V tiles by TMA, online softmax in registers).  No mask, no dropout, non-causal.

@@ -11,6 +11,7 @@
 //     128 halfs is two 128B-swizzled atoms (dims 0-63 | 64-127) 16 KB apart.
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -388,8 +389,20 @@ static int launch_attn128(const CUtensorMap& mQ, const CUtensorMap& mK, const CU
   return B200_OK;
 }
 
-// called from b200_attention (attention.cu) for Dh == 128
+int attention128s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st);
+
+// called from b200_attention (attention.cu) for Dh == 128.  B200_ATTN128_VER: 2 (default) = the small-CTA kernel of
+// attention64s.cu built for Dh = 128 (one query tile per CTA, 64-key blocks, P in TMEM, two CTAs per SM), 0 = this file's
+// kernel (two tiles per CTA, one CTA per SM, P through shared memory), kept for A/B.
 int attention128_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+  {
+    static int ver = -1;
+    if (ver < 0) {
+      const char* e = getenv("B200_ATTN128_VER");
+      ver = e ? atoi(e) : 2;
+    }
+    if (ver == 2) return attention128s_dispatch(q, k, v, o, d, st);
+  }
   Attn128Params p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;

@@ -73,8 +73,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 __device__ __forceinline__ void tmem_st_waits() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int kQTile = 128 * 128;  // bytes: 128 query rows x 64 halfs
-constexpr int kKVTile = 64 * 128;  // bytes: 64 key rows x 64 halfs
+constexpr int kQAtom = 128 * 128;  // bytes: 128 query rows x 64 halfs (one 128B-swizzle atom; a Dh = 128 tile is two of them)
+constexpr int kKVAtom = 64 * 128;  // bytes: 64 key rows x 64 halfs
 constexpr int kSlots = 4;
 constexpr float kRescale = 8.0f;   // log2(256): O is rescaled only when a row's block maximum exceeds the reference by more
 constexpr uint32_t kTmemCols = 128;
@@ -86,6 +86,10 @@ constexpr bool kPT = B200_ATTN64S_P_TMEM != 0;
 #ifndef B200_ATTN64S_POLY_PAIRS
 #define B200_ATTN64S_POLY_PAIRS 0x1
 #endif
+#ifndef B200_ATTN128S_POLY_PAIRS
+#define B200_ATTN128S_POLY_PAIRS 0x1
+#endif
+constexpr unsigned kPolyPairs128S = B200_ATTN128S_POLY_PAIRS;  // the same choice for the Dh = 128 build
 constexpr unsigned kPolyPairsS = B200_ATTN64S_POLY_PAIRS;  // element PAIRS (of the 4 per 8 elements) whose exp2 runs on the FMA pipe:
 // measured (B16 H10 L4096 / B16 H20 L1024, TF/s): none 772 / 643, 1 of 4 790 / 652, 2 of 4 727 / 611, 3 of 4 653 / 560
 
@@ -93,14 +97,26 @@ constexpr unsigned kPolyPairsS = B200_ATTN64S_POLY_PAIRS;  // element PAIRS (of 
 
 // __maxnreg__(80): 3 CTAs x 256 threads x 80 registers = 60 K of the SM's 64 K; with setmaxnreg in the kernel ptxas takes the
 // cap as the launch-time count, which the dec / inc below redistribute (4 x (80 - 24) released = 4 x (136 - 80) taken).
-template <bool BF16>
-__global__ void __maxnreg__(80)
+//
+// DH = 128 (Flux / SD3; round 2, late): the same pipeline with TWO CTAs per SM — per 64-key block the tensor core now has as
+// much work as the MUFU (Q.K^T + P.V = 2 x 256 clk against 512 clk of exponentials), so the second CTA's MMAs run under the
+// first one's softmax and vice versa.  Per CTA: Q 32 KB (one buffer: one query tile per CTA) + K/V ring 4 x 16 KB = 96 KB smem;
+// TMEM 256 columns: S [0,64) | O [64,192) | P [192,224); Q / K / V tiles are two 64-wide swizzle atoms side by side; 128
+// registers per thread at launch (48 control / 208 softmax after setmaxnreg).
+template <bool BF16, int DH>
+__global__ void __maxnreg__(DH == 64 ? 80 : 128)
 attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const Attn64sParams p) {
+  static_assert(DH == 64 || DH == 128, "head dim");
+  static_assert(kPT || DH == 64, "P through shared memory is only kept for Dh = 64");
+  constexpr int kAtoms = DH / 64;            // 64-wide swizzle atoms per row
+  constexpr int kQTile = kAtoms * kQAtom;    // bytes of one Q tile
+  constexpr int kKVTile = kAtoms * kKVAtom;  // bytes of one ring slot (64 keys)
+  constexpr int kQBufs = DH == 64 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem0 = base;                     // two Q buffers: tile t lives in buffer t & 1
-  const uint32_t ring_smem = base + 2 * kQTile;
+  const uint32_t q_smem0 = base;                     // Q buffers: tile t lives in buffer t % kQBufs
+  const uint32_t ring_smem = base + kQBufs * kQTile;
   const uint32_t p_smem = ring_smem + kSlots * kKVTile;        // P tile (only without kPT)
   const uint32_t bar_base = p_smem + (kPT ? 0u : (uint32_t)kQTile);
   auto q_full = [&](int i) { return bar_base + 8u * i; };
@@ -145,8 +161,12 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    if (kPT) tmem_alloc(tmem_slot + 4u, kTmemColsP);  // 3 CTAs x (128 + 32) columns fit the SM's 512
+    if constexpr (DH == 64) {
+      tmem_alloc(tmem_slot, kTmemCols);
+      if (kPT) tmem_alloc(tmem_slot + 4u, kTmemColsP);  // 3 CTAs x (128 + 32) columns fit the SM's 512
+    } else {
+      tmem_alloc(tmem_slot, 256);  // 2 CTAs x 256 columns
+    }
     tmem_relinquish();
   }
   tc_fence_before();
@@ -155,29 +175,40 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   uint32_t tmem_p = 0;
-  if (kPT) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_p) : "r"(tmem_slot + 4u));
+  if constexpr (DH == 64) {
+    if (kPT) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_p) : "r"(tmem_slot + 4u));
+  } else {
+    tmem_p = tmem_base + 192u;
+  }
   pdl_wait();  // set-up done; q / k / v are the predecessor's output
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if constexpr (DH == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // eight unrolled MMAs per Q.K^T: 24 registers spill in the issue loop
     if (warp >= 2) {
       // idle warps of the control warpgroup
     } else if (warp == 0) {
       if (lane == 0) {
         // ------------------------------------------------------------------ TMA producer
-        const uint32_t kv_bytes = (uint32_t)BKV * 128u;
+        const uint32_t kv_atom = (uint32_t)BKV * 128u;  // bytes of one 64-wide atom of a key block
+        const uint32_t kv_bytes = kv_atom * kAtoms;
         for (int t = 0; t < nt; ++t) {
-          const int buf = t & 1;
-          if (t >= 2) mbar_wait_quiet(q_empty(buf), (uint32_t)((t >> 1) - 1) & 1u);
+          const int buf = t % kQBufs;
+          if (t >= kQBufs) mbar_wait_quiet(q_empty(buf), (uint32_t)((t / kQBufs) - 1) & 1u);
           mbar_expect_tx(q_full(buf), (uint32_t)kQTile);
-          tma_load_3d(q_smem0 + buf * kQTile, &mapQ, q_full(buf), h * 64, (qt0 + t) * 128, b);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+            tma_load_3d(q_smem0 + buf * kQTile + a * kQAtom, &mapQ, q_full(buf), h * DH + a * 64, (qt0 + t) * 128, b);
           for (int i = 0; i < 2 * n_kv; ++i) {  // even: K_{i/2}, odd: V_{i/2}; the ring index runs on across tiles
             const int idx = t * 2 * n_kv + i;
             const int slot = idx % kSlots;
             const uint32_t phase = (uint32_t)(idx / kSlots) & 1u;
             mbar_wait_quiet(ring_empty(slot), phase ^ 1u);
             mbar_expect_tx(ring_full(slot), kv_bytes);
-            tma_load_3d(ring_smem + slot * kKVTile, (i & 1) ? &mapV : &mapK, ring_full(slot), h * 64, (i >> 1) * BKV, b);
+#pragma unroll
+            for (int a = 0; a < kAtoms; ++a)
+              tma_load_3d(ring_smem + slot * kKVTile + a * kv_atom, (i & 1) ? &mapV : &mapK, ring_full(slot), h * DH + a * 64,
+                          (i >> 1) * BKV, b);
           }
         }
       }
@@ -185,11 +216,13 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane)
       const uint64_t qdesc0 = make_smem_desc_sw128(q_smem0, 0, 1024);
       const uint64_t kdesc0 = make_smem_desc_sw128(ring_smem, 0, 1024);
-      const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kKVTile, 1024);  // MN-major V (one 64-wide atom)
+      const uint32_t kv_atom = (uint32_t)BKV * 128u;
+      const uint64_t vdesc0 = make_smem_desc_sw128(ring_smem, kv_atom, 1024);  // MN-major V: 64-dim atoms kv_atom apart (LBO)
       const uint64_t pdesc = make_smem_desc_sw128(p_smem, 0, 1024);
       const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
       const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64u;
       const int ksteps = BKV >> 4;
+      const uint64_t k_atom_enc = (uint64_t)(kv_atom >> 4);
       auto wait_full = [&](int idx) {
         mbar_wait_quiet(ring_full(idx % kSlots), (uint32_t)(idx / kSlots) & 1u);
         tc_fence_after();
@@ -198,19 +231,21 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       // tile's last block
       auto issue_qk = [&](int g, int t, int j) {
         if (j == 0) {
-          mbar_wait_quiet(q_full(t & 1), (uint32_t)(t >> 1) & 1u);
+          mbar_wait_quiet(q_full(t % kQBufs), (uint32_t)(t / kQBufs) & 1u);
           tc_fence_after();
         }
         const int idx = 2 * g;
         wait_full(idx);
-        const uint64_t qd = qdesc0 + (uint64_t)((t & 1) * (kQTile >> 4));
+        const uint64_t qd = qdesc0 + (uint64_t)((t % kQBufs) * (kQTile >> 4));
         const uint64_t kd = kdesc0 + (uint64_t)((idx % kSlots) * (kKVTile >> 4));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(s_tmem, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k)  // 16 dims per step: +32 B inside a swizzle atom, the next atom after four steps
+            umma_f16(s_tmem, qd + (uint64_t)((k >> 2) * (kQAtom >> 4) + (k & 3) * 2), kd + (uint64_t)(k >> 2) * k_atom_enc + (uint64_t)((k & 3) * 2),
+                     idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(s_full);
           umma_commit(ring_empty(idx % kSlots));
-          if (j == n_kv - 1) umma_commit(q_empty(t & 1));
+          if (j == n_kv - 1) umma_commit(q_empty(t % kQBufs));
         }
         __syncwarp();
       };
@@ -257,7 +292,8 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");  // 4 x 136 + 4 x 24 = 8 x 80 (the launch-time allocation)
+    if constexpr (DH == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");  // 4 x 136 + 4 x 24 = 8 x 80 (the launch-time allocation)
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");                      // 4 x 208 + 4 x 48 = 8 x 128
     // ------------------------------------------------------------------ softmax warpgroup (warps 4-7)
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;  // row inside the tile
@@ -314,7 +350,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         if (__any_sync(0xffffffffu, need)) {  // lazy rescale: rare after the first few key blocks
           const float alpha = need ? ex2s(m_ref - m_blk) : 1.0f;
 #pragma unroll
-          for (int c = 0; c < 64; c += 32) {
+          for (int c = 0; c < DH; c += 32) {
             uint32_t w[32];
             tmem_ld_32x32(o_addr + (uint32_t)c, w);
             tmem_ld_wait();
@@ -355,7 +391,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
           for (int q2 = 0; q2 < 4; ++q2) {
             const f32x2_t x = fma2(pk2(__uint_as_float(v[c + 2 * q2]), __uint_as_float(v[c + 2 * q2 + 1])), sl2p, nmp);
-            if ((kPolyPairsS >> q2) & 1) {
+            if (((DH == 64 ? kPolyPairsS : kPolyPairs128S) >> q2) & 1) {
               exp2_poly3_x2(x, pe[2 * q2], pe[2 * q2 + 1]);
             } else {
               float xa, xb;
@@ -406,10 +442,11 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const int q0 = (qt0 + t) * 128;
-    const uint32_t stg = (kPT ? q_smem0 + (uint32_t)(t & 1) * kQTile : p_smem) + (uint32_t)quad * 4096u;  // 32 rows x 128 B per warp
+    constexpr uint32_t kRowB = DH * 2;  // bytes of one output row
+    const uint32_t stg = (kPT ? q_smem0 + (uint32_t)(t % kQBufs) * kQTile : p_smem) + (uint32_t)quad * (32u * kRowB);  // 32 rows per warp
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
+    for (int c = 0; c < DH; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(o_addr + (uint32_t)c, v);
       tmem_ld_wait();
@@ -419,19 +456,21 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const uint32_t o1 = pack2<BF16>(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
         const uint32_t o2 = pack2<BF16>(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
         const uint32_t o3 = pack2<BF16>(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;  // 16B chunk index inside the 128B row
-        const uint32_t addr = stg + (uint32_t)lane * 128u + ((chunk ^ (uint32_t)(lane & 7)) << 4);
+        const uint32_t chunk = (uint32_t)(c >> 3) + (uint32_t)g;  // 16B chunk index inside the row
+        const uint32_t addr = stg + (uint32_t)lane * kRowB + ((chunk ^ (uint32_t)(lane & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
       }
     }
     __syncwarp();
     {
-      const int piece = lane & 7;
-      char* obase = reinterpret_cast<char*>(p.O) + ((size_t)b * p.o_stride_b + (size_t)h * 64) * 2;
+      constexpr int kPieces = DH / 8;       // 16-byte pieces per row: a warp's store covers 32 / kPieces whole rows
+      constexpr int kRowsPer = 32 / kPieces;
+      const int piece = lane & (kPieces - 1);
+      char* obase = reinterpret_cast<char*>(p.O) + ((size_t)b * p.o_stride_b + (size_t)h * DH) * 2;
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int rl = jj * 4 + (lane >> 3);
-        const uint32_t addr = stg + (uint32_t)rl * 128u + ((((uint32_t)piece) ^ (uint32_t)(rl & 7)) << 4);
+      for (int jj = 0; jj < 32 / kRowsPer; ++jj) {
+        const int rl = jj * kRowsPer + lane / kPieces;
+        const uint32_t addr = stg + (uint32_t)rl * kRowB + ((((uint32_t)piece) ^ (uint32_t)(rl & 7)) << 4);
         uint32_t o0, o1, o2, o3;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(addr));
         const int q = q0 + quad * 32 + rl;
@@ -440,7 +479,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
     }
     tc_fence_before();          // O has been read out of TMEM: the next tile's first P.V may overwrite it (ordered by p_full)
-    mbar_arrive(q_empty(t & 1));  // ... and this tile's Q buffer (the staging tile) may take the tile after next
+    mbar_arrive(q_empty(t % kQBufs));  // ... and this tile's Q buffer (the staging tile) may take the tile after next
     }  // tiles
   }
 
@@ -448,36 +487,42 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-    if (kPT) tmem_dealloc(tmem_p, kTmemColsP);
+    if constexpr (DH == 64) {
+      tmem_dealloc(tmem_base, kTmemCols);
+      if (kPT) tmem_dealloc(tmem_p, kTmemColsP);
+    } else {
+      tmem_dealloc(tmem_base, 256);
+    }
   }
 }
 
-template <bool BF16>
+template <bool BF16, int DH>
 static int launch_attn64s(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const Attn64sParams& p,
                           cudaStream_t stream) {
-  const size_t smem = (size_t)kQTile * (kPT ? 2 : 3) + (size_t)kSlots * kKVTile + 1024 + 256;
+  constexpr int kQTile = (DH / 64) * kQAtom, kKVTile = (DH / 64) * kKVAtom;
+  const size_t smem = DH == 64 ? (size_t)kQTile * (kPT ? 2 : 3) + (size_t)kSlots * kKVTile + 1024 + 256
+                               : (size_t)kQTile + (size_t)kSlots * kKVTile + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn64s_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn64s_kernel<BF16, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-      set_error("attention64s: smem attr: %s", cudaGetErrorString(e));
+      set_error("attention%ds: smem attr: %s", DH, cudaGetErrorString(e));
       return B200_ECUDA;
     }
     attr_done = true;
   }
   const int grid = ((p.q_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta) * p.H * p.B;
-  cudaError_t e = launch_pdl(attn64s_kernel<BF16>, dim3(grid), dim3(256), smem, stream, 1, mQ, mK, mV, p);
+  cudaError_t e = launch_pdl(attn64s_kernel<BF16, DH>, dim3(grid), dim3(256), smem, stream, 1, mQ, mK, mV, p);
   if (e != cudaSuccess) {
-    set_error("attention64s: launch failed: %s", cudaGetErrorString(e));
+    set_error("attention%ds: launch failed: %s", DH, cudaGetErrorString(e));
     return B200_ECUDA;
   }
   B200_CHECK_LAUNCH("attention64s");
   return B200_OK;
 }
 
-// called from attention64_dispatch (attention64.cu) when B200_ATTN64_VER = 2
-int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+template <int DH>
+static int attention_s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
   Attn64sParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;
@@ -490,7 +535,8 @@ int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, 
   // Short key sequences (cross-attention: 77 keys = 2 blocks): a CTA's life is a latency chain (set-up, Q from DRAM, two
   // MMA -> softmax round trips, output) with ~1 us of work in it; several consecutive query tiles per CTA put the next
   // tile's Q load and first Q.K^T under the current tile's softmax and output phases.  B200_ATTN64S_TP forces a count.
-  {
+  // (Dh = 128 has one Q buffer: always one tile per CTA.)
+  if (DH == 64) {
     static int forced = -1;
     if (forced < 0) {
       const char* e = getenv("B200_ATTN64S_TP");
@@ -508,6 +554,8 @@ int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, 
     if (tp < 1) tp = 1;
     if (tp > p.q_tiles) tp = p.q_tiles;
     p.tiles_per_cta = tp;
+  } else {
+    p.tiles_per_cta = 1;
   }
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.O = o;
@@ -515,8 +563,8 @@ int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, 
   p.o_stride_l = d->o_stride_l;
   const bool bf = d->dtype == B200_BF16;
   p.idesc_qk = make_idesc_f16(128, p.BKV, bf, false, false);
-  p.idesc_pv = make_idesc_f16(128, 64, bf, false, true);
-  const uint64_t cols = (uint64_t)d->H * 64;
+  p.idesc_pv = make_idesc_f16(128, DH, bf, false, true);
+  const uint64_t cols = (uint64_t)d->H * DH;
   CUtensorMap mQ, mK, mV;
   auto make3 = [&](CUtensorMap* m, const void* base, int L, long long sl, long long sb, int rows) {
     uint64_t dims[3] = {cols, (uint64_t)L, (uint64_t)d->B};
@@ -530,7 +578,16 @@ int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, 
   if (rc) return rc;
   rc = make3(&mV, v, d->Lk, d->v_stride_l, d->v_stride_b, p.BKV);
   if (rc) return rc;
-  return bf ? launch_attn64s<true>(mQ, mK, mV, p, st) : launch_attn64s<false>(mQ, mK, mV, p, st);
+  return bf ? launch_attn64s<true, DH>(mQ, mK, mV, p, st) : launch_attn64s<false, DH>(mQ, mK, mV, p, st);
+}
+
+// called from attention64_dispatch (attention64.cu) when B200_ATTN64_VER = 2
+int attention64s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+  return attention_s_dispatch<64>(q, k, v, o, d, st);
+}
+// called from attention128_dispatch (attention128.cu) unless B200_ATTN128_VER = 0
+int attention128s_dispatch(const void* q, const void* k, const void* v, void* o, const b200_attn_desc* d, cudaStream_t st) {
+  return attention_s_dispatch<128>(q, k, v, o, d, st);
 }
 
 }  // namespace b200

@@ -73,6 +73,12 @@ struct GemmKParams {
   // image (loads zero-fill, stores are masked); the epilogue decodes (image, y, x) per row instead of assuming that a
   // tile's 128 pixels are consecutive in NHWC order
   int img_n, img_h, img_w, tile_w_log2;
+  // mode 1 + generic tiling, nearest x2 upsample folded into the convolution (b200_conv3x3_up2x): the 3x3 filter on the
+  // upsampled image is, per output parity (py, px), a 2x2 filter on the LOW-RES image (taps at dy in {py-1, py}, dx in
+  // {px-1, px}; weights pre-summed on the host) — 16 instead of 36 MACs per output pixel and input channel, and the 4x tensor
+  // is never materialised.  M tiles enumerate (parity, low-res tile); B rows of parity q start at q * N; output row
+  // (img, y, x) of parity (py, px) is pixel (2y + py, 2x + px) of the [img_n, 2 img_h, 2 img_w] output.
+  int up2x, tiles_lr;
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
@@ -230,13 +236,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       // a pair's 256 rows never straddle a segment boundary (host-checked), so the weight set is per tile
       const CUtensorMap* mb = (EXT && p.seg_period && (m_unit * (CG * 128)) % p.seg_period >= p.seg_split) ? &mapB2 : &mapB;
       int cn = 0, ch = 0, cw = 0;
+      int ntaps = 9, taps_w = 3, b_row0 = 0;
       if (p.mode == 1) {
+        int mlr = m_blk;
+        if (p.up2x) {  // (parity, low-res tile): 2x2 taps shifted by the parity, this parity's weight rows
+          const int pa = m_blk / p.tiles_lr;
+          mlr = m_blk - pa * p.tiles_lr;
+          ntaps = 4;
+          taps_w = 2;
+          ch = pa >> 1;
+          cw = pa & 1;
+          b_row0 = pa * p.N;
+        }
         const int tpi = p.tiles_w * p.tiles_h;
-        const int img_grp = m_blk / tpi;
-        const int rem = m_blk - img_grp * tpi;
+        const int img_grp = mlr / tpi;
+        const int rem = mlr - img_grp * tpi;
         cn = img_grp * p.tile_n;
-        ch = (rem / p.tiles_w) * p.tile_h;
-        cw = (rem % p.tiles_w) * p.tile_w;
+        ch += (rem / p.tiles_w) * p.tile_h;
+        cw += (rem % p.tiles_w) * p.tile_w;
       }
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -253,14 +270,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             // k order = (64-channel slice, tap): the nine shifted boxes of one slice are fetched back to back, so
             // they hit L2 whatever the channel count (tap-major order re-streamed the whole activation from HBM nine
             // times once 74 pairs x 256 pixels x C channels outgrew L2).  The weight column follows the tap-major packing.
-            const int cc = kc / 9;
-            const int tap = kc - cc * 9;
-            const int ky = tap / 3, kx = tap - ky * 3;
+            const int cc = kc / ntaps;
+            const int tap = kc - cc * ntaps;
+            const int ky = tap / taps_w, kx = tap - ky * taps_w;
             bcol = (tap * p.chunks_per_tap + cc) * 64;
             if (cc < p.split_chunk) tma_load_4d(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d(b_dst, mb, fb, bcol, n_blk * BN);
+          tma_load_2d(b_dst, mb, fb, bcol, b_row0 + n_blk * BN);
         } else {
           // both CTAs' loads complete on the leader's barrier; the leader arms it for the pair's bytes
           if (cta_rank == 0) mbar_expect_tx(fb, tx_bytes);
@@ -269,14 +286,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (kc < p.split_chunk) tma_load_2d_cg2(a_dst, &mapA, fb, kc * 64, m_blk * 128);
             else tma_load_2d_cg2(a_dst, &mapA2, fb, (kc - p.split_chunk) * 64, m_blk * 128);
           } else {
-            const int cc = kc / 9;  // (slice, tap) order, see the single-CTA branch
-            const int tap = kc - cc * 9;
-            const int ky = tap / 3, kx = tap - ky * 3;
+            const int cc = kc / ntaps;  // (slice, tap) order, see the single-CTA branch
+            const int tap = kc - cc * ntaps;
+            const int ky = tap / taps_w, kx = tap - ky * taps_w;
             bcol = (tap * p.chunks_per_tap + cc) * 64;
             if (cc < p.split_chunk) tma_load_4d_cg2(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d_cg2(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d_cg2(b_dst, mb, fb, bcol, n_blk * BN + (int)cta_rank * (BN / 2));
+          tma_load_2d_cg2(b_dst, mb, fb, bcol, b_row0 + n_blk * BN + (int)cta_rank * (BN / 2));
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -367,16 +384,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + lane_addr;
       int gt_img = 0, gt_y0 = 0, gt_x0 = 0;  // GT: image and origin of this tile
+      int gt_py = 0, gt_px = 0;              // up2x: output parity of this tile
+      // GT: output row of pixel (img, y, x); with the folded upsample the tile's pixels land on one parity of the 2x grid
+      auto gt_row = [&](int img, int y, int x, int py, int px) -> int {
+        if (p.up2x) return (img * (2 * p.img_h) + 2 * y + py) * (2 * p.img_w) + 2 * x + px;
+        return (img * p.img_h + y) * p.img_w + x;
+      };
       if constexpr (GT) {
+        int mlr = m_blk;
+        if (p.up2x) {
+          const int pa = m_blk / p.tiles_lr;
+          mlr = m_blk - pa * p.tiles_lr;
+          gt_py = pa >> 1;
+          gt_px = pa & 1;
+        }
         const int tpi = p.tiles_w * p.tiles_h;
-        gt_img = m_blk / tpi;
-        const int rem = m_blk - gt_img * tpi;
+        gt_img = mlr / tpi;
+        const int rem = mlr - gt_img * tpi;
         const int ty = rem / p.tiles_w;
         gt_y0 = ty * p.tile_h;
         gt_x0 = (rem - ty * p.tiles_w) * p.tile_w;
         const int y = gt_y0 + (r >> p.tile_w_log2), x = gt_x0 + (r & (p.tile_w - 1));
         row_ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
-        m = (gt_img * p.img_h + y) * p.img_w + x;
+        m = gt_row(gt_img, y, x, gt_py, gt_px);
       }
       const int n0 = n_blk * BN;            // first accumulator column of this tile (weight row index)
       const int out_n0 = n_blk * ncols_out; // first output column
@@ -430,7 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const int rr = quad * 32 + rl;
           const int y = gt_y0 + (rr >> p.tile_w_log2), x = gt_x0 + (rr & (p.tile_w - 1));
           ok = gt_img < p.img_n && y < p.img_h && x < p.img_w;
-          mm = (gt_img * p.img_h + y) * p.img_w + x;
+          mm = gt_row(gt_img, y, x, gt_py, gt_px);
         }
         return ok;
       };
@@ -466,13 +496,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           int mm = t_mb * 128 + rr;
           bool ok = mm < p.M;
           if constexpr (GT) {
+            int t_lr = t_mb, py = 0, px = 0;
+            if (p.up2x) {
+              const int pa = t_mb / p.tiles_lr;
+              t_lr = t_mb - pa * p.tiles_lr;
+              py = pa >> 1;
+              px = pa & 1;
+            }
             const int tpi = p.tiles_w * p.tiles_h;
-            const int img = t_mb / tpi;
-            const int rem = t_mb - img * tpi;
+            const int img = t_lr / tpi;
+            const int rem = t_lr - img * tpi;
             const int ty = rem / p.tiles_w;
             const int y = ty * p.tile_h + (rr >> p.tile_w_log2), x = (rem - ty * p.tiles_w) * p.tile_w + (rr & (p.tile_w - 1));
             ok = img < p.img_n && y < p.img_h && x < p.img_w;
-            mm = (img * p.img_h + y) * p.img_w + x;
+            mm = gt_row(img, y, x, py, px);
           }
           if (!ok) return;
           const char* row = reinterpret_cast<const char*>(p.residual) + ((size_t)mm * p.ldr + (size_t)t_nb * ncols_out) * 2;
@@ -909,8 +946,8 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   return launch_gemm(mA, mA2, mB, mB2, p, d->dtype, cg, static_cast<cudaStream_t>(s));
 }
 
-extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y,
-                            const b200_conv3x3_desc* d, b200_stream_t s) {
+static int conv3x3_impl(const void* x1, const void* x2, const void* w_packed, void* y, const b200_conv3x3_desc* d,
+                        b200_stream_t s, bool up2x) {
   B200_CHECK_ARG(x1 && w_packed && y && d, "conv3x3: null argument");
   B200_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "conv3x3: bad shape");
   B200_CHECK_ARG(d->C1 > 0 && d->C1 % 64 == 0 && d->C2 >= 0 && d->C2 % 64 == 0,
@@ -924,7 +961,7 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   int tile_h = tile_w > 0 && 128 % tile_w == 0 ? 128 / tile_w : 1;
   if (tile_h > d->H) tile_h = d->H;
   int tile_n = (tile_w * tile_h) > 0 && 128 % (tile_w * tile_h) == 0 ? 128 / (tile_w * tile_h) : 0;
-  const bool exact = 128 % tile_w == 0 && d->W % tile_w == 0 && d->H % tile_h == 0 && tile_n > 0 &&
+  const bool exact = !up2x && 128 % tile_w == 0 && d->W % tile_w == 0 && d->H % tile_h == 0 && tile_n > 0 &&
                      (tile_n == 1 || (tile_w == d->W && tile_h == d->H));
   int gt_log2 = -1;
   if (!exact) {
@@ -933,7 +970,7 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
       const char* e = getenv("B200_CONV_GENERAL");
       general = (e && e[0] == '0') ? 0 : 1;
     }
-    if (!general) {
+    if (!general && !up2x) {
       set_error("conv3x3: %dx%d does not tile into 128-pixel boxes and generic tiling is disabled (B200_CONV_GENERAL=0)", d->H, d->W);
       return B200_EUNSUPPORTED;
     }
@@ -952,9 +989,10 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   p.M = d->N * d->H * d->W;
   p.N = d->Cout;
   p.mode = 1;
+  const int ntaps = up2x ? 4 : 9;
   p.chunks_per_tap = C / 64;
   p.split_chunk = d->C1 / 64;
-  p.num_k_chunks = 9 * p.chunks_per_tap;
+  p.num_k_chunks = ntaps * p.chunks_per_tap;
   p.tile_w = tile_w;
   p.tile_h = tile_h;
   p.tile_n = tile_n;
@@ -971,6 +1009,14 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   B200_CHECK_ARG(d->epilogue != B200_EPI_GEGLU, "conv3x3: GEGLU epilogue not supported");
   p.BN = bn;
   p.tiles_m = ((d->N + tile_n - 1) / tile_n) * p.tiles_w * p.tiles_h;
+  if (up2x) {
+    // four parities, each over all low-res tiles; an even tile count per parity keeps a CTA pair (two adjacent M tiles, one
+    // shared B tile) inside one parity — the padding tile lies past the last image (loads zero-fill, stores masked)
+    p.up2x = 1;
+    p.tiles_lr = (p.tiles_m + 1) & ~1;
+    p.tiles_m = 4 * p.tiles_lr;
+    p.M = 4 * d->N * d->H * d->W;
+  }
   p.tiles_n = (d->Cout + bn - 1) / bn;
   p.idesc = make_idesc_f16(128, bn, d->dtype == B200_BF16, false, false);
   p.C = y;
@@ -983,9 +1029,9 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   p.rowvec = d->temb;
   p.ld_rowvec = d->ld_temb;
   B200_CHECK_ARG(!d->temb || d->ld_temb % 8 == 0, "conv3x3: ld_temb");
-  p.rows_per_vec = d->H * d->W;
+  p.rows_per_vec = (up2x ? 4 : 1) * d->H * d->W;
   p.epilogue = d->epilogue;
-  p.n_fast = raster_n_fast((size_t)p.M * C, (size_t)d->Cout * 9 * C, p.tiles_n);  // activations vs weights (each tap re-reads the same activation rows)
+  p.n_fast = raster_n_fast((size_t)p.M * C, (size_t)d->Cout * ntaps * C, p.tiles_n);  // activations vs weights (each tap re-reads the same activation rows)
 
   CUtensorMap mA, mA2, mB;
   auto make4 = [&](CUtensorMap* m, const void* base, int Csrc) {
@@ -1004,11 +1050,21 @@ extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed
   }
   const int cg = gemm_cg(p);
   {
-    uint64_t dims[2] = {(uint64_t)(9 * C), (uint64_t)d->Cout};
-    uint64_t str[1] = {(uint64_t)(9 * C) * 2};
+    uint64_t dims[2] = {(uint64_t)(ntaps * C), (uint64_t)((up2x ? 4 : 1) * d->Cout)};
+    uint64_t str[1] = {(uint64_t)(ntaps * C) * 2};
     uint32_t box[2] = {64, (uint32_t)(bn / cg)};
     rc = make_tmap(&mB, d->dtype, w_packed, 2, dims, str, box);
     if (rc) return rc;
   }
   return launch_gemm(mA, mA2, mB, mB, p, d->dtype, cg, static_cast<cudaStream_t>(s));
+}
+
+extern "C" int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y,
+                            const b200_conv3x3_desc* d, b200_stream_t s) {
+  return conv3x3_impl(x1, x2, w_packed, y, d, s, false);
+}
+
+extern "C" int b200_conv3x3_up2x(const void* x1, const void* x2, const void* w_packed4, void* y,
+                                 const b200_conv3x3_desc* d, b200_stream_t s) {
+  return conv3x3_impl(x1, x2, w_packed4, y, d, s, true);
 }

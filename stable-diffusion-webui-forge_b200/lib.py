@@ -92,6 +92,7 @@ SIGNATURES = {
     "b200_gemm": (_i, [_vp, _vp, _vp, C.POINTER(GemmDesc), _vp]),
     "b200_gemm_row_stats_parts": (_i, [_i, _i, _i]),
     "b200_conv3x3": (_i, [_vp, _vp, _vp, _vp, C.POINTER(Conv3x3Desc), _vp]),
+    "b200_conv3x3_up2x": (_i, [_vp, _vp, _vp, _vp, C.POINTER(Conv3x3Desc), _vp]),
     "b200_attention": (_i, [_vp, _vp, _vp, _vp, C.POINTER(AttnDesc), _vp]),
     "b200_groupnorm_ws_bytes": (_sz, [C.POINTER(GnDesc)]),
     "b200_groupnorm_stats": (_i, [_vp, _vp, _vp, C.POINTER(GnDesc), _vp]),

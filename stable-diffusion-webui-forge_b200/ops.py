@@ -255,6 +255,59 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
+def pack_conv3x3_up2x(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [4*Cout, 4*Cin] for b200_conv3x3_up2x: the 3x3 filter applied to a nearest-x2-upsampled image
+    is, for output parity (py, px), a 2x2 filter on the low-res image whose taps are sums of the original ones
+    (rows {0 | 1+2} for py = 0, {0+1 | 2} for py = 1; same for columns).  Row (py*2+px)*Cout + co, k = (ty*2+tx)*Cin + c;
+    sums in fp32, rounded once to the weight dtype."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    wf = w.float()
+    sets = (((0,), (1, 2)), ((0, 1), (2,)))  # sets[parity][tap] = original taps folded into it
+    out = torch.empty((2, 2, co, 2, 2, ci), dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    acc = torch.zeros((co, ci), dtype=torch.float32, device=w.device)
+                    for ky in sets[py][ty]:
+                        for kx in sets[px][tx]:
+                            acc = acc + wf[:, :, ky, kx]
+                    out[py, px, :, ty, tx, :] = acc
+    return out.reshape(4 * co, 4 * ci).to(w.dtype).contiguous()
+
+
+def upconv_folded() -> bool:
+    """B200_UPCONV=0: upsample2x + conv3x3 (4x tensor materialised, 36 MACs) instead of the folded b200_conv3x3_up2x."""
+    import os
+    return os.environ.get("B200_UPCONV", "1") != "0"
+
+
+def conv3x3_up2x(x: torch.Tensor, w_packed4: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                 epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+    """conv3x3(upsample2x(x)) on a contiguous NHWC tensor without the 4x intermediate (w_packed4 from pack_conv3x3_up2x);
+    x [N, H, W, C] with C a multiple of 64, any H, W -> [N, 2H, 2W, Cout]."""
+    assert x.dim() == 4 and x.is_contiguous()
+    n, h, w_, c = x.shape
+    cout = w_packed4.shape[0] // 4
+    assert w_packed4.shape == (4 * cout, 4 * c) and w_packed4.is_contiguous() and c % 64 == 0
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * w_, cout), dtype=x.dtype, device=x.device)
+    assert out.is_contiguous() and out.shape == (n, 2 * h, 2 * w_, cout)
+    d = _l.Conv3x3Desc()
+    d.N, d.H, d.W, d.C1, d.C2, d.Cout = n, h, w_, c, 0, cout
+    d.dtype = _dt(x)
+    d.epilogue = epilogue
+    d.block_n = block_n
+    d.bias = _p(bias)
+    # FLOPs actually executed (16 MACs per output pixel and channel pair); the reference's upsample + conv does 36
+    with _prof("conv3x3", 2.0 * n * 4 * h * w_ * cout * 4 * c, 2.0 * (n * h * w_ * (c + 4 * cout) + cout * 16 * c),
+               f"conv-up2x {n}x{h}x{w_} {c}->{cout}"):
+        _l.check(_l.load().b200_conv3x3_up2x(x.data_ptr(), None, w_packed4.data_ptr(), out.data_ptr(), C.byref(d), _stream()))
+    _count()
+    return out
+
+
 def conv_route() -> str:
     """How 3x3 convolutions of images that do not tile into 128-pixel TMA boxes run (B200_CONV_ROUTE):
       generic (default)  inside the implicit-GEMM kernel with overhanging tiles and masked stores (FEAT = 4 build);

@@ -93,7 +93,12 @@ class VAEDecoderEngine:
                 res(f"decoder.up.{lvl}.block.{j}")
             if lvl != 0:
                 q = f"decoder.up.{lvl}.upsample.conv"
-                w[q + ".w"], w[q + ".b"] = ops.pack_conv3x3(g(q + ".weight")), g(q + ".bias")
+                uw = g(q + ".weight")
+                if uw.shape[1] % 64 == 0 and ops.upconv_folded():  # upsample folded into the convolution (ops.conv3x3_up2x)
+                    w[q + ".w4"] = ops.pack_conv3x3_up2x(uw)
+                else:
+                    w[q + ".w"] = ops.pack_conv3x3(uw)
+                w[q + ".b"] = g(q + ".bias")
         w["norm_out.g"], w["norm_out.b"] = g("decoder.norm_out.weight"), g("decoder.norm_out.bias")
         co = ops.pack_conv3x3(g("decoder.conv_out.weight"))  # [3, 9*ch] -> pad to 8 rows
         cop = torch.zeros((8, co.shape[1]), dtype=self.dtype, device=self.device)
@@ -215,7 +220,10 @@ class VAEDecoderEngine:
                 h = self._res(f"decoder.up.{lvl}.block.{j}", h)
             if lvl != 0:
                 q = f"decoder.up.{lvl}.upsample.conv"
-                h = ops.conv3x3_any(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
+                if q + ".w4" in w:
+                    h = ops.conv3x3_up2x(h, w[q + ".w4"], w[q + ".b"])
+                else:
+                    h = ops.conv3x3_any(ops.upsample2x(h), w[q + ".w"], w[q + ".b"])
         h = ops.groupnorm(h, w["norm_out.g"], w["norm_out.b"], eps=1e-6, silu=True)
         return ops.conv3x3_any(h, w["conv_out.w"], w["conv_out.b"])
 

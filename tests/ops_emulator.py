@@ -136,6 +136,24 @@ def conv3x3(x1, w_packed, bias=None, *, x2=None, residual=None, temb=None, epilo
     return _ret(y.contiguous(), out, x1.dtype)
 
 
+def conv3x3_up2x(x, w_packed4, bias=None, *, epilogue=EPI_NONE, out=None, block_n=0):
+    """The kernel's arithmetic, not upsample + conv: four 2x2 filters on the low-res image, one per output parity."""
+    n, h, w_, c = x.shape
+    cout = w_packed4.shape[0] // 4
+    w4 = w_packed4.float().view(2, 2, cout, 2, 2, c)
+    xin = x.float().permute(0, 3, 1, 2)
+    y = torch.zeros((n, cout, 2 * h, 2 * w_), dtype=torch.float32, device=x.device)
+    for py in range(2):
+        for px in range(2):
+            wt = w4[py, px].permute(0, 3, 1, 2)  # [cout, c, ty, tx]; tap (ty, tx) reads (y + py - 1 + ty, x + px - 1 + tx)
+            xp = F.pad(xin, (1 - px, px, 1 - py, py))
+            y[:, :, py::2, px::2] = F.conv2d(xp, wt)
+    if bias is not None:
+        y = y + bias.float()[None, :, None, None]
+    y = _act(y, epilogue).permute(0, 2, 3, 1)
+    return _ret(y.contiguous(), out, x.dtype)
+
+
 def attention(q, k, v, heads, *, scale=None, out=None):
     b, lq, hd = q.shape
     dh = hd // heads
@@ -396,7 +414,7 @@ def vae_posterior(moments, channels, noise=None, scale=1.0, out=None):
     return _ret((mean * scale).contiguous(), out, torch.float32)
 
 
-_NAMES = ["gemm", "row_stats_parts", "row_stats_buffer", "zero_", "conv3x3", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
+_NAMES = ["gemm", "row_stats_parts", "row_stats_buffer", "zero_", "conv3x3", "conv3x3_up2x", "attention", "attention_generic", "attention_blockdiag", "groupnorm", "layernorm",
           "upsample2x", "im2col3x3", "nchw_to_nhwc", "nhwc_to_nchw", "transpose_rows", "silu", "softmax_rows_",
           "timestep_embedding", "unet_input_im2col", "adaln", "rmsnorm_rows", "qk_norm_rope_", "flux_patchify", "flux_unpatchify",
           "sampler_step", "sampler_update", "eps_to_denoised", "add_nchw_", "vae_postprocess", "vae_preprocess", "vae_posterior",

@@ -414,3 +414,24 @@ def test_restart_and_lcm_sampler_host_logic(monkeypatch):
         if sig[i + 1] > 0:
             x = x + sig[i + 1] * noise[next(k)]
     assert (out - x).abs().max().item() <= 1e-5
+
+
+def test_upsample_folded_conv_weights_and_emulation():
+    """pack_conv3x3_up2x + the parity arithmetic of b200_conv3x3_up2x (as emulated in tests/ops_emulator.py) reproduce
+    F.interpolate(nearest, x2) followed by the 3x3 convolution (backend/nn/unet.py:330-355) exactly in fp32, borders and
+    odd sizes included."""
+    import torch
+    import torch.nn.functional as F
+    from b200forge import ops
+    from tests import ops_emulator as E
+    g = torch.Generator().manual_seed(7)
+    for (n, h, w, c, co) in [(2, 5, 7, 64, 64), (1, 1, 1, 64, 128), (1, 8, 8, 128, 64)]:
+        x = torch.randn(n, c, h, w, generator=g)
+        wt = torch.randn(co, c, 3, 3, generator=g) * (9 * c) ** -0.5
+        b = torch.randn(co, generator=g)
+        w4 = ops.pack_conv3x3_up2x(wt)
+        assert w4.shape == (4 * co, 4 * c)
+        y = E.conv3x3_up2x(x.permute(0, 2, 3, 1).contiguous(), w4, b)
+        ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), wt, b, padding=1).permute(0, 2, 3, 1)
+        assert y.shape == ref.shape
+        assert (y - ref).abs().max().item() < 2e-5

@@ -205,6 +205,28 @@ def test_attention_peaked_logits():
     assert_close("attention peaked", o, O.attention(q.float(), k.float(), v.float(), H), rel_rms=5e-3, max_rel=4.0e-02)
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 24, 4352, 4352), (2, 4, 200, 333), (1, 3, 1000, 129), (2, 2, 64, 4096)])
+def test_attention_dh128_flux_shapes(B, H, Lq, Lk):
+    """Dh = 128 (Flux / SD3) through the small-CTA kernel (attention64s.cu built for Dh = 128, two CTAs per SM): the benchmark's
+    4096 + 256 tokens, ragged query / key counts (last key block partly empty), q / k / v read as column slices of one fused
+    QKV buffer like flux_engine does, and large logits that force the lazy O rescale."""
+    ops = _ops()
+    Dh = 128
+    C = H * Dh
+    L = max(Lq, Lk)
+    qkv = _rand(B, L, 3 * C, dtype=torch.bfloat16, seed=110)
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:]
+    o = ops.attention(q, k, v, H)
+    torch.cuda.synchronize()
+    assert_close(f"attention d128 B{B} H{H} {Lq}x{Lk}", o, O.attention(q.float(), k.float(), v.float(), H), rel_rms=1.5e-2, max_rel=1.2e-1)
+    if Lq <= 1000:
+        q4 = (q.float() * 3.0).half().contiguous()
+        k4 = (k.float() * 3.0).half().contiguous()
+        o4 = ops.attention(q4, k4, v.half().contiguous(), H)
+        torch.cuda.synchronize()
+        assert_close("attention d128 peaked fp16", o4, O.attention(q4.float(), k4.float(), v.half().float(), H), rel_rms=5e-3, max_rel=4e-2)
+
+
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("N,H,W,C1,C2", [(2, 32, 32, 320, 0), (2, 64, 64, 640, 320), (3, 16, 16, 1280, 1280),
                                          (2, 128, 128, 320, 0), (1, 8, 8, 2560, 0)])
@@ -462,6 +484,35 @@ def test_conv3x3_generic_tiling(N, H, W, C1, C2, Cout):
     torch.cuda.synchronize()
     ref = (O.conv2d(x.float(), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
     assert_close(f"conv3x3 generic {N}x{H}x{W} {C1}+{C2}->{Cout}", y, ref, max_abs=2.5e-2, rel_rms=2e-3)
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout,dtype", [
+    (2, 32, 32, 1280, 1280, torch.float16),   # SDXL 32 -> 64
+    (2, 64, 64, 640, 640, torch.float16),     # SDXL 64 -> 128
+    (3, 52, 76, 640, 640, torch.float16),     # non-square bucket, 57 tiles per parity (padded to 58 for the CTA pairs)
+    (1, 13, 19, 1280, 1280, torch.float16),   # odd sizes: tile_w = 1
+    (4, 4, 4, 256, 128, torch.float16),       # image smaller than one tile, Cout != C
+    (1, 128, 128, 512, 512, torch.bfloat16),  # VAE 128 -> 256
+    (1, 256, 256, 256, 256, torch.bfloat16),  # VAE 256 -> 512 (shape of the 512 -> 1024 level, quarter size)
+])
+def test_conv3x3_up2x(N, H, W, C, Cout, dtype):
+    """Nearest x2 upsample folded into the 3x3 convolution (b200_conv3x3_up2x: four 2x2 parity filters on the low-res
+    image) against upsample + conv in fp32 (backend/nn/unet.py:330-355, backend/nn/vae.py:38-58).  The pre-summed weights
+    are rounded once to the operand type, so the bound is the plain convolution's plus one weight rounding."""
+    import torch.nn.functional as F
+    ops = _ops()
+    x = _rand(N, C, H, W, dtype=dtype, seed=100)
+    w = _rand(Cout, C, 3, 3, dtype=dtype, scale=(9 * C) ** -0.5, seed=101)
+    b = _rand(Cout, dtype=dtype, seed=102)
+    guard = torch.full((N, 2 * H, 2 * W, Cout), 7.0, device=DEV, dtype=dtype)
+    y = ops.conv3x3_up2x(x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3_up2x(w), b, out=guard)
+    torch.cuda.synchronize()
+    ref = O.conv2d(F.interpolate(x.float(), scale_factor=2, mode="nearest"), w.float(), b.float()).permute(0, 2, 3, 1)
+    assert_close(f"conv3x3_up2x {N}x{H}x{W} {C}->{Cout} {dtype}", y, ref, **_tol(dtype))
+    # the unfolded route gives the same image within the same bound
+    y2 = ops.conv3x3_any(ops.upsample2x(x.permute(0, 2, 3, 1).contiguous()), ops.pack_conv3x3(w), b)
+    torch.cuda.synchronize()
+    assert_close("upsample2x + conv3x3 (unfolded route)", y2, ref, **_tol(dtype))
 
 
 def test_sampler_step_and_denoised_v_prediction():
