@@ -50,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     launches = ops.LAUNCHES - n0
     fam = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-    for name, fl, by, s, e in ops.PROFILE:
+    for name, fl, by, s, e, *_ in ops.PROFILE:
         f = fam[name]
         f[0] += 1
         f[1] += s.elapsed_time(e)

@@ -79,6 +79,16 @@ struct GemmKParams {
   // is never materialised.  M tiles enumerate (parity, low-res tile); B rows of parity q start at q * N; output row
   // (img, y, x) of parity (py, px) is pixel (2y + py, 2x + px) of the [img_n, 2 img_h, 2 img_w] output.
   int up2x, tiles_lr;
+  // K-split of the LAST, partly filled wave of tiles (persistent kernel, static round-robin: T tiles on U units leave
+  // T mod U units busy and the rest idle for a whole tile time — 4.32 waves at M = 16384, N = 1280 cost 5): the T mod U tail
+  // tiles are cut into split_S shares of the k-chunk range, one per unit; shares 1.. dump their raw fp32 accumulators into a
+  // workspace (column-major 128-row blocks: coalesced for the thread-per-row TMEM layout) and raise a per-tile flag, share 0
+  // waits for the flag, adds the partials in a fixed order (bit-reproducible) and runs the normal epilogue.
+  int split_S;        // 0 = off
+  int split_first;    // first tail tile (= T when off): tiles below it are whole
+  int split_rem;      // tail tiles
+  float* split_ws;    // [split_rem][split_S - 1][CG] blocks of 256 x 128 floats
+  int* split_flags;   // [split_rem][CG], self-resetting
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
@@ -221,15 +231,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   pdl_wait();  // barriers, TMEM and descriptors are ready: from here on the predecessor's output is read
 
   const int tiles_mu = (p.tiles_m + CG - 1) / CG;  // M tiles per unit: a pair covers two adjacent 128-row tiles
-  const int total_tiles = tiles_mu * p.tiles_n;
   const int nk = p.num_k_chunks;
+  // work item i of this unit: whole tiles round-robin, then at most one share of a K-split tail tile.
+  // role 0 = whole tile, 1 = share 0 of a tail tile (reduces the others' partials, runs the epilogue), 2 = partial share
+  auto work_item = [&](int i, int& tile, int& kb, int& ke, int& role, int& tt, int& share) -> bool {
+    tile = unit + i * num_units;
+    kb = 0;
+    ke = nk;
+    role = 0;
+    tt = 0;
+    share = 0;
+    if (tile < p.split_first) return true;
+    if (p.split_S == 0) return false;
+    const int j = tile - p.split_first;  // = unit at the first index past the whole tiles (split_first is a multiple of num_units)
+    if (j >= p.split_rem * p.split_S) return false;
+    share = j / p.split_rem;
+    tt = j - share * p.split_rem;
+    tile = p.split_first + tt;
+    kb = (share * nk) / p.split_S;
+    ke = ((share + 1) * nk) / p.split_S;
+    role = share == 0 ? 1 : 2;
+    return true;
+  };
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx_bytes = ((uint32_t)kATileBytes + b_tile_bytes) * CG;
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int wi = 0;; ++wi) {
+      int tile, kb, ke, role, tt, share;
+      if (!work_item(wi, tile, kb, ke, role, tt, share)) break;
       const int m_unit = p.n_fast ? tile / p.tiles_n : tile % tiles_mu;
       const int n_blk = p.n_fast ? tile % p.tiles_n : tile / tiles_mu;
       const int m_blk = m_unit * CG + (int)cta_rank;
@@ -255,7 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ch += (rem / p.tiles_w) * p.tile_h;
         cw += (rem % p.tiles_w) * p.tile_w;
       }
-      for (int kc = 0; kc < nk; ++kc) {
+      for (int kc = kb; kc < ke; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t fb = full_bar(stage);
         const uint32_t a_dst = a_base + (uint32_t)stage * kATileBytes;
@@ -307,13 +339,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint64_t adesc0 = make_smem_desc_sw128(a_base, 0, 1024);
     const uint64_t bdesc0 = make_smem_desc_sw128(b_base, 0, 1024);
     const uint32_t idesc = p.idesc;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    for (;; ++it) {
+      int tile, kb, ke, role, tt, share;
+      if (!work_item(it, tile, kb, ke, role, tt, share)) break;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-      for (int kc = 0; kc < nk; ++kc) {
+      for (int kc = kb; kc < ke; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(((uint32_t)stage * kATileBytes) >> 4);
@@ -323,12 +357,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           for (int k = 0; k < 4; ++k) {
             // +32 bytes per 16-element k step inside the 128-byte swizzle atom (encoded >> 4)
             if constexpr (CG == 2)
-              umma_f16_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_f16_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((kc - kb) | k) != 0 ? 1u : 0u);
             else
-              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((kc - kb) | k) != 0 ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
-          if (kc == nk - 1) {
+          if (kc == ke - 1) {
             if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
           }
         }
@@ -353,13 +387,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
     const bool geglu = p.epilogue == B200_EPI_GEGLU;
     const int ncols_out = geglu ? (BN >> 1) : BN;
-    int it = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    for (int it = 0;; ++it) {
+      int tile, kb, ke, role, tt, share;
+      if (!work_item(it, tile, kb, ke, role, tt, share)) break;
       const int m_unit = p.n_fast ? tile / p.tiles_n : tile % tiles_mu;
       const int n_blk = p.n_fast ? tile % p.tiles_n : tile / tiles_mu;
       const int m_blk = m_unit * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      if (role == 2) {
+        // ---- partial share of a K-split tail tile: raw accumulators -> workspace (element (col, row) at col * 128 + row: a
+        // warp's store of one register is 128 contiguous bytes), release TMEM, publish
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        float* const blk = p.split_ws + ((size_t)(tt * (p.split_S - 1) + (share - 1)) * CG + cta_rank) * (256 * 128) + r;
+        const uint32_t t_addr_p = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
+        for (int c = chalf * 32; c < BN; c += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr_p + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) blk[(size_t)(c + i) * 128] = __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
+        __threadfence();
+        named_bar_sync(1, kEpiThreads);
+        if (threadIdx.x == 128) atomicAdd(p.split_flags + tt * CG + (int)cta_rank, 1);
+        continue;
+      }
       int m = m_blk * 128 + r;
       bool row_ok = m < p.M;
       // folded LayerNorm: merge the producer's partial statistics of this row (Chan et al.): fetched before the wait on
@@ -518,11 +575,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
         };
         if (it == 0) prefetch_res(tile);
-        if (tile + num_units < total_tiles) prefetch_res(tile + num_units);
+        if (role == 0 && tile + num_units < p.split_first) prefetch_res(tile + num_units);
         if (chalf * 32 < ncols_out) load_res(chalf * 32, rsc);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const float* split_src = nullptr;  // share 0 of a K-split tile: the other shares' partial accumulators of this row
+      if (role == 1) {
+        if (threadIdx.x == 128) {
+          volatile int* f = p.split_flags + tt * CG + (int)cta_rank;
+          while (*f < p.split_S - 1) __nanosleep(40);
+          *f = 0;  // self-resetting: the next launch's shares only start after this grid has completed
+          __threadfence();
+        }
+        named_bar_sync(1, kEpiThreads);
+        split_src = p.split_ws + ((size_t)(tt * (p.split_S - 1)) * CG + cta_rank) * (256 * 128) + r;
+      }
 
       for (int c = chalf * 32; c < ncols_out; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
@@ -567,6 +635,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         } else {
           tmem_ld_wait();
+          if (split_src) {  // + partial shares, fixed order; L2 loads (the lines were written by other SMs)
+            for (int sh = 0; sh < p.split_S - 1; ++sh) {
+              const float* src = split_src + (size_t)sh * CG * (256 * 128) + (size_t)c * 128;
+#pragma unroll
+              for (int i0 = 0; i0 < 32; i0 += 8) {
+                float t8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t8[i] = __ldcg(src + (size_t)(i0 + i) * 128);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i0 + i] = __float_as_uint(__uint_as_float(v[i0 + i]) + t8[i]);
+              }
+            }
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) xp[k] = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
           if (EXT && p.alpha != 0.f) {
@@ -762,6 +843,54 @@ static bool use_pair_kernel() {
   return v == 1;
 }
 
+// Workspace of the K-split tail (GemmKParams::split_*): one block of 256 x 128 floats per SM + one flag per SM, allocated once
+// per (device, stream) outside stream capture; a launch that cannot get it (first call of a stream inside a capture, more
+// than four streams) simply does not split.  B200_GEMM_SPLITK=0 turns the split off.
+struct SplitWs {
+  int dev;
+  cudaStream_t stream;
+  float* ws;
+  int* flags;
+};
+static bool split_ws_get(cudaStream_t stream, float** ws, int** flags) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("B200_GEMM_SPLITK");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return false;
+  static SplitWs table[4];
+  static int used = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  for (int i = 0; i < used; ++i)
+    if (table[i].dev == dev && table[i].stream == stream) {
+      *ws = table[i].ws;
+      *flags = table[i].flags;
+      return true;
+    }
+  if (used == 4) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;
+  }
+  const int n = num_sms();
+  float* w = nullptr;
+  int* f = nullptr;
+  if (cudaMalloc(&w, (size_t)n * 256 * 128 * sizeof(float)) != cudaSuccess || cudaMalloc(&f, (size_t)n * sizeof(int)) != cudaSuccess ||
+      cudaMemset(f, 0, (size_t)n * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    if (w) cudaFree(w);
+    if (f) cudaFree(f);
+    return false;
+  }
+  table[used++] = SplitWs{dev, stream, w, f};
+  *ws = w;
+  *flags = f;
+  return true;
+}
+
 template <bool BF16, int CG, int FEAT>
 static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                          const CUtensorMap& mapB2, GemmKParams& p, cudaStream_t stream) {
@@ -779,6 +908,27 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
     return B200_ENODEVICE;
   }
   if (units > total) units = total;
+  // K-split of the last, partly filled wave: rem tail tiles x S shares <= units, every share at least four k-chunks
+  p.split_S = 0;
+  p.split_first = total;
+  p.split_rem = 0;
+  {
+    const int rem = total % units;
+    if (rem > 0 && 2 * rem <= units && p.epilogue != B200_EPI_GEGLU) {
+      int S = units / rem;
+      if (S > 4) S = 4;
+      while (S > 1 && p.num_k_chunks / S < 4) --S;
+      float* ws = nullptr;
+      int* flags = nullptr;
+      if (S >= 2 && split_ws_get(stream, &ws, &flags)) {
+        p.split_S = S;
+        p.split_first = total - rem;
+        p.split_rem = rem;
+        p.split_ws = ws;
+        p.split_flags = flags;
+      }
+    }
+  }
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BF16, CG, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -47,6 +47,56 @@ def test_gemm_plain(M, N, K, dtype):
     assert_close(f"gemm {M}x{N}x{K} {dtype}", y, ref, **_tol(dtype))
 
 
+@pytest.mark.parametrize("M,N,K,dtype", [(16384, 1280, 1280, torch.float16),   # 64 pair tiles x 5 = 320 on 74 pairs: tail 24, 3 shares
+                                          (16384, 1280, 5120, torch.float16),
+                                          (16, 1280, 1280, torch.float16),      # 5 single-CTA tiles on 148 SMs: 4 shares
+                                          (1024, 1280, 2560, torch.bfloat16),   # 4 pair tiles x 5 = 20 on 74: 3 shares
+                                          (8192, 640, 640, torch.float16)])
+def test_gemm_k_split_tail(M, N, K, dtype):
+    """Shapes whose tile count leaves a partly filled last wave: the tail tiles are K-split across the idle units (partial
+    accumulators through a workspace, share 0 reduces them in a fixed order).  Results against the oracle, with the residual +
+    row-statistics epilogue, and bit-identical over repeated launches (flags self-reset, fixed summation order)."""
+    ops = _ops()
+    a = _rand(M, K, dtype=dtype, seed=120)
+    w = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=121)
+    b = _rand(N, dtype=dtype, seed=122)
+    res = _rand(M, N, dtype=dtype, seed=123)
+    ref = O.linear(a.float(), w.float(), b.float())
+    outs = []
+    for _ in range(3):
+        outs.append(ops.gemm(a, w, b).clone())
+    torch.cuda.synchronize()
+    assert_close(f"gemm k-split {M}x{N}x{K} {dtype}", outs[0], ref, **_tol(dtype))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "K-split GEMM must be bit-reproducible"
+    if dtype == torch.float16 and N % 32 == 0:
+        st = ops.row_stats_buffer(M, N, DEV)
+        y = ops.gemm(a, w, b, residual=res, row_stats_out=st)
+        torch.cuda.synchronize()
+        assert_close("gemm k-split + residual + statistics", y, ref + res.float(), **_tol(dtype))
+        cnt = st[..., 0].sum(0)
+        mean = (st[..., 0] * st[..., 1]).sum(0) / cnt
+        want = (ref + res.float()).mean(-1)
+        assert (mean - want).abs().max().item() < 2e-3
+
+
+def test_conv3x3_k_split_tail():
+    """conv 16 x 32 x 32, 1280 -> 1280 (the SDXL 1280-channel level): 320 pair tiles on 74 pairs, 180 k-chunks in 3 shares."""
+    ops = _ops()
+    N, H, W, C = 16, 32, 32, 1280
+    x = _rand(N, H, W, C, seed=124)
+    w = _rand(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=125)
+    b = _rand(C, seed=126)
+    temb = _rand(N, C, seed=127)
+    res = _rand(N, H, W, C, seed=128)
+    wp = ops.pack_conv3x3(w)
+    y = ops.conv3x3(x, wp, b, temb=temb, residual=res).clone()
+    y2 = ops.conv3x3(x, wp, b, temb=temb, residual=res)
+    torch.cuda.synchronize()
+    ref = (O.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float()) + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    assert_close("conv3x3 k-split", y, ref, rel_rms=2e-3, max_rel=1.6e-2)
+    assert torch.equal(y, y2)
+
+
 def test_gemm_no_bias_strided_output():
     ops = _ops()
     M, N, K = 512, 640, 640
