@@ -92,8 +92,16 @@ typedef struct {
   float alpha;    /* 0 or 1: off; else the fp32 accumulators are multiplied by alpha first: C = epi(alpha * A B^T + ...).
                      The GEMM-softmax-GEMM attention paths put Dh^-1/2 here so that the stored logits are the SCALED ones
                      (unscaled fp16 logits can overflow; the reference scales q or the fp32 product, backend/attention.py:64-70) */
+  /* K-split of the last, partly filled wave of output tiles (the persistent kernel walks T tiles on U = SMs [/ 2] units; the
+   * T mod U tail tiles otherwise keep a few units busy for a whole tile time while the rest idle — 4.3 waves cost 5): the
+   * tail tiles are cut along K into shares run by the idle units, which exchange fp32 partial accumulators through this
+   * caller-owned scratch buffer: b200_gemm_workspace_bytes() bytes, 16-byte aligned, ZEROED ONCE by the caller (the kernel
+   * leaves its flags zeroed), not shared by launches that may run concurrently (one buffer per stream).  NULL: no split.
+   * Results do not depend on timing (fixed summation order), but differ in the last fp32 rounding from the unsplit sum. */
+  void* workspace;
 } b200_gemm_desc;
 
+size_t b200_gemm_workspace_bytes(void);
 int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_desc* d, b200_stream_t s);
 /* number of float4 partials per row that a b200_gemm with this N / epilogue / block_n writes to row_stats_out */
 int b200_gemm_row_stats_parts(int N, int epilogue, int block_n);
@@ -117,6 +125,7 @@ typedef struct {
   int ldr;
   const void* temb;     /* [N, ld_temb] row n added to every pixel of image n (ResBlock emb_layers) */
   int ld_temb;
+  void* workspace;      /* K-split scratch, see b200_gemm_desc.workspace; NULL: no split */
 } b200_conv3x3_desc;
 
 int b200_conv3x3(const void* x1, const void* x2, const void* w_packed, void* y, const b200_conv3x3_desc* d,

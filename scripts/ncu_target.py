@@ -90,7 +90,24 @@ def producer_gemms():
     torch.cuda.synchronize()
 
 
-if which == "unetgemm":
+def upconv(N, H, W, C, dtype=torch.float16):
+    x = torch.randn(N, H, W, C, device=DEV, dtype=dtype)
+    w4 = ops.pack_conv3x3_up2x((torch.randn(C, C, 3, 3, device=DEV) * (9 * C) ** -0.5).to(dtype))
+    b = torch.randn(C, device=DEV, dtype=dtype)
+    out = torch.empty(N, 2 * H, 2 * W, C, device=DEV, dtype=dtype)
+    for _ in range(2):
+        ops.conv3x3_up2x(x, w4, b, out=out)
+    torch.cuda.synchronize()
+
+
+if which == "upconv":      # the folded upsample convolutions of the SDXL UNet (32 -> 64) and of the VAE decoder (256 -> 512)
+    upconv(16, 32, 32, 1280)
+    upconv(8, 256, 256, 512, torch.bfloat16)
+elif which == "attn128":   # Flux: 4096 + 256 tokens, 24 heads x 128
+    attn(4, 24, 4352, 4352, 128, torch.bfloat16)
+elif which == "ksplit":    # conv 1280 -> 1280 at 32 x 32: 320 pair tiles on 74 pairs, tail K-split
+    conv(16, 32, 32, 1280, 1280)
+elif which == "unetgemm":
     unet_gemms()
 elif which == "producer":
     producer_gemms()

@@ -86,8 +86,11 @@ constexpr bool kPT = B200_ATTN64S_P_TMEM != 0;
 #ifndef B200_ATTN64S_POLY_PAIRS
 #define B200_ATTN64S_POLY_PAIRS 0x1
 #endif
+#ifndef B200_ATTN128S_P2
+#define B200_ATTN128S_P2 0  // Dh = 128: 1 = P double-buffered in TMEM (measured: 1133 vs 1144-1151 TF/s single-buffered: no gain)
+#endif
 #ifndef B200_ATTN128S_POLY_PAIRS
-#define B200_ATTN128S_POLY_PAIRS 0x1
+#define B200_ATTN128S_POLY_PAIRS 0x0  // measured at B4 H24 L4352: none 1155, 1 of 4 1151, 2 of 4 1105 TF/s
 #endif
 constexpr unsigned kPolyPairs128S = B200_ATTN128S_POLY_PAIRS;  // the same choice for the Dh = 128 build
 constexpr unsigned kPolyPairsS = B200_ATTN64S_POLY_PAIRS;  // element PAIRS (of the 4 per 8 elements) whose exp2 runs on the FMA pipe:
@@ -101,7 +104,7 @@ constexpr unsigned kPolyPairsS = B200_ATTN64S_POLY_PAIRS;  // element PAIRS (of 
 // DH = 128 (Flux / SD3; round 2, late): the same pipeline with TWO CTAs per SM — per 64-key block the tensor core now has as
 // much work as the MUFU (Q.K^T + P.V = 2 x 256 clk against 512 clk of exponentials), so the second CTA's MMAs run under the
 // first one's softmax and vice versa.  Per CTA: Q 32 KB (one buffer: one query tile per CTA) + K/V ring 4 x 16 KB = 96 KB smem;
-// TMEM 256 columns: S [0,64) | O [64,192) | P [192,224); Q / K / V tiles are two 64-wide swizzle atoms side by side; 128
+// TMEM 256 columns: S [0,64) | O [64,192) | P [192,224) [224,256) (double-buffered); Q / K / V tiles are two 64-wide swizzle atoms side by side; 128
 // registers per thread at launch (48 control / 208 softmax after setmaxnreg).
 template <bool BF16, int DH>
 __global__ void __maxnreg__(DH == 64 ? 80 : 128)
@@ -125,9 +128,15 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   auto ring_empty = [&](int i) { return bar_base + 8u * (4 + kSlots + i); };
   const uint32_t s_full = bar_base + 8u * (4 + 2 * kSlots);
   const uint32_t s_cons = s_full + 8u;
-  const uint32_t p_full = s_full + 16u;
-  const uint32_t pv_done = s_full + 24u;
-  const uint32_t tmem_slot = s_full + 32u;
+  // Dh = 128: P is double-buffered in TMEM (block g in buffer g & 1, 2 x 32 columns fit the 256-column allocation), so the
+  // softmax of block g + 1 does not wait for P.V_g — it only needs P.V_{g-1} (its buffer's previous reader), and P.V_g itself
+  // only on the rare lazy rescale of O.  Each buffer has its own pair of barriers (a single barrier could run two phases
+  // ahead of a waiter, which a parity wait cannot tell from "not yet").
+  constexpr bool kP2 = DH == 128 && B200_ATTN128S_P2 != 0;
+  auto p_full = [&](int g) { return s_full + 16u + (kP2 ? 8u * (uint32_t)(g & 1) : 0u); };
+  auto pv_done = [&](int g) { return s_full + 32u + (kP2 ? 8u * (uint32_t)(g & 1) : 0u); };
+  auto pbuf_phase = [&](int g) { return (uint32_t)(kP2 ? (g >> 1) : g) & 1u; };
+  const uint32_t tmem_slot = s_full + 48u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,8 +165,10 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     }
     mbar_init(s_full, 1);
     mbar_init(s_cons, 128);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(p_full(i), 128);
+      mbar_init(pv_done(i), 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -262,18 +273,19 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
         wait_full(vidx);
         const uint64_t vd = vdesc0 + (uint64_t)((vidx % kSlots) * (kKVTile >> 4));
-        mbar_wait_quiet(p_full, (uint32_t)g & 1u);
+        mbar_wait_quiet(p_full(g), pbuf_phase(g));
         tc_fence_after();
+        const uint32_t pa = tmem_p + (kP2 ? (uint32_t)(g & 1) * 32u : 0u);
         const uint32_t acc0 = j != 0 ? 1u : 0u;  // a tile's first P.V overwrites O (its predecessor's O was read before P_g was published)
         if (elect_one()) {
           if (kPT) {  // A = P from TMEM: 16 keys = 8 columns per k step
             if (ksteps == 4) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ts(o_tmem, tmem_p + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+                umma_f16_ts(o_tmem, pa + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
             } else {
               for (int kk = 0; kk < ksteps; ++kk)
-                umma_f16_ts(o_tmem, tmem_p + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
+                umma_f16_ts(o_tmem, pa + (uint32_t)(kk * 8), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
             }
           } else if (ksteps == 4) {
 #pragma unroll
@@ -283,7 +295,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             for (int kk = 0; kk < ksteps; ++kk)
               umma_f16(o_tmem, pdesc + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk ? 1u : acc0);
           }
-          umma_commit(pv_done);
+          umma_commit(pv_done(g));
           umma_commit(ring_empty(vidx % kSlots));
         }
         __syncwarp();
@@ -300,7 +312,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr;
     const uint32_t o_addr = tmem_base + 64u + lane_addr;
-    const uint32_t p_addr = tmem_p + lane_addr;
+    const uint32_t p_addr0 = tmem_p + lane_addr;
     const uint32_t p_row = p_smem + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     const float sl2 = p.scale_log2;
@@ -339,8 +351,13 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       // PV_{g-1} must have retired before O is rescaled and before P is overwritten (a tile's first block: the previous
       // tile's output phase has waited for it).  Moving this wait behind the first 32 exponentials was measured: slower
       // (825 -> 785 TF/s at L4096) — the warps of a CTA then reach their MUFU phases together instead of staggered.
-      if (j > 0) {
-        mbar_wait(pv_done, (uint32_t)(g - 1) & 1u);
+      if (kP2) {
+        if (j > 1) {  // this P buffer's previous reader
+          mbar_wait(pv_done(g - 2), pbuf_phase(g - 2));
+          tc_fence_after();
+        }
+      } else if (j > 0) {
+        mbar_wait(pv_done(g - 1), pbuf_phase(g - 1));
         tc_fence_after();
       }
       if (j == 0) {
@@ -348,6 +365,10 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       } else {
         const bool need = m_blk > m_ref + kRescale;
         if (__any_sync(0xffffffffu, need)) {  // lazy rescale: rare after the first few key blocks
+          if (kP2) {  // O must hold every earlier block
+            mbar_wait(pv_done(g - 1), pbuf_phase(g - 1));
+            tc_fence_after();
+          }
           const float alpha = need ? ex2s(m_ref - m_blk) : 1.0f;
 #pragma unroll
           for (int c = 0; c < DH; c += 32) {
@@ -366,6 +387,7 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       // p = exp2(s * scale - m_ref), row sum, P -> TMEM (two 16-column stores, the first under the second half's
       // exponentials) or -> smem (128B-swizzled K-major A operand: one 64-key atom per row)
       const float nm = -m_ref;
+      const uint32_t p_addr = p_addr0 + (kP2 ? (uint32_t)(g & 1) * 32u : 0u);
       float rs;
       uint32_t pq[16];  // kPT: 32 keys of this row as fp16 / bf16 pairs
       auto put8 = [&](int c, const float (&pe)[8]) {
@@ -434,11 +456,11 @@ attn64s_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       if (kPT) tmem_st_waits();
       else fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full(g));
     }
 
     // ---- output: O / l -> fp16 / bf16 -> warp-private staging (the Q tile, or the smem P tile, is free now) -> coalesced stores
-    mbar_wait(pv_done, (uint32_t)(t * n_kv + n_kv - 1) & 1u);
+    mbar_wait(pv_done(t * n_kv + n_kv - 1), pbuf_phase(t * n_kv + n_kv - 1));
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const int q0 = (qt0 + t) * 128;

@@ -84,6 +84,10 @@ struct GemmKParams {
   // tiles are cut into split_S shares of the k-chunk range, one per unit; shares 1.. dump their raw fp32 accumulators into a
   // workspace (column-major 128-row blocks: coalesced for the thread-per-row TMEM layout) and raise a per-tile flag, share 0
   // waits for the flag, adds the partials in a fixed order (bit-reproducible) and runs the normal epilogue.
+  // last N tile narrower than BN (N = 640 or 1920 with 256-wide tiles): the MMA runs with N = bn_last (multiple of 32) instead
+  // of multiplying zero-filled weight rows, the epilogue walks bn_last columns; a CTA pair splits the bn_last rows evenly
+  int bn_last;
+  uint32_t idesc_last;
   int split_S;        // 0 = off
   int split_first;    // first tail tile (= T when off): tiles below it are whole
   int split_rem;      // tail tiles
@@ -100,6 +104,18 @@ static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps (tw
 static constexpr int kEpiThreads = 256;
 static constexpr uint32_t kStageBufs = 8;          // one private epilogue staging tile per epilogue warp
 static constexpr uint32_t kStageBufBytes = 32 * 64;  // 32 rows x 32 cols (64 B, swizzled)
+
+__device__ __forceinline__ void tmem_st_32x32_g(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 
 template <bool BF16>
 __device__ __forceinline__ void epi_add_vec8(const void* base, size_t elem_off, float (&x)[8]) {
@@ -325,7 +341,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (cc < p.split_chunk) tma_load_4d_cg2(a_dst, &mapA, fb, cc * 64, cw + kx - 1, ch + ky - 1, cn);
             else tma_load_4d_cg2(a_dst, &mapA2, fb, (cc - p.split_chunk) * 64, cw + kx - 1, ch + ky - 1, cn);
           }
-          tma_load_2d_cg2(b_dst, mb, fb, bcol, b_row0 + n_blk * BN + (int)cta_rank * (BN / 2));
+          tma_load_2d_cg2(b_dst, mb, fb, bcol, b_row0 + n_blk * BN + (int)cta_rank * ((n_blk == p.tiles_n - 1 ? p.bn_last : BN) / 2));
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -338,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     int it = 0;
     const uint64_t adesc0 = make_smem_desc_sw128(a_base, 0, 1024);
     const uint64_t bdesc0 = make_smem_desc_sw128(b_base, 0, 1024);
-    const uint32_t idesc = p.idesc;
+    const uint32_t idesc_full = p.idesc;
     for (;; ++it) {
       int tile, kb, ke, role, tt, share;
       if (!work_item(it, tile, kb, ke, role, tt, share)) break;
@@ -347,6 +363,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      const int n_blk_t = p.n_fast ? tile % p.tiles_n : tile / tiles_mu;
+      const uint32_t idesc = (n_blk_t == p.tiles_n - 1) ? p.idesc_last : idesc_full;
       for (int kc = kb; kc < ke; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -395,6 +413,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const int m_blk = m_unit * CG + (int)cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int bn_t = (n_blk == p.tiles_n - 1) ? p.bn_last : BN;  // accumulator columns of this tile
       if (role == 2) {
         // ---- partial share of a K-split tail tile: raw accumulators -> workspace (element (col, row) at col * 128 + row: a
         // warp's store of one register is 128 contiguous bytes), release TMEM, publish
@@ -402,7 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         tc_fence_after();
         float* const blk = p.split_ws + ((size_t)(tt * (p.split_S - 1) + (share - 1)) * CG + cta_rank) * (256 * 128) + r;
         const uint32_t t_addr_p = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
-        for (int c = chalf * 32; c < BN; c += 64) {
+        for (int c = chalf * 32; c < bn_t; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_addr_p + (uint32_t)c, v);
           tmem_ld_wait();
@@ -416,6 +435,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         named_bar_sync(1, kEpiThreads);
         if (threadIdx.x == 128) atomicAdd(p.split_flags + tt * CG + (int)cta_rank, 1);
         continue;
+      }
+      if (role == 1) {
+        // ---- share 0 of a K-split tail tile: before anything else of the epilogue is live in registers, add the other
+        // shares' partial accumulators into this CTA's TMEM accumulator (fixed order).  All loads of a chunk are in flight
+        // together — a dependent chain of small batches made this pass cost more than the split saved.
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (threadIdx.x == 128) {
+          volatile int* f = p.split_flags + tt * CG + (int)cta_rank;
+          while (*f < p.split_S - 1) __nanosleep(20);
+          *f = 0;  // self-resetting: the next launch's shares only start after this grid has completed
+          __threadfence();
+        }
+        named_bar_sync(1, kEpiThreads);
+        const float* const src0 = p.split_ws + ((size_t)(tt * (p.split_S - 1)) * CG + cta_rank) * (256 * 128) + r;
+        const float* const src1 = src0 + (size_t)CG * (256 * 128);
+        const bool two = p.split_S == 3;
+        const uint32_t t_addr_p = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
+        for (int c = chalf * 32; c < bn_t; c += 64) {
+          uint32_t v[32];
+          float pa[32], pb[32];
+          tmem_ld_32x32(t_addr_p + (uint32_t)c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pa[i] = __ldcg(src0 + (size_t)(c + i) * 128);  // L2 loads: written by other SMs
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pb[i] = __ldcg(src1 + (size_t)(c + i) * 128);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]) + pa[i];
+            if (two) x += pb[i];
+            v[i] = __float_as_uint(x);
+          }
+          tmem_st_32x32_g(t_addr_p + (uint32_t)c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       int m = m_blk * 128 + r;
       bool row_ok = m < p.M;
@@ -576,23 +633,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         };
         if (it == 0) prefetch_res(tile);
         if (role == 0 && tile + num_units < p.split_first) prefetch_res(tile + num_units);
-        if (chalf * 32 < ncols_out) load_res(chalf * 32, rsc);
+        if (chalf * 32 < (geglu ? ncols_out : bn_t)) load_res(chalf * 32, rsc);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const float* split_src = nullptr;  // share 0 of a K-split tile: the other shares' partial accumulators of this row
-      if (role == 1) {
-        if (threadIdx.x == 128) {
-          volatile int* f = p.split_flags + tt * CG + (int)cta_rank;
-          while (*f < p.split_S - 1) __nanosleep(40);
-          *f = 0;  // self-resetting: the next launch's shares only start after this grid has completed
-          __threadfence();
-        }
-        named_bar_sync(1, kEpiThreads);
-        split_src = p.split_ws + ((size_t)(tt * (p.split_S - 1)) * CG + cta_rank) * (256 * 128) + r;
-      }
 
-      for (int c = chalf * 32; c < ncols_out; c += 64) {
+      const int ncols_t = geglu ? ncols_out : bn_t;
+      for (int c = chalf * 32; c < ncols_t; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
         uint4 rv[4], rsn[4];
         const bool has_rv = RV && rowvec_p && row_ok && !geglu;
@@ -605,7 +652,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) rsn[j] = make_uint4(0, 0, 0, 0);
-        if (any_rs && c + 64 < ncols_out) load_res(c + 64, rsn);
+        if (any_rs && c + 64 < ncols_t) load_res(c + 64, rsn);
         uint32_t v[32];
         f32x2_t xp[16];
         tmem_ld_32x32(t_addr + (uint32_t)c, v);
@@ -635,19 +682,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         } else {
           tmem_ld_wait();
-          if (split_src) {  // + partial shares, fixed order; L2 loads (the lines were written by other SMs)
-            for (int sh = 0; sh < p.split_S - 1; ++sh) {
-              const float* src = split_src + (size_t)sh * CG * (256 * 128) + (size_t)c * 128;
-#pragma unroll
-              for (int i0 = 0; i0 < 32; i0 += 8) {
-                float t8[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t8[i] = __ldcg(src + (size_t)(i0 + i) * 128);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i0 + i] = __float_as_uint(__uint_as_float(v[i0 + i]) + t8[i]);
-              }
-            }
-          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) xp[k] = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
           if (EXT && p.alpha != 0.f) {
@@ -843,53 +877,17 @@ static bool use_pair_kernel() {
   return v == 1;
 }
 
-// Workspace of the K-split tail (GemmKParams::split_*): one block of 256 x 128 floats per SM + one flag per SM, allocated once
-// per (device, stream) outside stream capture; a launch that cannot get it (first call of a stream inside a capture, more
-// than four streams) simply does not split.  B200_GEMM_SPLITK=0 turns the split off.
-struct SplitWs {
-  int dev;
-  cudaStream_t stream;
-  float* ws;
-  int* flags;
-};
-static bool split_ws_get(cudaStream_t stream, float** ws, int** flags) {
+// Workspace of the K-split tail (GemmKParams::split_*), caller-owned (b200_gemm_desc::workspace): [num_sms ints of flags,
+// padded to 1 KB][num_sms blocks of 256 x 128 floats].  B200_GEMM_SPLITK=0 turns the split off.
+static bool split_enabled() {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("B200_GEMM_SPLITK");
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!enabled) return false;
-  static SplitWs table[4];
-  static int used = 0;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return false;
-  for (int i = 0; i < used; ++i)
-    if (table[i].dev == dev && table[i].stream == stream) {
-      *ws = table[i].ws;
-      *flags = table[i].flags;
-      return true;
-    }
-  if (used == 4) return false;
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
-    cudaGetLastError();
-    return false;
-  }
-  const int n = num_sms();
-  float* w = nullptr;
-  int* f = nullptr;
-  if (cudaMalloc(&w, (size_t)n * 256 * 128 * sizeof(float)) != cudaSuccess || cudaMalloc(&f, (size_t)n * sizeof(int)) != cudaSuccess ||
-      cudaMemset(f, 0, (size_t)n * sizeof(int)) != cudaSuccess) {
-    cudaGetLastError();
-    if (w) cudaFree(w);
-    if (f) cudaFree(f);
-    return false;
-  }
-  table[used++] = SplitWs{dev, stream, w, f};
-  *ws = w;
-  *flags = f;
-  return true;
+  return enabled == 1;
 }
+static size_t split_flag_bytes() { return ((size_t)num_sms() * sizeof(int) + 1023) & ~(size_t)1023; }
 
 template <bool BF16, int CG, int FEAT>
 static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
@@ -916,16 +914,21 @@ static int launch_gemm_t(const CUtensorMap& mapA, const CUtensorMap& mapA2, cons
     const int rem = total % units;
     if (rem > 0 && 2 * rem <= units && p.epilogue != B200_EPI_GEGLU) {
       int S = units / rem;
-      if (S > 4) S = 4;
-      while (S > 1 && p.num_k_chunks / S < 4) --S;
-      float* ws = nullptr;
-      int* flags = nullptr;
-      if (S >= 2 && split_ws_get(stream, &ws, &flags)) {
+      if (S > 3) S = 3;
+      // worth it only when the k-chunks a tail unit no longer runs outweigh the exchange (~4 us: dump, flag, one L2 round
+      // trip per accumulator chunk; a 256 x 256 x 64 chunk is ~0.45 us): measured break-even near 24 chunks
+      static int min_saved = -1;
+      if (min_saved < 0) {
+        const char* e = getenv("B200_GEMM_SPLITK_MIN");
+        min_saved = e ? atoi(e) : 24;
+      }
+      if (S >= 2 && p.num_k_chunks - p.num_k_chunks / S < min_saved) S = 1;
+      if (S >= 2 && p.split_ws && split_enabled()) {  // split_ws arrives holding the caller's workspace pointer
         p.split_S = S;
         p.split_first = total - rem;
         p.split_rem = rem;
-        p.split_ws = ws;
-        p.split_flags = flags;
+        p.split_flags = reinterpret_cast<int*>(p.split_ws);
+        p.split_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(p.split_ws) + split_flag_bytes());
       }
     }
   }
@@ -956,6 +959,20 @@ static int gemm_cg(const GemmKParams& p) { return (use_pair_kernel() && p.tiles_
 template <int FEAT>
 static int launch_gemm_e(const CUtensorMap& mapA, const CUtensorMap& mapA2, const CUtensorMap& mapB,
                          const CUtensorMap& mapB2, GemmKParams& p, int dtype, int cg, cudaStream_t stream) {
+  {
+    // width of the last N tile, in whole 32-column epilogue chunks (GEGLU tiles are always full: N % BN == 0 is required)
+    int last = p.N - (p.tiles_n - 1) * p.BN;
+    last = (last + 31) / 32 * 32;
+    if (last > p.BN || last <= 0 || p.epilogue == B200_EPI_GEGLU) last = p.BN;
+    static int narrow = -1;
+    if (narrow < 0) {
+      const char* e = getenv("B200_GEMM_NARROW_LAST");
+      narrow = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!narrow) last = p.BN;
+    p.bn_last = last;
+    p.idesc_last = make_idesc_f16(cg == 2 ? 256 : 128, last, dtype == B200_BF16, false, false);
+  }
   if (cg == 2) {
     p.idesc = make_idesc_f16(256, p.BN, dtype == B200_BF16, false, false);
     return dtype == B200_BF16 ? launch_gemm_t<true, 2, FEAT>(mapA, mapA2, mapB, mapB2, p, stream)
@@ -983,6 +1000,8 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapA2, const 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" size_t b200_gemm_workspace_bytes(void) { return split_flag_bytes() + (size_t)num_sms() * 256 * 128 * sizeof(float); }
 
 extern "C" int b200_gemm_row_stats_parts(int N, int epilogue, int block_n) {
   if (N <= 0) return 0;
@@ -1038,6 +1057,8 @@ extern "C" int b200_gemm(const void* A, const void* B, void* C, const b200_gemm_
   p.ln_d = d->ln_d;
   p.ln_eps = d->ln_eps;
   p.row_stats_out = reinterpret_cast<float4*>(d->row_stats_out);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0, "gemm: workspace must be 16-byte aligned");
+  p.split_ws = reinterpret_cast<float*>(d->workspace);
   B200_CHECK_ARG(!d->ln_stats || (d->ln_c && d->ln_d && !d->A2 && d->ln_stats_parts > 0),
                  "gemm: LayerNorm folding needs ln_c, ln_d and ln_stats_parts (single A source)");
   B200_CHECK_ARG(!d->row_stats_out || (d->epilogue != B200_EPI_GEGLU && d->N % 32 == 0),
@@ -1179,6 +1200,7 @@ static int conv3x3_impl(const void* x1, const void* x2, const void* w_packed, vo
   p.rowvec = d->temb;
   p.ld_rowvec = d->ld_temb;
   B200_CHECK_ARG(!d->temb || d->ld_temb % 8 == 0, "conv3x3: ld_temb");
+  p.split_ws = reinterpret_cast<float*>(d->workspace);
   p.rows_per_vec = (up2x ? 4 : 1) * d->H * d->W;
   p.epilogue = d->epilogue;
   p.n_fast = raster_n_fast((size_t)p.M * C, (size_t)d->Cout * ntaps * C, p.tiles_n);  // activations vs weights (each tap re-reads the same activation rows)

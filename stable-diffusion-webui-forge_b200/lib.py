@@ -41,6 +41,7 @@ class GemmDesc(C.Structure):
         ("B2", C.c_void_p), ("bias2", C.c_void_p), ("rowvec2", C.c_void_p),
         ("seg_period", C.c_int), ("seg_split", C.c_int), ("rowvec_mul", C.c_int), ("act_col0", C.c_int),
         ("alpha", C.c_float),
+        ("workspace", C.c_void_p),
     ]
 
 
@@ -51,6 +52,7 @@ class Conv3x3Desc(C.Structure):
         ("dtype", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int),
         ("temb", C.c_void_p), ("ld_temb", C.c_int),
+        ("workspace", C.c_void_p),
     ]
 
 
@@ -90,6 +92,7 @@ SIGNATURES = {
     "b200_device_ok": (_i, []),
     "b200_num_sms": (_i, []),
     "b200_gemm": (_i, [_vp, _vp, _vp, C.POINTER(GemmDesc), _vp]),
+    "b200_gemm_workspace_bytes": (_sz, []),
     "b200_gemm_row_stats_parts": (_i, [_i, _i, _i]),
     "b200_conv3x3": (_i, [_vp, _vp, _vp, _vp, C.POINTER(Conv3x3Desc), _vp]),
     "b200_conv3x3_up2x": (_i, [_vp, _vp, _vp, _vp, C.POINTER(Conv3x3Desc), _vp]),

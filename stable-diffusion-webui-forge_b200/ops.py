@@ -65,6 +65,23 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} / {t.stride()}")
 
 
+_WS: dict = {}
+
+
+def gemm_workspace(device: torch.device) -> int:
+    """Scratch buffer of the GEMM / convolution K-split (b200_gemm_desc.workspace) for the CURRENT stream of `device`: one
+    zero-initialised buffer per (device, stream) — launches on one stream never overlap, launches on different streams get
+    different buffers.  Allocated through torch's caching allocator, so a first use inside a CUDA-graph capture is legal (the
+    block then lives in the graph's pool for as long as this cache holds it)."""
+    st = torch.cuda.current_stream(device)
+    key = (st.device.index, st.cuda_stream)
+    t = _WS.get(key)
+    if t is None:
+        t = torch.zeros(_l.load().b200_gemm_workspace_bytes(), dtype=torch.uint8, device=st.device)
+        _WS[key] = t
+    return t.data_ptr()
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          residual: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 1,
          epilogue: int = EPI_NONE, a2: Optional[torch.Tensor] = None, bias_along_m: bool = False,
@@ -98,6 +115,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     assert out.shape[0] == M and out.shape[1] == n_out
     d = _l.GemmDesc()
     d.M, d.N, d.K = M, N, K
+    d.workspace = gemm_workspace(a.device)
     d.lda, d.ldb, d.ldc = a.stride(0), w.stride(0), out.stride(0)
     d.dtype = _dt(a)
     d.epilogue = epilogue
@@ -238,6 +256,7 @@ def conv3x3(x1: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tenso
     assert out.is_contiguous()
     d = _l.Conv3x3Desc()
     d.N, d.H, d.W, d.C1, d.C2, d.Cout = n, h, w_, c1, c2, cout
+    d.workspace = gemm_workspace(x1.device)
     d.dtype = _dt(x1)
     d.epilogue = epilogue
     d.block_n = block_n
@@ -296,6 +315,7 @@ def conv3x3_up2x(x: torch.Tensor, w_packed4: torch.Tensor, bias: Optional[torch.
     assert out.is_contiguous() and out.shape == (n, 2 * h, 2 * w_, cout)
     d = _l.Conv3x3Desc()
     d.N, d.H, d.W, d.C1, d.C2, d.Cout = n, h, w_, c, 0, cout
+    d.workspace = gemm_workspace(x.device)
     d.dtype = _dt(x)
     d.epilogue = epilogue
     d.block_n = block_n
