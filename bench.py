@@ -395,7 +395,7 @@ def run_flux(args):
         at = fam.get("attention", {"launches": 0, "flops": 0.0, "ms": 1.0})
         ach = at["flops"] / (at["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roof = {"kernel": "b200::attn128_kernel (joint txt+img attention, 24 heads x 128, 4352 tokens, batch %d)" % B,
+        roof = {"kernel": "b200::attn64s_kernel<DH=128> (small-CTA attention, joint txt+img attention, 24 heads x 128, 4352 tokens, batch %d)" % B,
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)", "launches": at["launches"],
                 "avg_launch_ms": at["ms"] / max(1, at["launches"]), "flops_per_launch_avg": at["flops"] / max(1, at["launches"])}

@@ -95,6 +95,9 @@ struct GemmKParams {
   int* split_flags;   // [split_rem][CG], self-resetting
 };
 
+#ifndef B200_GEMM_SETMAXNREG
+#define B200_GEMM_SETMAXNREG 1
+#endif
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 halfs
 // Two epilogue warps per TMEM lane quadrant.  Three (512 threads, setmaxnreg 48 / 152) were measured and are SLOWER on every
 // flavour (UNet step 118.3 vs 114.5 ms, LayerNorm-fold N3840 1187 vs 1296 TF/s): the mainloop sits on the shared-memory port
@@ -180,8 +183,15 @@ __device__ __forceinline__ void ln_apply8(uint32_t c_smem, uint32_t d_smem, int 
 // bit 1 (EXT) the Flux-path features (row segments with two weight sets, multiplicative rowvec, partial activation,
 // tanh GELU), bit 2 (GT) generic convolution tiling for image widths that are neither a power of two nor a multiple of
 // 128 (B200_CONV_GENERAL=0 turns it off).  Convolutions and plain linears run the FEAT = 0 build.
+// __maxnreg__ rather than __launch_bounds__: with setmaxnreg in the kernel ptxas takes the cap as the LAUNCH-time register
+// count and lets the code after setmaxnreg.inc use the raised count (under __launch_bounds__ the 168 stayed a hard cap for the
+// whole kernel and the epilogue spilled)
 template <bool BF16, int CG, int FEAT>
+#if B200_GEMM_SETMAXNREG
+__global__ void __maxnreg__(168)
+#else
 __global__ void __launch_bounds__(kThreads, 1)
+#endif
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
             const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
             const GemmKParams p) {
@@ -270,6 +280,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     return true;
   };
 
+#if B200_GEMM_SETMAXNREG
+  // Register split by warpgroup (setmaxnreg is warpgroup-wide; warps 0-3 = control, 4-11 = epilogue): the control warps keep
+  // 56 registers, the epilogue warps take 224 (4 x 56 + 8 x 224 = 2016 of the 2048 x 32 the CTA was launched with).  The
+  // epilogue of the K <= 1280 GEMMs is a latency chain (TMEM -> math -> staging -> stores) per 32-column chunk at 168 registers
+  // with spills; with 224 the next chunk's TMEM load and the residual loads fly under the current chunk's arithmetic.
+  // (each count governs the code of ITS branch only: the two roles must not share code after the instruction)
+#endif
+  if (warp < 4) {
+#if B200_GEMM_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+#endif
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
@@ -400,7 +421,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+#if B200_GEMM_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+#endif
     // ------------------------------------------------------------------ epilogue
     // Per 32-column chunk: TMEM -> registers -> (bias, temb row, activation, residual) -> fp16/bf16 ->
     // warp-private 64B-swizzled staging tile in smem -> coalesced full-sector global stores.
@@ -651,6 +676,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       tc_fence_after();
 
       const int ncols_t = geglu ? ncols_out : bn_t;
+      uint32_t v[32];  // accumulator chunk: loaded one chunk ahead (the next load is issued as soon as these registers are consumed)
+      if (chalf * 32 < ncols_t) tmem_ld_32x32(t_addr + (uint32_t)(chalf * 32), v);
       for (int c = chalf * 32; c < ncols_t; c += 64) {
         // issue this chunk's global operand loads first so their latency overlaps the TMEM read
         uint4 rv[4], rsn[4];
@@ -665,9 +692,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 4; ++j) rsn[j] = make_uint4(0, 0, 0, 0);
         if (any_rs && c + 64 < ncols_t) load_res(c + 64, rsn);
-        uint32_t v[32];
         f32x2_t xp[16];
-        tmem_ld_32x32(t_addr + (uint32_t)c, v);
         if (geglu) {
           uint32_t vg[32];
           tmem_ld_32x32(t_addr + (uint32_t)(ncols_out + c), vg);
@@ -692,10 +717,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             for (int i = 0; i < 8; i += 2)
               xp[g * 4 + (i >> 1)] = mul2(pk2(xv[i], xv[i + 1]), gelu_erf_x2(pk2(gt[i], gt[i + 1])));
           }
+          if (c + 64 < ncols_t) tmem_ld_32x32(t_addr + (uint32_t)(c + 64), v);
         } else {
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 16; ++k) xp[k] = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+          if (c + 64 < ncols_t) tmem_ld_32x32(t_addr + (uint32_t)(c + 64), v);
           if (EXT && p.alpha != 0.f) {
             const f32x2_t a2 = pk2(p.alpha, p.alpha);
 #pragma unroll
