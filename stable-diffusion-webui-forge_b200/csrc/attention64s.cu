@@ -1,4 +1,6 @@
-// b200forge — head-dim-64 attention forward, "small CTA" build: ONE 128-query tile per CTA, key blocks of 64, THREE CTAs per SM.
+// b200forge — attention forward, "small CTA" build: ONE 128-query tile per CTA, key blocks of 64, several CTAs per SM.
+// Written for head dim 64 (SD1.5 / SDXL: three CTAs per SM, described first); the same pipeline is also built for head dim 128
+// (Flux / SD3: two CTAs per SM — see the note above the kernel).
 //
 // Why a second organisation (measured on B200, profiles/experiments/README.md):
 //   * the exponential pipe (MUFU, 16 / clk / SM) bounds Dh = 64 attention; one softmax warp alone reaches ~10 clk per
