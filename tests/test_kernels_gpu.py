@@ -47,8 +47,8 @@ def test_gemm_plain(M, N, K, dtype):
 
 @pytest.mark.parametrize("M,N,K,dtype", [(16384, 1280, 5120, torch.float16),   # 64 pair tiles x 5 = 320 on 74 pairs: tail 24, 3 shares
                                           (5632, 1280, 5120, torch.float16),    # 110 tiles: tail 36, 2 shares
-                                          (1024, 1280, 2560, torch.bfloat16),   # 4 pair tiles x 5 = 20 on 74: 3 shares
-                                          (16, 1280, 4096, torch.float16),      # 5 single-CTA tiles on 148 SMs: 3 shares
+                                          (1024, 1280, 2560, torch.bfloat16),   # 20 pair tiles: fewer tiles than units, one wave, not split
+                                          (16, 1280, 4096, torch.float16),      # 5 single-CTA tiles: one wave, not split
                                           (16384, 1280, 1280, torch.float16)])  # same tail, too few k-chunks: not split
 def test_gemm_k_split_tail(M, N, K, dtype):
     """Shapes whose tile count leaves a partly filled last wave: the tail tiles are K-split across the idle units (partial
